@@ -1,0 +1,218 @@
+// extern "C" boundary (include/vqae_b200.h): argument checks, block composition, launch counting.
+#include <atomic>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vqae {
+
+static thread_local cudaError_t g_last_error = cudaSuccess;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_last_cuda_error(cudaError_t e) { g_last_error = e; }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct FixupScratch {
+    size_t t1, t2, t3, skip, total;  // byte offsets
+};
+
+// byte layout of the scratch buffer of one block call
+static FixupScratch fixup_layout(const vqae_fixup_params* p, int64_t B, int H, int W) {
+    FixupScratch s{};
+    const size_t px = (size_t)B * H * W;
+    const size_t cb = (size_t)p->c_branch, co = (size_t)p->c_out;
+    size_t off = 0;
+    auto take = [&](size_t elems) {
+        size_t o = off;
+        off += align256(elems * sizeof(float));
+        return o;
+    };
+    if (p->mode == VQAE_MODE_SAME) {
+        s.t1 = take(px * cb);
+        s.t2 = take(px * cb);
+    } else if (p->mode == VQAE_MODE_DOWN) {
+        s.t1 = take(px * cb);
+        s.t2 = take(px / 4 * cb);
+        s.skip = take(px / 4 * co);
+    } else {
+        s.t1 = take(px * cb);        // branch_conv1 output, low res
+        s.t2 = take(px * cb);        // 1x1 of branch_conv2 applied at low res
+        s.t3 = take(px * 4 * cb);    // ... upsampled
+        s.skip = take(px * 4 * co);  // upsampled skip
+        // the low-res skip conv output reuses t1 after branch_conv2 has consumed it
+    }
+    s.total = off;
+    return s;
+}
+
+}  // namespace vqae
+
+using namespace vqae;
+
+extern "C" {
+
+int vqae_abi_version(void) { return VQAE_ABI_VERSION; }
+
+const char* vqae_error_string(int code) {
+    switch (code) {
+        case VQAE_OK: return "ok";
+        case VQAE_ERR_BAD_ARG: return "bad argument (null pointer or non-positive extent)";
+        case VQAE_ERR_UNSUPPORTED: return "shape/dtype/layout not supported by the sm_100a kernels";
+        case VQAE_ERR_DIM_MISMATCH: return "VQ dim != channel dim not supported";
+        case VQAE_ERR_CUDA: return "CUDA runtime error";
+        case VQAE_ERR_SCRATCH: return "scratch buffer missing or too small";
+    }
+    return "unknown error";
+}
+
+const char* vqae_last_cuda_error(void) { return cudaGetErrorString(g_last_error); }
+
+uint64_t vqae_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int vqae_normalize_u8(const uint8_t* img, float* out, int64_t batch, int height, int width,
+                      const float* mean_host, const float* std_host, int out_layout,
+                      void* stream) {
+    return normalize_u8(img, out, batch, height, width, mean_host, std_host, out_layout,
+                        (cudaStream_t)stream);
+}
+
+int vqae_pack_conv_weight_f32(const float* w_oihw, float* packed, int out_ch, int in_ch, int kh,
+                              int kw, void* stream) {
+    return pack_conv_weight_f32(w_oihw, packed, out_ch, in_ch, kh * kw, (cudaStream_t)stream);
+}
+
+int vqae_stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w_oihw,
+                     const float* bias, float* out, int64_t batch, int height, int width,
+                     int c_out, const float* mean_host, const float* std_host, void* stream) {
+    return stem_in_f32(x, x_dtype, x_layout, w_oihw, bias, out, batch, height, width, c_out,
+                       mean_host, std_host, (cudaStream_t)stream);
+}
+
+int vqae_stem_out_f32(const float* x, const float* w_oihw, const float* bias, float* out,
+                      int out_layout, int64_t batch, int height, int width, int c_in,
+                      void* stream) {
+    return stem_out_f32(x, w_oihw, bias, out, out_layout, batch, height, width, c_in,
+                        (cudaStream_t)stream);
+}
+
+int vqae_conv_f32(int kind, const float* x, const float* w_packed, float* out,
+                  const float* residual, int64_t batch, int height, int width, int c_in,
+                  int c_out, float pre_add, int pre_elu, float post_add, float scale, float bias,
+                  void* stream) {
+    if (kind < CONV_1x1 || kind > CONV_3x3_CIRC) return VQAE_ERR_BAD_ARG;
+    return conv_f32(kind, x, w_packed, out, residual, batch, height, width, c_in, c_out,
+                    PreOp{pre_add, post_add, pre_elu}, scale, bias, (cudaStream_t)stream);
+}
+
+int vqae_bicubic_up2_f32(const float* x, float* out, int64_t batch, int height, int width, int c,
+                         float bias, void* stream) {
+    return bicubic_up2_f32(x, out, batch, height, width, c, bias, (cudaStream_t)stream);
+}
+
+size_t vqae_fixup_block_scratch_bytes(const vqae_fixup_params* p, int64_t batch, int height,
+                                      int width) {
+    if (!p || batch <= 0 || height <= 0 || width <= 0) return 0;
+    return fixup_layout(p, batch, height, width).total;
+}
+
+int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out, void* scratch,
+                         size_t scratch_bytes, int64_t B, int H, int W, void* stream_) {
+    if (!p || !x || !out || !p->w1 || !p->w2 || !p->w3 || B <= 0 || H <= 0 || W <= 0)
+        return VQAE_ERR_BAD_ARG;
+    if (x == out) return VQAE_ERR_BAD_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const FixupScratch L = fixup_layout(p, B, H, W);
+    if (!scratch || scratch_bytes < L.total) return VQAE_ERR_SCRATCH;
+    char* base = reinterpret_cast<char*>(scratch);
+    float* t1 = reinterpret_cast<float*>(base + L.t1);
+    float* t2 = reinterpret_cast<float*>(base + L.t2);
+    const int ci = p->c_in, co = p->c_out, cb = p->c_branch;
+    const PreOp pre1{p->bias1a, p->bias1b, 1};
+    const PreOp pre2{p->bias2a, p->bias2b, 1};
+    const PreOp pre3{p->bias3a, p->bias3b, 1};
+    const PreOp pre_skip{p->bias1c, 0.f, 0};
+    int rc;
+
+    // branch_conv1(act(x + bias1a) + bias1b)                      conv_block.py:199-200
+    rc = conv_f32(CONV_1x1, x, p->w1, t1, nullptr, B, H, W, ci, cb, pre1, 1.f, 0.f, stream);
+    if (rc) return rc;
+
+    if (p->mode == VQAE_MODE_SAME) {
+        if (ci != co || p->w_skip) return VQAE_ERR_UNSUPPORTED;
+        // branch_conv2: 3x3 circular                              conv_block.py:202-203
+        rc = conv_f32(CONV_3x3_CIRC, t1, p->w2, t2, nullptr, B, H, W, cb, cb, pre2, 1.f, 0.f,
+                      stream);
+        if (rc) return rc;
+        // branch_conv3, * scale + bias4, + inp                    conv_block.py:205-214
+        return conv_f32(CONV_1x1, t2, p->w3, out, x, B, H, W, cb, co, pre3, p->scale, p->bias4,
+                        stream);
+    }
+    if (!p->w_skip) return VQAE_ERR_BAD_ARG;
+    float* skip = reinterpret_cast<float*>(base + L.skip);
+
+    if (p->mode == VQAE_MODE_DOWN) {
+        if ((H | W) & 1) return VQAE_ERR_UNSUPPORTED;
+        rc = conv_f32(CONV_2x2S2, t1, p->w2, t2, nullptr, B, H, W, cb, cb, pre2, 1.f, 0.f, stream);
+        if (rc) return rc;
+        // skip_conv(inp + bias1c) + bias1d                        conv_block.py:211-213
+        rc = conv_f32(CONV_2x2S2, x, p->w_skip, skip, nullptr, B, H, W, ci, co, pre_skip, 1.f,
+                      p->bias1d, stream);
+        if (rc) return rc;
+        return conv_f32(CONV_1x1, t2, p->w3, out, skip, B, H / 2, W / 2, cb, co, pre3, p->scale,
+                        p->bias4, stream);
+    }
+    if (p->mode == VQAE_MODE_UP) {
+        // ResizeConv2D = conv1x1(bicubic_up2(.)) (layers/conv.py:10-11).  Both maps are linear and
+        // the conv has no bias, so the 1x1 runs at low resolution and the upsample follows.
+        float* t3 = reinterpret_cast<float*>(base + L.t3);
+        rc = conv_f32(CONV_1x1, t1, p->w2, t2, nullptr, B, H, W, cb, cb, pre2, 1.f, 0.f, stream);
+        if (rc) return rc;
+        rc = bicubic_up2_f32(t2, t3, B, H, W, cb, 0.f, stream);
+        if (rc) return rc;
+        // skip: conv1x1(inp + bias1c) at low res (into t1, now free), upsample, + bias1d
+        rc = conv_f32(CONV_1x1, x, p->w_skip, t1, nullptr, B, H, W, ci, co, pre_skip, 1.f, 0.f,
+                      stream);
+        if (rc) return rc;
+        rc = bicubic_up2_f32(t1, skip, B, H, W, co, p->bias1d, stream);
+        if (rc) return rc;
+        return conv_f32(CONV_1x1, t3, p->w3, out, skip, B, 2 * H, 2 * W, cb, co, pre3, p->scale,
+                        p->bias4, stream);
+    }
+    return VQAE_ERR_BAD_ARG;
+}
+
+int vqae_quantizer_prepare_f32(const float* embed, int num_codes, int dim, const float* w_out,
+                               const float* b_out, int c, float* table, void* stream) {
+    return quantizer_prepare_f32(embed, num_codes, dim, w_out, b_out, c, table,
+                                 (cudaStream_t)stream);
+}
+
+size_t vqae_quantizer_scratch_bytes(int64_t n_vectors) {
+    return quantizer_scratch_bytes(n_vectors);
+}
+
+int vqae_quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layout, float* out,
+                      int out_layout, int64_t* indices, float* loss, uint32_t* near_ties,
+                      float tie_rel_gap, float* z_out, void* scratch, size_t scratch_bytes,
+                      int64_t batch, int64_t spatial, void* stream) {
+    return quantize_f32(p, x, x_layout, out, out_layout, indices, loss, near_ties, tie_rel_gap,
+                        z_out, scratch, scratch_bytes, batch, spatial, (cudaStream_t)stream);
+}
+
+int vqae_embed_codes_f32(const void* indices, int idx_is_u8, const float* table, int num_codes,
+                         int c, float* out, int out_layout, int64_t batch, int64_t spatial,
+                         void* stream) {
+    return embed_codes_f32(indices, idx_is_u8, table, num_codes, c, out, out_layout, batch,
+                           spatial, (cudaStream_t)stream);
+}
+
+int vqae_codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw,
+                          int64_t first_patch, int grid_cols, uint8_t* map, int64_t map_rows,
+                          int64_t map_cols, void* stream) {
+    return codemap_place_u8(tiles, n_tiles, th, tw, first_patch, grid_cols, map, map_rows,
+                            map_cols, (cudaStream_t)stream);
+}
+
+}  // extern "C"

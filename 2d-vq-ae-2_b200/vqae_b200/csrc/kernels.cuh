@@ -1,0 +1,41 @@
+// Internal (C++) launch interface between the C-ABI in abi.cu and the kernel files.
+#pragma once
+#include "common.cuh"
+
+namespace vqae {
+
+enum ConvKind { CONV_1x1 = 0, CONV_2x2S2 = 1, CONV_3x3_CIRC = 2 };
+
+// conv_f32.cu
+int conv_f32(int kind, const float* in, const float* w, float* out, const float* res, int64_t B,
+             int Hi, int Wi, int Cin, int Cout, PreOp pre, float scale, float bias,
+             cudaStream_t stream);
+int bicubic_up2_f32(const float* in, float* out, int64_t B, int H, int W, int C, float bias,
+                    cudaStream_t stream);
+int pack_conv_weight_f32(const float* w, float* packed, int O, int I, int taps,
+                         cudaStream_t stream);
+
+// stems.cu
+int normalize_u8(const uint8_t* img, float* out, int64_t B, int H, int W, const float* mean,
+                 const float* stdv, int out_layout, cudaStream_t stream);
+int stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w, const float* bias,
+                float* out, int64_t B, int H, int W, int c_out, const float* mean,
+                const float* stdv, cudaStream_t stream);
+int stem_out_f32(const float* x, const float* w, const float* bias, float* out, int out_layout,
+                 int64_t B, int H, int W, int c_in, cudaStream_t stream);
+
+// quantize.cu
+int quantizer_prepare_f32(const float* embed, int K, int D, const float* w_out,
+                          const float* b_out, int C, float* table, cudaStream_t stream);
+size_t quantizer_scratch_bytes(int64_t n);
+int quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layout, float* out,
+                 int out_layout, int64_t* indices, float* loss, uint32_t* near_ties,
+                 float tie_rel_gap, float* z_out, void* scratch, size_t scratch_bytes,
+                 int64_t B, int64_t S, cudaStream_t stream);
+int embed_codes_f32(const void* indices, int idx_is_u8, const float* table, int K, int C,
+                    float* out, int out_layout, int64_t B, int64_t S, cudaStream_t stream);
+int codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw, int64_t first_patch,
+                     int grid_cols, uint8_t* map, int64_t map_rows, int64_t map_cols,
+                     cudaStream_t stream);
+
+}  // namespace vqae

@@ -1,0 +1,315 @@
+"""Host-side execution of the hot path over the C-ABI library.
+
+torch is plumbing here: device memory (``torch.empty``), the current CUDA stream, and
+``state_dict`` tensors.  Every FLOP is issued through ``libvqae_b200.so``.  There is no CPU
+path: tensors that are not on a CUDA device raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+
+# near-tie threshold on the relative top-2 gap of the un-rooted L4 sums
+NEAR_TIE_REL_GAP = 16.0 * 2.0 ** -23
+
+CAMELYON16_MEAN = (0.7279, 0.5955, 0.7762)   # conf/transforms/camelyon16_transforms.yaml:15-23
+CAMELYON16_STD = (0.2419, 0.3083, 0.1741)
+
+
+def _ptr(t: Optional[Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what}: tensor is on {t.device}; the B200 path has no CPU fallback "
+            "(move the module and its inputs to a CUDA device)")
+
+
+_workspaces: Dict[Tuple[int, int], Tensor] = {}
+
+
+def workspace(device: torch.device, nbytes: int) -> Tensor:
+    """Grow-only scratch buffer per (device, stream)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def is_channels_last(x: Tensor) -> bool:
+    return (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+            and not x.is_contiguous())
+
+
+def to_nhwc(x: Tensor) -> Tuple[Tensor, bool]:
+    """[B,C,H,W] (any strides) -> contiguous [B,H,W,C] fp32, and whether x was channels_last."""
+    cl = is_channels_last(x)
+    y = x.permute(0, 2, 3, 1)
+    if y.dtype != torch.float32:
+        y = y.float()
+    return y.contiguous(), cl
+
+
+def from_nhwc(y: Tensor, channels_last: bool) -> Tensor:
+    """contiguous [B,H,W,C] -> NCHW-shaped tensor whose strides follow the caller's format."""
+    v = y.permute(0, 3, 1, 2)
+    return v if channels_last else v.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# weight packing
+# ----------------------------------------------------------------------------------------------
+def pack_conv_weight(w: Tensor) -> Tensor:
+    """OIHW fp32 -> [KH*KW][I][O] fp32 on the device (vqae_pack_conv_weight_f32)."""
+    require_cuda(w, "pack_conv_weight")
+    w = w.detach().float().contiguous()
+    o, i, kh, kw = w.shape
+    out = torch.empty(kh * kw, i, o, dtype=torch.float32, device=w.device)
+    lib = L.load()
+    L.check(lib.vqae_pack_conv_weight_f32(_ptr(w), _ptr(out), o, i, kh, kw, _stream(w.device)),
+            "vqae_pack_conv_weight_f32")
+    return out
+
+
+_SCALARS = ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "scale",
+            "bias1c", "bias1d")
+
+
+class PackedFixup:
+    """Device-resident packed weights + the C struct of one PreActFixupResBlock."""
+
+    def __init__(self, block, scalars: Sequence[float]):
+        w2 = block.branch_conv2.weight
+        k2 = w2.shape[-1]
+        self.mode = {3: L.MODE_SAME, 2: L.MODE_DOWN, 1: L.MODE_UP}[k2]
+        self.c_in = block.branch_conv1.weight.shape[1]
+        self.c_branch = block.branch_conv1.weight.shape[0]
+        self.c_out = block.branch_conv3.weight.shape[0]
+        self.w1 = pack_conv_weight(block.branch_conv1.weight)
+        self.w2 = pack_conv_weight(w2)
+        self.w3 = pack_conv_weight(block.branch_conv3.weight)
+        self.w_skip = (pack_conv_weight(block.skip_conv.weight)
+                       if block.skip_conv is not None else None)
+        self.scalars = dict(zip(_SCALARS, scalars))
+        p = L.FixupParams()
+        p.mode, p.c_in, p.c_out, p.c_branch = self.mode, self.c_in, self.c_out, self.c_branch
+        p.w1, p.w2, p.w3 = self.w1.data_ptr(), self.w2.data_ptr(), self.w3.data_ptr()
+        p.w_skip = self.w_skip.data_ptr() if self.w_skip is not None else None
+        for name, val in self.scalars.items():
+            setattr(p, name, float(val))
+        self.params = p
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        if self.mode == L.MODE_DOWN:
+            return h // 2, w // 2
+        if self.mode == L.MODE_UP:
+            return 2 * h, 2 * w
+        return h, w
+
+
+def block_version(block) -> Tuple:
+    return tuple((p.data_ptr(), p._version) for p in block.parameters())
+
+
+def pack_blocks(blocks: Sequence) -> List[PackedFixup]:
+    """Pack a list of PreActFixupResBlocks; scalar parameters are read with ONE host copy."""
+    if not blocks:
+        return []
+    dev = blocks[0].bias1a.device
+    zero = torch.zeros(1, device=dev)
+    cols = []
+    for b in blocks:
+        for name in _SCALARS:
+            t = getattr(b, name, None)
+            cols.append(t.detach().float().reshape(1) if t is not None else zero)
+    host = torch.cat(cols).cpu().tolist()
+    n = len(_SCALARS)
+    return [PackedFixup(b, host[i * n:(i + 1) * n]) for i, b in enumerate(blocks)]
+
+
+# ----------------------------------------------------------------------------------------------
+# single calls
+# ----------------------------------------------------------------------------------------------
+def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """x: contiguous NHWC fp32 [B,H,W,c_in] -> NHWC fp32 [B,H',W',c_out]."""
+    lib = L.load()
+    b, h, w, c = x.shape
+    if c != pk.c_in:
+        raise ValueError(f"fixup block expects {pk.c_in} input channels, got {c}")
+    ho, wo = pk.out_hw(h, w)
+    if out is None:
+        out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
+    need = lib.vqae_fixup_block_scratch_bytes(C.byref(pk.params), b, h, w)
+    ws = workspace(x.device, need)
+    L.check(lib.vqae_fixup_block_f32(C.byref(pk.params), _ptr(x), _ptr(out), _ptr(ws),
+                                     ws.numel(), b, h, w, _stream(x.device)),
+            "vqae_fixup_block_f32")
+    return out
+
+
+def stem_in(x: Tensor, weight: Tensor, bias: Tensor, mean=None, std=None) -> Tensor:
+    """x: fp32 [B,3,H,W] (NCHW or channels_last strides) or u8 [B,H,W,3] -> NHWC fp32 [B,H,W,8]."""
+    lib = L.load()
+    require_cuda(x, "stem_in")
+    w = weight.detach().float().contiguous()
+    bi = bias.detach().float().contiguous()
+    if x.dtype == torch.uint8:
+        if x.dim() != 4 or x.shape[-1] != 3:
+            raise ValueError("uint8 input must be [B,H,W,3]")
+        x = x.contiguous()
+        b, h, wd, _ = x.shape
+        dt, lay = L.DT_U8, L.LAYOUT_NHWC
+        mean_a, std_a = L.f3(mean or CAMELYON16_MEAN), L.f3(std or CAMELYON16_STD)
+    else:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected [B,3,H,W] input, got {tuple(x.shape)}")
+        b, _, h, wd = x.shape
+        if x.dtype != torch.float32:
+            x = x.float()
+        if is_channels_last(x):
+            lay = L.LAYOUT_NHWC
+        else:
+            x = x.contiguous()
+            lay = L.LAYOUT_NCHW
+        dt, mean_a, std_a = L.DT_F32, None, None
+    out = torch.empty(b, h, wd, w.shape[0], dtype=torch.float32, device=x.device)
+    L.check(lib.vqae_stem_in_f32(_ptr(x), dt, lay, _ptr(w), _ptr(bi), _ptr(out), b, h, wd,
+                                 w.shape[0], mean_a, std_a, _stream(x.device)),
+            "vqae_stem_in_f32")
+    return out
+
+
+def stem_out(x_nhwc: Tensor, weight: Tensor, bias: Tensor, channels_last: bool) -> Tensor:
+    """NHWC fp32 [B,H,W,8] -> [B,3,H,W] (contiguous NCHW, or channels_last strides)."""
+    lib = L.load()
+    b, h, wd, c = x_nhwc.shape
+    w = weight.detach().float().contiguous()
+    bi = bias.detach().float().contiguous()
+    if channels_last:
+        out = torch.empty(b, h, wd, 3, dtype=torch.float32, device=x_nhwc.device)
+        lay = L.LAYOUT_NHWC
+    else:
+        out = torch.empty(b, 3, h, wd, dtype=torch.float32, device=x_nhwc.device)
+        lay = L.LAYOUT_NCHW
+    L.check(lib.vqae_stem_out_f32(_ptr(x_nhwc), _ptr(w), _ptr(bi), _ptr(out), lay, b, h, wd, c,
+                                  _stream(x_nhwc.device)), "vqae_stem_out_f32")
+    return out.permute(0, 3, 1, 2) if channels_last else out
+
+
+def normalize_u8(img: Tensor, mean=CAMELYON16_MEAN, std=CAMELYON16_STD,
+                 channels_last: bool = False) -> Tensor:
+    """u8 [B,H,W,3] -> fp32 [B,3,H,W]."""
+    lib = L.load()
+    require_cuda(img, "normalize_u8")
+    img = img.contiguous()
+    b, h, w, _ = img.shape
+    if channels_last:
+        out = torch.empty(b, h, w, 3, dtype=torch.float32, device=img.device)
+    else:
+        out = torch.empty(b, 3, h, w, dtype=torch.float32, device=img.device)
+    L.check(lib.vqae_normalize_u8(_ptr(img), _ptr(out), b, h, w, L.f3(mean), L.f3(std),
+                                  L.LAYOUT_NHWC if channels_last else L.LAYOUT_NCHW,
+                                  _stream(img.device)), "vqae_normalize_u8")
+    return out.permute(0, 3, 1, 2) if channels_last else out
+
+
+class PackedQuantizer:
+    """Codebook, proj_in weights and the proj_out(embed) table of one quantiser module."""
+
+    def __init__(self, embed: Tensor, commitment_cost: float, proj_in=None, proj_out=None):
+        lib = L.load()
+        require_cuda(embed, "quantizer")
+        self.embed = embed.detach().float().contiguous()
+        self.k, self.d = self.embed.shape
+        dev = embed.device
+        if proj_in is not None:
+            self.c = proj_in.weight.shape[1]
+            self.w_in = proj_in.weight.detach().float().reshape(self.d, self.c).contiguous()
+            self.b_in = proj_in.bias.detach().float().contiguous()
+            self.w_out = proj_out.weight.detach().float().reshape(self.c, self.d).contiguous()
+            self.b_out = proj_out.bias.detach().float().contiguous()
+        else:
+            self.c = self.d
+            self.w_in = self.b_in = self.w_out = self.b_out = None
+        self.table = torch.empty(self.k, self.c, dtype=torch.float32, device=dev)
+        L.check(lib.vqae_quantizer_prepare_f32(_ptr(self.embed), self.k, self.d, _ptr(self.w_out),
+                                               _ptr(self.b_out), self.c, _ptr(self.table),
+                                               _stream(dev)), "vqae_quantizer_prepare_f32")
+        p = L.QuantizerParams()
+        p.num_codes, p.dim, p.c = self.k, self.d, self.c
+        p.embed = self.embed.data_ptr()
+        p.w_in = self.w_in.data_ptr() if self.w_in is not None else None
+        p.b_in = self.b_in.data_ptr() if self.b_in is not None else None
+        p.table = self.table.data_ptr()
+        p.commitment_cost = float(commitment_cost)
+        self.params = p
+
+
+def quantize(pq: PackedQuantizer, x: Tensor, x_nhwc: bool, out_nhwc: bool, batch: int,
+             spatial: int, want_out: bool = True, want_z: bool = False
+             ) -> Tuple[Optional[Tensor], Tensor, Tensor, Tensor, Optional[Tensor]]:
+    """x: contiguous fp32, [B,S,c] if x_nhwc else [B,c,S].  Returns
+    (out or None, indices int64 [B*S], loss 0-dim, near_ties uint32 0-dim, z or None)."""
+    lib = L.load()
+    dev = x.device
+    n = batch * spatial
+    out = torch.empty(n * pq.c, dtype=torch.float32, device=dev) if want_out else None
+    idx = torch.empty(n, dtype=torch.int64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    ties = torch.empty((), dtype=torch.int32, device=dev)
+    z = torch.empty(n, pq.d, dtype=torch.float32, device=dev) if want_z else None
+    need = lib.vqae_quantizer_scratch_bytes(n)
+    ws = workspace(dev, need)
+    L.check(lib.vqae_quantize_f32(
+        C.byref(pq.params), _ptr(x), L.LAYOUT_NHWC if x_nhwc else L.LAYOUT_NCHW, _ptr(out),
+        L.LAYOUT_NHWC if out_nhwc else L.LAYOUT_NCHW, _ptr(idx), _ptr(loss), _ptr(ties),
+        NEAR_TIE_REL_GAP, _ptr(z), _ptr(ws), ws.numel(), batch, spatial, _stream(dev)),
+        "vqae_quantize_f32")
+    return out, idx, loss, ties, z
+
+
+def embed_codes(pq: PackedQuantizer, idx: Tensor, out_nhwc: bool, batch: int, spatial: int
+                ) -> Tensor:
+    """out[n,:] = table[idx[n],:] (embed_code -> proj_out); idx int64 or uint8, flat [B*S]."""
+    lib = L.load()
+    require_cuda(idx, "embed_codes")
+    is_u8 = idx.dtype == torch.uint8
+    if not is_u8 and idx.dtype != torch.int64:
+        idx = idx.long()
+    idx = idx.contiguous()
+    out = torch.empty(batch * spatial * pq.c, dtype=torch.float32, device=idx.device)
+    L.check(lib.vqae_embed_codes_f32(_ptr(idx), int(is_u8), _ptr(pq.table), pq.k, pq.c,
+                                     _ptr(out), L.LAYOUT_NHWC if out_nhwc else L.LAYOUT_NCHW,
+                                     batch, spatial, _stream(idx.device)),
+            "vqae_embed_codes_f32")
+    return out
+
+
+def codemap_place(tiles: Tensor, first_patch: int, grid_cols: int, code_map: Tensor) -> None:
+    """Place int64 code tiles [P,th,tw] into the u8 map [rows*th, cols*tw] (row-major patches)."""
+    lib = L.load()
+    require_cuda(tiles, "codemap_place")
+    tiles = tiles.contiguous()
+    p, th, tw = tiles.shape
+    L.check(lib.vqae_codemap_place_u8(_ptr(tiles), p, th, tw, first_patch, grid_cols,
+                                      _ptr(code_map), code_map.shape[0], code_map.shape[1],
+                                      _stream(tiles.device)), "vqae_codemap_place_u8")
+
+
+def launch_count() -> int:
+    return int(L.load().vqae_launch_count())

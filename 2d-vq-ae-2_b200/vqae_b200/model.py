@@ -1,0 +1,242 @@
+"""Counterpart of vq_ae/model.py: ``VQAE``, ``Encoder``, ``Decoder`` with the reference's
+constructor signatures, attribute names, ``state_dict`` keys and return tuples.
+
+``Encoder.forward`` / ``Decoder.forward`` in eval mode run a packed, NHWC, kernel-by-kernel
+plan over the C-ABI library instead of dispatching module by module.  The plan supports the
+shipped topology (one VQ level, no shortcut blocks: conf/model/vq_ae.yaml); the multi-level
+hierarchy of model.py:144-148,203-215 is row (f)-4 of the scope table and raises
+NotImplementedError.  Training (``shared_step``, SAM, logging) is out of scope.
+"""
+from __future__ import annotations
+
+from typing import Any, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import engine as E
+from ._instantiate import instantiate
+
+
+def maybe_repeat_layer(layer, repetitions: int):
+    """utils/train_helpers.py:27-32."""
+    if not isinstance(layer, (list, tuple)):
+        return [layer] * repetitions
+    assert len(layer) == repetitions
+    return layer
+
+
+def _flat_blocks(module: nn.Module) -> List[nn.Module]:
+    """All PreActFixupResBlocks below ``module`` in execution order."""
+    from .layers.conv_block import PreActFixupResBlock
+    return [m for m in module.modules() if isinstance(m, PreActFixupResBlock)]
+
+
+class _Plan:
+    """Packed blocks of one Sequential chain, re-packed when any parameter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.packed: List[E.PackedFixup] = []
+
+    def get(self, blocks: Sequence[nn.Module]) -> List[E.PackedFixup]:
+        key = tuple(E.block_version(b) for b in blocks)
+        if key != self.key:
+            for b in blocks:
+                b.check_supported()
+            self.packed = E.pack_blocks(blocks)
+            self.key = key
+        return self.packed
+
+    @staticmethod
+    def run(packed: Sequence[E.PackedFixup], h: Tensor) -> Tensor:
+        for pk in packed:
+            h = E.fixup_forward_nhwc(pk, h)
+        return h
+
+
+class Encoder(nn.Module):
+    """in_stem -> DownBlock pyramid -> trunk of 'same' blocks -> quantiser (model.py:129-217)."""
+
+    def __init__(self, stem_conf, down_block_conf, n_pre_enc_layers, vq_conf, conv_block_conf,
+                 shortcut_block_conf):
+        super().__init__()
+        self.in_stem = instantiate(stem_conf)
+        vq_layers = instantiate(vq_conf)
+
+        n_pre_enc_layers, down_block_conf, shortcut_block_conf = (
+            maybe_repeat_layer(n_pre_enc_layers, len(vq_layers)),
+            maybe_repeat_layer(down_block_conf, len(vq_layers)),
+            maybe_repeat_layer(shortcut_block_conf, len(vq_layers) - 1),
+        )
+        pre_enc_conf = [[{**conv_block_conf, **{'mode': 'same'}}] * n for n in n_pre_enc_layers]
+
+        down_layers, pre_enc_layers, shortcut_layers = [], [], []
+        current_in = self.in_stem.out_channels
+        for down_layer, pre_enc_layer, shortcut_layer in zip(
+                down_block_conf, pre_enc_conf, (None, *shortcut_block_conf)):
+            down_block = instantiate(down_layer, in_channels=current_in)
+            down_layers.append(down_block)
+            current_in = down_block.out_channels
+            shortcut_layers.append(instantiate(shortcut_layer, in_channels=current_in)
+                                   if shortcut_layer is not None else None)
+            pre_enc_layers.append(nn.Sequential(*(
+                instantiate(layer, in_channels=current_in, out_channels=current_in)
+                for layer in pre_enc_layer)))
+        del shortcut_layers[0]
+        shortcut_layers.append(None)
+
+        # stored low-res first, like the reference (model.py:182-187)
+        self.down_layers = nn.ModuleList(down_layers)
+        self.pre_enc_layers = nn.ModuleList(reversed(pre_enc_layers))
+        self.shortcut_layers = nn.ModuleList(reversed(shortcut_layers))
+        self.vq_layers = nn.ModuleList(reversed(vq_layers))
+        self._plan_down, self._plan_trunk = _Plan(), _Plan()
+
+    # -- B200 path -------------------------------------------------------------------------
+    def _check_topology(self) -> None:
+        if len(self.vq_layers) != 1 or any(s is not None for s in self.shortcut_layers):
+            raise NotImplementedError(
+                "the B200 plan covers the shipped single-level encoder "
+                "(conf/model/vq_ae.yaml); multi-level / shortcut hierarchies are not built")
+        if self.training:
+            raise RuntimeError("Encoder: training-mode forward is outside the B200 inference "
+                               "path; call .eval()")
+
+    def encode(self, x: Tensor, mean=None, std=None, want_quantized: bool = True,
+               want_latents: bool = False):
+        """Run the plan.  x: float [B,3,H,W] (NCHW or channels_last) or uint8 [B,H,W,3]
+        (normalised on the fly, a-N fused into the stem).  Returns
+        (enc or None, indices int64 [B,h,w], loss 0-dim, near_ties 0-dim int32, z or None)."""
+        self._check_topology()
+        E.require_cuda(x, "Encoder.forward")
+        cl = x.dtype == torch.uint8 or E.is_channels_last(x)
+        h = E.stem_in(x, self.in_stem.weight, self.in_stem.bias, mean, std)
+        h = _Plan.run(self._plan_down.get(_flat_blocks(self.down_layers)), h)
+        h = _Plan.run(self._plan_trunk.get(_flat_blocks(self.pre_enc_layers)), h)
+        vq = self.vq_layers[0]
+        pq = vq.packed()
+        b, hh, ww, c = h.shape
+        if c != pq.c:
+            raise NotImplementedError(
+                'VQ dim != channel dim not supported;'
+                f' found channel dim of {c}, expected {pq.c}')
+        out, idx, loss, ties, z = E.quantize(pq, h, True, cl, b, hh * ww,
+                                             want_out=want_quantized, want_z=want_latents)
+        vq.last_near_ties = ties
+        enc = None
+        if out is not None:
+            enc = (out.view(b, hh, ww, c).permute(0, 3, 1, 2) if cl else out.view(b, c, hh, ww))
+        return enc, idx.view(b, hh, ww), loss, ties, (z.view(b, hh, ww, -1) if z is not None
+                                                       else None)
+
+    def forward(self, x: Tensor) -> Tuple[Sequence[Tensor], Sequence[Tensor], Sequence[Tensor]]:
+        """((enc,), (indices,), (loss,)) -- low-res to high-res order (model.py:189-217)."""
+        enc, idx, loss, _, _ = self.encode(x)
+        return (enc,), (idx,), (loss,)
+
+
+class Decoder(nn.Module):
+    """trunk of 'same' blocks -> UpBlock pyramid -> out_stem (model.py:220-291)."""
+
+    def __init__(self, n_enc_layers: int, stem_conf, up_block_conf, n_post_enc_layers,
+                 conv_block_conf, shortcut_block_conf):
+        super().__init__()
+        self.out_stem = instantiate(stem_conf)
+        n_post_enc_layers, up_block_conf, shortcut_block_conf = (
+            maybe_repeat_layer(n_post_enc_layers, n_enc_layers),
+            maybe_repeat_layer(up_block_conf, n_enc_layers),
+            maybe_repeat_layer(shortcut_block_conf, n_enc_layers - 1),
+        )
+        post_enc_conf = [[{**conv_block_conf, **{'mode': 'same'}}] * n
+                         for n in n_post_enc_layers]
+
+        up_layers, post_enc_layers, shortcut_layers = [], [], []
+        current_out = self.out_stem.in_channels
+        for up_layer, post_enc_layer, shortcut_layer in zip(
+                up_block_conf, post_enc_conf, (None, *shortcut_block_conf)):
+            up_block = instantiate(up_layer, out_channels=current_out)
+            up_layers.append(up_block)
+            current_out = up_block.in_channels
+            shortcut_layers.append(instantiate(shortcut_layer, out_channels=current_out)
+                                   if shortcut_layer is not None else None)
+            post_enc_layers.append(nn.Sequential(*(
+                instantiate(layer, in_channels=current_out, out_channels=current_out)
+                for layer in post_enc_layer)))
+        del shortcut_layers[0]
+        shortcut_layers.append(None)
+
+        self.up_layers = nn.ModuleList(reversed(up_layers))
+        self.post_enc_layers = nn.ModuleList(reversed(post_enc_layers))
+        self.shortcut_layers = nn.ModuleList(reversed(shortcut_layers))
+        self._plan_trunk, self._plan_up = _Plan(), _Plan()
+
+    def forward(self, x: Sequence[Tensor]) -> Tensor:
+        if len(x) != 1 or len(self.up_layers) != 1 or any(
+                s is not None for s in self.shortcut_layers):
+            raise NotImplementedError(
+                "the B200 plan covers the shipped single-level decoder "
+                "(conf/model/vq_ae.yaml); multi-level / shortcut hierarchies are not built")
+        if self.training:
+            raise RuntimeError("Decoder: training-mode forward is outside the B200 inference "
+                               "path; call .eval()")
+        enc = x[0]
+        E.require_cuda(enc, "Decoder.forward")
+        h, cl = E.to_nhwc(enc)
+        h = _Plan.run(self._plan_trunk.get(_flat_blocks(self.post_enc_layers)), h)
+        h = _Plan.run(self._plan_up.get(_flat_blocks(self.up_layers)), h)
+        return E.stem_out(h, self.out_stem.weight, self.out_stem.bias, cl)
+
+
+class VQAE(nn.Module):
+    """Encoder + decoder assembly (model.py:13-48).  ``optim_conf`` / ``loss_f_conf`` are kept
+    for signature and checkpoint compatibility; the loss module is instantiated (it owns no
+    parameters in the shipped config) but nothing trains here."""
+
+    def __init__(self, optim_conf, loss_f_conf, encoder_conf, decoder_conf, **kwargs: Any):
+        super().__init__()
+        self.optim_conf = optim_conf
+        self.hparams_conf = dict(optim_conf=optim_conf, loss_f_conf=loss_f_conf,
+                                 encoder_conf=encoder_conf, decoder_conf=decoder_conf, **kwargs)
+        for attr_name, attr_conf in (('loss_f', loss_f_conf), ('encoder', encoder_conf),
+                                     ('decoder', decoder_conf)):
+            setattr(self, attr_name, instantiate(attr_conf))
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+
+    def forward(self, data: Tensor) -> Tuple[Tensor, Sequence[Tensor]]:
+        encodings, *_, encoding_loss = self.encoder(data)
+        out = self.decoder(encodings)
+        return out, encoding_loss
+
+    @torch.no_grad()
+    def decode_codes(self, indices: Tensor, channels_last: bool = False) -> Tensor:
+        """Decompress stored code maps: embed_code -> proj_out -> Decoder (scope row f-2)."""
+        enc = self.encoder.vq_layers[0].decode_codes(indices, channels_last)
+        return self.decoder((enc,))
+
+    def transfer_batch_to_device(self, batch: Tensor, device: torch.device,
+                                 dataloader_idx: int = 0) -> Tensor:
+        return batch.to(device, non_blocking=True, memory_format=torch.channels_last)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path: str, map_location=None, strict: bool = True,
+                             **overrides: Any) -> "VQAE":
+        """Load a Lightning checkpoint written by the reference (``hyper_parameters`` holds the
+        conf dicts saved by ``save_hyperparameters()``, model.py:25; ``state_dict`` the weights)."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu",
+                          weights_only=False)
+        hparams = _plain(ckpt.get("hyper_parameters", {}))
+        hparams.update(overrides)
+        model = cls(**hparams)
+        model.load_state_dict(ckpt["state_dict"], strict=strict)
+        return model
+
+
+def _plain(obj: Any) -> Any:
+    """DictConfig/ListConfig (if omegaconf objects were pickled) -> plain containers."""
+    if hasattr(obj, "items"):
+        return {k: _plain(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)) or type(obj).__name__ == "ListConfig":
+        return [_plain(v) for v in obj]
+    return obj

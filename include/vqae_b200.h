@@ -1,0 +1,167 @@
+/* vqae_b200.h -- C-ABI of the B200-native (sm_100a) inference hot path of 2D-VQ-AE-2.
+ *
+ * The reference (sara-nl/2D-VQ-AE-2) has no FFI of its own: every FLOP of its hot path is a
+ * PyTorch/cuDNN library call made from vq_ae/model.py and vq_ae/layers/*.py.  This header is
+ * therefore the boundary a maintainer would bind (ctypes) to replace those
+ * library calls.  Each entry point cites the reference call site(s) it replaces; paths are
+ * relative to the reference checkout.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - activations inside the path are NHWC ("channels last"), fp32 or bf16;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every call returns 0 on success or a VQAE_ERR_* code; nothing is thrown, nothing is
+ *     synchronised; kernels are only enqueued on `stream`;
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef VQAE_B200_H_
+#define VQAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQAE_ABI_VERSION 1
+
+enum {
+    VQAE_OK = 0,
+    VQAE_ERR_BAD_ARG = 1,        /* null pointer / non-positive extent                          */
+    VQAE_ERR_UNSUPPORTED = 2,    /* shape outside what the kernels are built for                */
+    VQAE_ERR_DIM_MISMATCH = 3,   /* mirrors NotImplementedError of layers/vq.py:100-104         */
+    VQAE_ERR_CUDA = 4,           /* a CUDA runtime call / launch failed (see vqae_last_cuda_error) */
+    VQAE_ERR_SCRATCH = 5         /* scratch buffer too small                                    */
+};
+
+/* layouts of tensors crossing the boundary */
+enum { VQAE_LAYOUT_NCHW = 0, VQAE_LAYOUT_NHWC = 1 };
+/* element types crossing the boundary */
+enum { VQAE_DT_F32 = 0, VQAE_DT_BF16 = 1, VQAE_DT_U8 = 2 };
+/* PreActFixupResBlock modes (layers/conv_block.py:147) */
+enum { VQAE_MODE_SAME = 0, VQAE_MODE_DOWN = 1, VQAE_MODE_UP = 2 };
+
+int vqae_abi_version(void);
+const char* vqae_error_string(int code);
+/* cudaGetErrorString of the last CUDA error seen by this library on the calling thread */
+const char* vqae_last_cuda_error(void);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches) */
+uint64_t vqae_launch_count(void);
+
+/* ---- a-N  input normalisation ------------------------------------------------------------
+ * Replaces albumentations Normalize + ToTensorV2 (conf/transforms/camelyon16_transforms.yaml:1-23,
+ * conf/transforms/normalize.yaml:1-11):  out = (u8 - 255*mean_c) * (1 / (255*std_c)).
+ * img: [B,H,W,3] u8;  out: fp32 [B,3,H,W] (NCHW) or [B,H,W,3] (NHWC).  mean/std: host float[3]. */
+int vqae_normalize_u8(const uint8_t* img, float* out, int64_t batch, int height, int width,
+                      const float* mean_host, const float* std_host, int out_layout, void* stream);
+
+/* ---- weight packing (once after load_state_dict()/eval()) ---------------------------------
+ * OIHW fp32 conv weight -> [KH*KW][I][O] fp32 ("tap-major, output-channel fastest").        */
+int vqae_pack_conv_weight_f32(const float* w_oihw, float* packed, int out_ch, int in_ch, int kh,
+                              int kw, void* stream);
+
+/* ---- a-S  stems --------------------------------------------------------------------------
+ * in_stem  (vq_ae/model.py:141,198; conv_layer/same2d.yaml: 3x3, zero pad, bias) 3 -> c_out.
+ * x is one of: fp32 NCHW [B,3,H,W], fp32 NHWC [B,H,W,3], u8 NHWC [B,H,W,3] (normalised on the
+ * fly with mean/std as in vqae_normalize_u8; mean/std may be NULL otherwise).
+ * w: OIHW [c_out,3,3,3] fp32, bias [c_out];  out: NHWC fp32 [B,H,W,c_out], c_out == 8.      */
+int vqae_stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w_oihw,
+                     const float* bias, float* out, int64_t batch, int height, int width,
+                     int c_out, const float* mean_host, const float* std_host, void* stream);
+/* out_stem (vq_ae/model.py:291): 3x3, zero pad, bias, c_in(8) -> 3.
+ * x NHWC fp32 [B,H,W,c_in];  out fp32 NCHW [B,3,H,W] or NHWC [B,H,W,3].                     */
+int vqae_stem_out_f32(const float* x, const float* w_oihw, const float* bias, float* out,
+                      int out_layout, int64_t batch, int height, int width, int c_in,
+                      void* stream);
+
+/* ---- building blocks of a-R, exported for per-piece parity tests and ResizeConv2D ----------
+ * One branch/skip conv of PreActFixupResBlock with its Fixup pre-activation and epilogue fused:
+ *   out = conv_kind( act?(x + pre_add) + post_add ) * scale + bias (+ residual)
+ * kind: 0 = 1x1 (proj2d.yaml), 1 = 2x2 stride 2 (down2d.yaml), 2 = 3x3 circular pad 1
+ * (same2d.yaml with padding_mode circular, pre_activation_fixup.yaml:40,60).
+ * x NHWC fp32 [B,H,W,c_in]; w packed [taps][c_in][c_out]; out/residual NHWC [B,H',W',c_out];
+ * c_in, c_out multiples of 8 (c_out in {8,16,32} or a multiple of 64).                       */
+int vqae_conv_f32(int kind, const float* x, const float* w_packed, float* out,
+                  const float* residual, int64_t batch, int height, int width, int c_in,
+                  int c_out, float pre_add, int pre_elu, float post_add, float scale, float bias,
+                  void* stream);
+/* nn.Upsample(mode='bicubic', scale_factor=2, align_corners=False) (layers/conv.py:8) + bias:
+ * x NHWC fp32 [B,H,W,c] -> out NHWC [B,2H,2W,c], c multiple of 4.                            */
+int vqae_bicubic_up2_f32(const float* x, float* out, int64_t batch, int height, int width, int c,
+                         float bias, void* stream);
+
+/* ---- a-R  PreActFixupResBlock.forward (layers/conv_block.py:196-216) ------------------------
+ * Weights are the packed form of vqae_pack_conv_weight_f32.  Scalars are the (1,)-shaped
+ * parameters bias1a..bias4, scale, bias1c, bias1d read to the host once at pack time.       */
+typedef struct vqae_fixup_params {
+    int mode;        /* VQAE_MODE_*                                                          */
+    int c_in, c_out, c_branch;
+    const float* w1;     /* branch_conv1: [1][c_in][c_branch]                                */
+    const float* w2;     /* branch_conv2: same [9][cb][cb] (3x3 circular), down [4][cb][cb]
+                            (2x2 stride 2), up [1][cb][cb] (1x1 after bicubic x2)            */
+    const float* w3;     /* branch_conv3: [1][c_branch][c_out]                               */
+    const float* w_skip; /* skip_conv: down [4][c_in][c_out], up [1][c_in][c_out], else NULL */
+    float bias1a, bias1b, bias2a, bias2b, bias3a, bias3b, bias4, scale, bias1c, bias1d;
+} vqae_fixup_params;
+
+/* bytes of scratch one block call needs for an input of [batch, height, width, c_in] */
+size_t vqae_fixup_block_scratch_bytes(const vqae_fixup_params* p, int64_t batch, int height,
+                                      int width);
+/* x: NHWC fp32 [B,H,W,c_in];  out: NHWC fp32 [B,H',W',c_out] (H' = H, H/2 or 2H by mode);
+ * x and out must not alias.                                                                 */
+int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out, void* scratch,
+                         size_t scratch_bytes, int64_t batch, int height, int width,
+                         void* stream);
+
+/* ---- a-P / a-Q / a-G  quantiser -------------------------------------------------------------
+ * ProjectedEMAVectorQuantizer2d.forward + EMAVectorQuantizer.forward in eval mode
+ * (layers/vq.py:96-154, 185-192):  z = proj_in(x);  idx = argmin_k sum_d (z_d - e_kd)^4
+ * (torch.cdist with p = inputs.dim() = 4, first index wins ties);  q = embed[idx];
+ * loss = mean((z - q)^2) * commitment_cost;  out = proj_out(q).
+ *
+ * vqae_quantizer_prepare builds the output table E' = proj_out(embed) ([K][c] fp32) once.
+ * If w_in == NULL the call is the bare EMAVectorQuantizer on c == dim inputs and the output
+ * rows are embed[idx] itself (table == embed).                                              */
+int vqae_quantizer_prepare_f32(const float* embed, int num_codes, int dim,
+                               const float* w_out /*[c][dim]*/, const float* b_out /*[c]*/,
+                               int c, float* table /*[num_codes][c]*/, void* stream);
+
+typedef struct vqae_quantizer_params {
+    int num_codes;          /* K (256)                                                       */
+    int dim;                /* D (8): distance space                                         */
+    int c;                  /* channel count of x / out (64 or 128; == dim when bare)        */
+    const float* embed;     /* [K][D]                                                        */
+    const float* w_in;      /* proj_in weight [D][c] (OIHW with 1x1 taps), or NULL           */
+    const float* b_in;      /* [D] or NULL                                                   */
+    const float* table;     /* [K][c] from vqae_quantizer_prepare_f32                        */
+    float commitment_cost;
+} vqae_quantizer_params;
+
+size_t vqae_quantizer_scratch_bytes(int64_t n_vectors);
+/* x: fp32, [B,c,S] (NCHW, S = prod(spatial)) or [B,S,c] (NHWC);  out: same shape, layout
+ * out_layout;  indices: int64 [B,S];  loss: 1 fp32;  near_ties: 1 uint32 (may be NULL) =
+ * number of vectors whose top-2 relative gap of the un-rooted L4 sums is < tie_rel_gap.
+ * z_out (may be NULL): fp32 [B*S][D] projected latents, for diagnostics/parity tests.      */
+int vqae_quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layout, float* out,
+                      int out_layout, int64_t* indices, float* loss, uint32_t* near_ties,
+                      float tie_rel_gap, float* z_out, void* scratch, size_t scratch_bytes,
+                      int64_t batch, int64_t spatial, void* stream);
+
+/* embed_code -> proj_out (layers/vq.py:44-45,192): out[n,:] = table[idx[n],:].
+ * indices: int64 or u8 (idx_dtype VQAE_DT_U8 / anything else = int64); out NHWC/NCHW fp32. */
+int vqae_embed_codes_f32(const void* indices, int idx_is_u8, const float* table, int num_codes,
+                         int c, float* out, int out_layout, int64_t batch, int64_t spatial,
+                         void* stream);
+
+/* ---- a-X  code-map placement (scripts/extract_embeddings/extract_embeddings.py:47-59,75-89) -
+ * Places n_tiles [th,tw] int64 code tiles at (row*th, col*tw) of a u8 map [rows*th, cols*tw];
+ * tile t has row-major patch index first_patch + t (datamodules/camelyon16.py:184-190).     */
+int vqae_codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw,
+                          int64_t first_patch, int grid_cols, uint8_t* map, int64_t map_rows,
+                          int64_t map_cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQAE_B200_H_ */

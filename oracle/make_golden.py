@@ -1,0 +1,175 @@
+"""TEST INFRASTRUCTURE ONLY -- writes tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   python oracle/make_golden.py
+
+The reference has no tests or golden vectors of its own, so the pin is
+the reference's own nn.Modules, imported through oracle/ref_shim.py, run on deterministic
+synthetic weights (vqae_b200/synthetic.py: values depend only on state_dict key + seed) and
+seeded inputs.  Every array written here is an output of reference code (torch 2.11 CPU
+kernels; the reference pins torch 1.11) -- the oracle restatement and the CUDA path are both
+tested against these files, which travel to the GPU box where /root/reference does not exist.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent
+sys.path.insert(0, str(HERE))
+sys.path.insert(0, str(REPO / "2d-vq-ae-2_b200"))
+
+import ref_shim  # noqa: E402
+from vqae_b200 import synthetic as S  # noqa: E402
+from vqae_b200.config import compose_vqae_conf, pre_activation_fixup  # noqa: E402
+
+GOLDEN = REPO / "tests" / "golden"
+
+
+def _np(t):
+    return t.detach().cpu().numpy().copy()   # copy: buffers are overwritten in place later
+
+
+def top2_gap(z_flat: torch.Tensor, embed: torch.Tensor):
+    """relative top-2 gap of the un-rooted L4 sums, from the reference's own cdist."""
+    d = torch.cdist(z_flat, embed, 4, compute_mode='donot_use_mm_for_euclid_dist') ** 4
+    t2 = torch.topk(d, 2, dim=1, largest=False).values
+    return ((t2[:, 1] - t2[:, 0]) / t2[:, 1].clamp_min(1e-30)).float()
+
+
+def stats(t: torch.Tensor) -> np.ndarray:
+    t = t.double()
+    return np.array([t.mean().item(), t.std().item(), t.abs().sum().item()])
+
+
+@torch.no_grad()
+def quantizer_cases(vq_mod):
+    out = {}
+    # (1) bare EMAVectorQuantizer on [4,8,16,16], constructor-default randn codebook
+    torch.manual_seed(42)
+    q = vq_mod.EMAVectorQuantizer(256, 8, 1.0, 0.99, 1e-5).eval()
+    g = torch.Generator().manual_seed(100)
+    q.embed.copy_(torch.randn(256, 8, generator=g))
+    x = torch.randn(4, 8, 16, 16, generator=g)
+    quant, idx, loss = q(x)
+    out.update(bare_embed=_np(q.embed), bare_x=_np(x), bare_idx=_np(idx).astype(np.int16),
+               bare_quant=_np(quant), bare_loss=_np(loss),
+               bare_gap=_np(top2_gap(x.permute(0, 2, 3, 1).reshape(-1, 8), q.embed)))
+    # (2) tie case: duplicated codebook rows -> lowest index wins (torch.argmin)
+    emb2 = q.embed.clone()
+    emb2[200] = emb2[3]
+    emb2[77] = emb2[3]
+    q.embed.copy_(emb2)
+    quant2, idx2, loss2 = q(x)
+    out.update(tie_embed=_np(emb2), tie_idx=_np(idx2).astype(np.int16), tie_loss=_np(loss2))
+    # (3) channels_last input: output strides follow input
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    qcl, icl, _ = q(xcl)
+    out.update(tie_cl_is_channels_last=np.array(
+        qcl.is_contiguous(memory_format=torch.channels_last) and not qcl.is_contiguous()),
+        tie_cl_idx_equal=np.array(bool((icl == idx2).all())))
+    # (4) projected quantiser, C = 64 and C = 128
+    for c in (64, 128):
+        pq = vq_mod.ProjectedEMAVectorQuantizer2d(256, c, 1.0, 0.99, 1e-5, 8).eval()
+        sd = S.make_state_dict(pq.state_dict(), seed=5, regime="perturbed")
+        pq.load_state_dict(sd)
+        g = torch.Generator().manual_seed(200 + c)
+        x = torch.randn(2, c, 32, 32, generator=g)
+        z = pq.proj_in(x).permute(0, 2, 3, 1).reshape(-1, 8)
+        # codebook rescaled to the latent statistics (what _init_ema would do, vq.py:76-94)
+        pq.embed.copy_(S.rescale_codebook(sd["embed"], z))
+        quant, idx, loss = pq(x)
+        out.update({f"proj{c}_embed": _np(pq.embed), f"proj{c}_idx": _np(idx).astype(np.int16),
+                    f"proj{c}_loss": _np(loss), f"proj{c}_quant_sub": _np(quant[:, :, ::4, ::4]),
+                    f"proj{c}_quant_stats": stats(quant), f"proj{c}_z": _np(z),
+                    f"proj{c}_gap": _np(top2_gap(z, pq.embed))})
+    return out
+
+
+@torch.no_grad()
+def block_cases(cb_mod):
+    out = {}
+    conf = pre_activation_fixup(n_layers=12)
+    conf.pop("_target_"), conf.pop("_recursive_"), conf.pop("in_channels"), conf.pop(
+        "out_channels"), conf.pop("mode")
+    for name, (cin, cout, mode, hw) in {
+        "same16": (16, 16, "same", 16), "same64": (64, 64, "same", 16),
+        "down8": (8, 16, "down", 16), "down32": (32, 64, "down", 8),
+        "up16": (16, 8, "up", 8), "up64": (64, 32, "up", 4),
+    }.items():
+        blk = cb_mod.PreActFixupResBlock(in_channels=cin, out_channels=cout, mode=mode,
+                                         **conf).eval()
+        blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=11, regime="perturbed",
+                                              n_layers=12))
+        g = torch.Generator().manual_seed(300 + cin)
+        x = torch.randn(2, cin, hw, hw, generator=g)
+        out[f"{name}_x"] = _np(x)
+        out[f"{name}_y"] = _np(blk(x))
+    return out
+
+
+@torch.no_grad()
+def model_case(model_mod, n_down: int, regime: str, batch: int, size: int, seed: int):
+    conf = compose_vqae_conf(n_down=n_down)
+    conf.pop("_target_"), conf.pop("_recursive_")
+    torch.manual_seed(42)
+    m = model_mod.VQAE(**conf).eval()
+    sd = S.make_state_dict(m.state_dict(), seed=seed, regime=regime)
+    m.load_state_dict(sd)
+    x = S.synthetic_patches(batch, size, seed + 1000)
+    enc = m.encoder
+    vq = enc.vq_layers[0]
+    h = enc.pre_enc_layers[0](enc.down_layers[0](enc.in_stem(x)))
+    z = vq.proj_in(h).permute(0, 2, 3, 1).reshape(-1, 8)
+    out = {}
+    if regime == "perturbed":
+        vq.embed.copy_(S.rescale_codebook(sd["encoder.vq_layers.0.embed"], z))
+        vq.embed_avg.copy_(vq.embed)
+    (e,), (idx,), (loss,) = enc(x)
+    recon, (loss2,) = m(x)
+    assert torch.equal(loss, loss2)
+    out.update(
+        embed=_np(vq.embed), x_stats=stats(x), pre_vq_sub=_np(h[:, ::8, ::4, ::4]),
+        pre_vq_stats=stats(h), z=_np(z), gap=_np(top2_gap(z, vq.embed)),
+        idx=_np(idx).astype(np.int16), loss=_np(loss), enc_sub=_np(e[:, ::8, ::4, ::4]),
+        enc_stats=stats(e), recon_sub=_np(recon[:, :, ::8, ::8]), recon_stats=stats(recon),
+        in_stem_sub=_np(enc.in_stem(x)[:, :, ::16, ::16]),
+        n_params=np.array(sum(p.numel() for p in m.parameters())),
+        n_state=np.array(len(sd)), codes_used=np.array(idx.unique().numel()),
+    )
+    # decode-from-codes (embed_code -> proj_out -> decoder), scope row f-2
+    q = vq.embed_code(idx).permute(0, 3, 1, 2)
+    dec = m.decoder((vq.proj_out(q),))
+    out["decode_codes_sub"] = _np(dec[:, :, ::8, ::8])
+    return out
+
+
+def main():
+    if not ref_shim.reference_available():
+        raise SystemExit("reference checkout not found; run this in the build container")
+    model_mod, vq_mod, cb_mod, _ = ref_shim.load_reference()
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    np.savez_compressed(GOLDEN / "quantizer.npz", **quantizer_cases(vq_mod))
+    np.savez_compressed(GOLDEN / "blocks.npz", **block_cases(cb_mod))
+    for tag, (n_down, regime, batch, size, seed) in {
+        "model_nd3_perturbed": (3, "perturbed", 2, 256, 1),
+        "model_nd3_fixup": (3, "fixup", 2, 256, 2),
+        "model_nd4_perturbed_256": (4, "perturbed", 2, 256, 3),   # as-shipped conf: 16x16 grid
+        "model_nd4_perturbed_512": (4, "perturbed", 1, 512, 4),   # 512^2 -> 32x32 grid
+    }.items():
+        np.savez_compressed(GOLDEN / f"{tag}.npz",
+                            **model_case(model_mod, n_down, regime, batch, size, seed),
+                            meta=np.array([n_down, batch, size, seed]))
+        print("wrote", tag)
+    for f in sorted(GOLDEN.glob("*.npz")):
+        print(f.name, f.stat().st_size // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

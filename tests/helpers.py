@@ -1,0 +1,74 @@
+"""Shared test helpers (CPU): golden loading, deterministic weights, oracle wrappers."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import torch
+
+import vqae_b200
+from vqae_b200 import synthetic as S
+from vqae_b200.config import compose_vqae_conf, pre_activation_fixup
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+# the committed model goldens: tag -> (n_down, regime, batch, size, seed)   (oracle/make_golden.py)
+MODEL_CASES = {
+    "model_nd3_perturbed": (3, "perturbed", 2, 256, 1),
+    "model_nd3_fixup": (3, "fixup", 2, 256, 2),
+    "model_nd4_perturbed_256": (4, "perturbed", 2, 256, 3),
+    "model_nd4_perturbed_512": (4, "perturbed", 1, 512, 4),
+}
+BLOCK_CASES = {
+    "same16": (16, 16, "same", 16), "same64": (64, 64, "same", 16),
+    "down8": (8, 16, "down", 16), "down32": (32, 64, "down", 8),
+    "up16": (16, 8, "up", 8), "up64": (64, 32, "up", 4),
+}
+# the reference's near-tie rule: indices must match wherever the top-2 relative gap of the
+# un-rooted L4 sums exceeds this (SURVEY.md section 7 hard part 2)
+NEAR_TIE_REL_GAP = 16.0 * 2.0 ** -23
+
+
+def golden(name: str):
+    return np.load(GOLDEN / f"{name}.npz")
+
+
+_models = {}
+
+
+def model_and_state(tag: str):
+    """(package VQAE on CPU in eval mode with the case's weights loaded, state_dict, x)."""
+    n_down, regime, batch, size, seed = MODEL_CASES[tag]
+    if tag not in _models:
+        m = vqae_b200.build_vqae(n_down=n_down).eval()
+        sd = S.make_state_dict(m.state_dict(), seed=seed, regime=regime)
+        g = golden(tag)
+        sd["encoder.vq_layers.0.embed"] = torch.from_numpy(g["embed"])
+        sd["encoder.vq_layers.0.embed_avg"] = torch.from_numpy(g["embed"]).clone()
+        m.load_state_dict(sd)
+        _models[tag] = (m, sd)
+    m, sd = _models[tag]
+    return m, sd, S.synthetic_patches(batch, size, seed + 1000)
+
+
+def make_block(name: str):
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    cin, cout, mode, hw = BLOCK_CASES[name]
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blk = PreActFixupResBlock(in_channels=cin, out_channels=cout, mode=mode, **conf).eval()
+    blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=11, regime="perturbed",
+                                          n_layers=12))
+    return blk
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def index_mismatches_outside_ties(idx, ref_idx, gap, thresh=NEAR_TIE_REL_GAP):
+    idx, ref_idx, gap = (np.asarray(v).reshape(-1) for v in (idx, ref_idx, gap))
+    bad = idx != ref_idx
+    return int((bad & (gap >= thresh)).sum()), int(bad.sum()), int((gap < thresh).sum())
