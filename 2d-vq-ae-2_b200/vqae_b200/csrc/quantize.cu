@@ -167,6 +167,21 @@ __global__ void __launch_bounds__(QT) quantize_kernel(QArgs a) {
         }
         a.idx[n] = bidx;
         tie = (second - best) < a.tie_rel_gap * second;
+        if (!PROJ && a.out != nullptr) {
+            // bare quantiser: the reference returns inputs + (quantized - inputs) (straight-through
+            // estimator, vq.py:146), which differs from the codebook row by up to one ulp
+            float o[QD];
+#pragma unroll
+            for (int d = 0; d < QD; ++d) o[d] = __fadd_rn(z[d], __fsub_rn(e[d], z[d]));
+            if (OL == VQAE_LAYOUT_NHWC) {
+                float4* po = reinterpret_cast<float4*>(a.out + n * QD);
+                po[0] = make_float4(o[0], o[1], o[2], o[3]);
+                po[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+#pragma unroll
+                for (int d = 0; d < QD; ++d) a.out[(b * QD + d) * a.S + s] = o[d];
+            }
+        }
         if (a.z_out) {
             float4* zo = reinterpret_cast<float4*>(a.z_out + n * QD);
             zo[0] = make_float4(z[0], z[1], z[2], z[3]);
@@ -192,7 +207,7 @@ __global__ void __launch_bounds__(QT) quantize_kernel(QArgs a) {
     }
 
     // ---- out rows = table[idx] ----
-    if (a.out == nullptr) return;
+    if (a.out == nullptr || !PROJ) return;
     if (OL == VQAE_LAYOUT_NHWC) {
         const int c4n = C / 4;
         const int64_t tile_f4 = (int64_t)QT * c4n;
