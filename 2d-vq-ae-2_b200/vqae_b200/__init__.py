@@ -20,7 +20,7 @@ from .layers import conv, conv_block, vq  # noqa: F401
 from .model import VQAE, Decoder, Encoder  # noqa: F401
 
 __all__ = ["VQAE", "Encoder", "Decoder", "build_vqae", "compose_vqae_conf",
-           "install_as_vq_ae", "instantiate", "engine"]
+           "install_as_vq_ae", "instantiate", "engine", "set_precision"]
 
 
 def build_vqae(n_down: int = 4, **conf_overrides) -> VQAE:
@@ -28,6 +28,18 @@ def build_vqae(n_down: int = 4, **conf_overrides) -> VQAE:
     ``n_down=4`` is the as-shipped 512^2 model, ``n_down=3`` the README's 256^2 -> 32x32 one."""
     conf = compose_vqae_conf(n_down=n_down, **conf_overrides)
     return instantiate(conf)
+
+
+def set_precision(module, precision: str):
+    """Select the arithmetic of every Encoder/Decoder below ``module``: "fp32" (exact CUDA-core
+    kernels, index parity with the reference) or "bf16" (tcgen05 tensor-core kernels with bf16
+    operands, fp32 accumulation and an fp32 residual stream)."""
+    if precision not in engine.PRECISIONS:
+        raise ValueError(f"precision must be one of {engine.PRECISIONS}")
+    for m in module.modules():
+        if isinstance(m, (Encoder, Decoder)):
+            m.precision = precision
+    return module
 
 
 def install_as_vq_ae() -> None:

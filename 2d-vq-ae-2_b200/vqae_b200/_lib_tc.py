@@ -7,4 +7,11 @@ from __future__ import annotations
 
 import ctypes as C
 
-SIGNATURES: dict = {}
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+_fp = C.POINTER(C.c_float)
+
+SIGNATURES: dict = {
+    "vqae_tc_selftest": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "vqae_pack_same_block_bf16": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "vqae_same_block_bf16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
+}

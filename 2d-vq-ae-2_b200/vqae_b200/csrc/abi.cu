@@ -183,6 +183,29 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
     return VQAE_ERR_BAD_ARG;
 }
 
+int vqae_tc_selftest(const void* a_bf16, int a_rows, int row_shift, const void* b_bf16, float* d,
+                     void* stream) {
+    return tc_selftest(a_bf16, a_rows, row_shift, b_bf16, d, (cudaStream_t)stream);
+}
+
+int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+                              int c, void* packed, void* stream) {
+    return pack_same_block_bf16(w1_oihw, w2_oihw, w3_oihw, c, packed, (cudaStream_t)stream);
+}
+
+int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
+                         const float* scalars8_host, int64_t batch, int height, int width, int c,
+                         void* stream) {
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        VQAE_CUDA_TRY(cudaGetDevice(&dev));
+        VQAE_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return same_block_tc(x, out, w_packed, scalars8_host, batch, height, width, c, sm_count,
+                         (cudaStream_t)stream);
+}
+
 int vqae_quantizer_prepare_f32(const float* embed, int num_codes, int dim, const float* w_out,
                                const float* b_out, int c, float* table, void* stream) {
     return quantizer_prepare_f32(embed, num_codes, dim, w_out, b_out, c, table,

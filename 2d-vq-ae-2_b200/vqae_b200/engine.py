@@ -113,6 +113,24 @@ class PackedFixup:
         for name, val in self.scalars.items():
             setattr(p, name, float(val))
         self.params = p
+        # tcgen05 path: bf16 operand pack of a 'same' block at the trunk width (C = 64)
+        self.tc_weights = None
+        self.tc_scalars = None
+        if self.mode == L.MODE_SAME and self.c_in == 64 and self.c_branch == 64:
+            lib = L.load()
+            dev = w2.device
+            self.tc_weights = torch.empty(11 * 64 * 64, dtype=torch.bfloat16, device=dev)
+            ws = [t.detach().float().contiguous() for t in
+                  (block.branch_conv1.weight, w2, block.branch_conv3.weight)]
+            L.check(lib.vqae_pack_same_block_bf16(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), 64,
+                                                  _ptr(self.tc_weights), _stream(dev)),
+                    "vqae_pack_same_block_bf16")
+            sc = self.scalars
+            self.tc_scalars = (C.c_float * 8)(*[float(sc[k]) for k in (
+                "bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "scale")])
+
+    def tc_ok(self, h: int, w: int) -> bool:
+        return self.tc_weights is not None and h == 32 and w == 32
 
     def out_hw(self, h: int, w: int) -> Tuple[int, int]:
         if self.mode == L.MODE_DOWN:
@@ -145,8 +163,16 @@ def pack_blocks(blocks: Sequence) -> List[PackedFixup]:
 # ----------------------------------------------------------------------------------------------
 # single calls
 # ----------------------------------------------------------------------------------------------
-def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None) -> Tensor:
-    """x: contiguous NHWC fp32 [B,H,W,c_in] -> NHWC fp32 [B,H',W',c_out]."""
+PRECISIONS = ("fp32", "bf16")
+
+
+def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
+                       precision: str = "fp32") -> Tensor:
+    """x: contiguous NHWC fp32 [B,H,W,c_in] -> NHWC fp32 [B,H',W',c_out].
+
+    precision "fp32": CUDA-core exact path.  "bf16": tcgen05 kernels (bf16 operands, fp32
+    accumulation and fp32 residual stream) wherever one is built for the block's shape, the
+    fp32 kernels elsewhere."""
     lib = L.load()
     b, h, w, c = x.shape
     if c != pk.c_in:
@@ -154,6 +180,10 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None)
     ho, wo = pk.out_hw(h, w)
     if out is None:
         out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
+    if precision == "bf16" and pk.tc_ok(h, w):
+        L.check(lib.vqae_same_block_bf16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
+                                         b, h, w, c, _stream(x.device)), "vqae_same_block_bf16")
+        return out
     need = lib.vqae_fixup_block_scratch_bytes(C.byref(pk.params), b, h, w)
     ws = workspace(x.device, need)
     L.check(lib.vqae_fixup_block_f32(C.byref(pk.params), _ptr(x), _ptr(out), _ptr(ws),

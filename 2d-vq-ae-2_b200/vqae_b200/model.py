@@ -49,9 +49,9 @@ class _Plan:
         return self.packed
 
     @staticmethod
-    def run(packed: Sequence[E.PackedFixup], h: Tensor) -> Tensor:
+    def run(packed: Sequence[E.PackedFixup], h: Tensor, precision: str = "fp32") -> Tensor:
         for pk in packed:
-            h = E.fixup_forward_nhwc(pk, h)
+            h = E.fixup_forward_nhwc(pk, h, precision=precision)
         return h
 
 
@@ -92,6 +92,9 @@ class Encoder(nn.Module):
         self.shortcut_layers = nn.ModuleList(reversed(shortcut_layers))
         self.vq_layers = nn.ModuleList(reversed(vq_layers))
         self._plan_down, self._plan_trunk = _Plan(), _Plan()
+        #: "fp32" (exact CUDA-core path) or "bf16" (tcgen05 kernels where built); see
+        #: vqae_b200.set_precision
+        self.precision = "fp32"
 
     # -- B200 path -------------------------------------------------------------------------
     def _check_topology(self) -> None:
@@ -112,8 +115,8 @@ class Encoder(nn.Module):
         E.require_cuda(x, "Encoder.forward")
         cl = x.dtype == torch.uint8 or E.is_channels_last(x)
         h = E.stem_in(x, self.in_stem.weight, self.in_stem.bias, mean, std)
-        h = _Plan.run(self._plan_down.get(_flat_blocks(self.down_layers)), h)
-        h = _Plan.run(self._plan_trunk.get(_flat_blocks(self.pre_enc_layers)), h)
+        h = _Plan.run(self._plan_down.get(_flat_blocks(self.down_layers)), h, self.precision)
+        h = _Plan.run(self._plan_trunk.get(_flat_blocks(self.pre_enc_layers)), h, self.precision)
         vq = self.vq_layers[0]
         pq = vq.packed()
         b, hh, ww, c = h.shape
@@ -170,6 +173,7 @@ class Decoder(nn.Module):
         self.post_enc_layers = nn.ModuleList(reversed(post_enc_layers))
         self.shortcut_layers = nn.ModuleList(reversed(shortcut_layers))
         self._plan_trunk, self._plan_up = _Plan(), _Plan()
+        self.precision = "fp32"
 
     def forward(self, x: Sequence[Tensor]) -> Tensor:
         if len(x) != 1 or len(self.up_layers) != 1 or any(
@@ -183,8 +187,8 @@ class Decoder(nn.Module):
         enc = x[0]
         E.require_cuda(enc, "Decoder.forward")
         h, cl = E.to_nhwc(enc)
-        h = _Plan.run(self._plan_trunk.get(_flat_blocks(self.post_enc_layers)), h)
-        h = _Plan.run(self._plan_up.get(_flat_blocks(self.up_layers)), h)
+        h = _Plan.run(self._plan_trunk.get(_flat_blocks(self.post_enc_layers)), h, self.precision)
+        h = _Plan.run(self._plan_up.get(_flat_blocks(self.up_layers)), h, self.precision)
         return E.stem_out(h, self.out_stem.weight, self.out_stem.bias, cl)
 
 

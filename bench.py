@@ -159,27 +159,9 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # GPU leg
 # --------------------------------------------------------------------------------------------
-def time_dominant_kernel(dev, peaks, precision: str):
-    """CUDA-event timing of the dominant kernel alone (trunk 3x3 circular conv, 64 -> 64 channels
-    at 32x32, batch 256), launched through the C-ABI on the current stream, rotating over
-    buffers larger than L2 together."""
-    from vqae_b200 import _lib as L
-    from vqae_b200 import engine as E
-    lib = L.load()
-    B, H, W, C = BATCH_PER_GPU, 32, 32, 64
-    nbuf = 4                                   # 4 x 67 MB inputs + outputs > 126 MB L2
-    xs = [torch.randn(B, H, W, C, device=dev) for _ in range(nbuf)]
-    ys = [torch.empty(B, H, W, C, device=dev) for _ in range(nbuf)]
-    w = E.pack_conv_weight(torch.randn(C, C, 3, 3, device=dev) * 0.05)
-    st = E._stream(dev)
-
-    def launch(i):
-        L.check(lib.vqae_conv_f32(L.CONV_3x3_CIRC, E._ptr(xs[i % nbuf]), E._ptr(w),
-                                  E._ptr(ys[i % nbuf]), None, B, H, W, C, C, 0.01, 1, 0.02,
-                                  1.0, 0.0, st), "vqae_conv_f32")
+def _event_time(launch, reps, dev):
     for i in range(3):
         launch(i)
-    reps = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
     e0.record()
@@ -187,16 +169,56 @@ def time_dominant_kernel(dev, peaks, precision: str):
         launch(i)
     e1.record()
     torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / reps
-    flops = 2.0 * B * H * W * C * C * 9
-    achieved = flops / (ms * 1e-3) / 1e12
+    return e0.elapsed_time(e1) / reps
+
+
+def time_dominant_kernel(dev, peaks, precision: str):
+    """CUDA-event timing of the dominant kernel alone at the bench shape (batch 256, 32x32, C=64),
+    launched through the C-ABI on the current stream, rotating over 4 buffer pairs (4 x 67 MB in
+    + 4 x 67 MB out > 126 MB L2)."""
+    from vqae_b200 import _lib as L
+    from vqae_b200 import engine as E
+    lib = L.load()
+    B, H, W, C = BATCH_PER_GPU, 32, 32, 64
+    nbuf = 4
+    xs = [torch.randn(B, H, W, C, device=dev) for _ in range(nbuf)]
+    ys = [torch.empty(B, H, W, C, device=dev) for _ in range(nbuf)]
+    st = E._stream(dev)
     peak = peaks["bf16_tflops_sustained"]
-    return {"bound": "tensor", "kernel": "conv_f32_kernel<3x3 circular, BN=64, BK=16> (trunk branch_conv2)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "us_per_launch": ms * 1e3,
-            "algorithmic_flops_per_launch": flops,
-            "note": "fp32 CUDA-core FFMA kernel measured against the bf16 tensor peak; "
-                    "timed alone with CUDA events on the launch stream, 4 rotating buffer pairs"}
+    if precision == "bf16":
+        import ctypes
+        ws = [torch.randn(C, C, k, k, device=dev) * 0.05 for k in (1, 3, 1)]
+        packed = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
+        L.check(lib.vqae_pack_same_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C,
+                                              E._ptr(packed), st), "pack")
+        sc = (ctypes.c_float * 8)(0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.9)
+
+        def launch(i):
+            L.check(lib.vqae_same_block_bf16(E._ptr(xs[i % nbuf]), E._ptr(ys[i % nbuf]),
+                                             E._ptr(packed), sc, B, H, W, C, st),
+                    "vqae_same_block_bf16")
+        ms = _event_time(launch, 20, dev)
+        flops = 2.0 * B * H * W * C * C * 11
+        name = "same_block_tc_kernel (fused PreActFixupResBlock 'same', C=64, 32x32; tcgen05 bf16)"
+        note = ("whole residual block per launch: 1x1 + 3x3 circular + 1x1 implicit GEMMs on "
+                "tcgen05 with bf16 operands, fp32 TMEM accumulation; timed alone with CUDA events "
+                "on the launch stream, 4 rotating buffer pairs")
+    else:
+        w = E.pack_conv_weight(torch.randn(C, C, 3, 3, device=dev) * 0.05)
+
+        def launch(i):
+            L.check(lib.vqae_conv_f32(L.CONV_3x3_CIRC, E._ptr(xs[i % nbuf]), E._ptr(w),
+                                      E._ptr(ys[i % nbuf]), None, B, H, W, C, C, 0.01, 1, 0.02,
+                                      1.0, 0.0, st), "vqae_conv_f32")
+        ms = _event_time(launch, 20, dev)
+        flops = 2.0 * B * H * W * C * C * 9
+        name = "conv_f32_kernel<3x3 circular, BN=64, BK=16> (trunk branch_conv2)"
+        note = ("fp32 CUDA-core FFMA kernel measured against the bf16 tensor peak; timed alone "
+                "with CUDA events on the launch stream, 4 rotating buffer pairs")
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops, "note": note}
 
 
 def time_quantizer(dev, peaks):
@@ -243,7 +265,8 @@ def run_gpu(args):
 
     peaks, peaks_kind = load_peaks()
     model, sd = build_model_and_state()
-    model = model.to(dev)
+    import vqae_b200
+    model = vqae_b200.set_precision(model.to(dev), args.precision)
     enc = model.encoder
     B = BATCH_PER_GPU
     # two distinct resident batches per rank (seeds 42 + rank), uint8 tiles (50 MB each)
@@ -337,7 +360,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

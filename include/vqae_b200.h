@@ -114,6 +114,22 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
                          size_t scratch_bytes, int64_t batch, int height, int width,
                          void* stream);
 
+/* ---- a-T / a-R on tensor cores (tcgen05, bf16 operands, fp32 accumulate + fp32 residual) -------
+ * One PreActFixupResBlock in mode 'same' (layers/conv_block.py:196-216) per call, all three
+ * convs and their pre-activations fused; built for the trunk shape c == 64, height == width == 32
+ * (model.py:150-153,240-263).  w_packed comes from vqae_pack_same_block_bf16 (11*c*c bf16);
+ * scalars8_host = {bias1a, bias1b, bias2a, bias2b, bias3a, bias3b, bias4, scale} on the HOST.
+ * x, out: NHWC fp32 [B,32,32,64], must not alias.                                            */
+int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+                              int c, void* packed, void* stream);
+int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
+                         const float* scalars8_host, int64_t batch, int height, int width, int c,
+                         void* stream);
+/* descriptor/TMEM self test: d[128][64] = a[row_shift + m][0..63] . b[n][0..63] (bf16 in, fp32 out),
+ * a: [a_rows][64] bf16 row-major, b: [64][64] bf16 row-major (device pointers)                */
+int vqae_tc_selftest(const void* a_bf16, int a_rows, int row_shift, const void* b_bf16, float* d,
+                     void* stream);
+
 /* ---- a-P / a-Q / a-G  quantiser -------------------------------------------------------------
  * ProjectedEMAVectorQuantizer2d.forward + EMAVectorQuantizer.forward in eval mode
  * (layers/vq.py:96-154, 185-192):  z = proj_in(x);  idx = argmin_k sum_d (z_d - e_kd)^4
