@@ -14,4 +14,5 @@ SIGNATURES: dict = {
     "vqae_tc_selftest": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vqae_pack_same_block_bf16": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "vqae_same_block_bf16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
+    "vqae_same_block_bf16_profile": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp, _vp]),
 }

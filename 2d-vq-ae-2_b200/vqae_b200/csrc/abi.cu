@@ -193,6 +193,26 @@ int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const 
     return pack_same_block_bf16(w1_oihw, w2_oihw, w3_oihw, c, packed, (cudaStream_t)stream);
 }
 
+static int device_sm_count(int* out) {
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        VQAE_CUDA_TRY(cudaGetDevice(&dev));
+        VQAE_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    *out = sm_count;
+    return VQAE_OK;
+}
+
+int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packed,
+                                 const float* scalars8_host, int64_t batch, int height, int width,
+                                 int c, long long* phase_clocks, void* stream) {
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return same_block_tc(x, out, w_packed, scalars8_host, batch, height, width, c, sm_count,
+                         phase_clocks, (cudaStream_t)stream);
+}
+
 int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c,
                          void* stream) {
@@ -203,7 +223,7 @@ int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
         VQAE_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     return same_block_tc(x, out, w_packed, scalars8_host, batch, height, width, c, sm_count,
-                         (cudaStream_t)stream);
+                         nullptr, (cudaStream_t)stream);
 }
 
 int vqae_quantizer_prepare_f32(const float* embed, int num_codes, int dim, const float* w_out,

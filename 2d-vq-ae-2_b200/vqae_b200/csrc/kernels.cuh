@@ -42,7 +42,8 @@ int codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw, int6
 int tc_selftest(const void* A, int a_rows, int row_shift, const void* B, float* D,
                 cudaStream_t stream);
 int same_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
-                  int64_t B, int H, int W, int C, int sm_count, cudaStream_t stream);
+                  int64_t B, int H, int W, int C, int sm_count, long long* prof,
+                  cudaStream_t stream);
 int pack_same_block_bf16(const float* w1, const float* w2, const float* w3, int C, void* packed,
                          cudaStream_t stream);
 

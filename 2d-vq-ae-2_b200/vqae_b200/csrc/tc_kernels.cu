@@ -93,47 +93,79 @@ tc_selftest_kernel(const __nv_bfloat16* __restrict__ A, int a_rows, int row_shif
 }
 
 // -----------------------------------------------------------------------------------------------
-// fused 'same' block, C = 64, 32 x 32 images, half-image tiles
+// fused 'same' block on tcgen05, any H x W that tiles into 16 x 32 pixel tiles.
+//   CP: channel count seen by the MMAs (16, 32, 64);  CR: real channels (8 runs zero-padded as 16)
+// Tile = 16 rows x 32 cols of one image plus a 1-pixel circular halo ring: 18 x 34 = 612 pixels in
+// "padded-linear" order q = lr * 34 + lc.  GEMM1 (1x1) is pointwise, so it is simply evaluated on
+// all 612 (5 M-tiles of 128); a 3x3 tap is then the constant operand shift dy * 34 + dx.
 // -----------------------------------------------------------------------------------------------
-constexpr int SB_C = 64;
-constexpr int SB_HW = 32;           // image height == width
-constexpr int SB_TH = 16;           // image rows per tile
-constexpr int SB_PW = SB_HW + 2;    // padded row pitch of U (pixels)
-constexpr int SB_KCH = SB_C / 8;    // 16-byte k-chunks per pixel
-constexpr int SB_XPIX = 641;        // A1 / V region: 5 M-tiles x 128 px, odd pitch
-constexpr int SB_UPIX = 711;        // U region: 35 + 5*128 + 35 px, odd pitch
+constexpr int SB_TH = 16, SB_TW = 32, SB_PW = SB_TW + 2;
+constexpr int SB_NPAD = (SB_TH + 2) * SB_PW;      // 612 padded pixels
+constexpr int SB_XPIX = 641;                       // operand region pitch: 5 x 128 px, odd
+constexpr int SB_UPIX = 711;                       // 35 + 5*128 + 35 px, odd
 constexpr uint32_t SB_XLBO = SB_XPIX * 16;
 constexpr uint32_t SB_ULBO = SB_UPIX * 16;
-constexpr uint32_t SB_WLBO = SB_C * 16;              // weights: [k-chunk][n][8]
-constexpr uint32_t SB_WTAP = SB_KCH * SB_WLBO;       // 8192 B per 64x64 bf16 matrix
 constexpr int SB_RING = 4;
-constexpr int SB_WORKERS = 256;
-constexpr int SB_THREADS = SB_WORKERS + 64;
-constexpr uint32_t SB_OFF_X = 0;
-constexpr uint32_t SB_OFF_U = SB_OFF_X + SB_KCH * SB_XLBO;
-constexpr uint32_t SB_OFF_W1 = SB_OFF_U + SB_KCH * SB_ULBO;
-constexpr uint32_t SB_OFF_W3 = SB_OFF_W1 + SB_WTAP;
-constexpr uint32_t SB_OFF_RING = SB_OFF_W3 + SB_WTAP;
-constexpr uint32_t SB_OFF_BAR = SB_OFF_RING + SB_RING * SB_WTAP;
-constexpr uint32_t SB_SMEM = SB_OFF_BAR + 128;
 
-struct SameBlockArgs {
-    const float* x;               // NHWC fp32 [B,32,32,64]
-    float* out;                   // NHWC fp32 [B,32,32,64]
-    const __nv_bfloat16* w;       // [W1 | W2 tap 0..8 | W3], each [k-chunk][n][8]
-    int n_tiles;                  // B * 2
-    float b1a, b1b, b2a, b2b, b3a, b3b, b4, scale;
+template <int CP, int CR>
+struct SameCfg {
+    static constexpr int KCH = CP / 8;             // 16-byte k-chunks per pixel seen by the MMA
+    static constexpr int KCR = CR / 8;             // ... that hold real channels
+    static constexpr bool RING = (CP == 64);       // W2 does not fit next to the operands: stream it
+    static constexpr int NW = (CP == 64) ? 8 : 4;  // worker warps
+    static constexpr int WORKERS = NW * 32;
+    static constexpr int THREADS = WORKERS + 64;   // + MMA warp + weight-producer warp
+    static constexpr int NC = (CP == 64) ? 32 : CP;                 // TMEM columns per epilogue unit
+    static constexpr int UCH = (CP == 64) ? 4 : KCR;                // real k-chunks per unit
+    static constexpr uint32_t WLBO = CP * 16;
+    static constexpr uint32_t WMAT = KCH * WLBO;                    // one CP x CP bf16 matrix
+    static constexpr uint32_t OFF_X = 0;
+    static constexpr uint32_t OFF_U = OFF_X + KCH * SB_XLBO;
+    static constexpr uint32_t OFF_W = OFF_U + KCH * SB_ULBO;        // RING: W1, W3, ring[4]; else all 11
+    static constexpr uint32_t W_BYTES = (RING ? (2 + SB_RING) : 11) * WMAT;
+    static constexpr uint32_t OFF_BAR = OFF_W + W_BYTES;
+    static constexpr uint32_t SMEM = OFF_BAR + 128;
+    static constexpr int TMEM_COLS = CP == 64 ? 512 : (CP == 32 ? 256 : 128);
+    static constexpr int MIN_CTAS = CP == 64 ? 1 : (CP == 32 ? 2 : 4);
 };
 
-__global__ void __launch_bounds__(SB_THREADS, 1) same_block_tc_kernel(SameBlockArgs a) {
+struct SameBlockArgs {
+    const float* x;               // NHWC fp32 [B,H,W,CR]
+    float* out;                   // NHWC fp32 [B,H,W,CR]
+    const __nv_bfloat16* w;       // 11 matrices [W1 | W2 tap 0..8 | W3], each [k-chunk][n][8]
+    int n_tiles, H, W, tiles_x, tiles_per_img;
+    float b1a, b1b, b2a, b2b, b3a, b3b, b4, scale;
+    long long* prof;              // optional [gridDim.x][8] phase timestamps of each CTA's 1st tile
+};
+
+
+__device__ __forceinline__ uint4 act_pack8(const float* v, float pre, float post) {
+    uint4 o;
+    o.x = pack_bf16(elu_fast(v[0] + pre) + post, elu_fast(v[1] + pre) + post);
+    o.y = pack_bf16(elu_fast(v[2] + pre) + post, elu_fast(v[3] + pre) + post);
+    o.z = pack_bf16(elu_fast(v[4] + pre) + post, elu_fast(v[5] + pre) + post);
+    o.w = pack_bf16(elu_fast(v[6] + pre) + post, elu_fast(v[7] + pre) + post);
+    return o;
+}
+
+template <int CP, int CR>
+__global__ void __launch_bounds__(SameCfg<CP, CR>::THREADS, SameCfg<CP, CR>::MIN_CTAS)
+same_block_tc_kernel(SameBlockArgs a) {
+    using Cfg = SameCfg<CP, CR>;
+    constexpr int KCH = Cfg::KCH, KCR = Cfg::KCR, NW = Cfg::NW, NC = Cfg::NC, UCH = Cfg::UCH;
+    constexpr uint32_t WLBO = Cfg::WLBO, WMAT = Cfg::WMAT;
+    constexpr int MMA_WARP = NW, PROD_WARP = NW + 1;
+
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t sX = sbase + SB_OFF_X, sU = sbase + SB_OFF_U, sW1 = sbase + SB_OFF_W1,
-                   sW3 = sbase + SB_OFF_W3, sRing = sbase + SB_OFF_RING;
-    const uint32_t bar_mma = sbase + SB_OFF_BAR;             // MMA phase complete
-    const uint32_t bar_full = bar_mma + 8;                   // [SB_RING] tap landed
-    const uint32_t bar_empty = bar_full + 8 * SB_RING;       // [SB_RING] tap consumed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SB_OFF_BAR + 8 + 16 * SB_RING);
+    const uint32_t sX = sbase + Cfg::OFF_X, sU = sbase + Cfg::OFF_U, sW = sbase + Cfg::OFF_W;
+    const uint32_t sW1 = sW;
+    const uint32_t sW3 = Cfg::RING ? sW + WMAT : sW + 10 * WMAT;
+    const uint32_t sW2 = Cfg::RING ? sW + 2 * WMAT : sW + WMAT;      // ring base / tap 0
+    const uint32_t bar_mma = sbase + Cfg::OFF_BAR;                   // MMA phase complete
+    const uint32_t bar_full = bar_mma + 8;                           // [SB_RING] tap landed
+    const uint32_t bar_empty = bar_full + 8 * SB_RING;               // [SB_RING] tap consumed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 + 16 * SB_RING);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -148,16 +180,21 @@ __global__ void __launch_bounds__(SB_THREADS, 1) same_block_tc_kernel(SameBlockA
         }
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
-    {   // resident W1 / W3 (generic-proxy copies; made visible to the async proxy below)
-        const uint4* g1 = reinterpret_cast<const uint4*>(a.w);
-        const uint4* g3 = reinterpret_cast<const uint4*>(a.w) + 10 * (SB_WTAP / 16);
-        for (int i = tid; i < (int)(SB_WTAP / 16); i += SB_THREADS) {
-            *reinterpret_cast<uint4*>(smem + SB_OFF_W1 + i * 16) = __ldg(g1 + i);
-            *reinterpret_cast<uint4*>(smem + SB_OFF_W3 + i * 16) = __ldg(g3 + i);
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(a.w);
+        if (Cfg::RING) {   // resident W1 / W3 only
+            for (int i = tid; i < (int)(WMAT / 16); i += Cfg::THREADS) {
+                *reinterpret_cast<uint4*>(smem + Cfg::OFF_W + i * 16) = __ldg(g + i);
+                *reinterpret_cast<uint4*>(smem + Cfg::OFF_W + WMAT + i * 16) =
+                    __ldg(g + 10 * (WMAT / 16) + i);
+            }
+        } else {
+            for (int i = tid; i < (int)(11 * WMAT / 16); i += Cfg::THREADS)
+                *reinterpret_cast<uint4*>(smem + Cfg::OFF_W + i * 16) = __ldg(g + i);
         }
-        // zero the activation regions once so never-written slack rows hold finite values
-        for (int i = tid; i < (int)(SB_OFF_W1 / 16); i += SB_THREADS)
+        // zero the operand regions once: slack rows and zero-padded channels stay finite / zero
+        for (int i = tid; i < (int)(Cfg::OFF_W / 16); i += Cfg::THREADS)
             *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0, 0, 0, 0);
     }
     fence_proxy_async_smem();
@@ -165,151 +202,195 @@ __global__ void __launch_bounds__(SB_THREADS, 1) same_block_tc_kernel(SameBlockA
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t idesc = make_idesc_bf16(128, SB_C);
-    const uint8_t* w2g = reinterpret_cast<const uint8_t*>(a.w) + SB_WTAP;
+    const uint32_t idesc = make_idesc_bf16(128, CP);
+    const uint8_t* w2g = reinterpret_cast<const uint8_t*>(a.w) + WMAT;
 
-    int taps_issued = 0;                  // producer state (warp 9, lane 0)
-    if (warp == 9 && lane == 0) {
+    int taps_issued = 0;                  // producer state (PROD_WARP lane 0, RING only)
+    if (Cfg::RING && warp == PROD_WARP && lane == 0) {
         for (; taps_issued < SB_RING && taps_issued < total_taps; ++taps_issued) {
             const uint32_t fb = bar_full + 8 * (taps_issued % SB_RING);
-            mbar_arrive_expect_tx(fb, SB_WTAP);
-            bulk_g2s(sRing + (taps_issued % SB_RING) * SB_WTAP, w2g + (taps_issued % 9) * SB_WTAP,
-                     SB_WTAP, fb);
+            mbar_arrive_expect_tx(fb, WMAT);
+            bulk_g2s(sW2 + (taps_issued % SB_RING) * WMAT, w2g + (taps_issued % 9) * WMAT, WMAT, fb);
         }
     }
-    int taps_used = 0;                    // consumer state (warp 8, lane 0)
+    int taps_used = 0;                    // consumer state (MMA_WARP lane 0, RING only)
     uint32_t mma_phase = 0;
 
-    // epilogue geometry of this worker thread
+    // epilogue geometry of a worker thread
     const int q4 = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = (warp >> 2) & 1;     // channel half: k-chunks 4*half .. 4*half+3
+    const int grp = (warp >> 2) & 1;      // CP == 64: channel half handled by this warp
     const int row_in_tile = q4 * 32 + lane;
     const uint32_t t_lane = (uint32_t)(q4 * 32) << 16;
+    const uint32_t t_col = (CP == 64) ? grp * 32 : 0;
+    const int kc0 = (CP == 64) ? grp * 4 : 0;     // first k-chunk of this thread's unit
+    // E3 staging (warp-private, in the U region once G3 has consumed V): [32 rows][NCR + 4] fp32
+    constexpr int NCR = UCH * 8;                  // real channels per epilogue unit
+    constexpr int F4 = NCR / 4;                   // float4 per staged row
+    constexpr int SROW = NCR + 4;
+    float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_U) + (warp < NW ? warp : 0) * 32 * SROW;
 
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int img = tile >> 1, r0 = (tile & 1) * SB_TH;
-        const float* ximg = a.x + (size_t)img * SB_HW * SB_HW * SB_C;
-        float* oimg = a.out + (size_t)img * SB_HW * SB_HW * SB_C;
+    // descriptor bases; per-MMA offsets are compile-time constants added to the low word
+    const uint64_t dX = make_desc(sX, SB_XLBO, 128);
+    const uint64_t dU = make_desc(sU, SB_ULBO, 128);
+    const uint64_t dW1 = make_desc(sW1, WLBO, 128);
+    const uint64_t dW3 = make_desc(sW3, WLBO, 128);
+    const uint64_t dW2 = make_desc(sW2, WLBO, 128);
 
-        // ---- P: A1 = bf16(elu(x + b1a) + b1b), 18 rows with circular y-halo ----
-        if (warp < 8) {
-            for (int id = tid; id < (SB_TH + 2) * SB_HW * SB_KCH; id += SB_WORKERS) {
-                const int p = id >> 3, kc = id & 7;
-                const int lr = p >> 5, col = p & 31;
-                const int row = (r0 - 1 + lr) & (SB_HW - 1);
-                const float4* src = reinterpret_cast<const float4*>(
-                    ximg + ((size_t)row * SB_HW + col) * SB_C + kc * 8);
-                const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-                uint4 o;
-                o.x = pack_bf16(elu_fast(v0.x + a.b1a) + a.b1b, elu_fast(v0.y + a.b1a) + a.b1b);
-                o.y = pack_bf16(elu_fast(v0.z + a.b1a) + a.b1b, elu_fast(v0.w + a.b1a) + a.b1b);
-                o.z = pack_bf16(elu_fast(v1.x + a.b1a) + a.b1b, elu_fast(v1.y + a.b1a) + a.b1b);
-                o.w = pack_bf16(elu_fast(v1.z + a.b1a) + a.b1b, elu_fast(v1.w + a.b1a) + a.b1b);
-                *reinterpret_cast<uint4*>(smem + SB_OFF_X + kc * SB_XLBO + p * 16) = o;
+    // P: A1 = bf16(elu(x + b1a) + b1b) on the 18 x 34 halo'd tile (circular wrap) -> X region.
+    // Loads are issued in batches of PB items per thread before any use (memory-level parallelism).
+    auto prologue = [&](int tile) {
+        const int img = tile / a.tiles_per_img;
+        const int trem = tile - img * a.tiles_per_img;
+        const int r0 = (trem / a.tiles_x) * SB_TH, c0 = (trem % a.tiles_x) * SB_TW;
+        const float* ximg = a.x + (size_t)img * a.H * a.W * CR;
+        constexpr int ITEMS = SB_NPAD * KCR;
+        constexpr int PB = 6;
+        for (int base = tid; base < ITEMS; base += Cfg::WORKERS * PB) {
+            float4 v0[PB], v1[PB];
+            int dst[PB];
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                const int id = base + u * Cfg::WORKERS;
+                dst[u] = -1;
+                if (id < ITEMS) {
+                    const int q = id / KCR, kc = id - q * KCR;
+                    const int lr = q / SB_PW, lc = q - lr * SB_PW;
+                    int row = r0 - 1 + lr, col = c0 - 1 + lc;
+                    row = row < 0 ? row + a.H : (row >= a.H ? row - a.H : row);
+                    col = col < 0 ? col + a.W : (col >= a.W ? col - a.W : col);
+                    const float4* src = reinterpret_cast<const float4*>(
+                        ximg + ((size_t)row * a.W + col) * CR + kc * 8);
+                    v0[u] = __ldg(src);
+                    v1[u] = __ldg(src + 1);
+                    dst[u] = kc * (int)SB_XLBO + q * 16;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                if (dst[u] >= 0) {
+                    const float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w,
+                                        v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+                    *reinterpret_cast<uint4*>(smem + Cfg::OFF_X + dst[u]) = act_pack8(v, a.b1a, a.b1b);
+                }
             }
         }
-        fence_proxy_async_smem();
-        __syncthreads();
+    };
 
-        // ---- G1: D1[t] = A1[t] . W1^T, 5 M-tiles (4.5 needed) ----
-        if (warp == 8) {
+    int tile = blockIdx.x;
+    const bool prof_cta = a.prof != nullptr && tid == 0;
+    if (prof_cta) a.prof[(size_t)blockIdx.x * 8 + 0] = clock64();
+    if (warp < NW && tile < a.n_tiles) prologue(tile);
+    fence_proxy_async_smem();
+    __syncthreads();
+    bool first = true;
+
+    for (; tile < a.n_tiles; tile += gridDim.x) {
+        const int img = tile / a.tiles_per_img;
+        const int trem = tile - img * a.tiles_per_img;
+        const int r0 = (trem / a.tiles_x) * SB_TH, c0 = (trem % a.tiles_x) * SB_TW;
+        const float* ximg = a.x + (size_t)img * a.H * a.W * CR;
+        float* oimg = a.out + (size_t)img * a.H * a.W * CR;
+        const bool prof = prof_cta && first;
+        if (prof) a.prof[(size_t)blockIdx.x * 8 + 1] = clock64();
+
+        // ---- G1: D1 = A1 . W1^T on 5 M-tiles of padded-linear pixels ----
+        if (warp == MMA_WARP) {
             if (lane == 0) {
                 tc_fence_after_sync();
+#pragma unroll
                 for (int t = 0; t < 5; ++t)
 #pragma unroll
-                    for (int ks = 0; ks < SB_C / 16; ++ks)
-                        umma_bf16(tmem_base + t * SB_C,
-                                  make_desc(sX + t * 128 * 16 + ks * 2 * SB_XLBO, SB_XLBO, 128),
-                                  make_desc(sW1 + ks * 2 * SB_WLBO, SB_WLBO, 128), idesc, ks > 0);
+                    for (int ks = 0; ks < CP / 16; ++ks)
+                        umma_bf16(tmem_base + t * CP,
+                                  dX + (uint64_t)((t * 128 * 16 + ks * 2 * SB_XLBO) >> 4),
+                                  dW1 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0);
                 umma_commit(bar_mma);
             }
             __syncwarp();
         }
-        // ---- E1: U = bf16(elu(D1 + b2a) + b2b) -> padded-linear with x-halo columns ----
-        if (warp < 8) {
+        // ---- E1: U[q] = bf16(elu(D1[q] + b2a) + b2b), same padded-linear order ----
+        if (warp < NW) {
             mbar_wait(bar_mma, mma_phase);
             tc_fence_after_sync();
+            if (prof) a.prof[(size_t)blockIdx.x * 8 + 2] = clock64();
             for (int t = 0; t < 5; ++t) {
-                float v[32];
-                tmem_ld32(tmem_base + t_lane + t * SB_C + half * 32, v);
+                float v[NC];
+                tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
                 tmem_ld_wait();
-                const int p = t * 128 + row_in_tile;
-                if (p < (SB_TH + 2) * SB_HW) {
-                    const int lr = p >> 5, col = p & 31;
-                    const int qu = lr * SB_PW + col + 1;
+                const int q = t * 128 + row_in_tile;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 o;
-                        o.x = pack_bf16(elu_fast(v[8 * j + 0] + a.b2a) + a.b2b, elu_fast(v[8 * j + 1] + a.b2a) + a.b2b);
-                        o.y = pack_bf16(elu_fast(v[8 * j + 2] + a.b2a) + a.b2b, elu_fast(v[8 * j + 3] + a.b2a) + a.b2b);
-                        o.z = pack_bf16(elu_fast(v[8 * j + 4] + a.b2a) + a.b2b, elu_fast(v[8 * j + 5] + a.b2a) + a.b2b);
-                        o.w = pack_bf16(elu_fast(v[8 * j + 6] + a.b2a) + a.b2b, elu_fast(v[8 * j + 7] + a.b2a) + a.b2b);
-                        uint8_t* dst = smem + SB_OFF_U + (half * 4 + j) * SB_ULBO + qu * 16;
-                        *reinterpret_cast<uint4*>(dst) = o;
-                        if (col == 0) *reinterpret_cast<uint4*>(dst + 32 * 16) = o;            // right halo
-                        if (col == SB_HW - 1) *reinterpret_cast<uint4*>(dst - 32 * 16) = o;   // left halo
-                    }
-                }
+                for (int j = 0; j < UCH; ++j)
+                    *reinterpret_cast<uint4*>(smem + Cfg::OFF_U + (kc0 + j) * SB_ULBO + q * 16) =
+                        act_pack8(v + 8 * j, a.b2a, a.b2b);
             }
             tc_fence_before_sync();
         }
         mma_phase ^= 1;
         fence_proxy_async_smem();
         __syncthreads();
+        if (prof) a.prof[(size_t)blockIdx.x * 8 + 3] = clock64();
 
-        // ---- G2: D2[t] = sum over 9 taps of U[shifted] . W2[tap]^T ----
-        if (warp == 9 && lane == 0) {
+        // ---- G2: D2[q] = sum over 9 taps of U[q + dy*34 + dx] . W2[tap]^T, q from 35;
+        //      meanwhile the workers build the NEXT tile's A1 (the X region is free after G1) ----
+        if (Cfg::RING && warp == PROD_WARP && lane == 0) {
             for (int i = 0; i < 9 && taps_issued < total_taps; ++i, ++taps_issued) {
                 const int slot = taps_issued % SB_RING;
                 mbar_wait(bar_empty + 8 * slot, ((taps_issued / SB_RING) - 1) & 1);
-                mbar_arrive_expect_tx(bar_full + 8 * slot, SB_WTAP);
-                bulk_g2s(sRing + slot * SB_WTAP, w2g + (taps_issued % 9) * SB_WTAP, SB_WTAP,
+                mbar_arrive_expect_tx(bar_full + 8 * slot, WMAT);
+                bulk_g2s(sW2 + slot * WMAT, w2g + (taps_issued % 9) * WMAT, WMAT,
                          bar_full + 8 * slot);
             }
         }
-        if (warp == 8) {
+        if (warp == MMA_WARP) {
             if (lane == 0) {
                 tc_fence_after_sync();
-                for (int tap = 0; tap < 9; ++tap, ++taps_used) {
-                    const int slot = taps_used % SB_RING;
-                    mbar_wait(bar_full + 8 * slot, (taps_used / SB_RING) & 1);
-                    tc_fence_after_sync();
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    uint64_t dW;
+                    int slot = 0;
+                    if (Cfg::RING) {
+                        slot = taps_used % SB_RING;
+                        mbar_wait(bar_full + 8 * slot, (taps_used / SB_RING) & 1);
+                        tc_fence_after_sync();
+                        dW = dW2 + (uint64_t)((slot * WMAT) >> 4);
+                        ++taps_used;
+                    } else {
+                        dW = dW2 + (uint64_t)((tap * WMAT) >> 4);
+                    }
                     const int shift = (tap / 3 - 1) * SB_PW + (tap % 3 - 1);
+#pragma unroll
                     for (int t = 0; t < 5; ++t)
 #pragma unroll
-                        for (int ks = 0; ks < SB_C / 16; ++ks)
-                            umma_bf16(tmem_base + t * SB_C,
-                                      make_desc(sU + (SB_PW + 1 + t * 128 + shift) * 16 + ks * 2 * SB_ULBO,
-                                                SB_ULBO, 128),
-                                      make_desc(sRing + slot * SB_WTAP + ks * 2 * SB_WLBO, SB_WLBO, 128),
-                                      idesc, (tap | ks) > 0);
-                    umma_commit(bar_empty + 8 * slot);
+                        for (int ks = 0; ks < CP / 16; ++ks)
+                            umma_bf16(tmem_base + t * CP,
+                                      dU + (uint64_t)(((SB_PW + 1 + t * 128 + shift) * 16 + ks * 2 * SB_ULBO) >> 4),
+                                      dW + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, (tap | ks) > 0);
+                    if (Cfg::RING) umma_commit(bar_empty + 8 * slot);
                 }
                 umma_commit(bar_mma);
             }
             __syncwarp();
         }
-        // ---- E2: V = bf16(elu(D2 + b3a) + b3b), interior pixels only ----
-        if (warp < 8) {
+        if (warp < NW) {
+            if (tile + (int)gridDim.x < a.n_tiles) prologue(tile + gridDim.x);
+            if (prof) a.prof[(size_t)blockIdx.x * 8 + 4] = clock64();
+            // ---- E2: V[p] = bf16(elu(D2 + b3a) + b3b), 16 x 32 interior, pixel-linear, written
+            //      over the U region (dead once G2 has completed) ----
             mbar_wait(bar_mma, mma_phase);
             tc_fence_after_sync();
+            if (prof) a.prof[(size_t)blockIdx.x * 8 + 5] = clock64();
             for (int t = 0; t < 5; ++t) {
-                float v[32];
-                tmem_ld32(tmem_base + t_lane + t * SB_C + half * 32, v);
+                float v[NC];
+                tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
                 tmem_ld_wait();
                 const int q = SB_PW + 1 + t * 128 + row_in_tile;
                 const int lr = q / SB_PW, pc = q - lr * SB_PW;
-                if (lr <= SB_TH && pc >= 1 && pc <= SB_HW) {
-                    const int p = (lr - 1) * SB_HW + pc - 1;
+                if (lr <= SB_TH && pc >= 1 && pc <= SB_TW) {
+                    const int p = (lr - 1) * SB_TW + pc - 1;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 o;
-                        o.x = pack_bf16(elu_fast(v[8 * j + 0] + a.b3a) + a.b3b, elu_fast(v[8 * j + 1] + a.b3a) + a.b3b);
-                        o.y = pack_bf16(elu_fast(v[8 * j + 2] + a.b3a) + a.b3b, elu_fast(v[8 * j + 3] + a.b3a) + a.b3b);
-                        o.z = pack_bf16(elu_fast(v[8 * j + 4] + a.b3a) + a.b3b, elu_fast(v[8 * j + 5] + a.b3a) + a.b3b);
-                        o.w = pack_bf16(elu_fast(v[8 * j + 6] + a.b3a) + a.b3b, elu_fast(v[8 * j + 7] + a.b3a) + a.b3b);
-                        *reinterpret_cast<uint4*>(smem + SB_OFF_X + (half * 4 + j) * SB_XLBO + p * 16) = o;
-                    }
+                    for (int j = 0; j < UCH; ++j)
+                        *reinterpret_cast<uint4*>(smem + Cfg::OFF_U + (kc0 + j) * SB_ULBO + p * 16) =
+                            act_pack8(v + 8 * j, a.b3a, a.b3b);
                 }
             }
             tc_fence_before_sync();
@@ -318,80 +399,116 @@ __global__ void __launch_bounds__(SB_THREADS, 1) same_block_tc_kernel(SameBlockA
         fence_proxy_async_smem();
         __syncthreads();
 
-        // ---- G3: D3[t] = V[t] . W3^T, 4 M-tiles ----
-        if (warp == 8) {
+        // ---- G3: D3 = V . W3^T, 4 M-tiles ----
+        if (warp == MMA_WARP) {
             if (lane == 0) {
                 tc_fence_after_sync();
+#pragma unroll
                 for (int t = 0; t < 4; ++t)
 #pragma unroll
-                    for (int ks = 0; ks < SB_C / 16; ++ks)
-                        umma_bf16(tmem_base + t * SB_C,
-                                  make_desc(sX + t * 128 * 16 + ks * 2 * SB_XLBO, SB_XLBO, 128),
-                                  make_desc(sW3 + ks * 2 * SB_WLBO, SB_WLBO, 128), idesc, ks > 0);
+                    for (int ks = 0; ks < CP / 16; ++ks)
+                        umma_bf16(tmem_base + t * CP,
+                                  dU + (uint64_t)((t * 128 * 16 + ks * 2 * SB_ULBO) >> 4),
+                                  dW3 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0);
                 umma_commit(bar_mma);
             }
             __syncwarp();
         }
-        // ---- E3: out = x + scale * D3 + b4 (fp32) ----
-        if (warp < 8) {
+        // ---- E3: out = x + scale * D3 + b4 (fp32).  Each warp transposes its 32 x NCR block
+        //      through shared memory so that global loads/stores are 128-bit and line-coalesced ----
+        if (warp < NW) {
             mbar_wait(bar_mma, mma_phase);
             tc_fence_after_sync();
+            if (prof) a.prof[(size_t)blockIdx.x * 8 + 6] = clock64();
+            const int rsub = lane / F4, c4 = lane % F4;
             for (int t = 0; t < 4; ++t) {
-                float v[32];
-                tmem_ld32(tmem_base + t_lane + t * SB_C + half * 32, v);
+                float v[NC];
+                tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
                 tmem_ld_wait();
-                const int p = t * 128 + row_in_tile;
-                const size_t off = ((size_t)(r0 + (p >> 5)) * SB_HW + (p & 31)) * SB_C + half * 32;
-                const float4* xr = reinterpret_cast<const float4*>(ximg + off);
-                float4* orow = reinterpret_cast<float4*>(oimg + off);
+                __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 r = __ldg(xr + j);
+                for (int j = 0; j < F4; ++j)
+                    *reinterpret_cast<float4*>(stage + lane * SROW + 4 * j) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < F4; ++k) {
+                    const int rr = rsub + k * (32 / F4);           // row within this warp's 32
+                    const int p = t * 128 + q4 * 32 + rr;
+                    const size_t off =
+                        ((size_t)(r0 + (p >> 5)) * a.W + c0 + (p & 31)) * CR + kc0 * 8 + c4 * 4;
+                    const float4 d = *reinterpret_cast<const float4*>(stage + rr * SROW + 4 * c4);
+                    const float4 r = __ldg(reinterpret_cast<const float4*>(ximg + off));
                     float4 o;
-                    o.x = fmaf(v[4 * j + 0], a.scale, a.b4) + r.x;
-                    o.y = fmaf(v[4 * j + 1], a.scale, a.b4) + r.y;
-                    o.z = fmaf(v[4 * j + 2], a.scale, a.b4) + r.z;
-                    o.w = fmaf(v[4 * j + 3], a.scale, a.b4) + r.w;
-                    orow[j] = o;
+                    o.x = fmaf(d.x, a.scale, a.b4) + r.x;
+                    o.y = fmaf(d.y, a.scale, a.b4) + r.y;
+                    o.z = fmaf(d.z, a.scale, a.b4) + r.z;
+                    o.w = fmaf(d.w, a.scale, a.b4) + r.w;
+                    *reinterpret_cast<float4*>(oimg + off) = o;
                 }
             }
             tc_fence_before_sync();
         }
         mma_phase ^= 1;
+        fence_proxy_async_smem();     // next tile's A1 (written during G2) -> async proxy
         __syncthreads();
+        if (prof) a.prof[(size_t)blockIdx.x * 8 + 7] = clock64();
+        first = false;
     }
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// OIHW fp32 weights of one 'same' block -> bf16 [11 matrices][k-chunk][n][8]:
-// matrix 0 = branch_conv1, 1..9 = branch_conv2 taps (ky*3+kx), 10 = branch_conv3
+// OIHW fp32 weights of one 'same' block -> bf16 [11 matrices][k-chunk][n][8], zero padded from
+// CR to CP channels: matrix 0 = branch_conv1, 1..9 = branch_conv2 taps (ky*3+kx), 10 = branch_conv3
 __global__ void __launch_bounds__(256)
 pack_same_block_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
-                       const float* __restrict__ w3, int C, __nv_bfloat16* __restrict__ out) {
-    const int per = C * C;
+                       const float* __restrict__ w3, int CR, int CP,
+                       __nv_bfloat16* __restrict__ out) {
+    const int per = CP * CP;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 11 * per) return;
     const int m = i / per, r = i % per;
-    const int kc = r / (C * 8), n = (r / 8) % C, k = kc * 8 + (r % 8);
-    float v;
-    if (m == 0) v = w1[n * C + k];
-    else if (m == 10) v = w3[n * C + k];
-    else v = w2[((size_t)n * C + k) * 9 + (m - 1)];
+    const int kc = r / (CP * 8), n = (r / 8) % CP, k = kc * 8 + (r % 8);
+    float v = 0.f;
+    if (n < CR && k < CR) {
+        if (m == 0) v = w1[n * CR + k];
+        else if (m == 10) v = w3[n * CR + k];
+        else v = w2[((size_t)n * CR + k) * 9 + (m - 1)];
+    }
     out[i] = __float2bfloat16_rn(v);
+}
+
+template <int CP, int CR>
+int launch_same_block(const SameBlockArgs& a, int sm_count, cudaStream_t stream) {
+    using Cfg = SameCfg<CP, CR>;
+    auto kern = same_block_tc_kernel<CP, CR>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    const int cap = sm_count * Cfg::MIN_CTAS;
+    const int grid = a.n_tiles < cap ? a.n_tiles : cap;
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(a);
+    return check_launch();
 }
 
 }  // namespace
 
+static inline int padded_channels(int C) { return C == 8 ? 16 : C; }
+
 int pack_same_block_bf16(const float* w1, const float* w2, const float* w3, int C, void* packed,
                          cudaStream_t stream) {
     if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
-    if (C % 8 != 0) return VQAE_ERR_UNSUPPORTED;
-    const int total = 11 * C * C;
+    if (C != 8 && C != 16 && C != 32 && C != 64) return VQAE_ERR_UNSUPPORTED;
+    const int CP = padded_channels(C);
+    const int total = 11 * CP * CP;
     pack_same_block_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(
-        w1, w2, w3, C, reinterpret_cast<__nv_bfloat16*>(packed));
+        w1, w2, w3, C, CP, reinterpret_cast<__nv_bfloat16*>(packed));
     return check_launch();
 }
 
@@ -411,25 +528,27 @@ int tc_selftest(const void* A, int a_rows, int row_shift, const void* B, float* 
 }
 
 int same_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
-                  int64_t B, int H, int W, int C, int sm_count, cudaStream_t stream) {
+                  int64_t B, int H, int W, int C, int sm_count, long long* prof,
+                  cudaStream_t stream) {
     if (!x || !out || !w_packed || !scalars8 || B <= 0) return VQAE_ERR_BAD_ARG;
     if (x == out) return VQAE_ERR_BAD_ARG;
-    if (H != SB_HW || W != SB_HW || C != SB_C) return VQAE_ERR_UNSUPPORTED;
+    if (H < SB_TH || W < SB_TW || H % SB_TH != 0 || W % SB_TW != 0) return VQAE_ERR_UNSUPPORTED;
     SameBlockArgs a;
     a.x = x; a.out = out; a.w = reinterpret_cast<const __nv_bfloat16*>(w_packed);
-    a.n_tiles = (int)(B * 2);
+    a.H = H; a.W = W; a.tiles_x = W / SB_TW; a.tiles_per_img = (H / SB_TH) * a.tiles_x;
+    const int64_t nt = B * a.tiles_per_img;
+    if (nt > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
+    a.n_tiles = (int)nt;
     a.b1a = scalars8[0]; a.b1b = scalars8[1]; a.b2a = scalars8[2]; a.b2b = scalars8[3];
     a.b3a = scalars8[4]; a.b3b = scalars8[5]; a.b4 = scalars8[6]; a.scale = scalars8[7];
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQAE_CUDA_TRY(cudaFuncSetAttribute(same_block_tc_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)SB_SMEM));
-        attr_set = true;
+    a.prof = prof;
+    switch (C) {
+        case 64: return launch_same_block<64, 64>(a, sm_count, stream);
+        case 32: return launch_same_block<32, 32>(a, sm_count, stream);
+        case 16: return launch_same_block<16, 16>(a, sm_count, stream);
+        case 8: return launch_same_block<16, 8>(a, sm_count, stream);
     }
-    const int grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
-    same_block_tc_kernel<<<grid, SB_THREADS, SB_SMEM, stream>>>(a);
-    return check_launch();
+    return VQAE_ERR_UNSUPPORTED;
 }
 
 }  // namespace vqae

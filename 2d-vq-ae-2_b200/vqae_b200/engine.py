@@ -116,21 +116,24 @@ class PackedFixup:
         # tcgen05 path: bf16 operand pack of a 'same' block at the trunk width (C = 64)
         self.tc_weights = None
         self.tc_scalars = None
-        if self.mode == L.MODE_SAME and self.c_in == 64 and self.c_branch == 64:
+        if self.mode == L.MODE_SAME and self.c_in in (8, 16, 32, 64) and \
+                self.c_branch == self.c_in and self.c_out == self.c_in:
             lib = L.load()
             dev = w2.device
-            self.tc_weights = torch.empty(11 * 64 * 64, dtype=torch.bfloat16, device=dev)
+            cp = 16 if self.c_in == 8 else self.c_in          # C = 8 runs zero-padded as 16
+            self.tc_weights = torch.empty(11 * cp * cp, dtype=torch.bfloat16, device=dev)
             ws = [t.detach().float().contiguous() for t in
                   (block.branch_conv1.weight, w2, block.branch_conv3.weight)]
-            L.check(lib.vqae_pack_same_block_bf16(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), 64,
-                                                  _ptr(self.tc_weights), _stream(dev)),
+            L.check(lib.vqae_pack_same_block_bf16(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]),
+                                                  self.c_in, _ptr(self.tc_weights), _stream(dev)),
                     "vqae_pack_same_block_bf16")
             sc = self.scalars
             self.tc_scalars = (C.c_float * 8)(*[float(sc[k]) for k in (
                 "bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "scale")])
 
     def tc_ok(self, h: int, w: int) -> bool:
-        return self.tc_weights is not None and h == 32 and w == 32
+        """a tcgen05 kernel is built for this block at this size (16 x 32 pixel tiles)"""
+        return self.tc_weights is not None and h % 16 == 0 and w % 32 == 0
 
     def out_hw(self, h: int, w: int) -> Tuple[int, int]:
         if self.mode == L.MODE_DOWN:

@@ -116,15 +116,22 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
 
 /* ---- a-T / a-R on tensor cores (tcgen05, bf16 operands, fp32 accumulate + fp32 residual) -------
  * One PreActFixupResBlock in mode 'same' (layers/conv_block.py:196-216) per call, all three
- * convs and their pre-activations fused; built for the trunk shape c == 64, height == width == 32
- * (model.py:150-153,240-263).  w_packed comes from vqae_pack_same_block_bf16 (11*c*c bf16);
+ * convs and their pre-activations fused in one kernel; c in {8, 16, 32, 64} (8 runs zero-padded
+ * as 16), height % 16 == 0, width % 32 == 0 -- every 'same' block of the shipped encoder and
+ * decoder (DownBlock/UpBlock pre/post layers and the 50-block trunks, model.py:150-153,240-263).
+ * w_packed comes from vqae_pack_same_block_bf16 (11 * cp * cp bf16, cp = max(c, 16));
  * scalars8_host = {bias1a, bias1b, bias2a, bias2b, bias3a, bias3b, bias4, scale} on the HOST.
- * x, out: NHWC fp32 [B,32,32,64], must not alias.                                            */
+ * x, out: NHWC fp32 [B,H,W,c], must not alias.                                               */
 int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                               int c, void* packed, void* stream);
 int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c,
                          void* stream);
+/* same call, additionally writing clock64() at the 8 phase boundaries of every CTA's first tile
+ * to phase_clocks[grid][8] (device memory, >= 8 * 4 * SM-count int64) -- profiling aid        */
+int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packed,
+                                 const float* scalars8_host, int64_t batch, int height, int width,
+                                 int c, long long* phase_clocks, void* stream);
 /* descriptor/TMEM self test: d[128][64] = a[row_shift + m][0..63] . b[n][0..63] (bf16 in, fp32 out),
  * a: [a_rows][64] bf16 row-major, b: [64][64] bf16 row-major (device pointers)                */
 int vqae_tc_selftest(const void* a_bf16, int a_rows, int row_shift, const void* b_bf16, float* d,

@@ -1,0 +1,73 @@
+"""Per-call CUDA-event breakdown of one encode step (batch 256, 256-model) -- a quick, un-profiled
+view of where the step goes (warm L2 state as in the real step).  usage:
+    python profiles/step_breakdown.py [fp32|bf16] [batch]
+"""
+import sys
+from collections import OrderedDict
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(REPO / "2d-vq-ae-2_b200"), str(REPO)]
+import torch  # noqa: E402
+
+import vqae_b200  # noqa: E402
+from vqae_b200 import engine as E  # noqa: E402
+from vqae_b200 import synthetic as S  # noqa: E402
+from vqae_b200.model import _flat_blocks  # noqa: E402
+
+
+def main():
+    precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    dev = torch.device("cuda:0")
+    m = vqae_b200.build_vqae(n_down=3).eval()
+    m.load_state_dict(S.make_state_dict(m.state_dict(), seed=1, regime="perturbed"))
+    m = m.to(dev)
+    enc = m.encoder
+    x = S.synthetic_patches_u8(batch, 256, 42).to(dev)
+    blocks = _flat_blocks(enc.down_layers) + _flat_blocks(enc.pre_enc_layers)
+    packed = E.pack_blocks(blocks)
+    pq = enc.vq_layers[0].packed()
+    names = {0: "same", 1: "down", 2: "up"}
+
+    def run(record):
+        ev = []
+
+        def mark(label):
+            if record:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                ev.append((label, e))
+        mark("start")
+        h = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias)
+        mark("stem_in")
+        for pk in packed:
+            hh = h.shape[1]
+            h = E.fixup_forward_nhwc(pk, h, precision=precision)
+            mark(f"{names[pk.mode]} C{pk.c_in}->{pk.c_out} @{hh}")
+        b, hh, ww, c = h.shape
+        E.quantize(pq, h, True, True, b, hh * ww, want_out=False)
+        mark("quantize")
+        return ev
+
+    with torch.no_grad():
+        for _ in range(3):
+            run(False)
+        torch.cuda.synchronize()
+        ev = run(True)
+        torch.cuda.synchronize()
+    agg = OrderedDict()
+    total = ev[0][1].elapsed_time(ev[-1][1])
+    for (_, e0), (label, e1) in zip(ev, ev[1:]):
+        a = agg.setdefault(label, [0, 0.0])
+        a[0] += 1
+        a[1] += e0.elapsed_time(e1)
+    print(f"# precision {precision}, batch {batch}: step {total:.3f} ms "
+          f"({batch / total * 1e3:.0f} patches/s)")
+    print(f"{'call':28s} {'n':>4s} {'ms':>9s} {'share':>7s} {'us/call':>9s}")
+    for label, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{label:28s} {n:4d} {ms:9.3f} {ms / total:7.1%} {ms / n * 1e3:9.1f}")
+
+
+if __name__ == "__main__":
+    main()

@@ -31,18 +31,21 @@ def test_tc_selftest_descriptor_shift(a_rows, shift):
     assert H.rel_err(d, ref) < 1e-5      # same bf16 inputs, fp32 accumulation
 
 
-@pytest.mark.parametrize("batch", [1, 3, 80])
-def test_same_block_bf16_vs_fp32_path(batch):
+@pytest.mark.parametrize("c,hw,batch", [(64, 32, 1), (64, 32, 3), (64, 32, 80), (64, 64, 2),
+                                        (32, 64, 2), (32, 32, 5), (16, 128, 2), (16, 32, 9),
+                                        (8, 256, 1), (8, 64, 3)])
+def test_same_block_bf16_vs_fp32_path(c, hw, batch):
     from vqae_b200.config import pre_activation_fixup
     from vqae_b200.layers.conv_block import PreActFixupResBlock
     conf = pre_activation_fixup(n_layers=12)
     for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
         conf.pop(k)
-    blk = PreActFixupResBlock(in_channels=64, out_channels=64, mode="same", **conf).eval()
+    blk = PreActFixupResBlock(in_channels=c, out_channels=c, mode="same", **conf).eval()
     blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=3, regime="perturbed", n_layers=12))
     blk = blk.to(DEV)
     pk = blk.packed()
-    x = torch.randn(batch, 32, 32, 64, device=DEV)
+    assert pk.tc_ok(hw, hw)
+    x = torch.randn(batch, hw, hw, c, device=DEV)
     y32 = E.fixup_forward_nhwc(pk, x, precision="fp32")
     y16 = E.fixup_forward_nhwc(pk, x, precision="bf16")
     torch.cuda.synchronize()
