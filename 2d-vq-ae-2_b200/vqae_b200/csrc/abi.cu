@@ -226,6 +226,24 @@ int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
                          nullptr, (cudaStream_t)stream);
 }
 
+size_t vqae_down_block_pack_elems(int c_in) { return down_block_pack_elems(c_in); }
+
+int vqae_pack_down_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+                              const float* wskip_oihw, int c_in, float scale, void* packed,
+                              void* stream) {
+    return pack_down_block_bf16(w1_oihw, w2_oihw, w3_oihw, wskip_oihw, c_in, scale, packed,
+                                (cudaStream_t)stream);
+}
+
+int vqae_down_block_bf16(const float* x, float* out, const void* w_packed,
+                         const float* scalars8_host, int64_t batch, int height, int width, int c_in,
+                         void* stream) {
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return down_block_tc(x, out, w_packed, scalars8_host, batch, height, width, c_in, sm_count,
+                         (cudaStream_t)stream);
+}
+
 int vqae_quantizer_prepare_f32(const float* embed, int num_codes, int dim, const float* w_out,
                                const float* b_out, int c, float* table, void* stream) {
     return quantizer_prepare_f32(embed, num_codes, dim, w_out, b_out, c, table,

@@ -161,5 +161,24 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // ELU(alpha=1) for the bf16 path: x > 0 ? x : e^x - 1 with the fast exponential
 __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
+// 8 fp32 -> 8 bf16 of  act(v + pre) + post  (the Fixup pre-activation, conv_block.py:199-208)
+__device__ __forceinline__ uint4 act_pack8(const float* v, float pre, float post) {
+    uint4 o;
+    o.x = pack_bf16(elu_fast(v[0] + pre) + post, elu_fast(v[1] + pre) + post);
+    o.y = pack_bf16(elu_fast(v[2] + pre) + post, elu_fast(v[3] + pre) + post);
+    o.z = pack_bf16(elu_fast(v[4] + pre) + post, elu_fast(v[5] + pre) + post);
+    o.w = pack_bf16(elu_fast(v[6] + pre) + post, elu_fast(v[7] + pre) + post);
+    return o;
+}
+// 8 fp32 -> 8 bf16 of  v + add  (skip path: no activation, conv_block.py:211-213)
+__device__ __forceinline__ uint4 add_pack8(const float* v, float add) {
+    uint4 o;
+    o.x = pack_bf16(v[0] + add, v[1] + add);
+    o.y = pack_bf16(v[2] + add, v[3] + add);
+    o.z = pack_bf16(v[4] + add, v[5] + add);
+    o.w = pack_bf16(v[6] + add, v[7] + add);
+    return o;
+}
+
 }  // namespace tc
 }  // namespace vqae

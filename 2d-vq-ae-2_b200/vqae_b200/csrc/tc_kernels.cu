@@ -139,15 +139,6 @@ struct SameBlockArgs {
 };
 
 
-__device__ __forceinline__ uint4 act_pack8(const float* v, float pre, float post) {
-    uint4 o;
-    o.x = pack_bf16(elu_fast(v[0] + pre) + post, elu_fast(v[1] + pre) + post);
-    o.y = pack_bf16(elu_fast(v[2] + pre) + post, elu_fast(v[3] + pre) + post);
-    o.z = pack_bf16(elu_fast(v[4] + pre) + post, elu_fast(v[5] + pre) + post);
-    o.w = pack_bf16(elu_fast(v[6] + pre) + post, elu_fast(v[7] + pre) + post);
-    return o;
-}
-
 template <int CP, int CR>
 __global__ void __launch_bounds__(SameCfg<CP, CR>::THREADS, SameCfg<CP, CR>::MIN_CTAS)
 same_block_tc_kernel(SameBlockArgs a) {

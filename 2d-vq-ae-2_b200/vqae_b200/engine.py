@@ -131,9 +131,29 @@ class PackedFixup:
             self.tc_scalars = (C.c_float * 8)(*[float(sc[k]) for k in (
                 "bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "scale")])
 
+        if self.mode == L.MODE_DOWN and self.c_in in (8, 16, 32) and \
+                self.c_branch == 2 * self.c_in and self.c_out == 2 * self.c_in:
+            lib = L.load()
+            dev = w2.device
+            sc = self.scalars
+            n = lib.vqae_down_block_pack_elems(self.c_in)
+            self.tc_weights = torch.empty(n, dtype=torch.bfloat16, device=dev)
+            ws = [t.detach().float().contiguous() for t in
+                  (block.branch_conv1.weight, w2, block.branch_conv3.weight,
+                   block.skip_conv.weight)]
+            L.check(lib.vqae_pack_down_block_bf16(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]),
+                                                  _ptr(ws[3]), self.c_in, float(sc["scale"]),
+                                                  _ptr(self.tc_weights), _stream(dev)),
+                    "vqae_pack_down_block_bf16")
+            self.tc_scalars = (C.c_float * 8)(*(
+                [float(sc[k]) for k in ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a",
+                                        "bias3b", "bias1c")]
+                + [float(sc["bias4"]) + float(sc["bias1d"])]))
+
     def tc_ok(self, h: int, w: int) -> bool:
         """a tcgen05 kernel is built for this block at this size (16 x 32 pixel tiles)"""
-        return self.tc_weights is not None and h % 16 == 0 and w % 32 == 0
+        return (self.tc_weights is not None and self.mode in (L.MODE_SAME, L.MODE_DOWN)
+                and h % 16 == 0 and w % 32 == 0)
 
     def out_hw(self, h: int, w: int) -> Tuple[int, int]:
         if self.mode == L.MODE_DOWN:
@@ -183,6 +203,10 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
     ho, wo = pk.out_hw(h, w)
     if out is None:
         out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
+    if precision == "bf16" and pk.tc_ok(h, w) and pk.mode == L.MODE_DOWN:
+        L.check(lib.vqae_down_block_bf16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
+                                         b, h, w, c, _stream(x.device)), "vqae_down_block_bf16")
+        return out
     if precision == "bf16" and pk.tc_ok(h, w):
         L.check(lib.vqae_same_block_bf16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
                                          b, h, w, c, _stream(x.device)), "vqae_same_block_bf16")

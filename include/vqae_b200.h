@@ -127,6 +127,19 @@ int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const 
 int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c,
                          void* stream);
+/* PreActFixupResBlock in mode 'down' (conv specs pre_activation_fixup.yaml:35-45): c_in ->
+ * 2*c_in, stride 2, branch + skip fused in one tcgen05 kernel; c_in in {8, 16, 32},
+ * height % 16 == 0, width % 32 == 0.  w_packed: vqae_down_block_pack_elems(c_in) bf16 from
+ * vqae_pack_down_block_bf16 (scale is folded into branch_conv3 there);
+ * scalars8_host = {bias1a, bias1b, bias2a, bias2b, bias3a, bias3b, bias1c, bias4 + bias1d}.
+ * x: NHWC fp32 [B,H,W,c_in];  out: NHWC fp32 [B,H/2,W/2,2*c_in].                             */
+size_t vqae_down_block_pack_elems(int c_in);
+int vqae_pack_down_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+                              const float* wskip_oihw, int c_in, float scale, void* packed,
+                              void* stream);
+int vqae_down_block_bf16(const float* x, float* out, const void* w_packed,
+                         const float* scalars8_host, int64_t batch, int height, int width, int c_in,
+                         void* stream);
 /* same call, additionally writing clock64() at the 8 phase boundaries of every CTA's first tile
  * to phase_clocks[grid][8] (device memory, >= 8 * 4 * SM-count int64) -- profiling aid        */
 int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packed,

@@ -55,6 +55,27 @@ def test_same_block_bf16_vs_fp32_path(c, hw, batch):
     assert H.rel_err(y16, y32) < 2e-3
 
 
+@pytest.mark.parametrize("c,hw,batch", [(32, 64, 2), (32, 32, 7), (16, 128, 2), (16, 32, 5),
+                                        (8, 256, 1), (8, 64, 6)])
+def test_down_block_bf16_vs_fp32_path(c, hw, batch):
+    from vqae_b200.config import pre_activation_fixup
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blk = PreActFixupResBlock(in_channels=c, out_channels=2 * c, mode="down", **conf).eval()
+    blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=4, regime="perturbed", n_layers=12))
+    blk = blk.to(DEV)
+    pk = blk.packed()
+    assert pk.tc_ok(hw, hw)
+    x = torch.randn(batch, hw, hw, c, device=DEV)
+    y32 = E.fixup_forward_nhwc(pk, x, precision="fp32")
+    y16 = E.fixup_forward_nhwc(pk, x, precision="bf16")
+    torch.cuda.synchronize()
+    assert y16.shape == (batch, hw // 2, hw // 2, 2 * c)
+    assert H.rel_err(y16, y32) < 1e-2, H.rel_err(y16, y32)
+
+
 def test_encoder_bf16_agreement_with_fp32():
     tag = "model_nd3_perturbed"
     m, sd, x = H.model_and_state(tag)
