@@ -47,6 +47,8 @@ int same_block_tc(const float* x, float* out, const void* w_packed, const float*
 int pack_same_block_bf16(const float* w1, const float* w2, const float* w3, int C, void* packed,
                          cudaStream_t stream);
 
+int tc_mma_bench(int N, int layout_type, int reps, int a_stride_rows, long long* out,
+                 cudaStream_t stream);
 // tc_down.cu
 size_t down_block_pack_elems(int CI);
 int pack_down_block_bf16(const float* w1, const float* w2, const float* w3, const float* ws, int CI,

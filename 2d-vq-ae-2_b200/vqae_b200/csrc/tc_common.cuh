@@ -134,23 +134,32 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
            ((uint32_t)(M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
+// D[tmem] (+)= A[smem] * B[smem]^T.  Called by ALL lanes of the (converged) MMA warp with
+// warp-uniform operands, so that descriptor arithmetic stays in uniform registers; only the lane
+// with `leader` set issues the instruction.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
+                                          uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+    (void)leader;
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
+        ".reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// arrive on an mbarrier when all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                     bar)
-                 : "memory");
+// arrive on an mbarrier when all previously issued MMAs of the elected thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
+    (void)leader;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar)
+        : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -159,7 +168,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 // ELU(alpha=1) for the bf16 path: x > 0 ? x : e^x - 1 with the fast exponential
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+// (one FMUL + one MUFU.EX2, flush-to-zero: no denormal fix-up code around the SFU call)
+__device__ __forceinline__ float elu_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.f;
+}
 
 // 8 fp32 -> 8 bf16 of  act(v + pre) + post  (the Fixup pre-activation, conv_block.py:199-208)
 __device__ __forceinline__ uint4 act_pack8(const float* v, float pre, float post) {

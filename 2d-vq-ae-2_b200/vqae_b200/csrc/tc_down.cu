@@ -77,7 +77,9 @@ down_block_tc_kernel(DownArgs a) {
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar_mma = sbase + Cfg::OFF_BAR;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 16);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // provably warp-uniform
+    const uint32_t leader = lane == 0;
 
     if (tid == 0) {
         mbar_init(bar_mma, 1);
@@ -95,7 +97,7 @@ down_block_tc_kernel(DownArgs a) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t idesc = make_idesc_bf16(128, CO);
     const uint32_t tD2 = tmem_base + 4 * CO;           // D2 / D3 tile after the four D1 tiles
 
@@ -163,8 +165,8 @@ down_block_tc_kernel(DownArgs a) {
         __syncthreads();
 
         // ---- G1: D1[plane] = A1[plane] . W1^T ----
-        if (warp == MMA_WARP) {
-            if (lane == 0) {
+        if (warp == MMA_WARP) {          // whole warp, warp-uniform operands; lane 0 issues
+            {
                 tc_fence_after_sync();
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl)
@@ -172,8 +174,8 @@ down_block_tc_kernel(DownArgs a) {
                     for (int ks = 0; ks < CIP / 16; ++ks)
                         umma_bf16(tmem_base + pl * CO,
                                   dA1 + (uint64_t)((pl * DB_PLANE * 16 + ks * 2 * DB_LBO) >> 4),
-                                  dW1 + (uint64_t)((ks * 2 * Cfg::W1_LBO) >> 4), idesc, ks > 0);
-                umma_commit(bar_mma);
+                                  dW1 + (uint64_t)((ks * 2 * Cfg::W1_LBO) >> 4), idesc, ks > 0, leader);
+                umma_commit(bar_mma, leader);
             }
             __syncwarp();
         }
@@ -198,8 +200,8 @@ down_block_tc_kernel(DownArgs a) {
         __syncthreads();
 
         // ---- G2: D2 = sum over the four taps (= planes) of U[plane] . W2[plane]^T ----
-        if (warp == MMA_WARP) {
-            if (lane == 0) {
+        if (warp == MMA_WARP) {          // whole warp, warp-uniform operands; lane 0 issues
+            {
                 tc_fence_after_sync();
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl)
@@ -207,8 +209,8 @@ down_block_tc_kernel(DownArgs a) {
                     for (int ks = 0; ks < CO / 16; ++ks)
                         umma_bf16(tD2, dU + (uint64_t)((pl * DB_PLANE * 16 + ks * 2 * DB_LBO) >> 4),
                                   dW2 + (uint64_t)((pl * Cfg::WO_BYTES + ks * 2 * Cfg::WO_LBO) >> 4),
-                                  idesc, (pl | ks) > 0);
-                umma_commit(bar_mma);
+                                  idesc, (pl | ks) > 0, leader);
+                umma_commit(bar_mma, leader);
             }
             __syncwarp();
         }
@@ -230,21 +232,21 @@ down_block_tc_kernel(DownArgs a) {
         __syncthreads();
 
         // ---- G3: D3 = V . (scale W3)^T + sum over planes of As[plane] . Ws[plane]^T ----
-        if (warp == MMA_WARP) {
-            if (lane == 0) {
+        if (warp == MMA_WARP) {          // whole warp, warp-uniform operands; lane 0 issues
+            {
                 tc_fence_after_sync();
 #pragma unroll
                 for (int ks = 0; ks < CO / 16; ++ks)
                     umma_bf16(tD2, dV + (uint64_t)((ks * 2 * DB_VLBO) >> 4),
-                              dW3 + (uint64_t)((ks * 2 * Cfg::WO_LBO) >> 4), idesc, ks > 0);
+                              dW3 + (uint64_t)((ks * 2 * Cfg::WO_LBO) >> 4), idesc, ks > 0, leader);
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl)
 #pragma unroll
                     for (int ks = 0; ks < CIP / 16; ++ks)
                         umma_bf16(tD2, dAS + (uint64_t)((pl * DB_PLANE * 16 + ks * 2 * DB_LBO) >> 4),
                                   dWS + (uint64_t)((pl * Cfg::W1_BYTES + ks * 2 * Cfg::W1_LBO) >> 4),
-                                  idesc, 1u);
-                umma_commit(bar_mma);
+                                  idesc, 1u, leader);
+                umma_commit(bar_mma, leader);
             }
             __syncwarp();
         }

@@ -19,6 +19,8 @@
 // pixel shift keeps the descriptor regular (tc_common.cuh).  W1/W3 stay resident in shared
 // memory, the nine 8 KB W2 taps stream through a 4-slot ring filled by bulk async copies
 // (UBLKCP) from L2.  Warps 0-7: prologue/epilogue math; warp 8: MMA issue; warp 9: W2 producer.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -44,7 +46,9 @@ tc_selftest_kernel(const __nv_bfloat16* __restrict__ A, int a_rows, int row_shif
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // provably warp-uniform
+    const uint32_t leader = lane == 0;
     for (int i = tid; i < a_rows * KCH; i += blockDim.x) {
         const int r = i / KCH, kc = i % KCH;
         *reinterpret_cast<uint4*>(sa + kc * a_lbo + r * 16) =
@@ -66,15 +70,15 @@ tc_selftest_kernel(const __nv_bfloat16* __restrict__ A, int a_rows, int row_shif
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (tid == 0) {
+    if (warp == 0) {                   // whole warp: umma_bf16 elects the issuing lane itself
         const uint32_t idesc = make_idesc_bf16(128, N);
 #pragma unroll
         for (int ks = 0; ks < K / 16; ++ks) {
             const uint64_t ad = make_desc(smem_u32(sa) + row_shift * 16 + ks * 2 * a_lbo, a_lbo, 128);
             const uint64_t bd = make_desc(smem_u32(sb) + ks * 2 * b_lbo, b_lbo, 128);
-            umma_bf16(tmem_base, ad, bd, idesc, ks > 0);
+            umma_bf16(tmem_base, ad, bd, idesc, ks > 0, 1u);
         }
-        umma_commit(smem_u32(&bar));
+        umma_commit(smem_u32(&bar), 1u);
     }
     __syncwarp();
     mbar_wait(smem_u32(&bar), 0);
@@ -90,6 +94,60 @@ tc_selftest_kernel(const __nv_bfloat16* __restrict__ A, int a_rows, int row_shif
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+// -----------------------------------------------------------------------------------------------
+// MMA issue-rate microbenchmark (timing only, operand contents are arbitrary): `reps` back-to-back
+// tcgen05.mma of shape 128 x N x 16 (bf16) from shared memory, layout_type 0 (no swizzle, the
+// canonical layout used by the block kernels) or 2 (SWIZZLE_128B).  out[0] = cycles, out[1] = reps.
+// -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+tc_mma_bench_kernel(int N, int layout_type, int reps, int a_stride_rows, long long* out) {
+    const int nacc = layout_type >> 4 ? (layout_type >> 4) : 2;   // independent accumulators
+    layout_type &= 15;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 160 * 1024 / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    if (tid == 0) {
+        mbar_init(smem_u32(&bar), 1);
+        fence_mbar_init();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    if (warp == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint32_t sa = smem_u32(smem), sb = sa + 96 * 1024;
+        uint64_t ad, bd;
+        if (layout_type == 0) {
+            ad = make_desc(sa, 641 * 16, 128);
+            bd = make_desc(sb, N * 16, 128);
+        } else {   // SW128 K-major: rows of 128 B, 8-row groups 1024 B apart
+            ad = make_desc(sa, 16, 1024) | (2ull << 61);
+            bd = make_desc(sb, 16, 1024) | (2ull << 61);
+        }
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            const uint32_t aoff = (uint32_t)((r % 5) * a_stride_rows * (layout_type == 0 ? 16 : 128)) >> 4;
+            umma_bf16(tmem_base + (r % nacc) * N, ad + aoff, bd + (uint64_t)((r & 3) * 2), idesc, 1u, 1u);
+        }
+        umma_commit(smem_u32(&bar), 1u);
+        mbar_wait(smem_u32(&bar), 0);
+        if (tid == 0) {
+            out[0] = clock64() - t0;
+            out[1] = reps;
+        }
+    }
+    __syncthreads();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -112,11 +170,12 @@ struct SameCfg {
     static constexpr int KCH = CP / 8;             // 16-byte k-chunks per pixel seen by the MMA
     static constexpr int KCR = CR / 8;             // ... that hold real channels
     static constexpr bool RING = (CP == 64);       // W2 does not fit next to the operands: stream it
-    static constexpr int NW = (CP == 64) ? 8 : 4;  // worker warps
+    static constexpr int NW = (CP == 64) ? 16 : (CP == 32 ? 8 : 4);   // worker warps
     static constexpr int WORKERS = NW * 32;
     static constexpr int THREADS = WORKERS + 64;   // + MMA warp + weight-producer warp
-    static constexpr int NC = (CP == 64) ? 32 : CP;                 // TMEM columns per epilogue unit
-    static constexpr int UCH = (CP == 64) ? 4 : KCR;                // real k-chunks per unit
+    static constexpr int NG = NW / 4;              // column groups (4 warps cover the 128 TMEM lanes)
+    static constexpr int NC = CP / NG;             // TMEM columns per epilogue unit (16)
+    static constexpr int UCH = (CR < CP) ? KCR : NC / 8;            // real k-chunks per unit
     static constexpr uint32_t WLBO = CP * 16;
     static constexpr uint32_t WMAT = KCH * WLBO;                    // one CP x CP bf16 matrix
     static constexpr uint32_t OFF_X = 0;
@@ -135,6 +194,7 @@ struct SameBlockArgs {
     const __nv_bfloat16* w;       // 11 matrices [W1 | W2 tap 0..8 | W3], each [k-chunk][n][8]
     int n_tiles, H, W, tiles_x, tiles_per_img;
     float b1a, b1b, b2a, b2b, b3a, b3b, b4, scale;
+    unsigned stagger_ns;          // start delay of CTAs with slack (0 = off)
     long long* prof;              // optional [gridDim.x][8] phase timestamps of each CTA's 1st tile
 };
 
@@ -158,7 +218,9 @@ same_block_tc_kernel(SameBlockArgs a) {
     const uint32_t bar_empty = bar_full + 8 * SB_RING;               // [SB_RING] tap consumed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 + 16 * SB_RING);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // provably warp-uniform
+    const uint32_t leader = lane == 0;
     const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_taps = my_tiles * 9;
 
@@ -192,7 +254,7 @@ same_block_tc_kernel(SameBlockArgs a) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t idesc = make_idesc_bf16(128, CP);
     const uint8_t* w2g = reinterpret_cast<const uint8_t*>(a.w) + WMAT;
 
@@ -209,11 +271,11 @@ same_block_tc_kernel(SameBlockArgs a) {
 
     // epilogue geometry of a worker thread
     const int q4 = warp & 3;              // TMEM lane quarter this warp may access
-    const int grp = (warp >> 2) & 1;      // CP == 64: channel half handled by this warp
+    const int grp = (warp >> 2) % Cfg::NG;        // column group handled by this warp
     const int row_in_tile = q4 * 32 + lane;
     const uint32_t t_lane = (uint32_t)(q4 * 32) << 16;
-    const uint32_t t_col = (CP == 64) ? grp * 32 : 0;
-    const int kc0 = (CP == 64) ? grp * 4 : 0;     // first k-chunk of this thread's unit
+    const uint32_t t_col = grp * NC;
+    const int kc0 = grp * (NC / 8);               // first k-chunk of this thread's unit
     // E3 staging (warp-private, in the U region once G3 has consumed V): [32 rows][NCR + 4] fp32
     constexpr int NCR = UCH * 8;                  // real channels per epilogue unit
     constexpr int F4 = NCR / 4;                   // float4 per staged row
@@ -235,7 +297,7 @@ same_block_tc_kernel(SameBlockArgs a) {
         const int r0 = (trem / a.tiles_x) * SB_TH, c0 = (trem % a.tiles_x) * SB_TW;
         const float* ximg = a.x + (size_t)img * a.H * a.W * CR;
         constexpr int ITEMS = SB_NPAD * KCR;
-        constexpr int PB = 6;
+        constexpr int PB = (NW >= 16) ? 3 : 6;
         for (int base = tid; base < ITEMS; base += Cfg::WORKERS * PB) {
             float4 v0[PB], v1[PB];
             int dst[PB];
@@ -268,6 +330,11 @@ same_block_tc_kernel(SameBlockArgs a) {
     };
 
     int tile = blockIdx.x;
+    // De-phase the CTAs: the tiles of all SMs otherwise march in lockstep and their memory phases
+    // (operand gather, residual epilogue) hit L2/HBM in the same burst.  CTAs that own one tile
+    // fewer than the busiest ones have a whole tile time of slack, so they start half a tile late.
+    if (a.stagger_ns > 0 && my_tiles < (a.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x)
+        __nanosleep(a.stagger_ns);
     const bool prof_cta = a.prof != nullptr && tid == 0;
     if (prof_cta) a.prof[(size_t)blockIdx.x * 8 + 0] = clock64();
     if (warp < NW && tile < a.n_tiles) prologue(tile);
@@ -285,8 +352,8 @@ same_block_tc_kernel(SameBlockArgs a) {
         if (prof) a.prof[(size_t)blockIdx.x * 8 + 1] = clock64();
 
         // ---- G1: D1 = A1 . W1^T on 5 M-tiles of padded-linear pixels ----
-        if (warp == MMA_WARP) {
-            if (lane == 0) {
+        if (warp == MMA_WARP) {          // whole warp, warp-uniform operands; lane 0 issues
+            {
                 tc_fence_after_sync();
 #pragma unroll
                 for (int t = 0; t < 5; ++t)
@@ -294,8 +361,8 @@ same_block_tc_kernel(SameBlockArgs a) {
                     for (int ks = 0; ks < CP / 16; ++ks)
                         umma_bf16(tmem_base + t * CP,
                                   dX + (uint64_t)((t * 128 * 16 + ks * 2 * SB_XLBO) >> 4),
-                                  dW1 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0);
-                umma_commit(bar_mma);
+                                  dW1 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0, leader);
+                umma_commit(bar_mma, leader);
             }
             __syncwarp();
         }
@@ -332,8 +399,8 @@ same_block_tc_kernel(SameBlockArgs a) {
                          bar_full + 8 * slot);
             }
         }
-        if (warp == MMA_WARP) {
-            if (lane == 0) {
+        if (warp == MMA_WARP) {          // whole warp, warp-uniform operands; lane 0 issues
+            {
                 tc_fence_after_sync();
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
@@ -355,10 +422,10 @@ same_block_tc_kernel(SameBlockArgs a) {
                         for (int ks = 0; ks < CP / 16; ++ks)
                             umma_bf16(tmem_base + t * CP,
                                       dU + (uint64_t)(((SB_PW + 1 + t * 128 + shift) * 16 + ks * 2 * SB_ULBO) >> 4),
-                                      dW + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, (tap | ks) > 0);
-                    if (Cfg::RING) umma_commit(bar_empty + 8 * slot);
+                                      dW + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, (tap | ks) > 0, leader);
+                    if (Cfg::RING) umma_commit(bar_empty + 8 * slot, leader);
                 }
-                umma_commit(bar_mma);
+                umma_commit(bar_mma, leader);
             }
             __syncwarp();
         }
@@ -391,8 +458,8 @@ same_block_tc_kernel(SameBlockArgs a) {
         __syncthreads();
 
         // ---- G3: D3 = V . W3^T, 4 M-tiles ----
-        if (warp == MMA_WARP) {
-            if (lane == 0) {
+        if (warp == MMA_WARP) {          // whole warp, warp-uniform operands; lane 0 issues
+            {
                 tc_fence_after_sync();
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
@@ -400,21 +467,36 @@ same_block_tc_kernel(SameBlockArgs a) {
                     for (int ks = 0; ks < CP / 16; ++ks)
                         umma_bf16(tmem_base + t * CP,
                                   dU + (uint64_t)((t * 128 * 16 + ks * 2 * SB_ULBO) >> 4),
-                                  dW3 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0);
-                umma_commit(bar_mma);
+                                  dW3 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0, leader);
+                umma_commit(bar_mma, leader);
             }
             __syncwarp();
         }
         // ---- E3: out = x + scale * D3 + b4 (fp32).  Each warp transposes its 32 x NCR block
-        //      through shared memory so that global loads/stores are 128-bit and line-coalesced ----
+        //      through shared memory so that global loads/stores are 128-bit and line-coalesced;
+        //      the residual rows of M-tile t+1 are requested before M-tile t is processed ----
         if (warp < NW) {
+            const int rsub = lane / F4, c4 = lane % F4;
+            auto x_off = [&](int t, int k) {
+                const int p = t * 128 + q4 * 32 + rsub + k * (32 / F4);
+                return ((size_t)(r0 + (p >> 5)) * a.W + c0 + (p & 31)) * CR + kc0 * 8 + c4 * 4;
+            };
+            float4 xr[F4], xn[F4];
+#pragma unroll
+            for (int k = 0; k < F4; ++k)
+                xr[k] = __ldg(reinterpret_cast<const float4*>(ximg + x_off(0, k)));
             mbar_wait(bar_mma, mma_phase);
             tc_fence_after_sync();
             if (prof) a.prof[(size_t)blockIdx.x * 8 + 6] = clock64();
-            const int rsub = lane / F4, c4 = lane % F4;
+#pragma unroll
             for (int t = 0; t < 4; ++t) {
                 float v[NC];
                 tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
+                if (t + 1 < 4) {
+#pragma unroll
+                    for (int k = 0; k < F4; ++k)
+                        xn[k] = __ldg(reinterpret_cast<const float4*>(ximg + x_off(t + 1, k)));
+                }
                 tmem_ld_wait();
                 __syncwarp();
 #pragma unroll
@@ -425,18 +507,16 @@ same_block_tc_kernel(SameBlockArgs a) {
 #pragma unroll
                 for (int k = 0; k < F4; ++k) {
                     const int rr = rsub + k * (32 / F4);           // row within this warp's 32
-                    const int p = t * 128 + q4 * 32 + rr;
-                    const size_t off =
-                        ((size_t)(r0 + (p >> 5)) * a.W + c0 + (p & 31)) * CR + kc0 * 8 + c4 * 4;
                     const float4 d = *reinterpret_cast<const float4*>(stage + rr * SROW + 4 * c4);
-                    const float4 r = __ldg(reinterpret_cast<const float4*>(ximg + off));
                     float4 o;
-                    o.x = fmaf(d.x, a.scale, a.b4) + r.x;
-                    o.y = fmaf(d.y, a.scale, a.b4) + r.y;
-                    o.z = fmaf(d.z, a.scale, a.b4) + r.z;
-                    o.w = fmaf(d.w, a.scale, a.b4) + r.w;
-                    *reinterpret_cast<float4*>(oimg + off) = o;
+                    o.x = fmaf(d.x, a.scale, a.b4) + xr[k].x;
+                    o.y = fmaf(d.y, a.scale, a.b4) + xr[k].y;
+                    o.z = fmaf(d.z, a.scale, a.b4) + xr[k].z;
+                    o.w = fmaf(d.w, a.scale, a.b4) + xr[k].w;
+                    *reinterpret_cast<float4*>(oimg + x_off(t, k)) = o;
                 }
+#pragma unroll
+                for (int k = 0; k < F4; ++k) xr[k] = xn[k];
             }
             tc_fence_before_sync();
         }
@@ -518,6 +598,16 @@ int tc_selftest(const void* A, int a_rows, int row_shift, const void* B, float* 
     return check_launch();
 }
 
+int tc_mma_bench(int N, int layout_type, int reps, int a_stride_rows, long long* out,
+                 cudaStream_t stream) {
+    if (!out || reps <= 0 || N < 16 || N > 256 || N % 16) return VQAE_ERR_BAD_ARG;
+    const size_t smem = 160 * 1024;
+    VQAE_CUDA_TRY(cudaFuncSetAttribute(tc_mma_bench_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_mma_bench_kernel<<<1, 128, smem, stream>>>(N, layout_type, reps, a_stride_rows, out);
+    return check_launch();
+}
+
 int same_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
                   int64_t B, int H, int W, int C, int sm_count, long long* prof,
                   cudaStream_t stream) {
@@ -533,6 +623,8 @@ int same_block_tc(const float* x, float* out, const void* w_packed, const float*
     a.b1a = scalars8[0]; a.b1b = scalars8[1]; a.b2a = scalars8[2]; a.b2b = scalars8[3];
     a.b3a = scalars8[4]; a.b3b = scalars8[5]; a.b4 = scalars8[6]; a.scale = scalars8[7];
     a.prof = prof;
+    a.stagger_ns = (C == 64) ? 9000u : 0u;
+    if (const char* e = getenv("VQAE_STAGGER_NS")) a.stagger_ns = (unsigned)atoi(e);
     switch (C) {
         case 64: return launch_same_block<64, 64>(a, sm_count, stream);
         case 32: return launch_same_block<32, 32>(a, sm_count, stream);

@@ -145,6 +145,10 @@ int vqae_down_block_bf16(const float* x, float* out, const void* w_packed,
 int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packed,
                                  const float* scalars8_host, int64_t batch, int height, int width,
                                  int c, long long* phase_clocks, void* stream);
+/* tcgen05.mma issue-rate microbenchmark (timing aid): `reps` MMAs of 128 x n x 16 bf16 from shared
+ * memory in layout_type 0 (un-swizzled K-major) or 2 (128-byte swizzle); out2[0] = cycles, [1] = reps */
+int vqae_tc_mma_bench(int n, int layout_type, int reps, int a_stride_rows, long long* out2,
+                      void* stream);
 /* descriptor/TMEM self test: d[128][64] = a[row_shift + m][0..63] . b[n][0..63] (bf16 in, fp32 out),
  * a: [a_rows][64] bf16 row-major, b: [64][64] bf16 row-major (device pointers)                */
 int vqae_tc_selftest(const void* a_bf16, int a_rows, int row_shift, const void* b_bf16, float* d,
