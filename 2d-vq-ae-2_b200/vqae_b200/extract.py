@@ -48,6 +48,71 @@ def compress_slide(encoder, batches: Iterable[Tuple[int, torch.Tensor]], grid: T
     return code_map
 
 
+class StreamingEncoder:
+    """Double-buffered host -> device -> host code extraction.
+
+    The copy of batch i+1 from pinned host memory runs on a side stream while batch i is encoded,
+    and the code indices of batch i return to pinned host memory asynchronously -- the B200
+    counterpart of the reference's DataLoader(pin_memory) + ``imgs.to(device, non_blocking=True)``
+    loop (extract_embeddings.py:95-101,118-122).  ``encode_stream`` yields one pinned int64
+    ``[B,h,w]`` tensor per input batch, in order; a yielded tensor is valid until two more
+    batches have been yielded."""
+
+    def __init__(self, encoder, device: torch.device, mean=None, std=None):
+        self.encoder, self.device, self.mean, self.std = encoder, device, mean, std
+        self.copy_stream = torch.cuda.Stream(device)
+        self._dev_in = [None, None]
+        self._host_out = [None, None]
+        self._h2d = [torch.cuda.Event() for _ in range(2)]
+        self._free = [torch.cuda.Event() for _ in range(2)]     # device input buffer consumed
+        self._d2h = [torch.cuda.Event() for _ in range(2)]
+
+    def _stage(self, slot: int, host_batch: torch.Tensor, first_use: bool) -> None:
+        if self._dev_in[slot] is None or self._dev_in[slot].shape != host_batch.shape:
+            self._dev_in[slot] = torch.empty(host_batch.shape, dtype=host_batch.dtype,
+                                             device=self.device)
+            first_use = True
+        with torch.cuda.stream(self.copy_stream):
+            if not first_use:
+                self.copy_stream.wait_event(self._free[slot])
+            self._dev_in[slot].copy_(host_batch, non_blocking=True)
+            self._h2d[slot].record(self.copy_stream)
+
+    @torch.no_grad()
+    def encode_stream(self, host_batches):
+        main = torch.cuda.current_stream(self.device)
+        it = iter(host_batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        self._stage(0, nxt, True)
+        i = 0
+        pending = []
+        while nxt is not None:
+            slot = i & 1
+            cur, nxt = nxt, next(it, None)
+            if nxt is not None:
+                self._stage(slot ^ 1, nxt, i == 0)
+            main.wait_event(self._h2d[slot])
+            idx = encode_patches(self.encoder, self._dev_in[slot], self.mean, self.std)
+            self._free[slot].record(main)
+            if self._host_out[slot] is None or self._host_out[slot].shape != idx.shape:
+                self._host_out[slot] = torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
+            elif len(pending) == 2:
+                pass
+            self._host_out[slot].copy_(idx, non_blocking=True)
+            self._d2h[slot].record(main)
+            pending.append(slot)
+            if len(pending) == 2:                  # results lag one batch behind the submission
+                done = pending.pop(0)
+                self._d2h[done].synchronize()
+                yield self._host_out[done]
+            i += 1
+        for done in pending:
+            self._d2h[done].synchronize()
+            yield self._host_out[done]
+
+
 def tiles_to_map(tiles_u8: torch.Tensor, grid: Tuple[int, int]) -> torch.Tensor:
     """[P,th,tw] tiles in row-major patch order -> [rows*th, cols*tw] map (pure view ops)."""
     rows, cols = grid
