@@ -69,6 +69,10 @@ SIGNATURES = {
     "vqae_quantizer_scratch_bytes": (_sz, [_i64]),
     "vqae_quantize_f32": (_i, [C.POINTER(QuantizerParams), _vp, _i, _vp, _i, _vp, _vp, _vp, _f,
                                _vp, _vp, _sz, _i64, _i64, _vp]),
+    "vqae_quantize_tc_set_profile": (None, [_vp]),
+    "vqae_quantize_tc_supported": (_i, [C.POINTER(QuantizerParams), _i, _i, _i]),
+    "vqae_quantize_tc_f32": (_i, [C.POINTER(QuantizerParams), _vp, _vp, _vp, _vp, _vp, _f, _vp,
+                                  _vp, _vp, _sz, _i64, _i64, _vp]),
     "vqae_embed_codes_f32": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i64, _i64, _vp]),
     "vqae_codemap_place_u8": (_i, [_vp, _i64, _i, _i, _i64, _i, _vp, _i64, _i64, _vp]),
 }
@@ -106,8 +110,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.vqae_abi_version() != 1:
-        raise RuntimeError(f"{path}: ABI version {lib.vqae_abi_version()} != 1")
+    if lib.vqae_abi_version() != 2:
+        raise RuntimeError(f"{path}: ABI version {lib.vqae_abi_version()} != 2")
     _lib = lib
     return lib
 

@@ -193,7 +193,9 @@ int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const 
     return pack_same_block_bf16(w1_oihw, w2_oihw, w3_oihw, c, packed, (cudaStream_t)stream);
 }
 
-static int device_sm_count(int* out) {
+}  // extern "C"
+namespace vqae {
+int device_sm_count(int* out) {
     static int sm_count = 0;
     if (sm_count == 0) {
         int dev = 0;
@@ -203,6 +205,8 @@ static int device_sm_count(int* out) {
     *out = sm_count;
     return VQAE_OK;
 }
+}  // namespace vqae
+extern "C" {
 
 int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packed,
                                  const float* scalars8_host, int64_t batch, int height, int width,
@@ -265,6 +269,31 @@ int vqae_quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layo
                       int64_t batch, int64_t spatial, void* stream) {
     return quantize_f32(p, x, x_layout, out, out_layout, indices, loss, near_ties, tie_rel_gap,
                         z_out, scratch, scratch_bytes, batch, spatial, (cudaStream_t)stream);
+}
+
+void vqae_quantize_tc_set_profile(long long* phase_clocks) { quantize_tc_set_prof(phase_clocks); }
+
+int vqae_quantize_tc_supported(const vqae_quantizer_params* p, int x_layout, int out_layout,
+                               int has_out) {
+    return p && quantize_tc_supported(p, x_layout, out_layout, has_out != 0) ? 1 : 0;
+}
+
+int vqae_quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out,
+                         int64_t* indices, float* loss, uint32_t* near_ties, float tie_rel_gap,
+                         float* z_out, float* diag, void* scratch, size_t scratch_bytes,
+                         int64_t batch, int64_t spatial, void* stream_) {
+    if (!p || !x || !indices || !loss || !p->embed || batch <= 0 || spatial <= 0)
+        return VQAE_ERR_BAD_ARG;
+    if (out && !p->table) return VQAE_ERR_BAD_ARG;
+    if (!quantize_tc_supported(p, VQAE_LAYOUT_NHWC, VQAE_LAYOUT_NHWC, out != nullptr))
+        return VQAE_ERR_UNSUPPORTED;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t N = batch * spatial;
+    if (!scratch || scratch_bytes < quantizer_scratch_bytes(N)) return VQAE_ERR_SCRATCH;
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return quantize_tc_f32(p, x, out, indices, loss, scratch, near_ties, tie_rel_gap, z_out, diag, N,
+                           sm_count, stream);
 }
 
 int vqae_embed_codes_f32(const void* indices, int idx_is_u8, const float* table, int num_codes,

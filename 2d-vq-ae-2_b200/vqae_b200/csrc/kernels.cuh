@@ -38,6 +38,16 @@ int codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw, int6
                      int grid_cols, uint8_t* map, int64_t map_rows, int64_t map_cols,
                      cudaStream_t stream);
 
+// quantize_tc.cu (tcgen05 candidate filter + exact fp32 argmin)
+bool quantize_tc_supported(const vqae_quantizer_params* p, int x_layout, int out_layout,
+                           bool has_out);
+int quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out, int64_t* indices,
+                    float* loss, void* scratch, uint32_t* near_ties, float tie_rel_gap,
+                    float* z_out, float* diag, int64_t N, int sm_count, cudaStream_t stream);
+size_t quantize_tc_scratch_bytes(int64_t n);
+void quantize_tc_set_prof(long long* dev_ptr);
+int device_sm_count(int* out);
+
 // tc_kernels.cu (tcgen05 bf16 path)
 int tc_selftest(const void* A, int a_rows, int row_shift, const void* B, float* D,
                 cudaStream_t stream);

@@ -325,7 +325,8 @@ int quantizer_prepare_f32(const float* embed, int K, int D, const float* w_out,
 
 size_t quantizer_scratch_bytes(int64_t n) {
     if (n <= 0) return 0;
-    return (size_t)((n + QT - 1) / QT) * sizeof(float);
+    const size_t a = (size_t)((n + QT - 1) / QT) * sizeof(float), b = quantize_tc_scratch_bytes(n);
+    return a > b ? a : b;
 }
 
 template <int XL, int OL, bool PROJ>
@@ -358,6 +359,14 @@ int quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layout, f
     a.near_ties = near_ties; a.z_out = z_out; a.embed = p->embed; a.w_in = p->w_in;
     a.b_in = p->b_in; a.table = p->table; a.N = N; a.S = S; a.K = p->num_codes; a.C = p->c;
     a.tie_rel_gap = tie_rel_gap;
+
+    if (quantize_tc_supported(p, x_layout, out_layout, out != nullptr)) {
+        // fused kernel: loss and near-tie totals are reduced by its last CTA (no memset / finalize)
+        int sm_count = 0;
+        if (int rc = device_sm_count(&sm_count)) return rc;
+        return quantize_tc_f32(p, x, out, indices, loss, scratch, near_ties, tie_rel_gap, z_out,
+                               nullptr, N, sm_count, stream);
+    }
     if (near_ties) VQAE_CUDA_TRY(cudaMemsetAsync(near_ties, 0, sizeof(uint32_t), stream));
 
     const unsigned grid = ceil_div_u(N, QT);

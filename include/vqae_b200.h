@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VQAE_ABI_VERSION 1
+#define VQAE_ABI_VERSION 2
 
 enum {
     VQAE_OK = 0,
@@ -187,6 +187,23 @@ int vqae_quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layo
                       int out_layout, int64_t* indices, float* loss, uint32_t* near_ties,
                       float tie_rel_gap, float* z_out, void* scratch, size_t scratch_bytes,
                       int64_t batch, int64_t spatial, void* stream);
+
+/* The tcgen05 form of the same call, taken automatically by vqae_quantize_f32 when
+ * vqae_quantize_tc_supported() is 1 (proj_in present, K = 256, D = 8, c = 64,
+ * NHWC in/out; env VQAE_QUANT_TC=0 disables it).  The tensor cores evaluate the quartic expansion
+ * of sum_d (z_d - e_kd)^4 from bf16 hi/lo splits as a candidate filter; indices, loss and the
+ * near-tie count come from the same exact fp32 evaluation as the CUDA-core kernel and are
+ * bit-identical to it.  diag (may be NULL): fp32 [N][4] = {min approximate distance (offset by
+ * -sum z^4), error scale T, number of candidates, 1 if the row took the full exact scan}.      */
+/* profiling aid: while non-NULL, CTA 0 of every tcgen05 quantiser launch writes clock64() stamps of
+ * its tiles 10..13 to phase_clocks[4][16] (device memory, 64 int64); NULL switches it off      */
+void vqae_quantize_tc_set_profile(long long* phase_clocks);
+int vqae_quantize_tc_supported(const vqae_quantizer_params* p, int x_layout, int out_layout,
+                               int has_out);
+int vqae_quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out,
+                         int64_t* indices, float* loss, uint32_t* near_ties, float tie_rel_gap,
+                         float* z_out, float* diag, void* scratch, size_t scratch_bytes,
+                         int64_t batch, int64_t spatial, void* stream);
 
 /* embed_code -> proj_out (layers/vq.py:44-45,192): out[n,:] = table[idx[n],:].
  * indices: int64 or u8 (idx_dtype VQAE_DT_U8 / anything else = int64); out NHWC/NCHW fp32. */

@@ -1,0 +1,166 @@
+"""GPU: the tcgen05 quantiser (csrc/quantize_tc.cu) against the exact CUDA-core kernel
+(csrc/quantize.cu, itself pinned to the reference goldens in test_gpu_parity.py), the plain-C
+oracle, and its own error bound.
+
+The tensor cores only *filter* candidates; indices / loss / near-tie count come from the same fp32
+evaluation as the CUDA-core kernel, so the comparison is bit-exact (indices, outputs, near-tie
+count) with no tolerance, and the filter's error bound (|D - exact| <= 2^-15 * T) is checked from
+the kernel's diagnostic output against a float64 evaluation.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from vqae_b200 import _lib as L
+from vqae_b200 import engine as E
+from vqae_b200 import synthetic as S
+from vqae_b200.layers.vq import ProjectedEMAVectorQuantizer2d
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ERR_C = 2.0 ** -15
+
+
+def _module(seed=5, embed_scale=1.0, embed=None):
+    pq = ProjectedEMAVectorQuantizer2d(256, 64, 1.0, 0.99, 1e-5, 8).eval()
+    sd = S.make_state_dict(pq.state_dict(), seed=seed, regime="perturbed")
+    g = torch.Generator().manual_seed(seed)
+    sd["embed"] = torch.randn(256, 8, generator=g) * embed_scale if embed is None else embed
+    pq.load_state_dict(sd)
+    return pq.to(DEV)
+
+
+def _run(pq, x_nhwc, tc: bool, want_out=True):
+    """x_nhwc: [B,S,64] contiguous.  Returns (out, idx, loss, ties, z)."""
+    old = os.environ.get("VQAE_QUANT_TC")
+    os.environ["VQAE_QUANT_TC"] = "1" if tc else "0"
+    try:
+        b, s, _ = x_nhwc.shape
+        packed = pq.packed()
+        lib = L.load()
+        sup = lib.vqae_quantize_tc_supported(C.byref(packed.params), L.LAYOUT_NHWC, L.LAYOUT_NHWC, 1)
+        assert sup == (1 if tc else 0)
+        res = E.quantize(packed, x_nhwc, True, True, b, s, want_out=want_out, want_z=True)
+        torch.cuda.synchronize()
+        return res
+    finally:
+        if old is None:
+            os.environ.pop("VQAE_QUANT_TC", None)
+        else:
+            os.environ["VQAE_QUANT_TC"] = old
+
+
+def _diag(pq, x_nhwc):
+    b, s, _ = x_nhwc.shape
+    n = b * s
+    packed = pq.packed()
+    lib = L.load()
+    idx = torch.empty(n, dtype=torch.int64, device=DEV)
+    loss = torch.empty((), device=DEV)
+    ties = torch.zeros((), dtype=torch.int32, device=DEV)
+    z = torch.empty(n, 8, device=DEV)
+    diag = torch.zeros(n, 4, device=DEV)
+    ws = E.workspace(x_nhwc.device, lib.vqae_quantizer_scratch_bytes(n))
+    L.check(lib.vqae_quantize_tc_f32(C.byref(packed.params), x_nhwc.data_ptr(), None,
+                                     idx.data_ptr(), loss.data_ptr(), ties.data_ptr(),
+                                     H.NEAR_TIE_REL_GAP, z.data_ptr(), diag.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), b, s, None), "vqae_quantize_tc_f32")
+    torch.cuda.synchronize()
+    return idx, z, diag
+
+
+@pytest.mark.parametrize("batch,spatial", [(2, 1024), (64, 1024), (3, 50), (1, 1), (5, 128)])
+def test_tc_bit_identical_to_cuda_core_kernel(batch, spatial):
+    pq = _module()
+    x = torch.randn(batch, spatial, 64, generator=torch.Generator().manual_seed(batch)).to(DEV)
+    out_a, idx_a, loss_a, ties_a, z_a = _run(pq, x, tc=False)
+    out_b, idx_b, loss_b, ties_b, z_b = _run(pq, x, tc=True)
+    assert torch.equal(z_a, z_b)                         # same FFMA chain, channel order
+    assert torch.equal(idx_a, idx_b)
+    assert torch.equal(out_a, out_b)
+    assert int(ties_a) == int(ties_b)
+    assert abs(loss_a.item() - loss_b.item()) <= 2e-6 * abs(loss_a.item())
+    # indices only (the extract_embeddings use): no output rows requested
+    _, idx_c, _, _, _ = _run(pq, x, tc=True, want_out=False)
+    assert torch.equal(idx_a, idx_c)
+
+
+def test_tc_vs_oracle():
+    import vqae_oracle as O
+    pq = _module(seed=9)
+    x = torch.randn(8, 1024, 64, generator=torch.Generator().manual_seed(77)).to(DEV)
+    _, idx, _, _, z = _run(pq, x, tc=True)
+    # the oracle restates cdist(p=4) + argmin (vq.py:121-129) on the projected latents
+    ref_idx, gap, _ = O.quantize_flat(z.cpu(), pq.embed.cpu())
+    bad, total_bad, n_ties = H.index_mismatches_outside_ties(idx.cpu(), ref_idx, gap)
+    assert bad == 0, (bad, total_bad, n_ties)
+
+
+@pytest.mark.parametrize("embed_scale,x_scale", [(1.0, 1.0), (0.05, 1.0), (20.0, 1.0), (1.0, 30.0),
+                                                 (1e-3, 1e-3), (1.0, 1e4)])
+def test_filter_error_bound_and_scales(embed_scale, x_scale):
+    pq = _module(seed=3, embed_scale=embed_scale)
+    x = (torch.randn(16, 1024, 64, generator=torch.Generator().manual_seed(4)) * x_scale).to(DEV)
+    idx, z, diag = _diag(pq, x)
+    zd, ed = z.double(), pq.embed.double()
+    dist = ((zd[:, None, :] - ed[None, :, :]) ** 4).sum(-1)          # [N,256] float64
+    true_min = dist.min(1).values - (zd ** 4).sum(-1)
+    mn, T, cnt, slow = diag.double().unbind(1)
+    finite = torch.isfinite(mn) & torch.isfinite(T)
+    err = ((mn - true_min).abs() / T)[finite]
+    # measured error of the hi/lo-split contraction, relative to the scale T the margin uses
+    assert err.numel() > 0.9 * mn.numel() or x_scale >= 1e4
+    if err.numel():
+        assert float(err.max()) < ERR_C / 2, float(err.max())          # 2x inside the bound
+    # and the result equals the exact kernel whatever the scale (slow path where needed)
+    _, idx_ref, _, _, _ = _run(pq, x, tc=False)
+    assert torch.equal(idx, idx_ref)
+    print(f"scale e={embed_scale} x={x_scale}: max err/T = {float(err.max()) if err.numel() else float('nan'):.3e} "
+          f"(bound {ERR_C:.3e}), mean candidates {float(cnt.mean()):.2f}, slow rows {int(slow.sum())}")
+
+
+def test_duplicate_codes_and_degenerate_inputs():
+    g = torch.Generator().manual_seed(1)
+    embed = torch.randn(256, 8, generator=g)
+    embed[200] = embed[3]                     # exact duplicates: lowest index must win
+    embed[17] = embed[3]
+    pq = _module(embed=embed)
+    x = torch.randn(4, 1024, 64, generator=g).to(DEV)
+    x[0, :64] = 0.0                            # identical rows
+    x[1, :8] = float("nan")
+    x[1, 8:16] = float("inf")
+    out_a, idx_a, loss_a, ties_a, _ = _run(pq, x, tc=False)
+    out_b, idx_b, loss_b, ties_b, _ = _run(pq, x, tc=True)
+    assert torch.equal(idx_a, idx_b)
+    assert int(ties_a) == int(ties_b)
+    assert not bool(((idx_b == 200) | (idx_b == 17)).any())
+    assert torch.equal(out_a, out_b)
+
+
+def test_all_codes_equal_evaluates_every_code():
+    pq = _module(embed=torch.ones(256, 8) * 0.25)
+    x = torch.randn(2, 1024, 64, generator=torch.Generator().manual_seed(2)).to(DEV)
+    idx, _, diag = _diag(pq, x)
+    assert bool((idx == 0).all())
+    assert bool((diag[:, 2] == 256).all())          # every column is a candidate
+
+
+def test_module_forward_uses_tc_path_channels_last():
+    pq = _module()
+    x = torch.randn(4, 64, 32, 32, generator=torch.Generator().manual_seed(8)).to(DEV)
+    x = x.contiguous(memory_format=torch.channels_last)
+    pq(x)                                                 # packs the module (table kernel)
+    before = E.launch_count()
+    out, idx, loss = pq(x)
+    torch.cuda.synchronize()
+    assert E.launch_count() - before == 1                 # one fused kernel, nothing else
+    os.environ["VQAE_QUANT_TC"] = "0"
+    try:
+        out2, idx2, loss2 = pq(x)
+    finally:
+        os.environ.pop("VQAE_QUANT_TC")
+    assert torch.equal(idx, idx2) and torch.equal(out, out2)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/vqae_b200.h but not exported"
     from vqae_b200 import _lib_tc
     assert declared == set(_lib.SIGNATURES) | set(_lib_tc.SIGNATURES)
-    assert lib.vqae_abi_version() == 1
+    assert lib.vqae_abi_version() == 2
     assert lib.vqae_error_string(3).decode().startswith("VQ dim != channel dim")
 
 
