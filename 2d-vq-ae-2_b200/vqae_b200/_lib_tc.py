@@ -15,6 +15,9 @@ SIGNATURES: dict = {
     "vqae_tc_selftest": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vqae_pack_same_block_bf16": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "vqae_same_block_bf16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
+    "vqae_same_chain_flag_bytes": (C.c_size_t, [_i, _i64]),
+    "vqae_same_chain_supported": (_i, [_i64, _i, _i, _i]),
+    "vqae_same_chain_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i, _i64, _i, _i, _i, _vp]),
     "vqae_down_block_pack_elems": (C.c_size_t, [_i]),
     "vqae_pack_down_block_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
     "vqae_down_block_bf16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),

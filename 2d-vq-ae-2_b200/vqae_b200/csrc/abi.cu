@@ -230,6 +230,25 @@ int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
                          nullptr, (cudaStream_t)stream);
 }
 
+size_t vqae_same_chain_flag_bytes(int n_blocks, int64_t batch) {
+    return same_chain_flag_bytes(n_blocks, batch);
+}
+
+int vqae_same_chain_supported(int64_t batch, int height, int width, int c) {
+    int sm_count = 0;
+    if (device_sm_count(&sm_count)) return 0;
+    return same_chain_supported(batch, height, width, c, sm_count) ? 1 : 0;
+}
+
+int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void* w_packed_all,
+                         const float* scalars_dev, void* flags, size_t flag_bytes, int n_blocks,
+                         int64_t batch, int height, int width, int c, void* stream) {
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return same_chain_tc(x, buf_a, buf_b, w_packed_all, scalars_dev, flags, flag_bytes, n_blocks,
+                         batch, height, width, c, sm_count, (cudaStream_t)stream);
+}
+
 int vqae_tc_mma_bench(int n, int layout_type, int reps, int a_stride_rows, long long* out2,
                       void* stream) {
     return tc_mma_bench(n, layout_type, reps, a_stride_rows, out2, (cudaStream_t)stream);

@@ -57,6 +57,13 @@ int same_block_tc(const float* x, float* out, const void* w_packed, const float*
 int pack_same_block_bf16(const float* w1, const float* w2, const float* w3, int C, void* packed,
                          cudaStream_t stream);
 
+// tc_chain.cu (persistent multi-block 'same' chain)
+size_t same_chain_flag_bytes(int n_blocks, int64_t B);
+bool same_chain_supported(int64_t B, int H, int W, int C, int sm_count);
+int same_chain_tc(const float* x, float* buf_a, float* buf_b, const void* w_packed_all,
+                  const float* scalars_dev, void* flags, size_t flag_bytes, int n_blocks, int64_t B,
+                  int H, int W, int C, int sm_count, cudaStream_t stream);
+
 int tc_mma_bench(int N, int layout_type, int reps, int a_stride_rows, long long* out,
                  cudaStream_t stream);
 // tc_down.cu

@@ -1,0 +1,458 @@
+// Persistent tcgen05 kernel for a RUN of consecutive PreActFixupResBlocks in mode 'same'
+// (reference: the Sequential chains of vq_ae/model.py:150-153,240-263 -- the 50-block trunks -- and
+// the post layers of DownBlock/UpBlock, conv_block.py:18-91; block arithmetic conv_block.py:196-216).
+//
+// One launch executes every (block, tile) task of the run: task t = block * n_tiles + tile, CTA c
+// takes tasks c, c + grid, c + 2 grid, ...  A tile of block i needs the two 16-row tiles of its
+// image from block i-1 (1-pixel circular halo), which are tasks >= 3 rounds older; each finished
+// task bumps a per-(block, image) counter with release semantics and the prologue of a dependent
+// task acquires it.  Against one launch per block this removes the partial last wave at every
+// block boundary (512 tiles on 148 SMs = 3.46 waves, rounded up to 4, fifty-four times), the
+// per-launch set-up, and keeps the ping-pong activation buffers hot in L2.
+//
+// The per-tile pipeline is the one of same_block_tc_kernel (tc_kernels.cu): P -> G1 -> E1 -> G2 ->
+// E2 -> G3 -> E3 with identical arithmetic, so a chain is bit-identical to block-by-block
+// execution.  All eleven weight matrices of a block (W1, nine taps, W3) stream through one ring of
+// bulk async copies, since consecutive tasks of a CTA can belong to different blocks.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace vqae {
+namespace {
+
+using namespace tc;
+
+constexpr int CH_TH = 16, CH_TW = 32, CH_PW = CH_TW + 2;
+constexpr int CH_NPAD = (CH_TH + 2) * CH_PW;      // 612 padded pixels
+constexpr int CH_XPIX = 641;                       // operand region pitch: 5 x 128 px, odd
+constexpr int CH_UPIX = 711;                       // 35 + 5*128 + 35 px, odd
+constexpr uint32_t CH_XLBO = CH_XPIX * 16;
+constexpr uint32_t CH_ULBO = CH_UPIX * 16;
+constexpr int CH_RING = 6;
+
+template <int CP, int CR>
+struct ChainCfg {
+    static constexpr int KCH = CP / 8;
+    static constexpr int KCR = CR / 8;
+    static constexpr int NW = (CP == 64) ? 16 : (CP == 32 ? 8 : 4);
+    static constexpr int WORKERS = NW * 32;
+    static constexpr int THREADS = WORKERS + 64;   // + MMA warp + weight-producer warp
+    static constexpr int NG = NW / 4;
+    static constexpr int NC = CP / NG;
+    static constexpr int UCH = (CR < CP) ? KCR : NC / 8;
+    static constexpr uint32_t WLBO = CP * 16;
+    static constexpr uint32_t WMAT = KCH * WLBO;
+    static constexpr uint32_t OFF_X = 0;
+    static constexpr uint32_t OFF_U = OFF_X + KCH * CH_XLBO;
+    static constexpr bool RING = true;
+    static constexpr uint32_t OFF_W = OFF_U + KCH * CH_ULBO;        // ring[CH_RING]
+    static constexpr uint32_t OFF_BAR = OFF_W + CH_RING * WMAT;
+    static constexpr uint32_t SMEM = OFF_BAR + 128;
+    static constexpr int TMEM_COLS = CP == 64 ? 512 : (CP == 32 ? 256 : 128);
+    static constexpr int MIN_CTAS = CP == 64 ? 1 : (CP == 32 ? 2 : 4);
+};
+
+struct ChainArgs {
+    const float* x0;              // input of block 0, NHWC fp32 [B,H,W,CR]
+    float* buf0;                  // block i writes (i & 1) ? buf1 : buf0
+    float* buf1;
+    const __nv_bfloat16* w;       // [n_blocks][11 matrices: W1 | W2 tap 0..8 | W3], each [k-chunk][n][8]
+    const float* scal;            // [n_blocks][8] = b1a b1b b2a b2b b3a b3b b4 scale   (device)
+    unsigned int* flags;          // [n_blocks][B] finished tiles per (block, image), zero on entry
+    int n_blocks, n_img, n_tiles, total, H, W, tiles_x, tiles_per_img;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int CP, int CR>
+__global__ void __launch_bounds__(ChainCfg<CP, CR>::THREADS, ChainCfg<CP, CR>::MIN_CTAS)
+same_chain_tc_kernel(ChainArgs a) {
+    using Cfg = ChainCfg<CP, CR>;
+    constexpr int KCR = Cfg::KCR, NW = Cfg::NW, NC = Cfg::NC, UCH = Cfg::UCH;
+    constexpr uint32_t WLBO = Cfg::WLBO, WMAT = Cfg::WMAT;
+    constexpr int MMA_WARP = NW, PROD_WARP = NW + 1;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sX = sbase + Cfg::OFF_X, sU = sbase + Cfg::OFF_U, sW = sbase + Cfg::OFF_W;
+    const uint32_t bar_mma = sbase + Cfg::OFF_BAR;
+    const uint32_t bar_full = bar_mma + 8;                           // [CH_RING] matrix landed
+    const uint32_t bar_empty = bar_full + 8 * CH_RING;               // [CH_RING] matrix consumed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 + 16 * CH_RING);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t leader = lane == 0;
+    const int my_tasks = (a.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        for (int s = 0; s < CH_RING; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    // zero the operand regions once: slack rows and zero-padded channels stay finite / zero
+    for (int i = tid; i < (int)(Cfg::OFF_W / 16); i += Cfg::THREADS)
+        *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const uint32_t idesc = make_idesc_bf16(128, CP);
+
+    // ---------------- weight producer: every matrix of every task of this CTA, in order ----------
+    if (warp == PROD_WARP) {
+        if (lane == 0) {
+            int cnt = 0;
+            for (int k = 0; k < my_tasks; ++k) {
+                const int task = blockIdx.x + k * gridDim.x;
+                const int blk = task / a.n_tiles;
+                const uint8_t* wb = reinterpret_cast<const uint8_t*>(a.w) + (size_t)blk * 11 * WMAT;
+                for (int m = 0; m < 11; ++m, ++cnt) {
+                    const int slot = cnt % CH_RING;
+                    if (cnt >= CH_RING) mbar_wait(bar_empty + 8 * slot, ((cnt / CH_RING) - 1) & 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * slot, WMAT);
+                    bulk_g2s(sW + slot * WMAT, wb + (size_t)m * WMAT, WMAT, bar_full + 8 * slot);
+                }
+            }
+        }
+    } else {
+        int wcnt = 0;                         // matrices consumed so far (MMA warp)
+        uint32_t mma_phase = 0;
+
+        // epilogue geometry of a worker thread
+        const int q4 = warp & 3;
+        const int grp = (warp >> 2) % Cfg::NG;
+        const int row_in_tile = q4 * 32 + lane;
+        const uint32_t t_lane = (uint32_t)(q4 * 32) << 16;
+        const uint32_t t_col = grp * NC;
+        const int kc0 = grp * (NC / 8);
+        constexpr int NCR = UCH * 8;
+        constexpr int F4 = NCR / 4;
+        constexpr int SROW = NCR + 4;
+        float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_U) + (warp < NW ? warp : 0) * 32 * SROW;
+
+        const uint64_t dX = make_desc(sX, CH_XLBO, 128);
+        const uint64_t dU = make_desc(sU, CH_ULBO, 128);
+        const uint64_t dW = make_desc(sW, WLBO, 128);
+
+        // P: A1 = bf16(elu(x + b1a) + b1b) on the 18 x 34 halo'd tile (circular wrap) -> X region.
+        // The source was written by other CTAs of this launch: wait for both tiles of the image in
+        // the previous block (acquire), and read with L2-coherent loads.
+        auto prologue = [&](int task) {
+            const int blk = task / a.n_tiles, tile = task - blk * a.n_tiles;
+            const int img = tile / a.tiles_per_img;
+            const int trem = tile - img * a.tiles_per_img;
+            const int r0 = (trem / a.tiles_x) * CH_TH, c0 = (trem % a.tiles_x) * CH_TW;
+            if (blk > 0) {
+                // Blocking is safe here although the CURRENT task of this CTA is still unpublished:
+                // the host only launches this kernel when grid <= n_tiles - tiles_per_img, so every
+                // producer of the next task has a smaller id than the current task, and waits can
+                // only chain towards smaller ids.
+                if (lane == 0) {
+                    const unsigned* f = a.flags + (size_t)(blk - 1) * a.n_img + img;
+                    while (ld_acquire_u32(f) < (unsigned)a.tiles_per_img) __nanosleep(64);
+                }
+                __syncwarp();
+            }
+            const float* src = blk == 0 ? a.x0 : (((blk - 1) & 1) ? a.buf1 : a.buf0);
+            const float* ximg = src + (size_t)img * a.H * a.W * CR;
+            const float b1a = __ldg(a.scal + blk * 8 + 0), b1b = __ldg(a.scal + blk * 8 + 1);
+            constexpr int ITEMS = CH_NPAD * KCR;
+            constexpr int PB = (NW >= 16) ? 3 : 6;
+            for (int base = tid; base < ITEMS; base += Cfg::WORKERS * PB) {
+                float4 v0[PB], v1[PB];
+                int dst[PB];
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const int id = base + u * Cfg::WORKERS;
+                    dst[u] = -1;
+                    if (id < ITEMS) {
+                        const int q = id / KCR, kc = id - q * KCR;
+                        const int lr = q / CH_PW, lc = q - lr * CH_PW;
+                        int row = r0 - 1 + lr, col = c0 - 1 + lc;
+                        row = row < 0 ? row + a.H : (row >= a.H ? row - a.H : row);
+                        col = col < 0 ? col + a.W : (col >= a.W ? col - a.W : col);
+                        const float4* s4 = reinterpret_cast<const float4*>(
+                            ximg + ((size_t)row * a.W + col) * CR + kc * 8);
+                        v0[u] = __ldcg(s4);
+                        v1[u] = __ldcg(s4 + 1);
+                        dst[u] = kc * (int)CH_XLBO + q * 16;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    if (dst[u] >= 0) {
+                        const float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w,
+                                            v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+                        *reinterpret_cast<uint4*>(smem + Cfg::OFF_X + dst[u]) = act_pack8(v, b1a, b1b);
+                    }
+                }
+            }
+        };
+
+        if (warp < NW && my_tasks > 0) prologue(blockIdx.x);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::WORKERS + 32) : "memory");
+
+        for (int k = 0; k < my_tasks; ++k) {
+            const int task = blockIdx.x + k * gridDim.x;
+            const int blk = task / a.n_tiles, tile = task - blk * a.n_tiles;
+            const int img = tile / a.tiles_per_img;
+            const int trem = tile - img * a.tiles_per_img;
+            const int r0 = (trem / a.tiles_x) * CH_TH, c0 = (trem % a.tiles_x) * CH_TW;
+            const float* scal = a.scal + blk * 8;        // loaded where used: keeps registers free
+
+            // ---- G1: D1 = A1 . W1^T on 5 M-tiles of padded-linear pixels ----
+            if (warp == MMA_WARP) {
+                int slot = 0;
+                if (Cfg::RING) {
+                    slot = wcnt % CH_RING;
+                    mbar_wait(bar_full + 8 * slot, (wcnt / CH_RING) & 1);
+                }
+                tc_fence_after_sync();
+                const uint64_t dW1 = dW + (uint64_t)((slot * WMAT) >> 4);
+#pragma unroll
+                for (int t = 0; t < 5; ++t)
+#pragma unroll
+                    for (int ks = 0; ks < CP / 16; ++ks)
+                        umma_bf16(tmem_base + t * CP,
+                                  dX + (uint64_t)((t * 128 * 16 + ks * 2 * CH_XLBO) >> 4),
+                                  dW1 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0, leader);
+                if (Cfg::RING) umma_commit(bar_empty + 8 * slot, leader);
+                umma_commit(bar_mma, leader);
+                ++wcnt;
+                __syncwarp();
+            }
+            // ---- E1: U[q] = bf16(elu(D1[q] + b2a) + b2b) ----
+            if (warp < NW) {
+                const float b2a = __ldg(scal + 2), b2b = __ldg(scal + 3);
+                mbar_wait(bar_mma, mma_phase);
+                tc_fence_after_sync();
+                for (int t = 0; t < 5; ++t) {
+                    float v[NC];
+                    tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
+                    tmem_ld_wait();
+                    const int q = t * 128 + row_in_tile;
+#pragma unroll
+                    for (int j = 0; j < UCH; ++j)
+                        *reinterpret_cast<uint4*>(smem + Cfg::OFF_U + (kc0 + j) * CH_ULBO + q * 16) =
+                            act_pack8(v + 8 * j, b2a, b2b);
+                }
+                tc_fence_before_sync();
+            }
+            mma_phase ^= 1;
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, %0;" ::"n"(Cfg::WORKERS + 32) : "memory");
+
+            // ---- G2: nine taps; meanwhile the workers build the NEXT task's A1 ----
+            if (warp == MMA_WARP) {
+                tc_fence_after_sync();
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    int slot = 1 + tap;
+                    if (Cfg::RING) {
+                        slot = wcnt % CH_RING;
+                        mbar_wait(bar_full + 8 * slot, (wcnt / CH_RING) & 1);
+                        tc_fence_after_sync();
+                    }
+                    const uint64_t dW2 = dW + (uint64_t)((slot * WMAT) >> 4);
+                    const int shift = (tap / 3 - 1) * CH_PW + (tap % 3 - 1);
+#pragma unroll
+                    for (int t = 0; t < 5; ++t)
+#pragma unroll
+                        for (int ks = 0; ks < CP / 16; ++ks)
+                            umma_bf16(tmem_base + t * CP,
+                                      dU + (uint64_t)(((CH_PW + 1 + t * 128 + shift) * 16 + ks * 2 * CH_ULBO) >> 4),
+                                      dW2 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, (tap | ks) > 0, leader);
+                    if (Cfg::RING) umma_commit(bar_empty + 8 * slot, leader);
+                    ++wcnt;
+                }
+                umma_commit(bar_mma, leader);
+                __syncwarp();
+            }
+            if (warp < NW) {
+                if (k + 1 < my_tasks) prologue(task + gridDim.x);
+                // ---- E2: V[p] over the U region ----
+                const float b3a = __ldg(scal + 4), b3b = __ldg(scal + 5);
+                mbar_wait(bar_mma, mma_phase);
+                tc_fence_after_sync();
+                for (int t = 0; t < 5; ++t) {
+                    float v[NC];
+                    tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
+                    tmem_ld_wait();
+                    const int q = CH_PW + 1 + t * 128 + row_in_tile;
+                    const int lr = q / CH_PW, pc = q - lr * CH_PW;
+                    if (lr <= CH_TH && pc >= 1 && pc <= CH_TW) {
+                        const int p = (lr - 1) * CH_TW + pc - 1;
+#pragma unroll
+                        for (int j = 0; j < UCH; ++j)
+                            *reinterpret_cast<uint4*>(smem + Cfg::OFF_U + (kc0 + j) * CH_ULBO + p * 16) =
+                                act_pack8(v + 8 * j, b3a, b3b);
+                    }
+                }
+                tc_fence_before_sync();
+            }
+            mma_phase ^= 1;
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, %0;" ::"n"(Cfg::WORKERS + 32) : "memory");
+
+            // ---- G3: D3 = V . W3^T, 4 M-tiles ----
+            if (warp == MMA_WARP) {
+                int slot = 10;
+                if (Cfg::RING) {
+                    slot = wcnt % CH_RING;
+                    mbar_wait(bar_full + 8 * slot, (wcnt / CH_RING) & 1);
+                }
+                tc_fence_after_sync();
+                const uint64_t dW3 = dW + (uint64_t)((slot * WMAT) >> 4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int ks = 0; ks < CP / 16; ++ks)
+                        umma_bf16(tmem_base + t * CP,
+                                  dU + (uint64_t)((t * 128 * 16 + ks * 2 * CH_ULBO) >> 4),
+                                  dW3 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0, leader);
+                if (Cfg::RING) umma_commit(bar_empty + 8 * slot, leader);
+                umma_commit(bar_mma, leader);
+                ++wcnt;
+                __syncwarp();
+            }
+            // ---- E3: out = x + scale * D3 + b4 (fp32), transposed through shared memory ----
+            if (warp < NW) {
+                const float b4 = __ldg(scal + 6), scale = __ldg(scal + 7);
+                const float* src = blk == 0 ? a.x0 : (((blk - 1) & 1) ? a.buf1 : a.buf0);
+                const float* ximg = src + (size_t)img * a.H * a.W * CR;
+                float* oimg = ((blk & 1) ? a.buf1 : a.buf0) + (size_t)img * a.H * a.W * CR;
+                const int rsub = lane / F4, c4 = lane % F4;
+                auto x_off = [&](int t, int kk) -> int {     // element offset inside the image (< 2^31)
+                    const int p = t * 128 + q4 * 32 + rsub + kk * (32 / F4);
+                    return ((r0 + (p >> 5)) * a.W + c0 + (p & 31)) * CR + kc0 * 8 + c4 * 4;
+                };
+                float4 xr[F4], xn[F4];
+#pragma unroll
+                for (int kk = 0; kk < F4; ++kk)
+                    xr[kk] = __ldcg(reinterpret_cast<const float4*>(ximg + x_off(0, kk)));
+                mbar_wait(bar_mma, mma_phase);
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int t = 0; t < 4; ++t) {
+                    float v[NC];
+                    tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
+                    if (t + 1 < 4) {
+#pragma unroll
+                        for (int kk = 0; kk < F4; ++kk)
+                            xn[kk] = __ldcg(reinterpret_cast<const float4*>(ximg + x_off(t + 1, kk)));
+                    }
+                    tmem_ld_wait();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < F4; ++j)
+                        *reinterpret_cast<float4*>(stage + lane * SROW + 4 * j) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int kk = 0; kk < F4; ++kk) {
+                        const int rr = rsub + kk * (32 / F4);
+                        const float4 d = *reinterpret_cast<const float4*>(stage + rr * SROW + 4 * c4);
+                        float4 o;
+                        o.x = fmaf(d.x, scale, b4) + xr[kk].x;
+                        o.y = fmaf(d.y, scale, b4) + xr[kk].y;
+                        o.z = fmaf(d.z, scale, b4) + xr[kk].z;
+                        o.w = fmaf(d.w, scale, b4) + xr[kk].w;
+                        *reinterpret_cast<float4*>(oimg + x_off(t, kk)) = o;
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < F4; ++kk) xr[kk] = xn[kk];
+                }
+                tc_fence_before_sync();
+            }
+            mma_phase ^= 1;
+            fence_proxy_async_smem();     // next task's A1 (written during G2) -> async proxy
+            asm volatile("bar.sync 1, %0;" ::"n"(Cfg::WORKERS + 32) : "memory");
+            // every store of this tile happened before the barrier: publish it
+            if (tid == 0) {
+                __threadfence();
+                red_release_add(a.flags + (size_t)blk * a.n_img + img, 1u);
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int CP, int CR>
+int launch_chain(const ChainArgs& a, int sm_count, cudaStream_t stream) {
+    using Cfg = ChainCfg<CP, CR>;
+    auto kern = same_chain_tc_kernel<CP, CR>;
+    static int max_ctas = 0;
+    if (max_ctas == 0) {
+        VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Cfg::SMEM));
+        // every CTA of the grid must be resident at once (tasks wait on flags set by other CTAs)
+        int per_sm = 0;
+        VQAE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS,
+                                                                    Cfg::SMEM));
+        if (per_sm < 1) return VQAE_ERR_UNSUPPORTED;
+        if (per_sm > Cfg::MIN_CTAS) per_sm = Cfg::MIN_CTAS;     // TMEM: TMEM_COLS * per_sm <= 512
+        max_ctas = per_sm * sm_count;
+    }
+    const int grid = a.total < max_ctas ? a.total : max_ctas;
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(a);
+    return check_launch();
+}
+
+}  // namespace
+
+// The persistent form is built for the trunk width (C = 64, one CTA per SM) and needs at least
+// grid + tiles_per_img tiles per block, so that every producer of a CTA's next task is older than
+// its current task (see the prologue); smaller problems run block by block.
+bool same_chain_supported(int64_t B, int H, int W, int C, int sm_count) {
+    if (C != 64 || B <= 0 || H < CH_TH || W < CH_TW || H % CH_TH != 0 || W % CH_TW != 0) return false;
+    const int64_t tpi = (int64_t)(H / CH_TH) * (W / CH_TW);
+    return B * tpi - tpi >= sm_count;
+}
+
+size_t same_chain_flag_bytes(int n_blocks, int64_t B) {
+    return (size_t)n_blocks * (size_t)B * sizeof(unsigned int);
+}
+
+int same_chain_tc(const float* x, float* buf_a, float* buf_b, const void* w_packed_all,
+                  const float* scalars_dev, void* flags, size_t flag_bytes, int n_blocks, int64_t B,
+                  int H, int W, int C, int sm_count, cudaStream_t stream) {
+    if (!x || !buf_a || !buf_b || !w_packed_all || !scalars_dev || !flags || B <= 0 || n_blocks <= 0)
+        return VQAE_ERR_BAD_ARG;
+    if (x == buf_a || x == buf_b || buf_a == buf_b) return VQAE_ERR_BAD_ARG;
+    if (H < CH_TH || W < CH_TW || H % CH_TH != 0 || W % CH_TW != 0) return VQAE_ERR_UNSUPPORTED;
+    if (flag_bytes < same_chain_flag_bytes(n_blocks, B)) return VQAE_ERR_SCRATCH;
+    ChainArgs a;
+    a.x0 = x; a.buf0 = buf_a; a.buf1 = buf_b;
+    a.w = reinterpret_cast<const __nv_bfloat16*>(w_packed_all);
+    a.scal = scalars_dev;
+    a.flags = reinterpret_cast<unsigned int*>(flags);
+    a.n_blocks = n_blocks; a.n_img = (int)B;
+    a.H = H; a.W = W; a.tiles_x = W / CH_TW; a.tiles_per_img = (H / CH_TH) * a.tiles_x;
+    const int64_t nt = B * a.tiles_per_img;
+    if (nt * n_blocks > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
+    a.n_tiles = (int)nt;
+    a.total = (int)(nt * n_blocks);
+    VQAE_CUDA_TRY(cudaMemsetAsync(flags, 0, same_chain_flag_bytes(n_blocks, B), stream));
+    if (!same_chain_supported(B, H, W, C, sm_count)) return VQAE_ERR_UNSUPPORTED;
+    return launch_chain<64, 64>(a, sm_count, stream);
+}
+
+}  // namespace vqae

@@ -219,6 +219,75 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
     return out
 
 
+class PackedChain:
+    """Back-to-back bf16 weight packs + device scalar table of a run of tcgen05 'same' blocks."""
+
+    def __init__(self, run: Sequence[PackedFixup]):
+        dev = run[0].tc_weights.device
+        self.n = len(run)
+        self.c = run[0].c_in
+        self.weights = torch.cat([pk.tc_weights for pk in run])
+        self.scalars = torch.tensor([[float(v) for v in pk.tc_scalars] for pk in run],
+                                    dtype=torch.float32).to(dev)
+
+
+def _chain_runs(packed: Sequence[PackedFixup], h: int, w: int, batch: int = 1 << 30
+                ) -> List[Tuple[int, int]]:
+    """Maximal runs [start, stop) of >= 2 consecutive tcgen05 'same' blocks of equal width for
+    which the persistent chain kernel is built (vqae_same_chain_supported)."""
+    lib = L.load()
+    runs, i, n = [], 0, len(packed)
+    while i < n:
+        pk = packed[i]
+        hh, ww = h, w
+        if pk.mode == L.MODE_SAME and pk.tc_ok(hh, ww):
+            j = i + 1
+            while j < n and packed[j].mode == L.MODE_SAME and packed[j].c_in == pk.c_in \
+                    and packed[j].tc_ok(hh, ww):
+                j += 1
+            if j - i >= 2 and lib.vqae_same_chain_supported(batch, hh, ww, pk.c_in):
+                runs.append((i, j))
+            i = j
+        else:
+            h, w = pk.out_hw(h, w)
+            i += 1
+    return runs
+
+
+def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "fp32",
+                    chain_cache: Optional[dict] = None) -> Tensor:
+    """A Sequential chain of PreActFixupResBlocks on an NHWC fp32 tensor.  In "bf16" mode runs of
+    consecutive tcgen05 'same' blocks execute as ONE persistent launch (vqae_same_chain_bf16)."""
+    if precision != "bf16":
+        for pk in packed:
+            h = fixup_forward_nhwc(pk, h, precision=precision)
+        return h
+    lib = L.load()
+    runs = dict(_chain_runs(packed, h.shape[1], h.shape[2], h.shape[0]))
+    cache = chain_cache if chain_cache is not None else {}
+    i, n = 0, len(packed)
+    while i < n:
+        if i not in runs:
+            h = fixup_forward_nhwc(packed[i], h, precision=precision)
+            i += 1
+            continue
+        j = runs[i]
+        key = (i, j, id(packed[i]))
+        chain = cache.get(key)
+        if chain is None:
+            chain = cache[key] = PackedChain(packed[i:j])
+        b, hh, ww, c = h.shape
+        bufs = [torch.empty_like(h), torch.empty_like(h)]
+        fbytes = lib.vqae_same_chain_flag_bytes(chain.n, b)
+        flags = torch.empty(fbytes, dtype=torch.uint8, device=h.device)
+        L.check(lib.vqae_same_chain_bf16(
+            _ptr(h), _ptr(bufs[0]), _ptr(bufs[1]), _ptr(chain.weights), _ptr(chain.scalars),
+            _ptr(flags), fbytes, chain.n, b, hh, ww, c, _stream(h.device)), "vqae_same_chain_bf16")
+        h = bufs[(chain.n - 1) & 1]
+        i = j
+    return h
+
+
 def stem_in(x: Tensor, weight: Tensor, bias: Tensor, mean=None, std=None) -> Tensor:
     """x: fp32 [B,3,H,W] (NCHW or channels_last strides) or u8 [B,H,W,3] -> NHWC fp32 [B,H,W,8]."""
     lib = L.load()

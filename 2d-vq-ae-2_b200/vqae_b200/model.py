@@ -38,6 +38,7 @@ class _Plan:
     def __init__(self):
         self.key = None
         self.packed: List[E.PackedFixup] = []
+        self.chains: dict = {}
 
     def get(self, blocks: Sequence[nn.Module]) -> List[E.PackedFixup]:
         key = tuple(E.block_version(b) for b in blocks)
@@ -45,14 +46,12 @@ class _Plan:
             for b in blocks:
                 b.check_supported()
             self.packed = E.pack_blocks(blocks)
+            self.chains = {}
             self.key = key
         return self.packed
 
-    @staticmethod
-    def run(packed: Sequence[E.PackedFixup], h: Tensor, precision: str = "fp32") -> Tensor:
-        for pk in packed:
-            h = E.fixup_forward_nhwc(pk, h, precision=precision)
-        return h
+    def run(self, blocks: Sequence[nn.Module], h: Tensor, precision: str = "fp32") -> Tensor:
+        return E.run_blocks_nhwc(self.get(blocks), h, precision, self.chains)
 
 
 class Encoder(nn.Module):
@@ -115,8 +114,8 @@ class Encoder(nn.Module):
         E.require_cuda(x, "Encoder.forward")
         cl = x.dtype == torch.uint8 or E.is_channels_last(x)
         h = E.stem_in(x, self.in_stem.weight, self.in_stem.bias, mean, std)
-        h = _Plan.run(self._plan_down.get(_flat_blocks(self.down_layers)), h, self.precision)
-        h = _Plan.run(self._plan_trunk.get(_flat_blocks(self.pre_enc_layers)), h, self.precision)
+        h = self._plan_down.run(_flat_blocks(self.down_layers), h, self.precision)
+        h = self._plan_trunk.run(_flat_blocks(self.pre_enc_layers), h, self.precision)
         vq = self.vq_layers[0]
         pq = vq.packed()
         b, hh, ww, c = h.shape
@@ -187,8 +186,8 @@ class Decoder(nn.Module):
         enc = x[0]
         E.require_cuda(enc, "Decoder.forward")
         h, cl = E.to_nhwc(enc)
-        h = _Plan.run(self._plan_trunk.get(_flat_blocks(self.post_enc_layers)), h, self.precision)
-        h = _Plan.run(self._plan_up.get(_flat_blocks(self.up_layers)), h, self.precision)
+        h = self._plan_trunk.run(_flat_blocks(self.post_enc_layers), h, self.precision)
+        h = self._plan_up.run(_flat_blocks(self.up_layers), h, self.precision)
         return E.stem_out(h, self.out_stem.weight, self.out_stem.bias, cl)
 
 

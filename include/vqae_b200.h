@@ -127,6 +127,22 @@ int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const 
 int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c,
                          void* stream);
+/* A run of n_blocks consecutive 'same' blocks of equal width in ONE persistent launch (the 50-block
+ * trunks model.py:150-153,240-263 and the post layers of DownBlock/UpBlock): every (block, tile)
+ * task is scheduled round-robin over the resident CTAs and ordered by per-(block, image) completion
+ * counters, so no SM idles at block boundaries.  Results are bit-identical to n_blocks calls of
+ * vqae_same_block_bf16.  w_packed_all: the blocks' vqae_pack_same_block_bf16 outputs back to back;
+ * scalars_dev: DEVICE float [n_blocks][8] in the order of scalars8_host above; block i reads
+ * (i ? buf[(i-1)&1] : x) and writes buf[i&1] with buf = {buf_a, buf_b}: the result is in
+ * buf[(n_blocks-1)&1]; flags: DEVICE scratch of vqae_same_chain_flag_bytes(n_blocks, batch).    */
+size_t vqae_same_chain_flag_bytes(int n_blocks, int64_t batch);
+/* 1 if the persistent form is built for this shape on the current device: c == 64 and at least
+ * SM-count + tiles-per-image tiles per block (the scheduling argument in csrc/tc_chain.cu needs
+ * that); otherwise run the blocks one by one with vqae_same_block_bf16.                       */
+int vqae_same_chain_supported(int64_t batch, int height, int width, int c);
+int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void* w_packed_all,
+                         const float* scalars_dev, void* flags, size_t flag_bytes, int n_blocks,
+                         int64_t batch, int height, int width, int c, void* stream);
 /* PreActFixupResBlock in mode 'down' (conv specs pre_activation_fixup.yaml:35-45): c_in ->
  * 2*c_in, stride 2, branch + skip fused in one tcgen05 kernel; c_in in {8, 16, 32},
  * height % 16 == 0, width % 32 == 0.  w_packed: vqae_down_block_pack_elems(c_in) bf16 from

@@ -29,6 +29,7 @@ def main():
     packed = E.pack_blocks(blocks)
     pq = enc.vq_layers[0].packed()
     names = {0: "same", 1: "down", 2: "up"}
+    chains = {}
 
     def run(record):
         ev = []
@@ -41,10 +42,20 @@ def main():
         mark("start")
         h = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias)
         mark("stem_in")
-        for pk in packed:
+        runs = dict(E._chain_runs(packed, h.shape[1], h.shape[2], h.shape[0])) if precision == "bf16" else {}
+        i = 0
+        while i < len(packed):
+            pk = packed[i]
             hh = h.shape[1]
-            h = E.fixup_forward_nhwc(pk, h, precision=precision)
-            mark(f"{names[pk.mode]} C{pk.c_in}->{pk.c_out} @{hh}")
+            if i in runs:
+                j = runs[i]
+                h = E.run_blocks_nhwc(packed[i:j], h, precision, chains)
+                mark(f"chain {j - i}x same C{pk.c_in} @{hh}")
+                i = j
+            else:
+                h = E.fixup_forward_nhwc(pk, h, precision=precision)
+                mark(f"{names[pk.mode]} C{pk.c_in}->{pk.c_out} @{hh}")
+                i += 1
         b, hh, ww, c = h.shape
         E.quantize(pq, h, True, True, b, hh * ww, want_out=False)
         mark("quantize")

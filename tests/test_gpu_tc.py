@@ -97,3 +97,35 @@ def test_encoder_bf16_agreement_with_fp32():
     finally:
         vqae_b200.set_precision(m, "fp32")
         m.cpu()
+
+
+@pytest.mark.parametrize("c,hw,batch,n", [(64, 32, 80, 6), (64, 32, 75, 3), (64, 32, 200, 11),
+                                          (64, 64, 20, 4), (64, 32, 3, 5), (32, 64, 4, 3)])
+def test_persistent_chain_bit_identical_to_block_by_block(c, hw, batch, n):
+    """vqae_same_chain_bf16 (one persistent launch, tiles of block i+1 ordered after their producers
+    in block i by release/acquire counters) against n launches of vqae_same_block_bf16."""
+    from vqae_b200.config import pre_activation_fixup
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blocks = []
+    for i in range(n):
+        blk = PreActFixupResBlock(in_channels=c, out_channels=c, mode="same", **conf).eval()
+        blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=20 + i, regime="perturbed",
+                                              n_layers=12))
+        blocks.append(blk.to(DEV))
+    packed = E.pack_blocks(blocks)
+    x = torch.randn(batch, hw, hw, c, device=DEV)
+    h = x
+    for pk in packed:
+        h = E.fixup_forward_nhwc(pk, h, precision="bf16")
+    for _ in range(3):                               # repeated: flags are re-zeroed every launch
+        before = E.launch_count()
+        hc = E.run_blocks_nhwc(packed, x, "bf16")
+        torch.cuda.synchronize()
+        chained = bool(L.load().vqae_same_chain_supported(batch, hw, hw, c))
+        assert chained == (c == 64 and batch * (hw // 16) * (hw // 32) - (hw // 16) * (hw // 32) >= 148)
+        assert E.launch_count() - before == (1 if chained else n)
+        assert torch.equal(h, hc)
+    assert H.rel_err(hc, E.run_blocks_nhwc(packed, x, "fp32")) < 5e-3
