@@ -412,7 +412,11 @@ int launch_chain(const ChainArgs& a, int sm_count, cudaStream_t stream) {
         max_ctas = per_sm * sm_count;
     }
     const int grid = a.total < max_ctas ? a.total : max_ctas;
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(a);
+    // cooperative launch: the driver guarantees that all CTAs are resident together (or refuses)
+    ChainArgs args = a;
+    void* params[] = {&args};
+    VQAE_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid),
+                                              dim3(Cfg::THREADS), params, Cfg::SMEM, stream));
     return check_launch();
 }
 

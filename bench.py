@@ -186,23 +186,35 @@ def time_dominant_kernel(dev, peaks, precision: str):
     st = E._stream(dev)
     peak = peaks["bf16_tflops_sustained"]
     if precision == "bf16":
-        import ctypes
-        ws = [torch.randn(C, C, k, k, device=dev) * 0.05 for k in (1, 3, 1)]
-        packed = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
-        L.check(lib.vqae_pack_same_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C,
-                                              E._ptr(packed), st), "pack")
-        sc = (ctypes.c_float * 8)(0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.9)
+        # the trunk as the step runs it: ONE persistent launch over 50 blocks (pre_enc_layers)
+        nblk = 50
+        gen = torch.Generator().manual_seed(7)
+        packs, scal = [], []
+        for i in range(nblk):
+            ws = [(torch.randn(C, C, k, k, generator=gen) * 0.05).to(dev) for k in (1, 3, 1)]
+            pk = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
+            L.check(lib.vqae_pack_same_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C,
+                                                  E._ptr(pk), st), "pack")
+            packs.append(pk)
+            scal.append([0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.2])
+        w_all = torch.cat(packs)
+        scal_dev = torch.tensor(scal, dtype=torch.float32).to(dev)
+        fbytes = lib.vqae_same_chain_flag_bytes(nblk, B)
+        flags = torch.empty(fbytes, dtype=torch.uint8, device=dev)
+        assert lib.vqae_same_chain_supported(B, H, W, C)
 
         def launch(i):
-            L.check(lib.vqae_same_block_bf16(E._ptr(xs[i % nbuf]), E._ptr(ys[i % nbuf]),
-                                             E._ptr(packed), sc, B, H, W, C, st),
-                    "vqae_same_block_bf16")
-        ms = _event_time(launch, 20, dev)
-        flops = 2.0 * B * H * W * C * C * 11
-        name = "same_block_tc_kernel (fused PreActFixupResBlock 'same', C=64, 32x32; tcgen05 bf16)"
-        note = ("whole residual block per launch: 1x1 + 3x3 circular + 1x1 implicit GEMMs on "
-                "tcgen05 with bf16 operands, fp32 TMEM accumulation; timed alone with CUDA events "
-                "on the launch stream, 4 rotating buffer pairs")
+            L.check(lib.vqae_same_chain_bf16(E._ptr(xs[i % 2]), E._ptr(ys[0]), E._ptr(ys[1]),
+                                             E._ptr(w_all), E._ptr(scal_dev), E._ptr(flags), fbytes,
+                                             nblk, B, H, W, C, st), "vqae_same_chain_bf16")
+        ms = _event_time(launch, 5, dev)
+        flops = 2.0 * B * H * W * C * C * 11 * nblk
+        name = ("same_chain_tc_kernel (50 fused PreActFixupResBlocks 'same' per launch, C=64, 32x32; "
+                "tcgen05 bf16, persistent)")
+        note = ("whole 50-block trunk per launch: per tile 1x1 + 3x3 circular + 1x1 implicit GEMMs on "
+                "tcgen05 with bf16 operands, fp32 TMEM accumulation, fp32 residual stream through L2 "
+                "(ping-pong buffers 2 x 67 MB); timed alone with CUDA events on the launch stream; "
+                "includes the 13 KB memset of the completion counters")
     else:
         w = E.pack_conv_weight(torch.randn(C, C, 3, 3, device=dev) * 0.05)
 
