@@ -118,6 +118,113 @@ stem_in_kernel(const void* __restrict__ xv, const float* __restrict__ w_oihw,
     o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
+// Tiled form of the same convolution for W % 128 == 0, H % 8 == 0: one CTA = 8 rows x 128 columns,
+// one thread = 4 adjacent pixels.  The (normalised) input tile with its zero-padded halo is staged
+// once in shared memory as fp32 planes [c][row][col + 3] (so a thread's 6-column window lies in two
+// aligned 128-bit loads), every broadcast weight load feeds 4 pixels, and a thread writes 128
+// contiguous bytes.  Accumulation order per output is that of stem_in_kernel (bias, then ky, kx, c).
+constexpr int ST_TH = 8, ST_TW = 128, ST_PW = ST_TW + 8;      // padded row pitch (floats)
+
+template <int XKIND>
+__global__ void __launch_bounds__(256)
+stem_in_tiled_kernel(const void* __restrict__ xv, const float* __restrict__ w_oihw,
+                     const float* __restrict__ bias, float* __restrict__ out, int H, int W,
+                     int tiles_x, int tiles_y, Norm3 n) {
+    // input tile [c][row][col] first, output staging [row][4-px group][8 + 1 float4] afterwards
+    __shared__ __align__(16) float ostage[ST_TH * 32 * 9 * 4];
+    float (*tile)[ST_TH + 2][ST_PW] = reinterpret_cast<float (*)[ST_TH + 2][ST_PW]>(ostage);
+    static_assert(sizeof(float) * 3 * (ST_TH + 2) * ST_PW <= sizeof(float) * ST_TH * 32 * 9 * 4, "tile fits");
+    __shared__ __align__(16) float ws[27][8];  // [(ky*3 + kx)*3 + c][o]
+    __shared__ float bs[8];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 27 * 8; i += 256) {
+        const int o = i / 27, r = i % 27;        // OIHW: o*27 + c*9 + ky*3 + kx
+        const int c = r / 9, t = r % 9;
+        ws[t * 3 + c][o] = w_oihw[i];
+    }
+    if (tid < 8) bs[tid] = bias[tid];
+    const int tx = blockIdx.x % tiles_x;
+    const int ty = (blockIdx.x / tiles_x) % tiles_y;
+    const int64_t b = blockIdx.x / (tiles_x * tiles_y);
+    const int x0 = tx * ST_TW, y0 = ty * ST_TH;
+    const int64_t hw = (int64_t)H * W;
+    // stage rows y0-1 .. y0+8, columns x0-1 .. x0+128 -> tile[c][r][col - x0 + 3]
+    for (int i = tid; i < (ST_TH + 2) * (ST_TW + 2); i += 256) {
+        const int r = i / (ST_TW + 2), cc = i % (ST_TW + 2);
+        const int iy = y0 - 1 + r, ix = x0 - 1 + cc;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            if (XKIND == 0) {
+                const float* s = reinterpret_cast<const float*>(xv) + b * 3 * hw + (int64_t)iy * W + ix;
+                v0 = __ldg(s); v1 = __ldg(s + hw); v2 = __ldg(s + 2 * hw);
+            } else if (XKIND == 1) {
+                const float* s = reinterpret_cast<const float*>(xv) + (b * hw + (int64_t)iy * W + ix) * 3;
+                v0 = __ldg(s); v1 = __ldg(s + 1); v2 = __ldg(s + 2);
+            } else {
+                const uint8_t* s = reinterpret_cast<const uint8_t*>(xv) + (b * hw + (int64_t)iy * W + ix) * 3;
+                v0 = norm_px(__ldg(s), n.sub[0], n.mul[0]);
+                v1 = norm_px(__ldg(s + 1), n.sub[1], n.mul[1]);
+                v2 = norm_px(__ldg(s + 2), n.sub[2], n.mul[2]);
+            }
+        }
+        tile[0][r][cc + 2] = v0;
+        tile[1][r][cc + 2] = v1;
+        tile[2][r][cc + 2] = v2;
+    }
+    __syncthreads();
+
+    const int gx = tid & 31, gy = tid >> 5;      // 4-pixel group, row in tile
+    float2 acc[4][4];                            // packed fp32x2 FMAs: the same per-output fmaf chains
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[p][o] = make_float2(bs[2 * o], bs[2 * o + 1]);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        float win[3][8];                         // padded columns 4gx .. 4gx+7 = image x-3 .. x+4
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4 a = *reinterpret_cast<const float4*>(&tile[c][gy + ky][4 * gx]);
+            const float4 d = *reinterpret_cast<const float4*>(&tile[c][gy + ky][4 * gx + 4]);
+            win[c][0] = a.x; win[c][1] = a.y; win[c][2] = a.z; win[c][3] = a.w;
+            win[c][4] = d.x; win[c][5] = d.y; win[c][6] = d.z; win[c][7] = d.w;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&ws[(ky * 3 + kx) * 3 + c][0]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&ws[(ky * 3 + kx) * 3 + c][4]);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float v = win[c][p + kx + 2];          // image column x + p + kx - 1
+                    const float2 vv = make_float2(v, v);
+                    acc[p][0] = __ffma2_rn(vv, make_float2(w0.x, w0.y), acc[p][0]);
+                    acc[p][1] = __ffma2_rn(vv, make_float2(w0.z, w0.w), acc[p][1]);
+                    acc[p][2] = __ffma2_rn(vv, make_float2(w1.x, w1.y), acc[p][2]);
+                    acc[p][3] = __ffma2_rn(vv, make_float2(w1.z, w1.w), acc[p][3]);
+                }
+            }
+    }
+    // stage the 8 x 128 x 8 output tile in shared memory (pitch 33 float4 per 4-pixel group row keeps
+    // the 128-byte-strided writes conflict-free), then store whole 512-byte lines per warp instruction
+    float4* stage = reinterpret_cast<float4*>(ostage);
+    __syncthreads();                             // every thread is done reading the input tile
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        stage[(gy * 32 + gx) * 9 + 2 * p] = make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
+        stage[(gy * 32 + gx) * 9 + 2 * p + 1] = make_float4(acc[p][2].x, acc[p][2].y, acc[p][3].x, acc[p][3].y);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = tid + 256 * k;             // float4 index in the tile: row (i >> 8), 256 per row
+        const int r = i >> 8, j = i & 255;       // j = 8 * group + chunk
+        float4* dst = reinterpret_cast<float4*>(out + ((b * H + y0 + r) * (int64_t)W + x0) * 8);
+        dst[j] = stage[(r * 32 + (j >> 3)) * 9 + (j & 7)];
+    }
+}
+
 template <int CIN>
 __global__ void __launch_bounds__(256)
 stem_out_kernel(const float* __restrict__ x, const float* __restrict__ w_oihw,
@@ -198,17 +305,25 @@ int stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w, const 
     if (c_out != 8) return VQAE_ERR_UNSUPPORTED;
     const int64_t npix = B * H * W;
     const unsigned grid = ceil_div_u(npix, 256);
+    const bool tiled = (W % ST_TW == 0) && (H % ST_TH == 0) &&
+                       B * (H / ST_TH) * (W / ST_TW) <= 0x7fffffff;
+    const int txs = W / ST_TW, tys = H / ST_TH;
+    const unsigned tgrid = tiled ? (unsigned)(B * txs * tys) : 0u;
     Norm3 n{};
     if (x_dtype == VQAE_DT_U8) {
         if (!mean || !stdv) return VQAE_ERR_BAD_ARG;
         if (x_layout != VQAE_LAYOUT_NHWC) return VQAE_ERR_UNSUPPORTED;
         n = make_norm(mean, stdv);
-        stem_in_kernel<2><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
+        if (tiled) stem_in_tiled_kernel<2><<<tgrid, 256, 0, stream>>>(x, w, bias, out, H, W, txs, tys, n);
+        else stem_in_kernel<2><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
     } else if (x_dtype == VQAE_DT_F32) {
-        if (x_layout == VQAE_LAYOUT_NCHW)
-            stem_in_kernel<0><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
-        else
-            stem_in_kernel<1><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
+        if (x_layout == VQAE_LAYOUT_NCHW) {
+            if (tiled) stem_in_tiled_kernel<0><<<tgrid, 256, 0, stream>>>(x, w, bias, out, H, W, txs, tys, n);
+            else stem_in_kernel<0><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
+        } else {
+            if (tiled) stem_in_tiled_kernel<1><<<tgrid, 256, 0, stream>>>(x, w, bias, out, H, W, txs, tys, n);
+            else stem_in_kernel<1><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
+        }
     } else {
         return VQAE_ERR_UNSUPPORTED;
     }
