@@ -24,7 +24,7 @@ def main():
         lines = [l for l in f if l.startswith('"')]
     for r in csv.DictReader(lines):
         rows.append((short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], float(r["Metric Value"])))
-    starts = [i for i, r in enumerate(rows) if r[0].startswith("stem_in_kernel")]
+    starts = [i for i, r in enumerate(rows) if r[0].startswith("stem_in")]
     lo = starts[step]
     hi = starts[step + 1] if step + 1 < len(starts) else len(rows)
     sel = rows[lo:hi]
