@@ -23,34 +23,48 @@ namespace {
 
 using namespace tc;
 
-constexpr int CH_TH = 16, CH_TW = 32, CH_PW = CH_TW + 2;
-constexpr int CH_NPAD = (CH_TH + 2) * CH_PW;      // 612 padded pixels
-constexpr int CH_XPIX = 641;                       // operand region pitch: 5 x 128 px, odd
-constexpr int CH_UPIX = 711;                       // 35 + 5*128 + 35 px, odd
-constexpr uint32_t CH_XLBO = CH_XPIX * 16;
-constexpr uint32_t CH_ULBO = CH_UPIX * 16;
-constexpr int CH_RING = 6;
+constexpr int CH_TW = 32, CH_PW = CH_TW + 2;
+constexpr int CH_RING_MAX = 6;
 
-template <int CP, int CR>
+// CP = channels seen by the MMAs, CR = real channels, TH = tile rows (tile = TH x 32 pixels + halo).
+//   C = 64 : TH = 16 (612 padded pixels, 5 M-tiles), A1 and U in separate regions so that the next
+//            task's prologue overlaps G2, 6-slot weight ring (8 KB matrices)
+//   C = 128: TH = 8 (340 padded pixels, 3 M-tiles), ONE operand buffer (A1 is dead once G1 has
+//            completed and E1 writes U over it), 3-slot ring of 32 KB matrices; the next task's
+//            prologue runs after this task has been published
+template <int CP, int CR, int TH>
 struct ChainCfg {
+    static constexpr bool UNI = (CP == 128);
+    static constexpr int NPAD = (TH + 2) * CH_PW;
+    static constexpr int MT1 = (NPAD + 127) / 128;                   // G1 / E1 M-tiles (padded pixels)
+    static constexpr int MT2 = (TH * CH_PW - 2 + 127) / 128;         // G2 / E2 M-tiles (outputs from q = 35)
+    static constexpr int MT3 = TH * CH_TW / 128;                     // G3 / E3 M-tiles (interior pixels)
+    static constexpr int XPIX = MT1 * 128 + 1;                       // odd pixel pitches: conflict-free
+    static constexpr int UPIX = (35 + MT2 * 128 + 35) | 1;
+    static constexpr uint32_t ULBO = UPIX * 16;
+    static constexpr uint32_t XLBO = UNI ? ULBO : XPIX * 16;
     static constexpr int KCH = CP / 8;
     static constexpr int KCR = CR / 8;
-    static constexpr int NW = (CP == 64) ? 16 : (CP == 32 ? 8 : 4);
+    static constexpr int NW = 16;
     static constexpr int WORKERS = NW * 32;
     static constexpr int THREADS = WORKERS + 64;   // + MMA warp + weight-producer warp
     static constexpr int NG = NW / 4;
-    static constexpr int NC = CP / NG;
-    static constexpr int UCH = (CR < CP) ? KCR : NC / 8;
+    static constexpr int NC = CP / NG;             // TMEM columns per worker (16 or 32)
+    static constexpr int UCH = NC / 8;
+    static constexpr int NSUB = NC / 16;           // E3 handles 16 columns at a time
+    static constexpr int RING = UNI ? 3 : 6;
     static constexpr uint32_t WLBO = CP * 16;
     static constexpr uint32_t WMAT = KCH * WLBO;
     static constexpr uint32_t OFF_X = 0;
-    static constexpr uint32_t OFF_U = OFF_X + KCH * CH_XLBO;
-    static constexpr bool RING = true;
-    static constexpr uint32_t OFF_W = OFF_U + KCH * CH_ULBO;        // ring[CH_RING]
-    static constexpr uint32_t OFF_BAR = OFF_W + CH_RING * WMAT;
+    static constexpr uint32_t OFF_U = UNI ? 0 : KCH * XLBO;
+    static constexpr uint32_t OFF_W = OFF_U + KCH * ULBO;
+    static constexpr uint32_t OFF_BAR = OFF_W + RING * WMAT;
     static constexpr uint32_t SMEM = OFF_BAR + 128;
-    static constexpr int TMEM_COLS = CP == 64 ? 512 : (CP == 32 ? 256 : 128);
-    static constexpr int MIN_CTAS = CP == 64 ? 1 : (CP == 32 ? 2 : 4);
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int MIN_CTAS = 1;
+    static_assert(MT1 * CP <= 512 && MT2 <= MT1 && RING <= CH_RING_MAX, "TMEM / ring budget");
+    static_assert(SMEM <= 232448, "shared memory budget");
+    static_assert(NW * 32 * 20 * 4 <= KCH * ULBO, "E3 staging fits the U region");
 };
 
 struct ChainArgs {
@@ -72,12 +86,14 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int CP, int CR>
-__global__ void __launch_bounds__(ChainCfg<CP, CR>::THREADS, ChainCfg<CP, CR>::MIN_CTAS)
+template <int CP, int CR, int TH>
+__global__ void __launch_bounds__(ChainCfg<CP, CR, TH>::THREADS, 1)
 same_chain_tc_kernel(ChainArgs a) {
-    using Cfg = ChainCfg<CP, CR>;
+    using Cfg = ChainCfg<CP, CR, TH>;
     constexpr int KCR = Cfg::KCR, NW = Cfg::NW, NC = Cfg::NC, UCH = Cfg::UCH;
-    constexpr uint32_t WLBO = Cfg::WLBO, WMAT = Cfg::WMAT;
+    constexpr int MT1 = Cfg::MT1, MT2 = Cfg::MT2, MT3 = Cfg::MT3, NSUB = Cfg::NSUB;
+    constexpr int CH_RING = Cfg::RING, CH_TH = TH, CH_NPAD = Cfg::NPAD;
+    constexpr uint32_t WLBO = Cfg::WLBO, WMAT = Cfg::WMAT, CH_XLBO = Cfg::XLBO, CH_ULBO = Cfg::ULBO;
     constexpr int MMA_WARP = NW, PROD_WARP = NW + 1;
 
     extern __shared__ __align__(128) uint8_t smem[];
@@ -85,8 +101,8 @@ same_chain_tc_kernel(ChainArgs a) {
     const uint32_t sX = sbase + Cfg::OFF_X, sU = sbase + Cfg::OFF_U, sW = sbase + Cfg::OFF_W;
     const uint32_t bar_mma = sbase + Cfg::OFF_BAR;
     const uint32_t bar_full = bar_mma + 8;                           // [CH_RING] matrix landed
-    const uint32_t bar_empty = bar_full + 8 * CH_RING;               // [CH_RING] matrix consumed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 + 16 * CH_RING);
+    const uint32_t bar_empty = bar_full + 8 * CH_RING_MAX;           // [CH_RING] matrix consumed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 + 16 * CH_RING_MAX);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -139,9 +155,8 @@ same_chain_tc_kernel(ChainArgs a) {
         const uint32_t t_lane = (uint32_t)(q4 * 32) << 16;
         const uint32_t t_col = grp * NC;
         const int kc0 = grp * (NC / 8);
-        constexpr int NCR = UCH * 8;
-        constexpr int F4 = NCR / 4;
-        constexpr int SROW = NCR + 4;
+        constexpr int F4 = 4;                 // E3 unit: 16 columns = 4 float4 per pixel row
+        constexpr int SROW = 16 + 4;
         float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_U) + (warp < NW ? warp : 0) * 32 * SROW;
 
         const uint64_t dX = make_desc(sX, CH_XLBO, 128);
@@ -157,10 +172,10 @@ same_chain_tc_kernel(ChainArgs a) {
             const int trem = tile - img * a.tiles_per_img;
             const int r0 = (trem / a.tiles_x) * CH_TH, c0 = (trem % a.tiles_x) * CH_TW;
             if (blk > 0) {
-                // Blocking is safe here although the CURRENT task of this CTA is still unpublished:
-                // the host only launches this kernel when grid <= n_tiles - tiles_per_img, so every
-                // producer of the next task has a smaller id than the current task, and waits can
-                // only chain towards smaller ids.
+                // Blocking is safe: either this CTA has nothing unpublished (C = 128: the prologue runs
+                // after the publish), or the host verified grid <= n_tiles - tiles_per_img (C = 64), so
+                // that every producer of the next task has a smaller id than the current task; either
+                // way waits can only chain towards smaller task ids.
                 if (lane == 0) {
                     const unsigned* f = a.flags + (size_t)(blk - 1) * a.n_img + img;
                     while (ld_acquire_u32(f) < (unsigned)a.tiles_per_img) __nanosleep(64);
@@ -217,21 +232,18 @@ same_chain_tc_kernel(ChainArgs a) {
 
             // ---- G1: D1 = A1 . W1^T on 5 M-tiles of padded-linear pixels ----
             if (warp == MMA_WARP) {
-                int slot = 0;
-                if (Cfg::RING) {
-                    slot = wcnt % CH_RING;
-                    mbar_wait(bar_full + 8 * slot, (wcnt / CH_RING) & 1);
-                }
+                const int slot = wcnt % CH_RING;
+                mbar_wait(bar_full + 8 * slot, (wcnt / CH_RING) & 1);
                 tc_fence_after_sync();
                 const uint64_t dW1 = dW + (uint64_t)((slot * WMAT) >> 4);
 #pragma unroll
-                for (int t = 0; t < 5; ++t)
+                for (int t = 0; t < MT1; ++t)
 #pragma unroll
                     for (int ks = 0; ks < CP / 16; ++ks)
                         umma_bf16(tmem_base + t * CP,
                                   dX + (uint64_t)((t * 128 * 16 + ks * 2 * CH_XLBO) >> 4),
                                   dW1 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0, leader);
-                if (Cfg::RING) umma_commit(bar_empty + 8 * slot, leader);
+                umma_commit(bar_empty + 8 * slot, leader);
                 umma_commit(bar_mma, leader);
                 ++wcnt;
                 __syncwarp();
@@ -241,7 +253,7 @@ same_chain_tc_kernel(ChainArgs a) {
                 const float b2a = __ldg(scal + 2), b2b = __ldg(scal + 3);
                 mbar_wait(bar_mma, mma_phase);
                 tc_fence_after_sync();
-                for (int t = 0; t < 5; ++t) {
+                for (int t = 0; t < MT1; ++t) {
                     float v[NC];
                     tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
                     tmem_ld_wait();
@@ -262,34 +274,31 @@ same_chain_tc_kernel(ChainArgs a) {
                 tc_fence_after_sync();
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    int slot = 1 + tap;
-                    if (Cfg::RING) {
-                        slot = wcnt % CH_RING;
-                        mbar_wait(bar_full + 8 * slot, (wcnt / CH_RING) & 1);
-                        tc_fence_after_sync();
-                    }
+                    const int slot = wcnt % CH_RING;
+                    mbar_wait(bar_full + 8 * slot, (wcnt / CH_RING) & 1);
+                    tc_fence_after_sync();
                     const uint64_t dW2 = dW + (uint64_t)((slot * WMAT) >> 4);
                     const int shift = (tap / 3 - 1) * CH_PW + (tap % 3 - 1);
 #pragma unroll
-                    for (int t = 0; t < 5; ++t)
+                    for (int t = 0; t < MT2; ++t)
 #pragma unroll
                         for (int ks = 0; ks < CP / 16; ++ks)
                             umma_bf16(tmem_base + t * CP,
                                       dU + (uint64_t)(((CH_PW + 1 + t * 128 + shift) * 16 + ks * 2 * CH_ULBO) >> 4),
                                       dW2 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, (tap | ks) > 0, leader);
-                    if (Cfg::RING) umma_commit(bar_empty + 8 * slot, leader);
+                    umma_commit(bar_empty + 8 * slot, leader);
                     ++wcnt;
                 }
                 umma_commit(bar_mma, leader);
                 __syncwarp();
             }
             if (warp < NW) {
-                if (k + 1 < my_tasks) prologue(task + gridDim.x);
+                if (!Cfg::UNI && k + 1 < my_tasks) prologue(task + gridDim.x);
                 // ---- E2: V[p] over the U region ----
                 const float b3a = __ldg(scal + 4), b3b = __ldg(scal + 5);
                 mbar_wait(bar_mma, mma_phase);
                 tc_fence_after_sync();
-                for (int t = 0; t < 5; ++t) {
+                for (int t = 0; t < MT2; ++t) {
                     float v[NC];
                     tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
                     tmem_ld_wait();
@@ -311,21 +320,18 @@ same_chain_tc_kernel(ChainArgs a) {
 
             // ---- G3: D3 = V . W3^T, 4 M-tiles ----
             if (warp == MMA_WARP) {
-                int slot = 10;
-                if (Cfg::RING) {
-                    slot = wcnt % CH_RING;
-                    mbar_wait(bar_full + 8 * slot, (wcnt / CH_RING) & 1);
-                }
+                const int slot = wcnt % CH_RING;
+                mbar_wait(bar_full + 8 * slot, (wcnt / CH_RING) & 1);
                 tc_fence_after_sync();
                 const uint64_t dW3 = dW + (uint64_t)((slot * WMAT) >> 4);
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
+                for (int t = 0; t < MT3; ++t)
 #pragma unroll
                     for (int ks = 0; ks < CP / 16; ++ks)
                         umma_bf16(tmem_base + t * CP,
                                   dU + (uint64_t)((t * 128 * 16 + ks * 2 * CH_ULBO) >> 4),
                                   dW3 + (uint64_t)((ks * 2 * WLBO) >> 4), idesc, ks > 0, leader);
-                if (Cfg::RING) umma_commit(bar_empty + 8 * slot, leader);
+                umma_commit(bar_empty + 8 * slot, leader);
                 umma_commit(bar_mma, leader);
                 ++wcnt;
                 __syncwarp();
@@ -337,10 +343,13 @@ same_chain_tc_kernel(ChainArgs a) {
                 const float* ximg = src + (size_t)img * a.H * a.W * CR;
                 float* oimg = ((blk & 1) ? a.buf1 : a.buf0) + (size_t)img * a.H * a.W * CR;
                 const int rsub = lane / F4, c4 = lane % F4;
-                auto x_off = [&](int t, int kk) -> int {     // element offset inside the image (< 2^31)
+                // unit u = (M-tile t, 16-column half h): element offset inside the image (< 2^31)
+                auto x_off = [&](int u, int kk) -> int {
+                    const int t = u / NSUB, h = u - t * NSUB;
                     const int p = t * 128 + q4 * 32 + rsub + kk * (32 / F4);
-                    return ((r0 + (p >> 5)) * a.W + c0 + (p & 31)) * CR + kc0 * 8 + c4 * 4;
+                    return ((r0 + (p >> 5)) * a.W + c0 + (p & 31)) * CR + kc0 * 8 + h * 16 + c4 * 4;
                 };
+                constexpr int NU = MT3 * NSUB;
                 float4 xr[F4], xn[F4];
 #pragma unroll
                 for (int kk = 0; kk < F4; ++kk)
@@ -348,13 +357,14 @@ same_chain_tc_kernel(ChainArgs a) {
                 mbar_wait(bar_mma, mma_phase);
                 tc_fence_after_sync();
 #pragma unroll 1
-                for (int t = 0; t < 4; ++t) {
-                    float v[NC];
-                    tmem_ld<NC>(tmem_base + t_lane + t * CP + t_col, v);
-                    if (t + 1 < 4) {
+                for (int u = 0; u < NU; ++u) {
+                    const int t = u / NSUB, h = u - t * NSUB;
+                    float v[16];
+                    tmem_ld<16>(tmem_base + t_lane + t * CP + t_col + h * 16, v);
+                    if (u + 1 < NU) {
 #pragma unroll
                         for (int kk = 0; kk < F4; ++kk)
-                            xn[kk] = __ldcg(reinterpret_cast<const float4*>(ximg + x_off(t + 1, kk)));
+                            xn[kk] = __ldcg(reinterpret_cast<const float4*>(ximg + x_off(u + 1, kk)));
                     }
                     tmem_ld_wait();
                     __syncwarp();
@@ -372,7 +382,7 @@ same_chain_tc_kernel(ChainArgs a) {
                         o.y = fmaf(d.y, scale, b4) + xr[kk].y;
                         o.z = fmaf(d.z, scale, b4) + xr[kk].z;
                         o.w = fmaf(d.w, scale, b4) + xr[kk].w;
-                        *reinterpret_cast<float4*>(oimg + x_off(t, kk)) = o;
+                        *reinterpret_cast<float4*>(oimg + x_off(u, kk)) = o;
                     }
 #pragma unroll
                     for (int kk = 0; kk < F4; ++kk) xr[kk] = xn[kk];
@@ -387,6 +397,13 @@ same_chain_tc_kernel(ChainArgs a) {
                 __threadfence();
                 red_release_add(a.flags + (size_t)blk * a.n_img + img, 1u);
             }
+            // late prologue: the operand buffer is shared (UNI) or an early blocking wait would not be
+            // provably cycle-free; this task is published, so blocking on the next one's producers is safe
+            if (Cfg::UNI && k + 1 < my_tasks) {
+                if (warp < NW) prologue(task + gridDim.x);
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, %0;" ::"n"(Cfg::WORKERS + 32) : "memory");
+            }
         }
     }
 
@@ -395,10 +412,17 @@ same_chain_tc_kernel(ChainArgs a) {
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int CP, int CR>
-int launch_chain(const ChainArgs& a, int sm_count, cudaStream_t stream) {
-    using Cfg = ChainCfg<CP, CR>;
-    auto kern = same_chain_tc_kernel<CP, CR>;
+template <int CP, int CR, int TH>
+int launch_chain(ChainArgs a, int64_t B, int sm_count, cudaStream_t stream) {
+    using Cfg = ChainCfg<CP, CR, TH>;
+    auto kern = same_chain_tc_kernel<CP, CR, TH>;
+    if (a.H % TH != 0) return VQAE_ERR_UNSUPPORTED;
+    a.tiles_x = a.W / CH_TW;
+    a.tiles_per_img = (a.H / TH) * a.tiles_x;
+    const int64_t nt = B * a.tiles_per_img;
+    if (nt * a.n_blocks > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
+    a.n_tiles = (int)nt;
+    a.total = (int)(nt * a.n_blocks);
     static int max_ctas = 0;
     if (max_ctas == 0) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -412,6 +436,9 @@ int launch_chain(const ChainArgs& a, int sm_count, cudaStream_t stream) {
         max_ctas = per_sm * sm_count;
     }
     const int grid = a.total < max_ctas ? a.total : max_ctas;
+    // the overlapped prologue of the C = 64 form blocks on the next task's producers while the
+    // current task is unpublished: only cycle-free if those producers are older than the current task
+    if (!Cfg::UNI && grid > a.n_tiles - a.tiles_per_img) return VQAE_ERR_UNSUPPORTED;
     // cooperative launch: the driver guarantees that all CTAs are resident together (or refuses)
     ChainArgs args = a;
     void* params[] = {&args};
@@ -422,13 +449,16 @@ int launch_chain(const ChainArgs& a, int sm_count, cudaStream_t stream) {
 
 }  // namespace
 
-// The persistent form is built for the trunk width (C = 64, one CTA per SM) and needs at least
-// grid + tiles_per_img tiles per block, so that every producer of a CTA's next task is older than
-// its current task (see the prologue); smaller problems run block by block.
+// C = 64: the persistent form pays off (and its overlapped prologue is provably cycle-free) with at
+// least grid + tiles_per_img tiles per block; smaller problems run block by block through
+// same_block_tc_kernel.  C = 128 (the 512-model trunk): this is the only tcgen05 kernel, used for
+// any batch and any run length, including a single block.
 bool same_chain_supported(int64_t B, int H, int W, int C, int sm_count) {
-    if (C != 64 || B <= 0 || H < CH_TH || W < CH_TW || H % CH_TH != 0 || W % CH_TW != 0) return false;
-    const int64_t tpi = (int64_t)(H / CH_TH) * (W / CH_TW);
-    return B * tpi - tpi >= sm_count;
+    if (B <= 0 || W < CH_TW || W % CH_TW != 0) return false;
+    if (C == 128) return H >= 8 && H % 8 == 0;          // late prologue: any batch is safe
+    if (C != 64 || H < 16 || H % 16 != 0) return false;
+    const int64_t tpi = (int64_t)(H / 16) * (W / CH_TW);
+    return B * tpi - tpi >= sm_count;                   // worth it (and early prologue is cycle-free)
 }
 
 size_t same_chain_flag_bytes(int n_blocks, int64_t B) {
@@ -441,7 +471,6 @@ int same_chain_tc(const float* x, float* buf_a, float* buf_b, const void* w_pack
     if (!x || !buf_a || !buf_b || !w_packed_all || !scalars_dev || !flags || B <= 0 || n_blocks <= 0)
         return VQAE_ERR_BAD_ARG;
     if (x == buf_a || x == buf_b || buf_a == buf_b) return VQAE_ERR_BAD_ARG;
-    if (H < CH_TH || W < CH_TW || H % CH_TH != 0 || W % CH_TW != 0) return VQAE_ERR_UNSUPPORTED;
     if (flag_bytes < same_chain_flag_bytes(n_blocks, B)) return VQAE_ERR_SCRATCH;
     ChainArgs a;
     a.x0 = x; a.buf0 = buf_a; a.buf1 = buf_b;
@@ -449,14 +478,11 @@ int same_chain_tc(const float* x, float* buf_a, float* buf_b, const void* w_pack
     a.scal = scalars_dev;
     a.flags = reinterpret_cast<unsigned int*>(flags);
     a.n_blocks = n_blocks; a.n_img = (int)B;
-    a.H = H; a.W = W; a.tiles_x = W / CH_TW; a.tiles_per_img = (H / CH_TH) * a.tiles_x;
-    const int64_t nt = B * a.tiles_per_img;
-    if (nt * n_blocks > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
-    a.n_tiles = (int)nt;
-    a.total = (int)(nt * n_blocks);
+    a.H = H; a.W = W;
     VQAE_CUDA_TRY(cudaMemsetAsync(flags, 0, same_chain_flag_bytes(n_blocks, B), stream));
     if (!same_chain_supported(B, H, W, C, sm_count)) return VQAE_ERR_UNSUPPORTED;
-    return launch_chain<64, 64>(a, sm_count, stream);
+    if (C == 128) return launch_chain<128, 128, 8>(a, B, sm_count, stream);
+    return launch_chain<64, 64, 16>(a, B, sm_count, stream);
 }
 
 }  // namespace vqae

@@ -575,7 +575,7 @@ static inline int padded_channels(int C) { return C == 8 ? 16 : C; }
 int pack_same_block_bf16(const float* w1, const float* w2, const float* w3, int C, void* packed,
                          cudaStream_t stream) {
     if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
-    if (C != 8 && C != 16 && C != 32 && C != 64) return VQAE_ERR_UNSUPPORTED;
+    if (C != 8 && C != 16 && C != 32 && C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
     const int CP = padded_channels(C);
     const int total = 11 * CP * CP;
     pack_same_block_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(

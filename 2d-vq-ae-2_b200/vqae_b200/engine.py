@@ -116,7 +116,7 @@ class PackedFixup:
         # tcgen05 path: bf16 operand pack of a 'same' block at the trunk width (C = 64)
         self.tc_weights = None
         self.tc_scalars = None
-        if self.mode == L.MODE_SAME and self.c_in in (8, 16, 32, 64) and \
+        if self.mode == L.MODE_SAME and self.c_in in (8, 16, 32, 64, 128) and \
                 self.c_branch == self.c_in and self.c_out == self.c_in:
             lib = L.load()
             dev = w2.device
@@ -151,9 +151,15 @@ class PackedFixup:
                 + [float(sc["bias4"]) + float(sc["bias1d"])]))
 
     def tc_ok(self, h: int, w: int) -> bool:
-        """a tcgen05 kernel is built for this block at this size (16 x 32 pixel tiles)"""
-        return (self.tc_weights is not None and self.mode in (L.MODE_SAME, L.MODE_DOWN)
-                and h % 16 == 0 and w % 32 == 0)
+        """a tcgen05 kernel is built for this block at this size (16 x 32 pixel tiles; 8 x 32 for
+        the C = 128 'same' blocks, which only exist in the persistent chain form)"""
+        if self.tc_weights is None or self.mode not in (L.MODE_SAME, L.MODE_DOWN) or w % 32:
+            return False
+        return h % 8 == 0 if self.chain_only else h % 16 == 0
+
+    @property
+    def chain_only(self) -> bool:
+        return self.mode == L.MODE_SAME and self.c_in == 128
 
     def out_hw(self, h: int, w: int) -> Tuple[int, int]:
         if self.mode == L.MODE_DOWN:
@@ -207,6 +213,8 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
         L.check(lib.vqae_down_block_bf16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
                                          b, h, w, c, _stream(x.device)), "vqae_down_block_bf16")
         return out
+    if precision == "bf16" and pk.tc_ok(h, w) and pk.chain_only:
+        return run_blocks_nhwc([pk], x, "bf16")
     if precision == "bf16" and pk.tc_ok(h, w):
         L.check(lib.vqae_same_block_bf16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
                                          b, h, w, c, _stream(x.device)), "vqae_same_block_bf16")
@@ -245,7 +253,8 @@ def _chain_runs(packed: Sequence[PackedFixup], h: int, w: int, batch: int = 1 <<
             while j < n and packed[j].mode == L.MODE_SAME and packed[j].c_in == pk.c_in \
                     and packed[j].tc_ok(hh, ww):
                 j += 1
-            if j - i >= 2 and lib.vqae_same_chain_supported(batch, hh, ww, pk.c_in):
+            if (j - i >= 2 or pk.chain_only) and \
+                    lib.vqae_same_chain_supported(batch, hh, ww, pk.c_in):
                 runs.append((i, j))
             i = j
         else:

@@ -19,12 +19,13 @@ from vqae_b200.model import _flat_blocks  # noqa: E402
 def main():
     precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    n_down = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     dev = torch.device("cuda:0")
-    m = vqae_b200.build_vqae(n_down=3).eval()
+    m = vqae_b200.build_vqae(n_down=n_down).eval()
     m.load_state_dict(S.make_state_dict(m.state_dict(), seed=1, regime="perturbed"))
     m = m.to(dev)
     enc = m.encoder
-    x = S.synthetic_patches_u8(batch, 256, 42).to(dev)
+    x = S.synthetic_patches_u8(batch, 256 if n_down == 3 else 512, 42).to(dev)
     blocks = _flat_blocks(enc.down_layers) + _flat_blocks(enc.pre_enc_layers)
     packed = E.pack_blocks(blocks)
     pq = enc.vq_layers[0].packed()

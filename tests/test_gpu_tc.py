@@ -129,3 +129,38 @@ def test_persistent_chain_bit_identical_to_block_by_block(c, hw, batch, n):
         assert E.launch_count() - before == (1 if chained else n)
         assert torch.equal(h, hc)
     assert H.rel_err(hc, E.run_blocks_nhwc(packed, x, "fp32")) < 5e-3
+
+
+@pytest.mark.parametrize("hw,batch,n", [(32, 3, 1), (32, 40, 3), (96, 1, 2), (64, 2, 2)])
+def test_c128_chain_kernel_vs_fp32_path(hw, batch, n):
+    """C = 128 'same' blocks (the trunk of the as-shipped n_down = 4 model) exist only in the
+    persistent chain form (8-row tiles, one shared operand buffer): against the fp32 exact path,
+    relative error of the bf16 branch < 1e-2; any batch and run length, deterministic."""
+    from vqae_b200.config import pre_activation_fixup
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blocks = []
+    for i in range(n):
+        blk = PreActFixupResBlock(in_channels=128, out_channels=128, mode="same", **conf).eval()
+        blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=40 + i, regime="perturbed",
+                                              n_layers=12))
+        blocks.append(blk.to(DEV))
+    packed = E.pack_blocks(blocks)
+    assert all(pk.tc_ok(hw, hw) and pk.chain_only for pk in packed)
+    x = torch.randn(batch, hw, hw, 128, device=DEV)
+    y32 = E.run_blocks_nhwc(packed, x, "fp32")
+    before = E.launch_count()
+    y16 = E.run_blocks_nhwc(packed, x, "bf16")
+    torch.cuda.synchronize()
+    assert E.launch_count() - before == 1
+    branch = y32 - x
+    assert float((y16 - y32).abs().max() / branch.abs().max()) < 1e-2
+    assert H.rel_err(y16, y32) < 5e-3
+    assert torch.equal(y16, E.run_blocks_nhwc(packed, x, "bf16"))
+    # block by block through the same kernel (n_blocks = 1 each) gives the same bits
+    h = x
+    for pk in packed:
+        h = E.fixup_forward_nhwc(pk, h, precision="bf16")
+    assert torch.equal(h, y16)
