@@ -84,7 +84,6 @@ struct TqArgs {
     uint32_t* near_ties;     // or null
     float* z_out;            // [N][8] or null
     float* diag;             // [N][4] = {min D, T, #candidates, slow-path flag} or null
-    int dbg;                 // experiment switches (0 in production)
     long long* prof;         // [4][16] clock64 phase stamps of CTA 0, tiles 10..13 (or null)
     const float* embed;      // [256][8]
     const float* table;      // [256][C]
@@ -448,11 +447,6 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
             mbar_wait(bar_acc_full + 8 * b, (it >> 1) & 1);
             tc_fence_after_sync();
             if (wq == 0) TQ_PROF(7);
-            if (a.dbg & 1) {                           // experiment: epilogue does nothing
-                tc_fence_before_sync();
-                mbar_arrive(bar_acc_free + 8 * b);
-                continue;
-            }
             const float* zr =
                 reinterpret_cast<const float*>(smem + Cfg::OFF_Z + (b * TQ_M + row) * Cfg::ZPITCH);
             const float4 za = *reinterpret_cast<const float4*>(zr);
@@ -735,7 +729,7 @@ int quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out, 
     TqArgs<C> a;
     a.x = x; a.out = out; a.idx = indices; a.near_ties = near_ties;
     a.z_out = z_out; a.diag = diag; a.prof = g_tq_prof;
-    a.dbg = getenv("VQAE_QTC_DBG") ? atoi(getenv("VQAE_QTC_DBG")) : 0; a.embed = p->embed; a.table = p->table; a.N = N;
+    a.embed = p->embed; a.table = p->table; a.N = N;
     a.num_tiles = (int)((N + TQ_M - 1) / TQ_M);
     a.tie_rel_gap = tie_rel_gap;
     a.margin = 4.f * TQ_ERR_C + 2.f * tie_rel_gap;

@@ -164,3 +164,28 @@ def test_c128_chain_kernel_vs_fp32_path(hw, batch, n):
     for pk in packed:
         h = E.fixup_forward_nhwc(pk, h, precision="bf16")
     assert torch.equal(h, y16)
+
+
+def test_encoder_nd4_512_bf16_agreement_with_fp32():
+    """The as-shipped topology (n_down = 4, C_lat = 128, 512^2 -> 32x32 codes): reduced-precision path
+    (C = 128 trunk on the persistent tcgen05 kernel) against the fp32 exact path that is pinned to the
+    reference golden in test_gpu_parity.py."""
+    tag = "model_nd4_perturbed_512"
+    m, sd, x = H.model_and_state(tag)
+    m = m.to(DEV)
+    try:
+        with torch.no_grad():
+            vqae_b200.set_precision(m, "fp32")
+            (e32,), (i32,), (l32,) = m.encoder(x.to(DEV))
+            vqae_b200.set_precision(m, "bf16")
+            before = E.launch_count()
+            (e16,), (i16,), (l16,) = m.encoder(x.to(DEV))
+            launches = E.launch_count() - before
+        agree = float((i32 == i16).float().mean())
+        assert agree > 0.90, agree
+        assert abs(l16.item() - l32.item()) < 3e-2 * abs(l32.item())
+        assert launches < 40                  # trunk + post-down blocks collapse into chain launches
+        print(f"nd4/512 bf16/fp32 code agreement {agree:.4f}, {launches} launches")
+    finally:
+        vqae_b200.set_precision(m, "fp32")
+        m.cpu()
