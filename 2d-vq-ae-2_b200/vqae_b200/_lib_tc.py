@@ -18,6 +18,11 @@ SIGNATURES: dict = {
     "vqae_same_chain_flag_bytes": (C.c_size_t, [_i, _i64]),
     "vqae_same_chain_supported": (_i, [_i64, _i, _i, _i]),
     "vqae_same_chain_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i, _i64, _i, _i, _i, _vp]),
+    "vqae_trunk_resident_set_profile": (None, [_vp]),
+    "vqae_trunk_resident_max_clusters": (_i, []),
+    "vqae_trunk_resident_supported": (_i, [_i64, _i, _i, _i]),
+    "vqae_pack_resident_block_bf16": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp]),
+    "vqae_trunk_resident_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "vqae_down_block_pack_elems": (C.c_size_t, [_i]),
     "vqae_pack_down_block_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
     "vqae_down_block_bf16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),

@@ -249,6 +249,30 @@ int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void*
                          batch, height, width, c, sm_count, (cudaStream_t)stream);
 }
 
+void vqae_trunk_resident_set_profile(long long* phase_clocks) { trunk_resident_set_prof(phase_clocks); }
+
+int vqae_trunk_resident_max_clusters(void) {
+    int n = 0;
+    return trunk_resident_max_clusters(&n) == VQAE_OK ? n : -1;
+}
+
+int vqae_trunk_resident_supported(int64_t batch, int height, int width, int c) {
+    return trunk_resident_supported(batch, height, width, c) ? 1 : 0;
+}
+
+int vqae_pack_resident_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+                                  int c, float scale, void* packed, void* stream) {
+    return pack_resident_block_bf16(w1_oihw, w2_oihw, w3_oihw, c, scale, packed,
+                                    (cudaStream_t)stream);
+}
+
+int vqae_trunk_resident_bf16(const float* x, float* out, const void* w_packed_all,
+                             const float* scalars_dev, int n_blocks, int64_t batch, int height,
+                             int width, int c, void* stream) {
+    return trunk_resident_tc(x, out, w_packed_all, scalars_dev, n_blocks, batch, height, width, c,
+                             (cudaStream_t)stream);
+}
+
 int vqae_tc_mma_bench(int n, int layout_type, int reps, int a_stride_rows, long long* out2,
                       void* stream) {
     return tc_mma_bench(n, layout_type, reps, a_stride_rows, out2, (cudaStream_t)stream);

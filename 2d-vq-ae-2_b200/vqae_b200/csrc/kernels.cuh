@@ -64,6 +64,15 @@ int same_chain_tc(const float* x, float* buf_a, float* buf_b, const void* w_pack
                   const float* scalars_dev, void* flags, size_t flag_bytes, int n_blocks, int64_t B,
                   int H, int W, int C, int sm_count, cudaStream_t stream);
 
+// tc_resident.cu (image-resident trunk: residual stream in tensor memory, 4-CTA clusters)
+bool trunk_resident_supported(int64_t B, int H, int W, int C);
+int pack_resident_block_bf16(const float* w1, const float* w2, const float* w3, int C, float scale,
+                             void* packed, cudaStream_t stream);
+int trunk_resident_max_clusters(int* out);
+void trunk_resident_set_prof(long long* dev_ptr);
+int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, const float* scalars_dev,
+                      int n_blocks, int64_t B, int H, int W, int C, cudaStream_t stream);
+
 int tc_mma_bench(int N, int layout_type, int reps, int a_stride_rows, long long* out,
                  cudaStream_t stream);
 // tc_down.cu

@@ -1,0 +1,538 @@
+// Image-resident tcgen05 kernel for a RUN of consecutive PreActFixupResBlocks in mode 'same' at the
+// latent resolution (C = 64, 32 x 32): the 50-block trunks (vq_ae/model.py:150-153,240-263) and the
+// post layers of the last DownBlock / first UpBlock (conv_block.py:18-91); block arithmetic
+// conv_block.py:196-216.
+//
+// The fp32 residual stream never leaves the SM: a cluster of four CTAs owns one image per *slot*,
+// CTA r holding rows 8r .. 8r+7 (256 pixels = two 128-lane M-tiles) of the residual in TENSOR MEMORY
+// (2 x 64 fp32 columns).  Per block and slot:
+//     P   workers: tcgen05.ld residual -> A1 = bf16(elu(x + b1a) + b1b) -> shared operand buffer
+//     G1  tcgen05.mma  D  = A1 . W1^T                      (2 M-tiles x 4 k-steps)
+//     E1  workers: U = bf16(elu(D + b2a) + b2b) -> operand buffer, wrap-around columns duplicated,
+//         first/last row pushed into the neighbour CTAs' halo rows through distributed shared memory
+//     G2  nine taps accumulate into D; a tap is a constant start-address shift of the A descriptor
+//     E2  workers: V = bf16(elu(D + b3a) + b3b) -> operand buffer
+//     G3  tcgen05.mma  R += V . (scale W3)^T               accumulates straight into the residual
+// so the residual add costs nothing and there is no global-memory traffic between the first load and
+// the last store of an image (bias4 is carried as a running scalar and folded into the next b1a).
+// Pixels of a tile are stored COLUMN-major with a 10-row pitch (8 rows + 2 halo rows): eight
+// consecutive rows of one column are one 8-row core-matrix group, 16 columns at a constant stride
+// (SBO = 160 B) are one M-tile, so an 8 x 32 tile is exactly two M-tiles -- no padded pixels are
+// multiplied -- and tap (dy, dx) is the shift (dx * 10 + dy) * 16 B.
+// Each CTA runs TWO slots (two different images, 2 x (128 residual + 128 accumulator) = 512 TMEM
+// columns) half a block out of phase: while the nine taps of one slot occupy the tensor pipe, the
+// workers run E2 -> P -> E1 of the other slot, whose short G3 / G1 are issued between the taps.  The
+// issue order is static, so all weight matrices stream through one ring of bulk copies in program
+// order.  Operand buffers are double-buffered by block parity so a neighbour can push the halo rows
+// of block i+1 while block i's taps are still reading.
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace vqae {
+namespace {
+
+using namespace tc;
+
+constexpr int RS_C = 64, RS_TH = 8, RS_W = 32, RS_H = 32, RS_CL = RS_H / RS_TH;
+constexpr int RS_PR = RS_TH + 2;                        // rows per stored column (with halo rows)
+constexpr int RS_NPIX = (RS_W + 2) * RS_PR;             // 340 stored pixels per operand buffer
+constexpr uint32_t RS_LBO = RS_NPIX * 16;               // k-chunk (8 channels) stride
+constexpr uint32_t RS_SBO = RS_PR * 16;                 // 8-row group stride = one column
+constexpr uint32_t RS_BUF = (RS_C / 8) * RS_LBO;        // 43 520 B per (slot, parity)
+constexpr uint32_t RS_WMAT = RS_C * RS_C * 2;           // 8 KB per weight matrix
+constexpr uint32_t RS_WLBO = RS_C * 16;
+constexpr int RS_RING = 6;
+constexpr uint32_t RS_HALO_BYTES = (RS_W + 2) * RS_C * 2;  // one halo row incl. wrap-around columns
+constexpr int RS_NW = 16;                               // worker warps
+constexpr int RS_THREADS = RS_NW * 32 + 64;             // + MMA warp + weight-producer warp
+constexpr uint32_t RS_OFF_W = 4 * RS_BUF;
+constexpr uint32_t RS_OFF_BAR = RS_OFF_W + RS_RING * RS_WMAT;
+constexpr uint32_t RS_SMEM = RS_OFF_BAR + 256;
+static_assert(RS_SMEM <= 232448, "shared memory budget");
+
+struct ResidentArgs {
+    const float* x;               // NHWC fp32 [B,32,32,64]
+    float* out;                   // NHWC fp32 [B,32,32,64] (may alias x)
+    const __nv_bfloat16* w;       // [n_blocks][11]: W1 | W2 tap 0..8 | scale*W3, each [k-chunk][n][8]
+    const float* scal;            // [n_blocks][8] = b1a b1b b2a b2b b3a b3b b4 scale   (device)
+    int n_blocks, n_img;
+    int split1, split2;           // G3 of the other slot is issued after tap split1, its G1 after split2
+    long long* prof;              // optional [RS_PROF_HR][32] clock64 stamps of CTA 0 (profiling aid)
+};
+constexpr int RS_PROF_HR0 = 20, RS_PROF_HR = 8;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;"
+                 ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cta_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+// 16 bytes into a peer CTA's shared memory through the async proxy (the proxy tcgen05.mma reads
+// operands with), completing 16 transaction bytes on the peer's mbarrier: no fences on either side
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint32_t cluster_bar) {
+    asm volatile(
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::
+            "r"(cluster_addr),
+        "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_bar)
+        : "memory");
+}
+// wait with a watchdog: a protocol error traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    uint32_t spins = 0;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();
+    } while (!done);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// Issue order of the nine taps: the three dy = 0 taps need no halo row and go first, so the pushes of
+// the neighbours (DSMEM moves ~20 B/clk) overlap them; then dy = -1 (row from above), dy = +1 (below).
+__device__ __forceinline__ int tap_of(int i) { return i < 3 ? i + 3 : (i < 6 ? i - 3 : i); }
+
+// The static issue schedule, shared by the three roles.  Half-round hr (from -1): slot a = hr & 1
+// runs the nine taps of its step ja = hr >> 1; the other slot b gets G3 of step jprev and G1 of step
+// jprev + 1 in between (slot 1 lags slot 0 by half a block).
+struct HalfRound {
+    int a, b, ja, jprev;
+    bool g2, g3, g1;
+};
+__device__ __forceinline__ HalfRound half_round(int hr, int T0, int T1) {
+    HalfRound h;
+    h.a = hr & 1;
+    h.b = h.a ^ 1;
+    h.ja = hr >> 1;
+    h.jprev = h.a ? h.ja : h.ja - 1;
+    const int Ta = h.a ? T1 : T0, Tb = h.b ? T1 : T0;
+    h.g2 = h.ja >= 0 && h.ja < Ta;
+    h.g3 = h.jprev >= 0 && h.jprev < Tb;
+    h.g1 = h.jprev + 1 < Tb;
+    return h;
+}
+
+__global__ void __cluster_dims__(RS_CL, 1, 1) __launch_bounds__(RS_THREADS, 1)
+trunk_resident_tc_kernel(ResidentArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sW = sbase + RS_OFF_W;
+    const uint32_t bar0 = sbase + RS_OFF_BAR;
+    // barrier map (8 B each): acc[2] | wrk[2] | halo[slot][dir][parity] (8) | full[RING] | empty[RING]
+    const uint32_t bar_acc = bar0, bar_wrk = bar0 + 16, bar_halo = bar0 + 32;
+    const uint32_t bar_full = bar0 + 96, bar_empty = bar_full + 8 * RS_RING;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 96 + 16 * RS_RING);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t leader = lane == 0;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x / RS_CL;                 // one image pair per cluster
+    const int n = a.n_blocks;
+    const int img0 = 2 * pair, img1 = 2 * pair + 1;
+    const int T0 = img0 < a.n_img ? n : 0, T1 = img1 < a.n_img ? n : 0;
+    const int hr_last = 2 * (T0 > T1 ? T0 : T1);
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_acc + 8 * s, 1);
+            mbar_init(bar_wrk + 8 * s, RS_NW);
+        }
+        for (int i = 0; i < 8; ++i) mbar_init(bar_halo + 8 * i, 1);
+        for (int s = 0; s < RS_RING; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == RS_NW) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    cluster_sync_all();                                  // peers' barriers are initialised
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(128, RS_C);
+
+    if (warp == RS_NW + 1) {
+        // ---------------- weight producer: one ring, the MMA warp's issue order -----------------
+        if (lane == 0) {
+            int cnt = 0;
+            auto push = [&](int blk, int m) {
+                const int slot = cnt % RS_RING;
+                if (cnt >= RS_RING) mbar_wait_wd(bar_empty + 8 * slot, ((cnt / RS_RING) - 1) & 1);
+                mbar_arrive_expect_tx(bar_full + 8 * slot, RS_WMAT);
+                bulk_g2s(sW + slot * RS_WMAT,
+                         reinterpret_cast<const uint8_t*>(a.w) + ((size_t)blk * 11 + m) * RS_WMAT,
+                         RS_WMAT, bar_full + 8 * slot);
+                ++cnt;
+            };
+            for (int hr = -1; hr <= hr_last; ++hr) {
+                const HalfRound h = half_round(hr, T0, T1);
+                const int blk2 = h.g2 ? h.ja % n : 0;
+                if (h.g2) for (int i = 0; i < a.split1; ++i) push(blk2, 1 + tap_of(i));
+                if (h.g3) push(h.jprev % n, 10);
+                if (h.g2) for (int i = a.split1; i < a.split2; ++i) push(blk2, 1 + tap_of(i));
+                if (h.g1) push((h.jprev + 1) % n, 0);
+                if (h.g2) for (int i = a.split2; i < 9; ++i) push(blk2, 1 + tap_of(i));
+            }
+        }
+    } else if (warp == RS_NW) {
+        // ---------------- MMA issue warp ---------------------------------------------------------
+        int wcnt = 0;
+        uint32_t wrk_par = 0;                            // bit s: parity of bar_wrk[s] to wait for next
+        const uint64_t dW = make_desc(sW, RS_WLBO, 128);
+        // A operand of M-tile m in buffer (slot, parity): own pixels start at column 16m + 1, row 1
+        auto a_desc = [&](int slot, int par, int m, int shift_px) -> uint64_t {
+            const uint32_t addr = sbase + (uint32_t)(2 * slot + par) * RS_BUF +
+                                  (uint32_t)(((16 * m + 1) * RS_PR + 1 + shift_px) * 16);
+            return make_desc(addr, RS_LBO, RS_SBO);
+        };
+        auto wait_wrk = [&](int s) {
+            mbar_wait_wd(bar_wrk + 8 * s, (wrk_par >> s) & 1);
+            wrk_par ^= 1u << s;
+            tc_fence_after_sync();
+        };
+        // one weight matrix against both M-tiles of a slot: D(+)= A(shift) . W^T
+        auto gemm = [&](int slot, int par, int shift_px, uint32_t d_col, bool acc_first) {
+            const int rs = wcnt % RS_RING;
+            mbar_wait_wd(bar_full + 8 * rs, (wcnt / RS_RING) & 1);
+            tc_fence_after_sync();
+            const uint64_t dWm = dW + (uint64_t)((rs * RS_WMAT) >> 4);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const uint64_t dA = a_desc(slot, par, m, shift_px);
+#pragma unroll
+                for (int ks = 0; ks < RS_C / 16; ++ks)
+                    umma_bf16(tmem_base + d_col + m * RS_C, dA + (uint64_t)((ks * 2 * RS_LBO) >> 4),
+                              dWm + (uint64_t)((ks * 2 * RS_WLBO) >> 4), idesc,
+                              (acc_first || ks > 0) ? 1u : 0u, leader);
+            }
+            umma_commit(bar_empty + 8 * rs, leader);
+            ++wcnt;
+        };
+        for (int hr = -1; hr <= hr_last; ++hr) {
+            const HalfRound h = half_round(hr, T0, T1);
+            const bool pf = a.prof && blockIdx.x == 0 && lane == 0 && hr >= RS_PROF_HR0 &&
+                            hr < RS_PROF_HR0 + RS_PROF_HR;
+            long long* pp = a.prof + (hr - RS_PROF_HR0) * 32;
+            if (pf) pp[0] = clock64();
+            const uint32_t Ra = h.a * 256, Da = Ra + 128, Rb = h.b * 256, Db = Rb + 128;
+            const int para = h.ja & 1;
+            const uint32_t hb = bar_halo + 8 * (h.a * 4 + para);
+            const uint32_t hp = (h.ja >> 1) & 1;
+            auto taps = [&](int i0, int i1) {
+                for (int i = i0; i < i1; ++i) {
+                    if (i == 3) mbar_wait_wd(hb, hp);            // halo row from the CTA above
+                    if (i == 6) mbar_wait_wd(hb + 16, hp);       // halo row from the CTA below
+                    const int t = tap_of(i);
+                    gemm(h.a, para, (t % 3 - 1) * RS_PR + (t / 3 - 1), Da, i > 0);
+                }
+            };
+            if (h.g2) {
+                if (leader) {                            // 34 pixels x 128 B from each neighbour
+                    mbar_arrive_expect_tx(hb, RS_HALO_BYTES);
+                    mbar_arrive_expect_tx(hb + 16, RS_HALO_BYTES);
+                }
+                wait_wrk(h.a);                           // own U rows written (E1)
+                if (pf) pp[1] = clock64();
+                taps(0, a.split1);
+            }
+            if (pf) pp[2] = clock64();
+            if (h.g3) {                                  // R += V . (scale W3)^T
+                wait_wrk(h.b);
+                if (pf) pp[3] = clock64();
+                gemm(h.b, h.jprev & 1, 0, Rb, true);
+                umma_commit(bar_acc + 8 * h.b, leader);
+            }
+            if (h.g2) taps(a.split1, a.split2);
+            if (pf) pp[4] = clock64();
+            if (h.g1) {                                  // D = A1 . W1^T
+                wait_wrk(h.b);
+                if (pf) pp[5] = clock64();
+                gemm(h.b, (h.jprev + 1) & 1, 0, Db, false);
+                umma_commit(bar_acc + 8 * h.b, leader);
+            }
+            if (h.g2) {
+                taps(a.split2, 9);
+                umma_commit(bar_acc + 8 * h.a, leader);
+            }
+            if (pf) pp[6] = clock64();
+            __syncwarp();
+        }
+    } else {
+        // ---------------- workers: one pixel x 32 channels per thread and phase -------------------
+        const int q4 = warp & 3, mt = (warp >> 2) & 1, chh = warp >> 3;
+        const int col = 16 * mt + 4 * q4 + (lane >> 3), row = lane & 7;
+        const uint32_t t_off = ((uint32_t)(q4 * 32) << 16) + mt * RS_C + chh * 32;
+        const uint32_t pix_own = (uint32_t)((col + 1) * RS_PR + row + 1) * 16 + (uint32_t)(chh * 4) * RS_LBO;
+        // wrap-around duplicate of a boundary column (circular padding): column 0 -> stored column 33,
+        // column 31 -> stored column 0
+        const bool wrap = col == 0 || col == RS_W - 1;
+        const uint32_t pix_wrap = (uint32_t)((col == 0 ? (RS_W + 1) : 0) * RS_PR + row + 1) * 16 +
+                                  (uint32_t)(chh * 4) * RS_LBO;
+        // halo pushes: my row 0 is row 8 of the CTA above, my row 7 is row -1 of the CTA below
+        const bool push = row == 0 || row == RS_TH - 1;
+        const uint32_t nb_rank = row == 0 ? (rank + RS_CL - 1) % RS_CL : (rank + 1) % RS_CL;
+        const int nb_row = row == 0 ? RS_TH + 1 : 0;     // stored row index in the neighbour's buffer
+        const uint32_t nb_base = mapa_u32(sbase, nb_rank);
+        const uint32_t nb_own = (uint32_t)((col + 1) * RS_PR + nb_row) * 16 + (uint32_t)(chh * 4) * RS_LBO;
+        const uint32_t nb_wrap = (uint32_t)((col == 0 ? (RS_W + 1) : 0) * RS_PR + nb_row) * 16 +
+                                 (uint32_t)(chh * 4) * RS_LBO;
+        const uint32_t nb_bar = mapa_u32(bar_halo + (row == 0 ? 16 : 0), nb_rank);
+        const size_t g_pix = ((size_t)(rank * RS_TH + row) * RS_W + col) * RS_C + chh * 32;
+
+        uint32_t acc_par = 0;                            // bit s: parity of bar_acc[s] to wait for next
+        float cum0 = 0.f, cum1 = 0.f;                    // running sum of bias4 per slot
+        auto wait_acc = [&](int s) {
+            mbar_wait_wd(bar_acc + 8 * s, (acc_par >> s) & 1);
+            acc_par ^= 1u << s;
+            tc_fence_after_sync();
+        };
+        auto signal_wrk = [&](int s, long long* st = nullptr) {
+            if (st) st[0] = clock64();
+            tc_fence_before_sync();
+            fence_proxy_async_smem();
+            if (st) st[1] = clock64();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_wrk + 8 * s);
+        };
+
+        for (int hr = -1; hr <= hr_last; ++hr) {
+            const HalfRound h = half_round(hr, T0, T1);
+            const int b = h.b;
+            const bool pf = a.prof && blockIdx.x == 0 && tid == 0 && hr >= RS_PROF_HR0 &&
+                            hr < RS_PROF_HR0 + RS_PROF_HR;
+            long long* pp = a.prof + (hr - RS_PROF_HR0) * 32;
+            if (pf) pp[8] = clock64();
+            const uint32_t Rb = tmem_base + b * 256 + t_off, Db = Rb + 128;
+            // the scalars of both blocks this half-round touches, fetched ahead of the first wait
+            const int blk_p = h.g3 ? h.jprev % n : 0, blk_n = h.g1 ? (h.jprev + 1) % n : 0;
+            const float4 sp1 = __ldg(reinterpret_cast<const float4*>(a.scal + blk_p * 8) + 1);
+            const float4 sn0 = __ldg(reinterpret_cast<const float4*>(a.scal + blk_n * 8));
+            if (h.g3) {
+                const int blk = blk_p;
+                // ---- E2: V over U (own pixels) ----
+                {
+                    const float b3a = sp1.x, b3b = sp1.y;
+                    wait_acc(b);                         // nine taps of step jprev complete
+                    if (pf) pp[9] = clock64();
+                    float v[32];
+                    tmem_ld32(Db, v);
+                    tmem_ld_wait();
+                    const uint32_t dst = sbase + (uint32_t)(2 * b + (h.jprev & 1)) * RS_BUF + pix_own;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st_cta_v4(dst + j * RS_LBO, act_pack8(v + 8 * j, b3a, b3b));
+                    signal_wrk(b);
+                    if (pf) pp[10] = clock64();
+                }
+                // ---- after G3: the residual holds x_{blk+1} - sum(bias4) ----
+                wait_acc(b);
+                if (pf) pp[11] = clock64();
+                const float b4 = sp1.z;
+                if (b) cum1 += b4; else cum0 += b4;
+                if (blk == n - 1) {
+                    const int img = (b ? img1 : img0);
+                    const float cum = b ? cum1 : cum0;
+                    float v[32];
+                    tmem_ld32(Rb, v);
+                    tmem_ld_wait();
+                    float4* o = reinterpret_cast<float4*>(a.out + (size_t)img * RS_H * RS_W * RS_C + g_pix);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        o[j] = make_float4(v[4 * j] + cum, v[4 * j + 1] + cum, v[4 * j + 2] + cum,
+                                           v[4 * j + 3] + cum);
+                    if (b) cum1 = 0.f; else cum0 = 0.f;
+                }
+            }
+            if (h.g1) {
+                const int j1 = h.jprev + 1, blk = blk_n;
+                const uint32_t buf = (uint32_t)(2 * b + (j1 & 1)) * RS_BUF;
+                // ---- P: A1 from the residual (first block of an image: from global memory) ----
+                {
+                    float v[32];
+                    if (blk == 0) {
+                        const int img = (b ? img1 : img0);
+                        const float4* s4 = reinterpret_cast<const float4*>(
+                            a.x + (size_t)img * RS_H * RS_W * RS_C + g_pix);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = __ldg(s4 + j);
+                            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                        }
+                        tmem_st32(Rb, v);
+                        tmem_st_wait();
+                    } else {
+                        tmem_ld32(Rb, v);
+                        tmem_ld_wait();
+                    }
+                    if (pf) pp[16] = clock64();
+                    const float pre = (b ? cum1 : cum0) + sn0.x, post = sn0.y;
+                    const uint32_t dst = sbase + buf + pix_own;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st_cta_v4(dst + j * RS_LBO, act_pack8(v + 8 * j, pre, post));
+                    signal_wrk(b, pf ? pp + 17 : nullptr);
+                    if (pf) pp[12] = clock64();
+                }
+                // ---- E1: U over A1, wrap columns, halo rows into the neighbours ----
+                {
+                    const float b2a = sn0.z, b2b = sn0.w;
+                    wait_acc(b);
+                    if (pf) pp[13] = clock64();
+                    float v[32];
+                    tmem_ld32(Db, v);
+                    tmem_ld_wait();
+                    if (pf) pp[19] = clock64();
+                    uint4 u[4];
+                    const uint32_t dst = sbase + buf + pix_own, dw = sbase + buf + pix_wrap;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        u[j] = act_pack8(v + 8 * j, b2a, b2b);
+                        st_cta_v4(dst + j * RS_LBO, u[j]);
+                        if (wrap) st_cta_v4(dw + j * RS_LBO, u[j]);
+                    }
+                    if (pf) pp[20] = clock64();
+                    signal_wrk(b, pf ? pp + 21 : nullptr);
+                    if (pf) pp[14] = clock64();
+                    // halo pushes after the local hand-over: the dy = 0 taps run meanwhile.  My row 0
+                    // completes bytes on the upper CTA's "from below" barrier, my row 7 on the lower
+                    // CTA's "from above" barrier: halo[slot][dir][parity], dir 0 = from above
+                    if (push) {
+                        const uint32_t nbar = nb_bar + 8 * (b * 4 + (j1 & 1));
+                        const uint32_t dn = nb_base + buf + nb_own, dnw = nb_base + buf + nb_wrap;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            st_async_v4(dn + j * RS_LBO, u[j], nbar);
+                            if (wrap) st_async_v4(dnw + j * RS_LBO, u[j], nbar);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();                                  // no CTA leaves while a peer may still push
+    if (warp == RS_NW) tmem_dealloc(tmem_base, 512);
+}
+
+// like pack_same_block_kernel (tc_kernels.cu) with branch_conv3 pre-multiplied by the Fixup scale
+__global__ void __launch_bounds__(256)
+pack_resident_block_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
+                           const float* __restrict__ w3, float scale, __nv_bfloat16* __restrict__ out) {
+    constexpr int per = RS_C * RS_C;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 11 * per) return;
+    const int m = i / per, r = i % per;
+    const int kc = r / (RS_C * 8), nn = (r / 8) % RS_C, k = kc * 8 + (r % 8);
+    float v;
+    if (m == 0) v = w1[nn * RS_C + k];
+    else if (m == 10) v = scale * w3[nn * RS_C + k];
+    else v = w2[((size_t)nn * RS_C + k) * 9 + (m - 1)];
+    out[i] = __float2bfloat16_rn(v);
+}
+
+}  // namespace
+
+static long long* g_resident_prof = nullptr;
+void trunk_resident_set_prof(long long* dev_ptr) { g_resident_prof = dev_ptr; }
+
+bool trunk_resident_supported(int64_t B, int H, int W, int C) {
+    return B > 0 && H == RS_H && W == RS_W && C == RS_C;
+}
+
+// resident clusters the device can hold at once (each runs one image pair)
+int trunk_resident_max_clusters(int* out) {
+    VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(RS_CL * 64);
+    cfg.blockDim = dim3(RS_THREADS);
+    cfg.dynamicSmemBytes = RS_SMEM;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = RS_CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    VQAE_CUDA_TRY(cudaOccupancyMaxActiveClusters(out, trunk_resident_tc_kernel, &cfg));
+    return VQAE_OK;
+}
+
+int pack_resident_block_bf16(const float* w1, const float* w2, const float* w3, int C, float scale,
+                             void* packed, cudaStream_t stream) {
+    if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
+    if (C != RS_C) return VQAE_ERR_UNSUPPORTED;
+    const int total = 11 * RS_C * RS_C;
+    pack_resident_block_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(
+        w1, w2, w3, scale, reinterpret_cast<__nv_bfloat16*>(packed));
+    return check_launch();
+}
+
+int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, const float* scalars_dev,
+                      int n_blocks, int64_t B, int H, int W, int C, cudaStream_t stream) {
+    if (!x || !out || !w_packed_all || !scalars_dev || B <= 0 || n_blocks <= 0) return VQAE_ERR_BAD_ARG;
+    if (!trunk_resident_supported(B, H, W, C)) return VQAE_ERR_UNSUPPORTED;
+    if ((B + 1) / 2 * RS_CL > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+        attr_set = true;
+    }
+    ResidentArgs a;
+    a.x = x; a.out = out;
+    a.w = reinterpret_cast<const __nv_bfloat16*>(w_packed_all);
+    a.scal = scalars_dev;
+    a.n_blocks = n_blocks; a.n_img = (int)B;
+    a.prof = g_resident_prof;
+    a.split1 = 2; a.split2 = 5;
+    if (const char* e = getenv("VQAE_RS_SPLIT")) {       // tuning aid: "s1,s2" with 0 <= s1 <= s2 <= 9
+        int s1 = 2, s2 = 5;
+        if (sscanf(e, "%d,%d", &s1, &s2) == 2 && s1 >= 0 && s1 <= s2 && s2 <= 9) {
+            a.split1 = s1; a.split2 = s2;
+        }
+    }
+    const unsigned grid = (unsigned)((B + 1) / 2) * RS_CL;
+    trunk_resident_tc_kernel<<<grid, RS_THREADS, RS_SMEM, stream>>>(a);
+    return check_launch();
+}
+
+}  // namespace vqae

@@ -115,6 +115,7 @@ class PackedFixup:
         self.params = p
         # tcgen05 path: bf16 operand pack of a 'same' block at the trunk width (C = 64)
         self.tc_weights = None
+        self.tc_weights_res = None
         self.tc_scalars = None
         if self.mode == L.MODE_SAME and self.c_in in (8, 16, 32, 64, 128) and \
                 self.c_branch == self.c_in and self.c_out == self.c_in:
@@ -130,6 +131,12 @@ class PackedFixup:
             sc = self.scalars
             self.tc_scalars = (C.c_float * 8)(*[float(sc[k]) for k in (
                 "bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "scale")])
+            if self.c_in == 64:
+                # image-resident trunk kernel: branch_conv3 pre-multiplied by the Fixup scale
+                self.tc_weights_res = torch.empty(11 * cp * cp, dtype=torch.bfloat16, device=dev)
+                L.check(lib.vqae_pack_resident_block_bf16(
+                    _ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), self.c_in, float(sc["scale"]),
+                    _ptr(self.tc_weights_res), _stream(dev)), "vqae_pack_resident_block_bf16")
 
         if self.mode == L.MODE_DOWN and self.c_in in (8, 16, 32) and \
                 self.c_branch == 2 * self.c_in and self.c_out == 2 * self.c_in:
@@ -193,6 +200,9 @@ def pack_blocks(blocks: Sequence) -> List[PackedFixup]:
 # single calls
 # ----------------------------------------------------------------------------------------------
 PRECISIONS = ("fp32", "bf16")
+# C = 64 runs of 'same' blocks at 32 x 32 use the image-resident kernel (tc_resident.cu); False selects
+# the persistent tile-chain kernel (tc_chain.cu) for A/B measurements (profiles/step_breakdown.py)
+TRUNK_RESIDENT = True
 
 
 def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
@@ -230,11 +240,12 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
 class PackedChain:
     """Back-to-back bf16 weight packs + device scalar table of a run of tcgen05 'same' blocks."""
 
-    def __init__(self, run: Sequence[PackedFixup]):
+    def __init__(self, run: Sequence[PackedFixup], resident: bool = False):
         dev = run[0].tc_weights.device
         self.n = len(run)
         self.c = run[0].c_in
-        self.weights = torch.cat([pk.tc_weights for pk in run])
+        self.resident = resident
+        self.weights = torch.cat([pk.tc_weights_res if resident else pk.tc_weights for pk in run])
         self.scalars = torch.tensor([[float(v) for v in pk.tc_scalars] for pk in run],
                                     dtype=torch.float32).to(dev)
 
@@ -242,7 +253,8 @@ class PackedChain:
 def _chain_runs(packed: Sequence[PackedFixup], h: int, w: int, batch: int = 1 << 30
                 ) -> List[Tuple[int, int]]:
     """Maximal runs [start, stop) of >= 2 consecutive tcgen05 'same' blocks of equal width for
-    which the persistent chain kernel is built (vqae_same_chain_supported)."""
+    which a multi-block kernel is built (vqae_trunk_resident_supported: C = 64 at 32 x 32, any
+    batch; else vqae_same_chain_supported)."""
     lib = L.load()
     runs, i, n = [], 0, len(packed)
     while i < n:
@@ -253,8 +265,10 @@ def _chain_runs(packed: Sequence[PackedFixup], h: int, w: int, batch: int = 1 <<
             while j < n and packed[j].mode == L.MODE_SAME and packed[j].c_in == pk.c_in \
                     and packed[j].tc_ok(hh, ww):
                 j += 1
+            resident = TRUNK_RESIDENT and pk.tc_weights_res is not None and \
+                lib.vqae_trunk_resident_supported(batch, hh, ww, pk.c_in)
             if (j - i >= 2 or pk.chain_only) and \
-                    lib.vqae_same_chain_supported(batch, hh, ww, pk.c_in):
+                    (resident or lib.vqae_same_chain_supported(batch, hh, ww, pk.c_in)):
                 runs.append((i, j))
             i = j
         else:
@@ -266,7 +280,8 @@ def _chain_runs(packed: Sequence[PackedFixup], h: int, w: int, batch: int = 1 <<
 def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "fp32",
                     chain_cache: Optional[dict] = None) -> Tensor:
     """A Sequential chain of PreActFixupResBlocks on an NHWC fp32 tensor.  In "bf16" mode runs of
-    consecutive tcgen05 'same' blocks execute as ONE persistent launch (vqae_same_chain_bf16)."""
+    consecutive tcgen05 'same' blocks execute as ONE launch: image-resident (vqae_trunk_resident_bf16)
+    for C = 64 at 32 x 32, the persistent tile chain (vqae_same_chain_bf16) otherwise."""
     if precision != "bf16":
         for pk in packed:
             h = fixup_forward_nhwc(pk, h, precision=precision)
@@ -281,11 +296,20 @@ def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "
             i += 1
             continue
         j = runs[i]
-        key = (i, j, id(packed[i]))
+        b, hh, ww, c = h.shape
+        resident = TRUNK_RESIDENT and bool(lib.vqae_trunk_resident_supported(b, hh, ww, c))
+        key = (i, j, id(packed[i]), resident)
         chain = cache.get(key)
         if chain is None:
-            chain = cache[key] = PackedChain(packed[i:j])
-        b, hh, ww, c = h.shape
+            chain = cache[key] = PackedChain(packed[i:j], resident)
+        if resident:
+            out = torch.empty_like(h)
+            L.check(lib.vqae_trunk_resident_bf16(
+                _ptr(h), _ptr(out), _ptr(chain.weights), _ptr(chain.scalars), chain.n, b, hh, ww, c,
+                _stream(h.device)), "vqae_trunk_resident_bf16")
+            h = out
+            i = j
+            continue
         bufs = [torch.empty_like(h), torch.empty_like(h)]
         fbytes = lib.vqae_same_chain_flag_bytes(chain.n, b)
         flags = torch.empty(fbytes, dtype=torch.uint8, device=h.device)

@@ -1,0 +1,56 @@
+"""Launch the image-resident trunk kernel (vqae_trunk_resident_bf16) at the bench shape (timing / ncu).
+usage: python profiles/run_resident.py [n_blocks=54] [reps=3] [batch=256]"""
+import sys
+from pathlib import Path
+REPO = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(REPO / "2d-vq-ae-2_b200")]
+import torch  # noqa: E402
+from vqae_b200 import _lib as L  # noqa: E402
+from vqae_b200 import engine as E  # noqa: E402
+
+H, W, C = 32, 32, 64
+nblk = int(sys.argv[1]) if len(sys.argv) > 1 else 54
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+dev = torch.device("cuda:0")
+lib = L.load()
+st = E._stream(dev)
+gen = torch.Generator().manual_seed(7)
+packs = []
+for i in range(nblk):
+    ws = [(torch.randn(C, C, k, k, generator=gen) * 0.05).to(dev) for k in (1, 3, 1)]
+    pk = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
+    L.check(lib.vqae_pack_resident_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, 0.2,
+                                              E._ptr(pk), st), "pack")
+    packs.append(pk)
+w_all = torch.cat(packs)
+scal = torch.tensor([[0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.2]] * nblk, dtype=torch.float32).to(dev)
+print("resident clusters per device:", lib.vqae_trunk_resident_max_clusters())
+xs = [torch.randn(B, H, W, C, device=dev) for _ in range(2)]
+y = torch.empty(B, H, W, C, device=dev)
+for i in range(reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(lib.vqae_trunk_resident_bf16(E._ptr(xs[i % 2]), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B,
+                                         H, W, C, st), "resident")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"resident {nblk} blocks, batch {B}: {ms:.3f} ms, {ms / nblk * 1e3:.1f} us/block, "
+          f"{2.0 * B * H * W * C * C * 11 * nblk / ms / 1e9:.1f} TFLOP/s")
+
+# phase clocks of CTA 0, eight steady-state half-rounds
+prof = torch.zeros(8 * 32, dtype=torch.int64, device=dev)
+lib.vqae_trunk_resident_set_profile(E._ptr(prof))
+L.check(lib.vqae_trunk_resident_bf16(E._ptr(xs[0]), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, H, W, C, st), "resident")
+torch.cuda.synchronize()
+lib.vqae_trunk_resident_set_profile(None)
+p = prof.cpu().view(8, 32)
+t0 = int(p[0, 0])
+print("MMA warp:  hr_start  G2wait_done  taps0-2_issued  Vwait_done  G3+taps3-5_issued  A1wait_done  all_issued")
+print("workers :  hr_start  G2_done  E2_signalled  G3_done  P_signalled  G1_done  E1_signalled")
+for r in range(8):
+    print("hr%2d mma" % r, " ".join("%7d" % (int(v) - t0) for v in p[r, 0:7]))
+    print("     wrk", " ".join("%7d" % (int(v) - t0) for v in p[r, 8:15]))
+    print("     P: ld_done %d stores_done %d fence_done %d | E1: ld_done %d own_stores %d pushes_done %d fence_done %d" % tuple(
+        int(v) - t0 for v in p[r, 16:23]))

@@ -101,7 +101,7 @@ def test_encoder_bf16_agreement_with_fp32():
 
 @pytest.mark.parametrize("c,hw,batch,n", [(64, 32, 80, 6), (64, 32, 75, 3), (64, 32, 200, 11),
                                           (64, 64, 20, 4), (64, 32, 3, 5), (32, 64, 4, 3)])
-def test_persistent_chain_bit_identical_to_block_by_block(c, hw, batch, n):
+def test_persistent_chain_bit_identical_to_block_by_block(c, hw, batch, n, monkeypatch):
     """vqae_same_chain_bf16 (one persistent launch, tiles of block i+1 ordered after their producers
     in block i by release/acquire counters) against n launches of vqae_same_block_bf16."""
     from vqae_b200.config import pre_activation_fixup
@@ -115,6 +115,7 @@ def test_persistent_chain_bit_identical_to_block_by_block(c, hw, batch, n):
         blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=20 + i, regime="perturbed",
                                               n_layers=12))
         blocks.append(blk.to(DEV))
+    monkeypatch.setattr(E, "TRUNK_RESIDENT", False)  # this test is about the tile-chain kernel
     packed = E.pack_blocks(blocks)
     x = torch.randn(batch, hw, hw, c, device=DEV)
     h = x
@@ -129,6 +130,86 @@ def test_persistent_chain_bit_identical_to_block_by_block(c, hw, batch, n):
         assert E.launch_count() - before == (1 if chained else n)
         assert torch.equal(h, hc)
     assert H.rel_err(hc, E.run_blocks_nhwc(packed, x, "fp32")) < 5e-3
+
+
+def _same_blocks(c, n, seed0):
+    from vqae_b200.config import pre_activation_fixup
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blocks = []
+    for i in range(n):
+        blk = PreActFixupResBlock(in_channels=c, out_channels=c, mode="same", **conf).eval()
+        blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=seed0 + i, regime="perturbed",
+                                              n_layers=12))
+        blocks.append(blk.to(DEV))
+    return blocks
+
+
+@pytest.mark.parametrize("batch,n", [(1, 2), (2, 2), (3, 5), (8, 3), (80, 6), (151, 2), (256, 11)])
+def test_resident_trunk_vs_block_by_block_and_fp32(batch, n):
+    """vqae_trunk_resident_bf16 (residual stream in tensor memory, 4-CTA clusters, halo rows through
+    distributed shared memory, branch_conv3 accumulating into the residual) against n launches of
+    vqae_same_block_bf16 (same bf16 operands up to the rounding of scale * W3) and against the fp32
+    exact path.  Tolerance: 1e-2 of the branch magnitude (north_star bf16 bar)."""
+    packed = E.pack_blocks(_same_blocks(64, n, 60))
+    x = torch.randn(batch, 32, 32, 64, generator=torch.Generator().manual_seed(batch + n)).to(DEV)
+    h = x
+    for pk in packed:
+        h = E.fixup_forward_nhwc(pk, h, precision="bf16")
+    y32 = E.run_blocks_nhwc(packed, x, "fp32")
+    before = E.launch_count()
+    y = E.run_blocks_nhwc(packed, x, "bf16")
+    torch.cuda.synchronize()
+    assert E.launch_count() - before == 1
+    branch = float((y32 - x).abs().max())
+    # two bf16 evaluations that round scale * W3 differently: each is within the bf16 bar of fp32
+    assert float((y - h).abs().max()) / branch < 8e-3, float((y - h).abs().max()) / branch
+    assert float((y - y32).abs().max()) / branch < 1e-2
+    assert H.rel_err(y, y32) < 5e-3
+    for _ in range(2):                               # deterministic, no state left behind
+        assert torch.equal(y, E.run_blocks_nhwc(packed, x, "bf16"))
+    # in place (out aliases x) gives the same bits
+    xc = x.clone()
+    lib = L.load()
+    chain = E.PackedChain(packed, resident=True)
+    L.check(lib.vqae_trunk_resident_bf16(E._ptr(xc), E._ptr(xc), E._ptr(chain.weights),
+                                         E._ptr(chain.scalars), chain.n, batch, 32, 32, 64,
+                                         E._stream(xc.device)), "vqae_trunk_resident_bf16")
+    torch.cuda.synchronize()
+    assert torch.equal(xc, y)
+
+
+def test_resident_trunk_halo_and_wrap_exactness():
+    """Identity-like weights make the 3x3 stage a pure circular shift: every pixel of the output must
+    equal its shifted neighbour, which checks the halo rows pushed between CTAs, the wrap-around
+    columns and the tap -> descriptor-shift mapping without any tolerance."""
+    blocks = _same_blocks(64, 1, 90)
+    blk = blocks[0]
+    with torch.no_grad():
+        for name in ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4"):
+            getattr(blk, name).zero_()
+        blk.scale.fill_(1.0)
+        eye = torch.eye(64, device=DEV)
+        blk.branch_conv1.weight.copy_(eye[:, :, None, None])
+        blk.branch_conv3.weight.copy_(eye[:, :, None, None])
+    for ky in range(3):
+        for kx in range(3):
+            with torch.no_grad():
+                blk.branch_conv2.weight.zero_()
+                blk.branch_conv2.weight[:, :, ky, kx] = eye
+            packed = E.pack_blocks([blk, blk])[:1]
+            # positive bf16-exact inputs: ELU is the identity, bf16 rounding is exact
+            x = torch.randint(1, 200, (3, 32, 32, 64), device=DEV).float() / 8.0
+            chain = E.PackedChain(packed, resident=True)
+            out = torch.empty_like(x)
+            L.check(L.load().vqae_trunk_resident_bf16(
+                E._ptr(x), E._ptr(out), E._ptr(chain.weights), E._ptr(chain.scalars), 1, 3, 32, 32,
+                64, E._stream(x.device)), "vqae_trunk_resident_bf16")
+            torch.cuda.synchronize()
+            ref = x + torch.roll(x, shifts=(-(ky - 1), -(kx - 1)), dims=(1, 2))
+            assert torch.equal(out, ref), (ky, kx, float((out - ref).abs().max()))
 
 
 @pytest.mark.parametrize("hw,batch,n", [(32, 3, 1), (32, 40, 3), (96, 1, 2), (64, 2, 2)])
