@@ -186,35 +186,38 @@ def time_dominant_kernel(dev, peaks, precision: str):
     st = E._stream(dev)
     peak = peaks["bf16_tflops_sustained"]
     if precision == "bf16":
-        # the trunk as the step runs it: ONE persistent launch over 50 blocks (pre_enc_layers)
-        nblk = 50
+        # the trunk as the step runs it: ONE image-resident launch over 54 blocks (the 4 post layers
+        # of the last DownBlock + the 50 pre_enc_layers)
+        nblk = 54
         gen = torch.Generator().manual_seed(7)
         packs, scal = [], []
         for i in range(nblk):
             ws = [(torch.randn(C, C, k, k, generator=gen) * 0.05).to(dev) for k in (1, 3, 1)]
             pk = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
-            L.check(lib.vqae_pack_same_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C,
-                                                  E._ptr(pk), st), "pack")
+            L.check(lib.vqae_pack_resident_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C,
+                                                      0.2, E._ptr(pk), st), "pack")
             packs.append(pk)
             scal.append([0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.2])
         w_all = torch.cat(packs)
         scal_dev = torch.tensor(scal, dtype=torch.float32).to(dev)
-        fbytes = lib.vqae_same_chain_flag_bytes(nblk, B)
-        flags = torch.empty(fbytes, dtype=torch.uint8, device=dev)
-        assert lib.vqae_same_chain_supported(B, H, W, C)
+        assert lib.vqae_trunk_resident_supported(B, H, W, C)
 
         def launch(i):
-            L.check(lib.vqae_same_chain_bf16(E._ptr(xs[i % 2]), E._ptr(ys[0]), E._ptr(ys[1]),
-                                             E._ptr(w_all), E._ptr(scal_dev), E._ptr(flags), fbytes,
-                                             nblk, B, H, W, C, st), "vqae_same_chain_bf16")
+            L.check(lib.vqae_trunk_resident_bf16(E._ptr(xs[i % nbuf]), E._ptr(ys[i % nbuf]),
+                                                 E._ptr(w_all), E._ptr(scal_dev), nblk, B, H, W, C, st),
+                    "vqae_trunk_resident_bf16")
         ms = _event_time(launch, 5, dev)
         flops = 2.0 * B * H * W * C * C * 11 * nblk
-        name = ("same_chain_tc_kernel (50 fused PreActFixupResBlocks 'same' per launch, C=64, 32x32; "
-                "tcgen05 bf16, persistent)")
-        note = ("whole 50-block trunk per launch: per tile 1x1 + 3x3 circular + 1x1 implicit GEMMs on "
-                "tcgen05 with bf16 operands, fp32 TMEM accumulation, fp32 residual stream through L2 "
-                "(ping-pong buffers 2 x 67 MB); timed alone with CUDA events on the launch stream; "
-                "includes the 13 KB memset of the completion counters")
+        name = ("trunk_resident_tc_kernel (54 fused PreActFixupResBlocks 'same' per launch, C=64, "
+                "32x32; tcgen05 bf16, fp32 residual resident in tensor memory, 4-CTA clusters)")
+        note = ("whole 54-block run per launch: per 8x32-pixel tile 1x1 + 3x3 circular + 1x1 implicit "
+                "GEMMs on tcgen05 (bf16 operands, fp32 TMEM accumulation); the residual stream stays in "
+                "tensor memory and branch_conv3 accumulates into it, halo rows go through distributed "
+                "shared memory, so HBM traffic is one read + one write of the activations per launch; "
+                "every tcgen05.mma is 128x64x16 (N = C = 64), which the tensor pipe issues at 84 "
+                "cycles against 32 at full rate (profiles/mma_bench_shift.py), i.e. the kernel's own "
+                "ceiling is 38 % of the dense peak; timed alone with CUDA events on the launch stream, "
+                f"{nbuf} rotating buffer pairs")
     else:
         w = E.pack_conv_weight(torch.randn(C, C, 3, 3, device=dev) * 0.05)
 
@@ -228,8 +231,11 @@ def time_dominant_kernel(dev, peaks, precision: str):
         note = ("fp32 CUDA-core FFMA kernel measured against the bf16 tensor peak; timed alone "
                 "with CUDA events on the launch stream, 4 rotating buffer pairs")
     achieved = flops / (ms * 1e-3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the committed
+    # ncu --set full capture (profiles/r1_trunk_resident_ncu_summary.txt): 72.4 MB + 20.1 MB
+    traffic = 92.49e6 if precision == "bf16" else None
     return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops, "note": note}
 
 
