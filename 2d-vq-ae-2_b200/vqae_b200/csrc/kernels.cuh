@@ -75,6 +75,9 @@ int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, cons
 
 int tc_mma_bench(int N, int layout_type, int reps, int a_stride_rows, long long* out,
                  cudaStream_t stream);
+// tc_bench.cu
+int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, long long* out,
+                  cudaStream_t stream);
 // tc_down.cu
 size_t down_block_pack_elems(int CI);
 int pack_down_block_bf16(const float* w1, const float* w2, const float* w3, const float* ws, int CI,

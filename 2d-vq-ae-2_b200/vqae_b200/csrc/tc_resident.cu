@@ -20,14 +20,14 @@
 // (SBO = 160 B) are one M-tile, so an 8 x 32 tile is exactly two M-tiles -- no padded pixels are
 // multiplied -- and tap (dy, dx) is the shift (dx * 10 + dy) * 16 B.
 // Each CTA runs TWO slots (two different images, 2 x (128 residual + 128 accumulator) = 512 TMEM
-// columns) half a block out of phase: while the nine taps of one slot occupy the tensor pipe, the
-// workers run E2 -> P -> E1 of the other slot, whose short G3 / G1 are issued between the taps.  The
-// issue order is static, so all weight matrices stream through one ring of bulk copies in program
-// order.  Operand buffers are double-buffered by block parity so a neighbour can push the halo rows
-// of block i+1 while block i's taps are still reading.
-#include <cstdio>
-#include <cstdlib>
-
+// columns) half a block out of phase: while the nine taps of one slot occupy the tensor pipe, the 16
+// worker warps run E2 -> P -> E1 of the other slot.  Every (slot, M-tile) has its OWN MMA issue warp:
+// one issuing thread only gets a 128 x 64 x 16 MMA every ~80 cycles out of the tensor pipe, several
+// streams together reach 48 (profiles/mma_bench_issuers.py).  Each slot streams its weight matrices
+// through its own ring of bulk copies, fed by one producer thread that never blocks on either ring.
+// There is ONE operand buffer per slot (A1, U and V overwrite each other in place); a neighbour pushes
+// the halo rows of block i+1 only after this CTA has signalled that the taps of block i have read the
+// old rows (free barriers), which leaves 2 x 64 KB of shared memory for the weight rings.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -45,13 +45,15 @@ constexpr uint32_t RS_SBO = RS_PR * 16;                 // 8-row group stride = 
 constexpr uint32_t RS_BUF = (RS_C / 8) * RS_LBO;        // 43 520 B per (slot, parity)
 constexpr uint32_t RS_WMAT = RS_C * RS_C * 2;           // 8 KB per weight matrix
 constexpr uint32_t RS_WLBO = RS_C * 16;
-constexpr int RS_RING = 6;
+constexpr int RS_RING = 8;                              // weight matrices in flight per slot
+constexpr int RS_IPS = 1;                               // MMA issue warps per slot (1 or 2)
+constexpr int RS_ISSUERS = 2 * RS_IPS;
 constexpr uint32_t RS_HALO_BYTES = (RS_W + 2) * RS_C * 2;  // one halo row incl. wrap-around columns
 constexpr int RS_NW = 16;                               // worker warps
-constexpr int RS_THREADS = RS_NW * 32 + 64;             // + MMA warp + weight-producer warp
-constexpr uint32_t RS_OFF_W = 4 * RS_BUF;
-constexpr uint32_t RS_OFF_BAR = RS_OFF_W + RS_RING * RS_WMAT;
-constexpr uint32_t RS_SMEM = RS_OFF_BAR + 256;
+constexpr int RS_THREADS = (RS_NW + RS_ISSUERS + 1) * 32;  // + MMA issue warps + weight producer
+constexpr uint32_t RS_OFF_W = 2 * RS_BUF;
+constexpr uint32_t RS_OFF_BAR = RS_OFF_W + 2 * RS_RING * RS_WMAT;
+constexpr uint32_t RS_SMEM = RS_OFF_BAR + 512;
 static_assert(RS_SMEM <= 232448, "shared memory budget");
 
 struct ResidentArgs {
@@ -60,7 +62,6 @@ struct ResidentArgs {
     const __nv_bfloat16* w;       // [n_blocks][11]: W1 | W2 tap 0..8 | scale*W3, each [k-chunk][n][8]
     const float* scal;            // [n_blocks][8] = b1a b1b b2a b2b b3a b3b b4 scale   (device)
     int n_blocks, n_img;
-    int split1, split2;           // G3 of the other slot is issued after tap split1, its G1 after split2
     long long* prof;              // optional [RS_PROF_HR][32] clock64 stamps of CTA 0 (profiling aid)
 };
 constexpr int RS_PROF_HR0 = 20, RS_PROF_HR = 8;
@@ -83,6 +84,26 @@ __device__ __forceinline__ void st_cta_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),
                  "r"(v.z), "r"(v.w)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    uint32_t spins = 0;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();
+    } while (!done);
 }
 // 16 bytes into a peer CTA's shared memory through the async proxy (the proxy tcgen05.mma reads
 // operands with), completing 16 transaction bytes on the peer's mbarrier: no fences on either side
@@ -110,6 +131,19 @@ __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
         if (!done && ++spins > (1u << 26)) __trap();
     } while (!done);
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
     asm volatile(
@@ -131,9 +165,9 @@ __device__ __forceinline__ void tmem_st_wait() {
 // the neighbours (DSMEM moves ~20 B/clk) overlap them; then dy = -1 (row from above), dy = +1 (below).
 __device__ __forceinline__ int tap_of(int i) { return i < 3 ? i + 3 : (i < 6 ? i - 3 : i); }
 
-// The static issue schedule, shared by the three roles.  Half-round hr (from -1): slot a = hr & 1
-// runs the nine taps of its step ja = hr >> 1; the other slot b gets G3 of step jprev and G1 of step
-// jprev + 1 in between (slot 1 lags slot 0 by half a block).
+// The workers' static schedule.  Half-round hr (from -1): while slot a = hr & 1 runs the nine taps of
+// its step ja = hr >> 1, the workers serve the other slot b: E2 of step jprev, then P and E1 of step
+// jprev + 1 (slot 1 lags slot 0 by half a block).
 struct HalfRound {
     int a, b, ja, jprev;
     bool g2, g3, g1;
@@ -157,10 +191,13 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sW = sbase + RS_OFF_W;
     const uint32_t bar0 = sbase + RS_OFF_BAR;
-    // barrier map (8 B each): acc[2] | wrk[2] | halo[slot][dir][parity] (8) | full[RING] | empty[RING]
-    const uint32_t bar_acc = bar0, bar_wrk = bar0 + 16, bar_halo = bar0 + 32;
-    const uint32_t bar_full = bar0 + 96, bar_empty = bar_full + 8 * RS_RING;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 96 + 16 * RS_RING);
+    // barrier map (8 B each): acc[2] | wrk[2] | halo[slot][dir] (4): row data landed (dir 0 = from the
+    // CTA above) | free[slot][dir] (4): the neighbour has consumed my last push (dir 0 = the CTA above) |
+    // full[2][RING] | empty[2][RING]
+    const uint32_t bar_acc = bar0, bar_wrk = bar0 + 16, bar_halo = bar0 + 32, bar_free = bar0 + 64;
+    const uint32_t bar_full = bar0 + 96, bar_empty = bar_full + 16 * RS_RING;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 96 + 32 * RS_RING);
+    static_assert(96 + 32 * RS_RING + 4 <= 512, "barrier region");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -174,13 +211,16 @@ trunk_resident_tc_kernel(ResidentArgs a) {
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_acc + 8 * s, 1);
+            mbar_init(bar_acc + 8 * s, RS_IPS);
             mbar_init(bar_wrk + 8 * s, RS_NW);
         }
-        for (int i = 0; i < 8; ++i) mbar_init(bar_halo + 8 * i, 1);
-        for (int s = 0; s < RS_RING; ++s) {
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bar_halo + 8 * i, 1);
+            mbar_init(bar_free + 8 * i, 1);
+        }
+        for (int s = 0; s < 2 * RS_RING; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, RS_IPS);
         }
         fence_mbar_init();
     }
@@ -192,109 +232,129 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint32_t idesc = make_idesc_bf16(128, RS_C);
 
-    if (warp == RS_NW + 1) {
-        // ---------------- weight producer: one ring, the MMA warp's issue order -----------------
+    if (warp == RS_NW + RS_ISSUERS) {
+        // ---------------- weight producer: one ring per slot, each in its issuers' order ----------
+        // One thread serves both rings without ever blocking on either (a slot whose issuers wait for
+        // the workers must not starve the other slot's taps).
         if (lane == 0) {
-            int cnt = 0;
-            auto push = [&](int blk, int m) {
-                const int slot = cnt % RS_RING;
-                if (cnt >= RS_RING) mbar_wait_wd(bar_empty + 8 * slot, ((cnt / RS_RING) - 1) & 1);
-                mbar_arrive_expect_tx(bar_full + 8 * slot, RS_WMAT);
-                bulk_g2s(sW + slot * RS_WMAT,
-                         reinterpret_cast<const uint8_t*>(a.w) + ((size_t)blk * 11 + m) * RS_WMAT,
-                         RS_WMAT, bar_full + 8 * slot);
-                ++cnt;
-            };
-            for (int hr = -1; hr <= hr_last; ++hr) {
-                const HalfRound h = half_round(hr, T0, T1);
-                const int blk2 = h.g2 ? h.ja % n : 0;
-                if (h.g2) for (int i = 0; i < a.split1; ++i) push(blk2, 1 + tap_of(i));
-                if (h.g3) push(h.jprev % n, 10);
-                if (h.g2) for (int i = a.split1; i < a.split2; ++i) push(blk2, 1 + tap_of(i));
-                if (h.g1) push((h.jprev + 1) % n, 0);
-                if (h.g2) for (int i = a.split2; i < 9; ++i) push(blk2, 1 + tap_of(i));
+            int cnt[2] = {0, 0};
+            const int tot[2] = {T0 * 11, T1 * 11};
+            uint32_t spins = 0;
+            while (cnt[0] < tot[0] || cnt[1] < tot[1]) {
+                bool progress = false;
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    const int c = cnt[sl];
+                    if (c >= tot[sl]) continue;
+                    const int rs = c % RS_RING;
+                    const uint32_t be = bar_empty + 8 * (sl * RS_RING + rs);
+                    if (c >= RS_RING && !mbar_test(be, ((c / RS_RING) - 1) & 1)) continue;
+                    const int blk = (c / 11) % n, q = c % 11;
+                    const int m = q == 0 ? 0 : (q == 10 ? 10 : 1 + tap_of(q - 1));
+                    const uint32_t bf = bar_full + 8 * (sl * RS_RING + rs);
+                    mbar_arrive_expect_tx(bf, RS_WMAT);
+                    bulk_g2s(sW + (sl * RS_RING + rs) * RS_WMAT,
+                             reinterpret_cast<const uint8_t*>(a.w) + ((size_t)blk * 11 + m) * RS_WMAT,
+                             RS_WMAT, bf);
+                    cnt[sl] = c + 1;
+                    progress = true;
+                }
+                if (progress) spins = 0;
+                else {
+                    __nanosleep(64);                     // do not steal issue slots from the workers
+                    if (++spins > (1u << 24)) __trap();
+                }
             }
         }
-    } else if (warp == RS_NW) {
-        // ---------------- MMA issue warp ---------------------------------------------------------
+    } else if (warp >= RS_NW) {
+        // ---------------- MMA issue warps: one per (slot, M-tile group) ---------------------------
+        // A single issuing thread gets one 128 x 64 x 16 MMA per ~80 cycles out of the tensor pipe; two
+        // or more streams reach 48 (the shared-memory operand rate), profiles/mma_bench_issuers.py.
+        const int iw = warp - RS_NW;
+        const int slot = iw / RS_IPS, mh = iw % RS_IPS;
+        constexpr int MPI = 2 / RS_IPS;                  // M-tiles per issuer
+        const int T = slot ? T1 : T0;
+        const uint32_t R = slot * 256, D = R + 128;
         int wcnt = 0;
-        uint32_t wrk_par = 0;                            // bit s: parity of bar_wrk[s] to wait for next
-        const uint64_t dW = make_desc(sW, RS_WLBO, 128);
+        uint32_t wrk_par = 0;
+        const uint64_t dW = make_desc(sW + slot * RS_RING * RS_WMAT, RS_WLBO, 128);
         // A operand of M-tile m in buffer (slot, parity): own pixels start at column 16m + 1, row 1
-        auto a_desc = [&](int slot, int par, int m, int shift_px) -> uint64_t {
-            const uint32_t addr = sbase + (uint32_t)(2 * slot + par) * RS_BUF +
+        auto a_desc = [&](int m, int shift_px) -> uint64_t {
+            const uint32_t addr = sbase + (uint32_t)slot * RS_BUF +
                                   (uint32_t)(((16 * m + 1) * RS_PR + 1 + shift_px) * 16);
             return make_desc(addr, RS_LBO, RS_SBO);
         };
-        auto wait_wrk = [&](int s) {
-            mbar_wait_wd(bar_wrk + 8 * s, (wrk_par >> s) & 1);
-            wrk_par ^= 1u << s;
+        auto wait_wrk = [&]() {
+            mbar_wait_wd(bar_wrk + 8 * slot, wrk_par);
+            wrk_par ^= 1u;
             tc_fence_after_sync();
         };
-        // one weight matrix against both M-tiles of a slot: D(+)= A(shift) . W^T
-        auto gemm = [&](int slot, int par, int shift_px, uint32_t d_col, bool acc_first) {
+        // one weight matrix against this issuer's M-tiles: D(+)= A(shift) . W^T
+        auto gemm = [&](int shift_px, uint32_t d_col, bool acc_first) {
             const int rs = wcnt % RS_RING;
-            mbar_wait_wd(bar_full + 8 * rs, (wcnt / RS_RING) & 1);
+            mbar_wait_wd(bar_full + 8 * (slot * RS_RING + rs), (wcnt / RS_RING) & 1);
             tc_fence_after_sync();
             const uint64_t dWm = dW + (uint64_t)((rs * RS_WMAT) >> 4);
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const uint64_t dA = a_desc(slot, par, m, shift_px);
+            for (int mi = 0; mi < MPI; ++mi) {
+                const int m = mh * MPI + mi;
+                const uint64_t dA = a_desc(m, shift_px);
 #pragma unroll
                 for (int ks = 0; ks < RS_C / 16; ++ks)
                     umma_bf16(tmem_base + d_col + m * RS_C, dA + (uint64_t)((ks * 2 * RS_LBO) >> 4),
                               dWm + (uint64_t)((ks * 2 * RS_WLBO) >> 4), idesc,
                               (acc_first || ks > 0) ? 1u : 0u, leader);
             }
-            umma_commit(bar_empty + 8 * rs, leader);
+            umma_commit(bar_empty + 8 * (slot * RS_RING + rs), leader);
             ++wcnt;
         };
-        for (int hr = -1; hr <= hr_last; ++hr) {
-            const HalfRound h = half_round(hr, T0, T1);
-            const bool pf = a.prof && blockIdx.x == 0 && lane == 0 && hr >= RS_PROF_HR0 &&
-                            hr < RS_PROF_HR0 + RS_PROF_HR;
-            long long* pp = a.prof + (hr - RS_PROF_HR0) * 32;
+        const uint32_t hb = bar_halo + 16 * slot;
+        // the neighbours' "my push has been consumed" barriers: I am the CTA below my upper neighbour
+        // (its free[slot][1]) and the CTA above my lower neighbour (its free[slot][0])
+        const uint32_t up_free = mapa_u32(bar_free + 16 * slot + 8, (rank + RS_CL - 1) % RS_CL);
+        const uint32_t dn_free = mapa_u32(bar_free + 16 * slot, (rank + 1) % RS_CL);
+        for (int j = 0; j < T; ++j) {
+            const bool pf = a.prof && blockIdx.x == 0 && lane == 0 && iw == 0 && j >= RS_PROF_HR0 / 2 &&
+                            j < (RS_PROF_HR0 + RS_PROF_HR) / 2;
+            long long* pp = a.prof + (j - RS_PROF_HR0 / 2) * 64;
+            // ---- G1: D = A1 . W1^T ----
             if (pf) pp[0] = clock64();
-            const uint32_t Ra = h.a * 256, Da = Ra + 128, Rb = h.b * 256, Db = Rb + 128;
-            const int para = h.ja & 1;
-            const uint32_t hb = bar_halo + 8 * (h.a * 4 + para);
-            const uint32_t hp = (h.ja >> 1) & 1;
-            auto taps = [&](int i0, int i1) {
-                for (int i = i0; i < i1; ++i) {
-                    if (i == 3) mbar_wait_wd(hb, hp);            // halo row from the CTA above
-                    if (i == 6) mbar_wait_wd(hb + 16, hp);       // halo row from the CTA below
-                    const int t = tap_of(i);
-                    gemm(h.a, para, (t % 3 - 1) * RS_PR + (t / 3 - 1), Da, i > 0);
-                }
-            };
-            if (h.g2) {
-                if (leader) {                            // 34 pixels x 128 B from each neighbour
-                    mbar_arrive_expect_tx(hb, RS_HALO_BYTES);
-                    mbar_arrive_expect_tx(hb + 16, RS_HALO_BYTES);
-                }
-                wait_wrk(h.a);                           // own U rows written (E1)
-                if (pf) pp[1] = clock64();
-                taps(0, a.split1);
+            wait_wrk();
+            if (pf) pp[1] = clock64();
+            gemm(0, D, false);
+            umma_commit(bar_acc + 8 * slot, leader);
+            // ---- G2: nine taps; dy = 0 first, then the halo rows as they arrive ----
+            const uint32_t hp = j & 1;
+            if (mh == 0 && leader) {                     // 34 pixels x 128 B from each neighbour
+                mbar_arrive_expect_tx(hb, RS_HALO_BYTES);
+                mbar_arrive_expect_tx(hb + 8, RS_HALO_BYTES);
             }
             if (pf) pp[2] = clock64();
-            if (h.g3) {                                  // R += V . (scale W3)^T
-                wait_wrk(h.b);
-                if (pf) pp[3] = clock64();
-                gemm(h.b, h.jprev & 1, 0, Rb, true);
-                umma_commit(bar_acc + 8 * h.b, leader);
+            wait_wrk();                                  // own U rows written (E1)
+            if (pf) pp[3] = clock64();
+            for (int i = 0; i < 9; ++i) {
+                if (i == 3) mbar_wait_wd(hb, hp);        // halo row from the CTA above
+                if (i == 6) mbar_wait_wd(hb + 8, hp);    // halo row from the CTA below
+                const int t = tap_of(i);
+                gemm((t % 3 - 1) * RS_PR + (t / 3 - 1), D, i > 0);
             }
-            if (h.g2) taps(a.split1, a.split2);
+            umma_commit(bar_acc + 8 * slot, leader);
             if (pf) pp[4] = clock64();
-            if (h.g1) {                                  // D = A1 . W1^T
-                wait_wrk(h.b);
-                if (pf) pp[5] = clock64();
-                gemm(h.b, (h.jprev + 1) & 1, 0, Db, false);
-                umma_commit(bar_acc + 8 * h.b, leader);
+            if (mh == 0) {
+                // the taps have read the halo rows: hand them back to the neighbours for the next block
+                // (phase 3j + 1 of bar_acc: G1, G2, G3 commits per step)
+                mbar_wait_wd(bar_acc + 8 * slot, (3 * j + 1) & 1);
+                if (leader && j + 1 < T) {
+                    mbar_arrive_remote(up_free);
+                    mbar_arrive_remote(dn_free);
+                }
+                __syncwarp();
             }
-            if (h.g2) {
-                taps(a.split2, 9);
-                umma_commit(bar_acc + 8 * h.a, leader);
-            }
+            // ---- G3: R += V . (scale W3)^T ----
+            wait_wrk();
+            if (pf) pp[5] = clock64();
+            gemm(0, R, true);
+            umma_commit(bar_acc + 8 * slot, leader);
             if (pf) pp[6] = clock64();
             __syncwarp();
         }
@@ -317,7 +377,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         const uint32_t nb_own = (uint32_t)((col + 1) * RS_PR + nb_row) * 16 + (uint32_t)(chh * 4) * RS_LBO;
         const uint32_t nb_wrap = (uint32_t)((col == 0 ? (RS_W + 1) : 0) * RS_PR + nb_row) * 16 +
                                  (uint32_t)(chh * 4) * RS_LBO;
-        const uint32_t nb_bar = mapa_u32(bar_halo + (row == 0 ? 16 : 0), nb_rank);
+        const uint32_t nb_bar = mapa_u32(bar_halo + (row == 0 ? 8 : 0), nb_rank);
         const size_t g_pix = ((size_t)(rank * RS_TH + row) * RS_W + col) * RS_C + chh * 32;
 
         uint32_t acc_par = 0;                            // bit s: parity of bar_acc[s] to wait for next
@@ -358,7 +418,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                     float v[32];
                     tmem_ld32(Db, v);
                     tmem_ld_wait();
-                    const uint32_t dst = sbase + (uint32_t)(2 * b + (h.jprev & 1)) * RS_BUF + pix_own;
+                    const uint32_t dst = sbase + (uint32_t)b * RS_BUF + pix_own;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) st_cta_v4(dst + j * RS_LBO, act_pack8(v + 8 * j, b3a, b3b));
                     signal_wrk(b);
@@ -385,7 +445,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             }
             if (h.g1) {
                 const int j1 = h.jprev + 1, blk = blk_n;
-                const uint32_t buf = (uint32_t)(2 * b + (j1 & 1)) * RS_BUF;
+                const uint32_t buf = (uint32_t)b * RS_BUF;
                 // ---- P: A1 from the residual (first block of an image: from global memory) ----
                 {
                     float v[32];
@@ -434,9 +494,11 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                     if (pf) pp[14] = clock64();
                     // halo pushes after the local hand-over: the dy = 0 taps run meanwhile.  My row 0
                     // completes bytes on the upper CTA's "from below" barrier, my row 7 on the lower
-                    // CTA's "from above" barrier: halo[slot][dir][parity], dir 0 = from above
+                    // CTA's "from above" barrier: halo[slot][dir], dir 0 = from above
                     if (push) {
-                        const uint32_t nbar = nb_bar + 8 * (b * 4 + (j1 & 1));
+                        // the neighbour's taps of the previous block must have read the old row
+                        if (j1 > 0) mbar_wait_cluster(bar_free + 16 * b + (row == 0 ? 0 : 8), (j1 - 1) & 1);
+                        const uint32_t nbar = nb_bar + 16 * b;
                         const uint32_t dn = nb_base + buf + nb_own, dnw = nb_base + buf + nb_wrap;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -523,13 +585,6 @@ int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, cons
     a.scal = scalars_dev;
     a.n_blocks = n_blocks; a.n_img = (int)B;
     a.prof = g_resident_prof;
-    a.split1 = 2; a.split2 = 5;
-    if (const char* e = getenv("VQAE_RS_SPLIT")) {       // tuning aid: "s1,s2" with 0 <= s1 <= s2 <= 9
-        int s1 = 2, s2 = 5;
-        if (sscanf(e, "%d,%d", &s1, &s2) == 2 && s1 >= 0 && s1 <= s2 && s2 <= 9) {
-            a.split1 = s1; a.split2 = s2;
-        }
-    }
     const unsigned grid = (unsigned)((B + 1) / 2) * RS_CL;
     trunk_resident_tc_kernel<<<grid, RS_THREADS, RS_SMEM, stream>>>(a);
     return check_launch();

@@ -47,7 +47,7 @@ torch.cuda.synchronize()
 lib.vqae_trunk_resident_set_profile(None)
 p = prof.cpu().view(8, 32)
 t0 = int(p[0, 0])
-print("MMA warp:  hr_start  G2wait_done  taps0-2_issued  Vwait_done  G3+taps3-5_issued  A1wait_done  all_issued")
+print("issuer 0 (slot 0, even rows): step_start  A1wait_done  G1_issued  Uwait_done  taps_issued  Vwait_done  G3_issued")
 print("workers :  hr_start  G2_done  E2_signalled  G3_done  P_signalled  G1_done  E1_signalled")
 for r in range(8):
     print("hr%2d mma" % r, " ".join("%7d" % (int(v) - t0) for v in p[r, 0:7]))
