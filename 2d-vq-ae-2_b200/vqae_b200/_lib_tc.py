@@ -12,7 +12,7 @@ _fp = C.POINTER(C.c_float)
 
 SIGNATURES: dict = {
     "vqae_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
-    "vqae_tc_mma_bench2": (_i, [_i, _i, _i, _i, _i, _vp, _vp]),
+    "vqae_tc_mma_bench2": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
     "vqae_tc_selftest": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vqae_pack_same_block_bf16": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "vqae_same_block_bf16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),

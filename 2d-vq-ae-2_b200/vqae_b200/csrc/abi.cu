@@ -278,9 +278,9 @@ int vqae_tc_mma_bench(int n, int layout_type, int reps, int a_stride_rows, long 
     return tc_mma_bench(n, layout_type, reps, a_stride_rows, out2, (cudaStream_t)stream);
 }
 
-int vqae_tc_mma_bench2(int m, int n, int reps, int n_issuers, int ctas_per_sm, long long* out_per_cta,
-                       void* stream) {
-    return tc_mma_bench2(m, n, reps, n_issuers, ctas_per_sm, out_per_cta, (cudaStream_t)stream);
+int vqae_tc_mma_bench2(int m, int n, int reps, int n_issuers, int ctas_per_sm, int mode,
+                       long long* out_per_cta, void* stream) {
+    return tc_mma_bench2(m, n, reps, n_issuers, ctas_per_sm, mode, out_per_cta, (cudaStream_t)stream);
 }
 
 size_t vqae_down_block_pack_elems(int c_in) { return down_block_pack_elems(c_in); }

@@ -76,7 +76,7 @@ int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, cons
 int tc_mma_bench(int N, int layout_type, int reps, int a_stride_rows, long long* out,
                  cudaStream_t stream);
 // tc_bench.cu
-int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, long long* out,
+int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, int mode, long long* out,
                   cudaStream_t stream);
 // tc_down.cu
 size_t down_block_pack_elems(int CI);

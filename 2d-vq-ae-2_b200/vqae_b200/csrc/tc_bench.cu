@@ -10,7 +10,7 @@ namespace {
 using namespace tc;
 
 __global__ void __launch_bounds__(256)
-tc_mma_bench2_kernel(int M, int N, int reps, int n_issuers, int tmem_cols, long long* out) {
+tc_mma_bench2_kernel(int M, int N, int reps, int n_issuers, int tmem_cols, int mode, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[8];
     __shared__ uint32_t tmem_base_s;
@@ -31,8 +31,11 @@ tc_mma_bench2_kernel(int M, int N, int reps, int n_issuers, int tmem_cols, long 
     const long long t0 = clock64();
     if (warp < n_issuers) {
         const uint32_t idesc = make_idesc_bf16(M, N);
-        const uint32_t sa = smem_u32(smem), sb = sa + 32 * 1024;
-        const uint64_t ad = make_desc(sa, 129 * 16, 128), bd = make_desc(sb, N * 16, 128);
+        // mode bit 0: every issuer reads its OWN A and B regions (else all issuers share them);
+        // mode bit 1: 8-row groups of A 160 B apart (the resident kernel's column-major tile) else 128 B
+        const uint32_t a_off = (mode & 1) ? warp * 5 * 1024 : 0, b_off = (mode & 1) ? warp * 2 * 1024 : 0;
+        const uint32_t sa = smem_u32(smem) + a_off, sb = smem_u32(smem) + 32 * 1024 + b_off;
+        const uint64_t ad = make_desc(sa, 340 * 16, (mode & 2) ? 160 : 128), bd = make_desc(sb, N * 16, 128);
         const uint32_t d = tmem_base + warp * N;
         for (int r = 0; r < reps; ++r)
             umma_bf16(d, ad + (uint64_t)(((r % 5) * 16) >> 4), bd + (uint64_t)((r & 3) * 2), idesc, 1u,
@@ -52,7 +55,7 @@ tc_mma_bench2_kernel(int M, int N, int reps, int n_issuers, int tmem_cols, long 
 }
 }  // namespace
 
-int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, long long* out,
+int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, int mode, long long* out,
                   cudaStream_t stream) {
     if (!out || reps <= 0 || N < 16 || N > 256 || N % 16 || (M != 64 && M != 128) || n_issuers < 1 ||
         n_issuers > 8 || ctas_per_sm < 1 || ctas_per_sm > 4)
@@ -67,7 +70,7 @@ int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, long l
                         : (ctas_per_sm == 3 ? 70 * 1024 : 52 * 1024));
     VQAE_CUDA_TRY(cudaFuncSetAttribute(tc_mma_bench2_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_mma_bench2_kernel<<<sm_count * ctas_per_sm, 256, smem, stream>>>(M, N, reps, n_issuers, cols, out);
+    tc_mma_bench2_kernel<<<sm_count * ctas_per_sm, 256, smem, stream>>>(M, N, reps, n_issuers, cols, mode, out);
     return check_launch();
 }
 }  // namespace vqae

@@ -46,7 +46,7 @@ constexpr uint32_t RS_BUF = (RS_C / 8) * RS_LBO;        // 43 520 B per (slot, p
 constexpr uint32_t RS_WMAT = RS_C * RS_C * 2;           // 8 KB per weight matrix
 constexpr uint32_t RS_WLBO = RS_C * 16;
 constexpr int RS_RING = 8;                              // weight matrices in flight per slot
-constexpr int RS_IPS = 1;                               // MMA issue warps per slot (1 or 2)
+constexpr int RS_IPS = 2;                               // MMA issue warps per slot (1 or 2)
 constexpr int RS_ISSUERS = 2 * RS_IPS;
 constexpr uint32_t RS_HALO_BYTES = (RS_W + 2) * RS_C * 2;  // one halo row incl. wrap-around columns
 constexpr int RS_NW = 16;                               // worker warps
@@ -157,6 +157,24 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         "r"(r[30]), "r"(r[31])
         : "memory");
 }
+// 32 lanes x 8 columns (asynchronous until tcgen05.wait::ld)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                   "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -191,13 +209,19 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sW = sbase + RS_OFF_W;
     const uint32_t bar0 = sbase + RS_OFF_BAR;
-    // barrier map (8 B each): acc[2] | wrk[2] | halo[slot][dir] (4): row data landed (dir 0 = from the
-    // CTA above) | free[slot][dir] (4): the neighbour has consumed my last push (dir 0 = the CTA above) |
-    // full[2][RING] | empty[2][RING]
-    const uint32_t bar_acc = bar0, bar_wrk = bar0 + 16, bar_halo = bar0 + 32, bar_free = bar0 + 64;
-    const uint32_t bar_full = bar0 + 96, bar_empty = bar_full + 16 * RS_RING;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 96 + 32 * RS_RING);
-    static_assert(96 + 32 * RS_RING + 4 <= 512, "barrier region");
+    // barrier map (8 B each):
+    //   acc[slot][m]  (4)  MMA -> workers: G1 / G2 / G3 of M-tile m complete (tcgen05.commit)
+    //   wrk[slot][m]  (4)  workers -> MMA: A1 / V of M-tile m written (16 warps)
+    //   u[slot]       (2)  workers -> MMA: U of BOTH M-tiles written (the taps read across them)
+    //   halo[slot][dir] (4) row data from a neighbour landed (dir 0 = from the CTA above)
+    //   free[slot][dir] (4) the neighbour's taps have consumed my last push (dir 0 = the CTA above)
+    //   full[2][RING] | empty[2][RING]   weight rings
+    const uint32_t bar_acc = bar0, bar_wrk = bar0 + 32, bar_u = bar0 + 64, bar_halo = bar0 + 80;
+    const uint32_t bar_free = bar0 + 112;
+    const uint32_t bar_full = bar0 + 144, bar_empty = bar_full + 16 * RS_RING;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 144 + 32 * RS_RING);
+    static_assert(144 + 32 * RS_RING + 4 <= 512, "barrier region");
+    static_assert(RS_IPS == 2, "one MMA issue warp per (slot, M-tile)");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -210,14 +234,14 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const int hr_last = 2 * (T0 > T1 ? T0 : T1);
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_acc + 8 * s, RS_IPS);
-            mbar_init(bar_wrk + 8 * s, RS_NW);
-        }
         for (int i = 0; i < 4; ++i) {
+            mbar_init(bar_acc + 8 * i, 1);
+            mbar_init(bar_wrk + 8 * i, RS_NW);
             mbar_init(bar_halo + 8 * i, 1);
-            mbar_init(bar_free + 8 * i, 1);
+            mbar_init(bar_free + 8 * i, 2);              // both issue warps of the neighbour's slot
         }
+        mbar_init(bar_u, 2 * RS_NW);
+        mbar_init(bar_u + 8, 2 * RS_NW);
         for (int s = 0; s < 2 * RS_RING; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, RS_IPS);
@@ -271,40 +295,35 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         // A single issuing thread gets one 128 x 64 x 16 MMA per ~80 cycles out of the tensor pipe; two
         // or more streams reach 48 (the shared-memory operand rate), profiles/mma_bench_issuers.py.
         const int iw = warp - RS_NW;
-        const int slot = iw / RS_IPS, mh = iw % RS_IPS;
-        constexpr int MPI = 2 / RS_IPS;                  // M-tiles per issuer
+        const int slot = iw >> 1, m = iw & 1;
         const int T = slot ? T1 : T0;
-        const uint32_t R = slot * 256, D = R + 128;
+        const uint32_t R = slot * 256 + m * RS_C, D = R + 128;
         int wcnt = 0;
         uint32_t wrk_par = 0;
         const uint64_t dW = make_desc(sW + slot * RS_RING * RS_WMAT, RS_WLBO, 128);
-        // A operand of M-tile m in buffer (slot, parity): own pixels start at column 16m + 1, row 1
-        auto a_desc = [&](int m, int shift_px) -> uint64_t {
-            const uint32_t addr = sbase + (uint32_t)slot * RS_BUF +
-                                  (uint32_t)(((16 * m + 1) * RS_PR + 1 + shift_px) * 16);
-            return make_desc(addr, RS_LBO, RS_SBO);
-        };
+        // A operand of this M-tile: own pixels start at stored column 16m + 1, row 1
+        const uint32_t a_base = sbase + (uint32_t)slot * RS_BUF + (uint32_t)(((16 * m + 1) * RS_PR + 1) * 16);
+        const uint32_t b_acc = bar_acc + 8 * iw, b_wrk = bar_wrk + 8 * iw, b_u = bar_u + 8 * slot;
         auto wait_wrk = [&]() {
-            mbar_wait_wd(bar_wrk + 8 * slot, wrk_par);
+            mbar_wait_wd(b_wrk, wrk_par);
             wrk_par ^= 1u;
             tc_fence_after_sync();
         };
-        // one weight matrix against this issuer's M-tiles: D(+)= A(shift) . W^T
+        // one weight matrix against this M-tile: D(+)= A(shift) . W^T
+        long long ring_wait = 0;
         auto gemm = [&](int shift_px, uint32_t d_col, bool acc_first) {
             const int rs = wcnt % RS_RING;
+            const long long tw = a.prof ? clock64() : 0;
             mbar_wait_wd(bar_full + 8 * (slot * RS_RING + rs), (wcnt / RS_RING) & 1);
+            if (a.prof) ring_wait += clock64() - tw;
             tc_fence_after_sync();
             const uint64_t dWm = dW + (uint64_t)((rs * RS_WMAT) >> 4);
+            const uint64_t dA = make_desc(a_base + shift_px * 16, RS_LBO, RS_SBO);
 #pragma unroll
-            for (int mi = 0; mi < MPI; ++mi) {
-                const int m = mh * MPI + mi;
-                const uint64_t dA = a_desc(m, shift_px);
-#pragma unroll
-                for (int ks = 0; ks < RS_C / 16; ++ks)
-                    umma_bf16(tmem_base + d_col + m * RS_C, dA + (uint64_t)((ks * 2 * RS_LBO) >> 4),
-                              dWm + (uint64_t)((ks * 2 * RS_WLBO) >> 4), idesc,
-                              (acc_first || ks > 0) ? 1u : 0u, leader);
-            }
+            for (int ks = 0; ks < RS_C / 16; ++ks)
+                umma_bf16(tmem_base + d_col, dA + (uint64_t)((ks * 2 * RS_LBO) >> 4),
+                          dWm + (uint64_t)((ks * 2 * RS_WLBO) >> 4), idesc,
+                          (acc_first || ks > 0) ? 1u : 0u, leader);
             umma_commit(bar_empty + 8 * (slot * RS_RING + rs), leader);
             ++wcnt;
         };
@@ -322,78 +341,82 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             wait_wrk();
             if (pf) pp[1] = clock64();
             gemm(0, D, false);
-            umma_commit(bar_acc + 8 * slot, leader);
+            umma_commit(b_acc, leader);
             // ---- G2: nine taps; dy = 0 first, then the halo rows as they arrive ----
             const uint32_t hp = j & 1;
-            if (mh == 0 && leader) {                     // 34 pixels x 128 B from each neighbour
+            if (m == 0 && leader) {                      // 34 pixels x 128 B from each neighbour
                 mbar_arrive_expect_tx(hb, RS_HALO_BYTES);
                 mbar_arrive_expect_tx(hb + 8, RS_HALO_BYTES);
             }
             if (pf) pp[2] = clock64();
-            wait_wrk();                                  // own U rows written (E1)
+            mbar_wait_wd(b_u, hp);                       // U of both M-tiles written (E1)
+            tc_fence_after_sync();
             if (pf) pp[3] = clock64();
             for (int i = 0; i < 9; ++i) {
                 if (i == 3) mbar_wait_wd(hb, hp);        // halo row from the CTA above
                 if (i == 6) mbar_wait_wd(hb + 8, hp);    // halo row from the CTA below
                 const int t = tap_of(i);
+                if (pf) pp[23 + i] = clock64();
                 gemm((t % 3 - 1) * RS_PR + (t / 3 - 1), D, i > 0);
             }
-            umma_commit(bar_acc + 8 * slot, leader);
+            umma_commit(b_acc, leader);
             if (pf) pp[4] = clock64();
-            if (mh == 0) {
-                // the taps have read the halo rows: hand them back to the neighbours for the next block
-                // (phase 3j + 1 of bar_acc: G1, G2, G3 commits per step)
-                mbar_wait_wd(bar_acc + 8 * slot, (3 * j + 1) & 1);
-                if (leader && j + 1 < T) {
-                    mbar_arrive_remote(up_free);
-                    mbar_arrive_remote(dn_free);
-                }
-                __syncwarp();
+            // my taps have read the halo rows: hand them back to the neighbours for the next block
+            // (phase 3j + 1 of acc[slot][m]: G1, G2, G3 commits per step; their free barriers count
+            // both issue warps of the slot)
+            mbar_wait_wd(b_acc, (3 * j + 1) & 1);
+            if (pf) { pp[7] = clock64(); pp[20] = ring_wait; }
+            if (leader && j + 1 < T) {
+                mbar_arrive_remote(up_free);
+                mbar_arrive_remote(dn_free);
             }
+            __syncwarp();
             // ---- G3: R += V . (scale W3)^T ----
             wait_wrk();
             if (pf) pp[5] = clock64();
             gemm(0, R, true);
-            umma_commit(bar_acc + 8 * slot, leader);
+            umma_commit(b_acc, leader);
             if (pf) pp[6] = clock64();
             __syncwarp();
         }
     } else {
-        // ---------------- workers: one pixel x 32 channels per thread and phase -------------------
-        const int q4 = warp & 3, mt = (warp >> 2) & 1, chh = warp >> 3;
-        const int col = 16 * mt + 4 * q4 + (lane >> 3), row = lane & 7;
-        const uint32_t t_off = ((uint32_t)(q4 * 32) << 16) + mt * RS_C + chh * 32;
-        const uint32_t pix_own = (uint32_t)((col + 1) * RS_PR + row + 1) * 16 + (uint32_t)(chh * 4) * RS_LBO;
-        // wrap-around duplicate of a boundary column (circular padding): column 0 -> stored column 33,
-        // column 31 -> stored column 0
-        const bool wrap = col == 0 || col == RS_W - 1;
-        const uint32_t pix_wrap = (uint32_t)((col == 0 ? (RS_W + 1) : 0) * RS_PR + row + 1) * 16 +
-                                  (uint32_t)(chh * 4) * RS_LBO;
+        // ---------------- workers: per unit (slot, M-tile, phase) one pixel x 16 channels per thread --
+        // All 16 warps work on ONE M-tile at a time, so the MMA of M-tile 0 runs under the workers'
+        // pass over M-tile 1 and the G3 / G1 round trips disappear from the chain.
+        const int q4 = warp & 3, cq = warp >> 2;         // TMEM lane quarter, 16-column quarter
+        const int col0 = 4 * q4 + (lane >> 3), row = lane & 7;     // pixel inside M-tile 0
+        const uint32_t t_off = ((uint32_t)(q4 * 32) << 16) + cq * 16;
+        const uint32_t kc_off = (uint32_t)(cq * 2) * RS_LBO;
+        constexpr uint32_t M_PIX = 16 * RS_PR * 16;      // byte offset of M-tile 1's pixels (16 columns)
+        const uint32_t pix_own = (uint32_t)((col0 + 1) * RS_PR + row + 1) * 16 + kc_off;
+        // wrap-around duplicates (circular padding): column 0 (M-tile 0) -> stored column 33,
+        // column 31 (M-tile 1) -> stored column 0
+        const bool wrap0 = col0 == 0, wrap1 = col0 == 15;
+        const uint32_t pix_wrap0 = (uint32_t)((RS_W + 1) * RS_PR + row + 1) * 16 + kc_off;
+        const uint32_t pix_wrap1 = (uint32_t)(row + 1) * 16 + kc_off;
         // halo pushes: my row 0 is row 8 of the CTA above, my row 7 is row -1 of the CTA below
         const bool push = row == 0 || row == RS_TH - 1;
         const uint32_t nb_rank = row == 0 ? (rank + RS_CL - 1) % RS_CL : (rank + 1) % RS_CL;
         const int nb_row = row == 0 ? RS_TH + 1 : 0;     // stored row index in the neighbour's buffer
         const uint32_t nb_base = mapa_u32(sbase, nb_rank);
-        const uint32_t nb_own = (uint32_t)((col + 1) * RS_PR + nb_row) * 16 + (uint32_t)(chh * 4) * RS_LBO;
-        const uint32_t nb_wrap = (uint32_t)((col == 0 ? (RS_W + 1) : 0) * RS_PR + nb_row) * 16 +
-                                 (uint32_t)(chh * 4) * RS_LBO;
+        const uint32_t nb_own = (uint32_t)((col0 + 1) * RS_PR + nb_row) * 16 + kc_off;
+        const uint32_t nb_wrap0 = (uint32_t)((RS_W + 1) * RS_PR + nb_row) * 16 + kc_off;
+        const uint32_t nb_wrap1 = (uint32_t)nb_row * 16 + kc_off;
         const uint32_t nb_bar = mapa_u32(bar_halo + (row == 0 ? 8 : 0), nb_rank);
-        const size_t g_pix = ((size_t)(rank * RS_TH + row) * RS_W + col) * RS_C + chh * 32;
+        const size_t g_pix = ((size_t)(rank * RS_TH + row) * RS_W + col0) * RS_C + cq * 16;
 
-        uint32_t acc_par = 0;                            // bit s: parity of bar_acc[s] to wait for next
+        uint32_t acc_par = 0;                            // bit 2s+m: parity of acc[s][m] to wait for next
         float cum0 = 0.f, cum1 = 0.f;                    // running sum of bias4 per slot
-        auto wait_acc = [&](int s) {
-            mbar_wait_wd(bar_acc + 8 * s, (acc_par >> s) & 1);
-            acc_par ^= 1u << s;
+        auto wait_acc = [&](int sm) {
+            mbar_wait_wd(bar_acc + 8 * sm, (acc_par >> sm) & 1);
+            acc_par ^= 1u << sm;
             tc_fence_after_sync();
         };
-        auto signal_wrk = [&](int s, long long* st = nullptr) {
-            if (st) st[0] = clock64();
+        auto signal = [&](uint32_t bar) {
             tc_fence_before_sync();
             fence_proxy_async_smem();
-            if (st) st[1] = clock64();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_wrk + 8 * s);
+            if (lane == 0) mbar_arrive(bar);
         };
 
         for (int hr = -1; hr <= hr_last; ++hr) {
@@ -403,110 +426,131 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                             hr < RS_PROF_HR0 + RS_PROF_HR;
             long long* pp = a.prof + (hr - RS_PROF_HR0) * 32;
             if (pf) pp[8] = clock64();
-            const uint32_t Rb = tmem_base + b * 256 + t_off, Db = Rb + 128;
+            const uint32_t buf = sbase + (uint32_t)b * RS_BUF;
             // the scalars of both blocks this half-round touches, fetched ahead of the first wait
             const int blk_p = h.g3 ? h.jprev % n : 0, blk_n = h.g1 ? (h.jprev + 1) % n : 0;
             const float4 sp1 = __ldg(reinterpret_cast<const float4*>(a.scal + blk_p * 8) + 1);
             const float4 sn0 = __ldg(reinterpret_cast<const float4*>(a.scal + blk_n * 8));
             if (h.g3) {
-                const int blk = blk_p;
-                // ---- E2: V over U (own pixels) ----
-                {
-                    const float b3a = sp1.x, b3b = sp1.y;
-                    wait_acc(b);                         // nine taps of step jprev complete
-                    if (pf) pp[9] = clock64();
-                    float v[32];
-                    tmem_ld32(Db, v);
-                    tmem_ld_wait();
-                    const uint32_t dst = sbase + (uint32_t)b * RS_BUF + pix_own;
+                // ---- E2: V over U (own pixels), M-tile by M-tile ----
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) st_cta_v4(dst + j * RS_LBO, act_pack8(v + 8 * j, b3a, b3b));
-                    signal_wrk(b);
-                    if (pf) pp[10] = clock64();
+                for (int m = 0; m < 2; ++m) {
+                    wait_acc(2 * b + m);                 // nine taps of step jprev complete
+                    if (pf) pp[9 + m] = clock64();
+                    // two 8-column loads: the second is in flight while the first half is activated
+                    // (TMEM reads run at 64 B/clk per SM, as long as the SFU work of a unit)
+                    float v[16];
+                    const uint32_t Dm = tmem_base + b * 256 + 128 + m * RS_C + t_off;
+                    tmem_ld8(Dm, v);
+                    tmem_ld_wait();
+                    tmem_ld8(Dm + 8, v + 8);
+                    const uint32_t dst = buf + pix_own + m * M_PIX;
+                    st_cta_v4(dst, act_pack8(v, sp1.x, sp1.y));
+                    tmem_ld_wait();
+                    st_cta_v4(dst + RS_LBO, act_pack8(v + 8, sp1.x, sp1.y));
+                    signal(bar_wrk + 8 * (2 * b + m));
                 }
-                // ---- after G3: the residual holds x_{blk+1} - sum(bias4) ----
-                wait_acc(b);
                 if (pf) pp[11] = clock64();
-                const float b4 = sp1.z;
-                if (b) cum1 += b4; else cum0 += b4;
-                if (blk == n - 1) {
-                    const int img = (b ? img1 : img0);
-                    const float cum = b ? cum1 : cum0;
-                    float v[32];
-                    tmem_ld32(Rb, v);
-                    tmem_ld_wait();
-                    float4* o = reinterpret_cast<float4*>(a.out + (size_t)img * RS_H * RS_W * RS_C + g_pix);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        o[j] = make_float4(v[4 * j] + cum, v[4 * j + 1] + cum, v[4 * j + 2] + cum,
-                                           v[4 * j + 3] + cum);
-                    if (b) cum1 = 0.f; else cum0 = 0.f;
-                }
             }
-            if (h.g1) {
-                const int j1 = h.jprev + 1, blk = blk_n;
-                const uint32_t buf = (uint32_t)b * RS_BUF;
-                // ---- P: A1 from the residual (first block of an image: from global memory) ----
-                {
-                    float v[32];
-                    if (blk == 0) {
-                        const int img = (b ? img1 : img0);
-                        const float4* s4 = reinterpret_cast<const float4*>(
-                            a.x + (size_t)img * RS_H * RS_W * RS_C + g_pix);
+            // the residual holds x_{blk+1} - sum(bias4) once G3 has completed
+            const float cum_prev = b ? cum1 : cum0;
+            const float cum = h.g3 ? cum_prev + sp1.z : cum_prev;
+            const bool last = h.g3 && blk_p == n - 1;
+            if (h.g3 || h.g1) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 t = __ldg(s4 + j);
-                            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-                        }
-                        tmem_st32(Rb, v);
-                        tmem_st_wait();
-                    } else {
-                        tmem_ld32(Rb, v);
+                for (int m = 0; m < 2; ++m) {
+                    const uint32_t Rm = tmem_base + b * 256 + m * RS_C + t_off;
+                    float v[16];
+                    if (h.g3) {
+                        wait_acc(2 * b + m);             // G3 of step jprev complete
+                        if (pf) pp[12 + m] = clock64();
+                    }
+                    if (last) {
+                        const int img = b ? img1 : img0;
+                        tmem_ld16(Rm, v);
                         tmem_ld_wait();
-                    }
-                    if (pf) pp[16] = clock64();
-                    const float pre = (b ? cum1 : cum0) + sn0.x, post = sn0.y;
-                    const uint32_t dst = sbase + buf + pix_own;
+                        float4* o = reinterpret_cast<float4*>(a.out + (size_t)img * RS_H * RS_W * RS_C +
+                                                              g_pix + m * 16 * RS_C);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) st_cta_v4(dst + j * RS_LBO, act_pack8(v + 8 * j, pre, post));
-                    signal_wrk(b, pf ? pp + 17 : nullptr);
-                    if (pf) pp[12] = clock64();
+                        for (int k = 0; k < 4; ++k)
+                            o[k] = make_float4(v[4 * k] + cum, v[4 * k + 1] + cum, v[4 * k + 2] + cum,
+                                               v[4 * k + 3] + cum);
+                    }
+                    if (h.g1) {
+                        // ---- P: A1 from the residual (first block of an image: from global memory) ----
+                        float pre = sn0.x;
+                        if (blk_n == 0) {
+                            const int img = b ? img1 : img0;
+                            const float4* s4 = reinterpret_cast<const float4*>(
+                                a.x + (size_t)img * RS_H * RS_W * RS_C + g_pix + m * 16 * RS_C);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float4 t = __ldg(s4 + k);
+                                v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+                            }
+                            tmem_st16(Rm, v);
+                            tmem_st_wait();
+                        } else {
+                            pre += cum;
+                            tmem_ld8(Rm, v);
+                            tmem_ld_wait();
+                            tmem_ld8(Rm + 8, v + 8);
+                        }
+                        const uint32_t dst = buf + pix_own + m * M_PIX;
+                        st_cta_v4(dst, act_pack8(v, pre, sn0.y));
+                        tmem_ld_wait();
+                        st_cta_v4(dst + RS_LBO, act_pack8(v + 8, pre, sn0.y));
+                        signal(bar_wrk + 8 * (2 * b + m));
+                    }
                 }
+                if (pf) pp[14] = clock64();
+            }
+            if (b) cum1 = last ? 0.f : cum; else cum0 = last ? 0.f : cum;
+            if (h.g1) {
+                const int j1 = h.jprev + 1;
                 // ---- E1: U over A1, wrap columns, halo rows into the neighbours ----
-                {
-                    const float b2a = sn0.z, b2b = sn0.w;
-                    wait_acc(b);
-                    if (pf) pp[13] = clock64();
-                    float v[32];
-                    tmem_ld32(Db, v);
-                    tmem_ld_wait();
-                    if (pf) pp[19] = clock64();
-                    uint4 u[4];
-                    const uint32_t dst = sbase + buf + pix_own, dw = sbase + buf + pix_wrap;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        u[j] = act_pack8(v + 8 * j, b2a, b2b);
-                        st_cta_v4(dst + j * RS_LBO, u[j]);
-                        if (wrap) st_cta_v4(dw + j * RS_LBO, u[j]);
+                for (int m = 0; m < 2; ++m) {
+                    wait_acc(2 * b + m);                 // G1 of step j1 complete
+                    if (pf) pp[15 + m] = clock64();
+                    float v[16];
+                    const uint32_t Dm = tmem_base + b * 256 + 128 + m * RS_C + t_off;
+                    tmem_ld8(Dm, v);
+                    tmem_ld_wait();
+                    tmem_ld8(Dm + 8, v + 8);
+                    const uint4 u0 = act_pack8(v, sn0.z, sn0.w);
+                    const uint32_t dst = buf + pix_own + m * M_PIX;
+                    st_cta_v4(dst, u0);
+                    tmem_ld_wait();
+                    const uint4 u1 = act_pack8(v + 8, sn0.z, sn0.w);
+                    st_cta_v4(dst + RS_LBO, u1);
+                    const bool wrap = m ? wrap1 : wrap0;
+                    if (wrap) {
+                        const uint32_t dw = buf + (m ? pix_wrap1 : pix_wrap0);
+                        st_cta_v4(dw, u0);
+                        st_cta_v4(dw + RS_LBO, u1);
                     }
-                    if (pf) pp[20] = clock64();
-                    signal_wrk(b, pf ? pp + 21 : nullptr);
-                    if (pf) pp[14] = clock64();
+                    signal(bar_u + 8 * b);
                     // halo pushes after the local hand-over: the dy = 0 taps run meanwhile.  My row 0
                     // completes bytes on the upper CTA's "from below" barrier, my row 7 on the lower
                     // CTA's "from above" barrier: halo[slot][dir], dir 0 = from above
                     if (push) {
                         // the neighbour's taps of the previous block must have read the old row
-                        if (j1 > 0) mbar_wait_cluster(bar_free + 16 * b + (row == 0 ? 0 : 8), (j1 - 1) & 1);
+                        if (j1 > 0 && m == 0)
+                            mbar_wait_cluster(bar_free + 16 * b + (row == 0 ? 0 : 8), (j1 - 1) & 1);
                         const uint32_t nbar = nb_bar + 16 * b;
-                        const uint32_t dn = nb_base + buf + nb_own, dnw = nb_base + buf + nb_wrap;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            st_async_v4(dn + j * RS_LBO, u[j], nbar);
-                            if (wrap) st_async_v4(dnw + j * RS_LBO, u[j], nbar);
+                        const uint32_t nbuf = nb_base + (uint32_t)b * RS_BUF;
+                        const uint32_t dn = nbuf + nb_own + m * M_PIX;
+                        st_async_v4(dn, u0, nbar);
+                        st_async_v4(dn + RS_LBO, u1, nbar);
+                        if (wrap) {
+                            const uint32_t dnw = nbuf + (m ? nb_wrap1 : nb_wrap0);
+                            st_async_v4(dnw, u0, nbar);
+                            st_async_v4(dnw + RS_LBO, u1, nbar);
                         }
                     }
                 }
+                if (pf) pp[17] = clock64();
             }
         }
     }

@@ -188,10 +188,11 @@ int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packe
 int vqae_tc_mma_bench(int n, int layout_type, int reps, int a_stride_rows, long long* out2,
                       void* stream);
 /* the same measurement with n_issuers warps per CTA issuing concurrently (own accumulators) and
- * ctas_per_sm CTAs resident per SM; m in {64, 128}; out_per_cta: DEVICE int64 [SMs * ctas_per_sm]
+ * ctas_per_sm CTAs resident per SM; m in {64, 128}; mode bit 0: every issuer has its own A and B
+ * regions, bit 1: A row groups 160 B apart (the resident kernel's tile layout); out_per_cta: DEVICE int64 [SMs * ctas_per_sm]
  * cycles until every issuer's `reps` MMAs have completed                                       */
-int vqae_tc_mma_bench2(int m, int n, int reps, int n_issuers, int ctas_per_sm, long long* out_per_cta,
-                       void* stream);
+int vqae_tc_mma_bench2(int m, int n, int reps, int n_issuers, int ctas_per_sm, int mode,
+                       long long* out_per_cta, void* stream);
 /* descriptor/TMEM self test: d[128][64] = a[row_shift + m][0..63] . b[n][0..63] (bf16 in, fp32 out),
  * a: [a_rows][64] bf16 row-major, b: [64][64] bf16 row-major (device pointers)                */
 int vqae_tc_selftest(const void* a_bf16, int a_rows, int row_shift, const void* b_bf16, float* d,

@@ -47,10 +47,11 @@ torch.cuda.synchronize()
 lib.vqae_trunk_resident_set_profile(None)
 p = prof.cpu().view(8, 32)
 t0 = int(p[0, 0])
-print("issuer 0 (slot 0, even rows): step_start  A1wait_done  G1_issued  Uwait_done  taps_issued  Vwait_done  G3_issued")
-print("workers :  hr_start  G2_done  E2_signalled  G3_done  P_signalled  G1_done  E1_signalled")
+print("issuer (slot 0, M-tile 0), even rows: step_start  A1wait_done  G1_issued  Uwait_done  taps_issued  Vwait_done  G3_issued")
+print("workers, every row (half-round): start  E2m0_go  E2m1_go  E2_done  Pm0_go  Pm1_go  P_done  E1m0_go  E1m1_go  E1_done")
 for r in range(8):
-    print("hr%2d mma" % r, " ".join("%7d" % (int(v) - t0) for v in p[r, 0:7]))
-    print("     wrk", " ".join("%7d" % (int(v) - t0) for v in p[r, 8:15]))
-    print("     P: ld_done %d stores_done %d fence_done %d | E1: ld_done %d own_stores %d pushes_done %d fence_done %d" % tuple(
-        int(v) - t0 for v in p[r, 16:23]))
+    if r % 2 == 0:
+        print("step%2d issuer " % (r // 2), " ".join("%7d" % (int(v) - t0) for v in p[r, 0:7]),
+              "| G2_complete %d, cumulative ring-wait cycles %d" % (int(p[r, 7]) - t0, int(p[r, 20])))
+        print("        tap issue starts (after halo waits):", " ".join("%7d" % (int(v) - t0) for v in p[r, 23:32]))
+    print("   hr%2d workers" % r, " ".join("%7d" % (int(v) - t0) for v in p[r, 8:18]))
