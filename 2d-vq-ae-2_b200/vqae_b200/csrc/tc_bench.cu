@@ -31,6 +31,7 @@ tc_mma_bench2_kernel(int M, int N, int reps, int n_issuers, int tmem_cols, int m
     const long long t0 = clock64();
     if (warp < n_issuers) {
         const uint32_t idesc = make_idesc_bf16(M, N);
+        // mode bit 2: launched as 4-CTA clusters (host side);
         // mode bit 0: every issuer reads its OWN A and B regions (else all issuers share them);
         // mode bit 1: 8-row groups of A 160 B apart (the resident kernel's column-major tile) else 128 B
         const uint32_t a_off = (mode & 1) ? warp * 5 * 1024 : 0, b_off = (mode & 1) ? warp * 2 * 1024 : 0;
@@ -70,6 +71,19 @@ int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, int mo
                         : (ctas_per_sm == 3 ? 70 * 1024 : 52 * 1024));
     VQAE_CUDA_TRY(cudaFuncSetAttribute(tc_mma_bench2_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (mode & 4) {                                      // launched as clusters of four CTAs
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((sm_count / 4) * 4 * ctas_per_sm);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        VQAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_mma_bench2_kernel, M, N, reps, n_issuers, cols, mode, out));
+        return check_launch();
+    }
     tc_mma_bench2_kernel<<<sm_count * ctas_per_sm, 256, smem, stream>>>(M, N, reps, n_issuers, cols, mode, out);
     return check_launch();
 }

@@ -114,8 +114,10 @@ class Encoder(nn.Module):
         E.require_cuda(x, "Encoder.forward")
         cl = x.dtype == torch.uint8 or E.is_channels_last(x)
         h = E.stem_in(x, self.in_stem.weight, self.in_stem.bias, mean, std)
-        h = self._plan_down.run(_flat_blocks(self.down_layers), h, self.precision)
-        h = self._plan_trunk.run(_flat_blocks(self.pre_enc_layers), h, self.precision)
+        # one plan over pyramid + trunk: the 'same' blocks that close the last DownBlock and the
+        # trunk are one run of equal-width blocks, i.e. ONE image-resident launch
+        h = self._plan_down.run(_flat_blocks(self.down_layers) + _flat_blocks(self.pre_enc_layers), h,
+                                self.precision)
         vq = self.vq_layers[0]
         pq = vq.packed()
         b, hh, ww, c = h.shape
@@ -186,8 +188,8 @@ class Decoder(nn.Module):
         enc = x[0]
         E.require_cuda(enc, "Decoder.forward")
         h, cl = E.to_nhwc(enc)
-        h = self._plan_trunk.run(_flat_blocks(self.post_enc_layers), h, self.precision)
-        h = self._plan_up.run(_flat_blocks(self.up_layers), h, self.precision)
+        h = self._plan_trunk.run(_flat_blocks(self.post_enc_layers) + _flat_blocks(self.up_layers), h,
+                                 self.precision)
         return E.stem_out(h, self.out_stem.weight, self.out_stem.bias, cl)
 
 
