@@ -37,24 +37,33 @@ namespace {
 
 using namespace tc;
 
-constexpr int RS_C = 64, RS_TH = 8, RS_W = 32, RS_H = 32, RS_CL = RS_H / RS_TH;
+constexpr int RS_TH = 8, RS_W = 32, RS_H = 32, RS_CL = RS_H / RS_TH;
 constexpr int RS_PR = RS_TH + 2;                        // rows per stored column (with halo rows)
 constexpr int RS_NPIX = (RS_W + 2) * RS_PR;             // 340 stored pixels per operand buffer
 constexpr uint32_t RS_LBO = RS_NPIX * 16;               // k-chunk (8 channels) stride
 constexpr uint32_t RS_SBO = RS_PR * 16;                 // 8-row group stride = one column
-constexpr uint32_t RS_BUF = (RS_C / 8) * RS_LBO;        // 43 520 B per (slot, parity)
-constexpr uint32_t RS_WMAT = RS_C * RS_C * 2;           // 8 KB per weight matrix
-constexpr uint32_t RS_WLBO = RS_C * 16;
-constexpr int RS_RING = 8;                              // weight matrices in flight per slot
-constexpr int RS_IPS = 2;                               // MMA issue warps per slot (1 or 2)
-constexpr int RS_ISSUERS = 2 * RS_IPS;
-constexpr uint32_t RS_HALO_BYTES = (RS_W + 2) * RS_C * 2;  // one halo row incl. wrap-around columns
 constexpr int RS_NW = 16;                               // worker warps
-constexpr int RS_THREADS = (RS_NW + RS_ISSUERS + 1) * 32;  // + MMA issue warps + weight producer
-constexpr uint32_t RS_OFF_W = 2 * RS_BUF;
-constexpr uint32_t RS_OFF_BAR = RS_OFF_W + 2 * RS_RING * RS_WMAT;
-constexpr uint32_t RS_SMEM = RS_OFF_BAR + 512;
-static_assert(RS_SMEM <= 232448, "shared memory budget");
+
+// C = 64: two image slots per CTA (2 x (128 residual + 128 accumulator) TMEM columns), 8 KB weight
+// matrices, 8-deep ring per slot.  C = 128 (the trunk of the as-shipped n_down = 4 model): one slot
+// (256 + 256 columns), 32 KB matrices, 4-deep ring; the two M-tiles still pipeline against each other.
+template <int C>
+struct RsCfg {
+    static_assert(C == 64 || C == 128, "resident trunk kernel: C = 64 or 128");
+    static constexpr int NSLOT = C == 64 ? 2 : 1;
+    static constexpr int ISSUERS = 2 * NSLOT;           // one MMA issue warp per (slot, M-tile)
+    static constexpr int THREADS = (RS_NW + ISSUERS + 1) * 32;   // + weight producer warp
+    static constexpr int RING = C == 64 ? 8 : 4;        // weight matrices in flight per slot
+    static constexpr uint32_t BUF = (C / 8) * RS_LBO;   // operand buffer of one slot
+    static constexpr uint32_t WMAT = C * C * 2;
+    static constexpr uint32_t WLBO = C * 16;
+    static constexpr uint32_t HALO_BYTES = (RS_W + 2) * C * 2;   // one halo row incl. wrap columns
+    static constexpr uint32_t OFF_W = NSLOT * BUF;
+    static constexpr uint32_t OFF_BAR = OFF_W + NSLOT * RING * WMAT;
+    static constexpr uint32_t SMEM = OFF_BAR + 512;
+    static constexpr int CPT = C / 4;                   // TMEM columns (channels) per worker thread
+    static_assert(SMEM <= 232448, "shared memory budget");
+};
 
 struct ResidentArgs {
     const float* x;               // NHWC fp32 [B,32,32,64]
@@ -203,8 +212,15 @@ __device__ __forceinline__ HalfRound half_round(int hr, int T0, int T1) {
     return h;
 }
 
-__global__ void __cluster_dims__(RS_CL, 1, 1) __launch_bounds__(RS_THREADS, 1)
+template <int C>
+__global__ void __cluster_dims__(RS_CL, 1, 1) __launch_bounds__(RsCfg<C>::THREADS, 1)
 trunk_resident_tc_kernel(ResidentArgs a) {
+    using Cfg = RsCfg<C>;
+    constexpr int RS_C = C, RS_RING = Cfg::RING, RS_ISSUERS = Cfg::ISSUERS, NSLOT = Cfg::NSLOT;
+    constexpr int CPT = Cfg::CPT, HC = CPT / 2;          // columns per thread / per half load
+    constexpr uint32_t RS_BUF = Cfg::BUF, RS_WMAT = Cfg::WMAT, RS_WLBO = Cfg::WLBO;
+    constexpr uint32_t RS_HALO_BYTES = Cfg::HALO_BYTES, RS_OFF_W = Cfg::OFF_W, RS_OFF_BAR = Cfg::OFF_BAR;
+    constexpr uint32_t SLOT_COLS = 4 * C, ACC_COL = 2 * C;      // TMEM: per slot [R m0 | R m1 | D m0 | D m1]
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sW = sbase + RS_OFF_W;
@@ -221,16 +237,15 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const uint32_t bar_full = bar0 + 144, bar_empty = bar_full + 16 * RS_RING;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 144 + 32 * RS_RING);
     static_assert(144 + 32 * RS_RING + 4 <= 512, "barrier region");
-    static_assert(RS_IPS == 2, "one MMA issue warp per (slot, M-tile)");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t leader = lane == 0;
     const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x / RS_CL;                 // one image pair per cluster
+    const int pair = blockIdx.x / RS_CL;                 // one image per slot and cluster
     const int n = a.n_blocks;
-    const int img0 = 2 * pair, img1 = 2 * pair + 1;
-    const int T0 = img0 < a.n_img ? n : 0, T1 = img1 < a.n_img ? n : 0;
+    const int img0 = NSLOT * pair, img1 = NSLOT * pair + 1;
+    const int T0 = img0 < a.n_img ? n : 0, T1 = (NSLOT == 2 && img1 < a.n_img) ? n : 0;
     const int hr_last = 2 * (T0 > T1 ? T0 : T1);
 
     if (tid == 0) {
@@ -244,7 +259,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         mbar_init(bar_u + 8, 2 * RS_NW);
         for (int s = 0; s < 2 * RS_RING; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, RS_IPS);
+            mbar_init(bar_empty + 8 * s, 2);             // both issue warps of the slot
         }
         fence_mbar_init();
     }
@@ -254,7 +269,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     tc_fence_after_sync();
     cluster_sync_all();                                  // peers' barriers are initialised
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    constexpr uint32_t idesc = make_idesc_bf16(128, RS_C);
+    constexpr uint32_t idesc = make_idesc_bf16(128, C);
 
     if (warp == RS_NW + RS_ISSUERS) {
         // ---------------- weight producer: one ring per slot, each in its issuers' order ----------
@@ -297,7 +312,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         const int iw = warp - RS_NW;
         const int slot = iw >> 1, m = iw & 1;
         const int T = slot ? T1 : T0;
-        const uint32_t R = slot * 256 + m * RS_C, D = R + 128;
+        const uint32_t R = slot * SLOT_COLS + m * RS_C, D = R + ACC_COL;
         int wcnt = 0;
         uint32_t wrk_par = 0;
         const uint64_t dW = make_desc(sW + slot * RS_RING * RS_WMAT, RS_WLBO, 128);
@@ -385,8 +400,8 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         // pass over M-tile 1 and the G3 / G1 round trips disappear from the chain.
         const int q4 = warp & 3, cq = warp >> 2;         // TMEM lane quarter, 16-column quarter
         const int col0 = 4 * q4 + (lane >> 3), row = lane & 7;     // pixel inside M-tile 0
-        const uint32_t t_off = ((uint32_t)(q4 * 32) << 16) + cq * 16;
-        const uint32_t kc_off = (uint32_t)(cq * 2) * RS_LBO;
+        const uint32_t t_off = ((uint32_t)(q4 * 32) << 16) + cq * CPT;
+        const uint32_t kc_off = (uint32_t)(cq * (CPT / 8)) * RS_LBO;
         constexpr uint32_t M_PIX = 16 * RS_PR * 16;      // byte offset of M-tile 1's pixels (16 columns)
         const uint32_t pix_own = (uint32_t)((col0 + 1) * RS_PR + row + 1) * 16 + kc_off;
         // wrap-around duplicates (circular padding): column 0 (M-tile 0) -> stored column 33,
@@ -403,7 +418,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         const uint32_t nb_wrap0 = (uint32_t)((RS_W + 1) * RS_PR + nb_row) * 16 + kc_off;
         const uint32_t nb_wrap1 = (uint32_t)nb_row * 16 + kc_off;
         const uint32_t nb_bar = mapa_u32(bar_halo + (row == 0 ? 8 : 0), nb_rank);
-        const size_t g_pix = ((size_t)(rank * RS_TH + row) * RS_W + col0) * RS_C + cq * 16;
+        const size_t g_pix = ((size_t)(rank * RS_TH + row) * RS_W + col0) * RS_C + cq * CPT;
 
         uint32_t acc_par = 0;                            // bit 2s+m: parity of acc[s][m] to wait for next
         float cum0 = 0.f, cum1 = 0.f;                    // running sum of bias4 per slot
@@ -411,6 +426,21 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             mbar_wait_wd(bar_acc + 8 * sm, (acc_par >> sm) & 1);
             acc_par ^= 1u << sm;
             tc_fence_after_sync();
+        };
+        // CPT columns in two loads: the second is in flight while the first half is activated
+        // (TMEM reads run at 64 B/clk per SM sub-partition, comparable to the SFU time of a unit)
+        auto load_lo = [&](uint32_t taddr, float* v) {
+            if constexpr (HC == 8) tmem_ld8(taddr, v);
+            else tmem_ld16(taddr, *reinterpret_cast<float(*)[16]>(v));
+            tmem_ld_wait();
+            if constexpr (HC == 8) tmem_ld8(taddr + HC, v + HC);
+            else tmem_ld16(taddr + HC, *reinterpret_cast<float(*)[16]>(v + HC));
+        };
+        // store the bf16 chunks of the first / second half of a thread's channels
+        auto store_half = [&](uint32_t dst, const float* v, int half, float pre, float post) {
+#pragma unroll
+            for (int k = 0; k < HC / 8; ++k)
+                st_cta_v4(dst + (half * (HC / 8) + k) * RS_LBO, act_pack8(v + half * HC + 8 * k, pre, post));
         };
         auto signal = [&](uint32_t bar) {
             tc_fence_before_sync();
@@ -437,17 +467,12 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                 for (int m = 0; m < 2; ++m) {
                     wait_acc(2 * b + m);                 // nine taps of step jprev complete
                     if (pf) pp[9 + m] = clock64();
-                    // two 8-column loads: the second is in flight while the first half is activated
-                    // (TMEM reads run at 64 B/clk per SM, as long as the SFU work of a unit)
-                    float v[16];
-                    const uint32_t Dm = tmem_base + b * 256 + 128 + m * RS_C + t_off;
-                    tmem_ld8(Dm, v);
-                    tmem_ld_wait();
-                    tmem_ld8(Dm + 8, v + 8);
+                    float v[CPT];
+                    load_lo(tmem_base + b * SLOT_COLS + ACC_COL + m * RS_C + t_off, v);
                     const uint32_t dst = buf + pix_own + m * M_PIX;
-                    st_cta_v4(dst, act_pack8(v, sp1.x, sp1.y));
+                    store_half(dst, v, 0, sp1.x, sp1.y);
                     tmem_ld_wait();
-                    st_cta_v4(dst + RS_LBO, act_pack8(v + 8, sp1.x, sp1.y));
+                    store_half(dst, v, 1, sp1.x, sp1.y);
                     signal(bar_wrk + 8 * (2 * b + m));
                 }
                 if (pf) pp[11] = clock64();
@@ -459,20 +484,20 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             if (h.g3 || h.g1) {
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
-                    const uint32_t Rm = tmem_base + b * 256 + m * RS_C + t_off;
-                    float v[16];
+                    const uint32_t Rm = tmem_base + b * SLOT_COLS + m * RS_C + t_off;
+                    float v[CPT];
                     if (h.g3) {
                         wait_acc(2 * b + m);             // G3 of step jprev complete
                         if (pf) pp[12 + m] = clock64();
                     }
                     if (last) {
                         const int img = b ? img1 : img0;
-                        tmem_ld16(Rm, v);
+                        load_lo(Rm, v);
                         tmem_ld_wait();
                         float4* o = reinterpret_cast<float4*>(a.out + (size_t)img * RS_H * RS_W * RS_C +
                                                               g_pix + m * 16 * RS_C);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int k = 0; k < CPT / 4; ++k)
                             o[k] = make_float4(v[4 * k] + cum, v[4 * k + 1] + cum, v[4 * k + 2] + cum,
                                                v[4 * k + 3] + cum);
                     }
@@ -484,22 +509,21 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                             const float4* s4 = reinterpret_cast<const float4*>(
                                 a.x + (size_t)img * RS_H * RS_W * RS_C + g_pix + m * 16 * RS_C);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
+                            for (int k = 0; k < CPT / 4; ++k) {
                                 const float4 t = __ldg(s4 + k);
                                 v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
                             }
-                            tmem_st16(Rm, v);
+                            if constexpr (CPT == 16) tmem_st16(Rm, *reinterpret_cast<float(*)[16]>(v));
+                            else tmem_st32(Rm, *reinterpret_cast<float(*)[32]>(v));
                             tmem_st_wait();
                         } else {
                             pre += cum;
-                            tmem_ld8(Rm, v);
-                            tmem_ld_wait();
-                            tmem_ld8(Rm + 8, v + 8);
+                            load_lo(Rm, v);
                         }
                         const uint32_t dst = buf + pix_own + m * M_PIX;
-                        st_cta_v4(dst, act_pack8(v, pre, sn0.y));
+                        store_half(dst, v, 0, pre, sn0.y);
                         tmem_ld_wait();
-                        st_cta_v4(dst + RS_LBO, act_pack8(v + 8, pre, sn0.y));
+                        store_half(dst, v, 1, pre, sn0.y);
                         signal(bar_wrk + 8 * (2 * b + m));
                     }
                 }
@@ -513,22 +537,19 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                 for (int m = 0; m < 2; ++m) {
                     wait_acc(2 * b + m);                 // G1 of step j1 complete
                     if (pf) pp[15 + m] = clock64();
-                    float v[16];
-                    const uint32_t Dm = tmem_base + b * 256 + 128 + m * RS_C + t_off;
-                    tmem_ld8(Dm, v);
-                    tmem_ld_wait();
-                    tmem_ld8(Dm + 8, v + 8);
-                    const uint4 u0 = act_pack8(v, sn0.z, sn0.w);
+                    float v[CPT];
+                    load_lo(tmem_base + b * SLOT_COLS + ACC_COL + m * RS_C + t_off, v);
+                    constexpr int NCH = CPT / 8;         // 16-byte chunks per thread
+                    uint4 u[NCH];
                     const uint32_t dst = buf + pix_own + m * M_PIX;
-                    st_cta_v4(dst, u0);
-                    tmem_ld_wait();
-                    const uint4 u1 = act_pack8(v + 8, sn0.z, sn0.w);
-                    st_cta_v4(dst + RS_LBO, u1);
                     const bool wrap = m ? wrap1 : wrap0;
-                    if (wrap) {
-                        const uint32_t dw = buf + (m ? pix_wrap1 : pix_wrap0);
-                        st_cta_v4(dw, u0);
-                        st_cta_v4(dw + RS_LBO, u1);
+                    const uint32_t dw = buf + (m ? pix_wrap1 : pix_wrap0);
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        if (k == NCH / 2) tmem_ld_wait();
+                        u[k] = act_pack8(v + 8 * k, sn0.z, sn0.w);
+                        st_cta_v4(dst + k * RS_LBO, u[k]);
+                        if (wrap) st_cta_v4(dw + k * RS_LBO, u[k]);
                     }
                     signal(bar_u + 8 * b);
                     // halo pushes after the local hand-over: the dy = 0 taps run meanwhile.  My row 0
@@ -541,12 +562,11 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                         const uint32_t nbar = nb_bar + 16 * b;
                         const uint32_t nbuf = nb_base + (uint32_t)b * RS_BUF;
                         const uint32_t dn = nbuf + nb_own + m * M_PIX;
-                        st_async_v4(dn, u0, nbar);
-                        st_async_v4(dn + RS_LBO, u1, nbar);
-                        if (wrap) {
-                            const uint32_t dnw = nbuf + (m ? nb_wrap1 : nb_wrap0);
-                            st_async_v4(dnw, u0, nbar);
-                            st_async_v4(dnw + RS_LBO, u1, nbar);
+                        const uint32_t dnw = nbuf + (m ? nb_wrap1 : nb_wrap0);
+#pragma unroll
+                        for (int k = 0; k < NCH; ++k) {
+                            st_async_v4(dn + k * RS_LBO, u[k], nbar);
+                            if (wrap) st_async_v4(dnw + k * RS_LBO, u[k], nbar);
                         }
                     }
                 }
@@ -564,17 +584,33 @@ trunk_resident_tc_kernel(ResidentArgs a) {
 // like pack_same_block_kernel (tc_kernels.cu) with branch_conv3 pre-multiplied by the Fixup scale
 __global__ void __launch_bounds__(256)
 pack_resident_block_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
-                           const float* __restrict__ w3, float scale, __nv_bfloat16* __restrict__ out) {
-    constexpr int per = RS_C * RS_C;
+                           const float* __restrict__ w3, int C, float scale,
+                           __nv_bfloat16* __restrict__ out) {
+    const int per = C * C;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 11 * per) return;
     const int m = i / per, r = i % per;
-    const int kc = r / (RS_C * 8), nn = (r / 8) % RS_C, k = kc * 8 + (r % 8);
+    const int kc = r / (C * 8), nn = (r / 8) % C, k = kc * 8 + (r % 8);
     float v;
-    if (m == 0) v = w1[nn * RS_C + k];
-    else if (m == 10) v = scale * w3[nn * RS_C + k];
-    else v = w2[((size_t)nn * RS_C + k) * 9 + (m - 1)];
+    if (m == 0) v = w1[nn * C + k];
+    else if (m == 10) v = scale * w3[nn * C + k];
+    else v = w2[((size_t)nn * C + k) * 9 + (m - 1)];
     out[i] = __float2bfloat16_rn(v);
+}
+
+template <int C>
+int launch_resident(const ResidentArgs& a, int64_t B, cudaStream_t stream) {
+    using Cfg = RsCfg<C>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<C>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    const int64_t clusters = (B + Cfg::NSLOT - 1) / Cfg::NSLOT;      // one image per slot
+    if (clusters * RS_CL > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
+    trunk_resident_tc_kernel<C><<<(unsigned)clusters * RS_CL, Cfg::THREADS, Cfg::SMEM, stream>>>(a);
+    return check_launch();
 }
 
 }  // namespace
@@ -583,32 +619,33 @@ static long long* g_resident_prof = nullptr;
 void trunk_resident_set_prof(long long* dev_ptr) { g_resident_prof = dev_ptr; }
 
 bool trunk_resident_supported(int64_t B, int H, int W, int C) {
-    return B > 0 && H == RS_H && W == RS_W && C == RS_C;
+    return B > 0 && H == RS_H && W == RS_W && (C == 64 || C == 128);
 }
 
-// resident clusters the device can hold at once (each runs one image pair)
+// resident clusters of the C = 64 kernel the device can hold at once (each runs one image pair)
 int trunk_resident_max_clusters(int* out) {
-    VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+    using Cfg = RsCfg<64>;
+    VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<64>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(RS_CL * 64);
-    cfg.blockDim = dim3(RS_THREADS);
-    cfg.dynamicSmemBytes = RS_SMEM;
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = RS_CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    VQAE_CUDA_TRY(cudaOccupancyMaxActiveClusters(out, trunk_resident_tc_kernel, &cfg));
+    VQAE_CUDA_TRY(cudaOccupancyMaxActiveClusters(out, trunk_resident_tc_kernel<64>, &cfg));
     return VQAE_OK;
 }
 
 int pack_resident_block_bf16(const float* w1, const float* w2, const float* w3, int C, float scale,
                              void* packed, cudaStream_t stream) {
     if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
-    if (C != RS_C) return VQAE_ERR_UNSUPPORTED;
-    const int total = 11 * RS_C * RS_C;
+    if (C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
+    const int total = 11 * C * C;
     pack_resident_block_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(
-        w1, w2, w3, scale, reinterpret_cast<__nv_bfloat16*>(packed));
+        w1, w2, w3, C, scale, reinterpret_cast<__nv_bfloat16*>(packed));
     return check_launch();
 }
 
@@ -616,22 +653,13 @@ int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, cons
                       int n_blocks, int64_t B, int H, int W, int C, cudaStream_t stream) {
     if (!x || !out || !w_packed_all || !scalars_dev || B <= 0 || n_blocks <= 0) return VQAE_ERR_BAD_ARG;
     if (!trunk_resident_supported(B, H, W, C)) return VQAE_ERR_UNSUPPORTED;
-    if ((B + 1) / 2 * RS_CL > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
-        attr_set = true;
-    }
     ResidentArgs a;
     a.x = x; a.out = out;
     a.w = reinterpret_cast<const __nv_bfloat16*>(w_packed_all);
     a.scal = scalars_dev;
     a.n_blocks = n_blocks; a.n_img = (int)B;
     a.prof = g_resident_prof;
-    const unsigned grid = (unsigned)((B + 1) / 2) * RS_CL;
-    trunk_resident_tc_kernel<<<grid, RS_THREADS, RS_SMEM, stream>>>(a);
-    return check_launch();
+    return C == 64 ? launch_resident<64>(a, B, stream) : launch_resident<128>(a, B, stream);
 }
 
 }  // namespace vqae

@@ -147,17 +147,22 @@ def _same_blocks(c, n, seed0):
     return blocks
 
 
-@pytest.mark.parametrize("batch,n", [(1, 2), (2, 2), (3, 5), (8, 3), (80, 6), (151, 2), (256, 11)])
-def test_resident_trunk_vs_block_by_block_and_fp32(batch, n):
+@pytest.mark.parametrize("c,batch,n", [(64, 1, 2), (64, 2, 2), (64, 3, 5), (64, 8, 3), (64, 80, 6),
+                                       (64, 151, 2), (64, 256, 11), (128, 1, 1), (128, 3, 2),
+                                       (128, 40, 3), (128, 70, 5)])
+def test_resident_trunk_vs_block_by_block_and_fp32(c, batch, n, monkeypatch):
     """vqae_trunk_resident_bf16 (residual stream in tensor memory, 4-CTA clusters, halo rows through
     distributed shared memory, branch_conv3 accumulating into the residual) against n launches of
     vqae_same_block_bf16 (same bf16 operands up to the rounding of scale * W3) and against the fp32
     exact path.  Tolerance: 1e-2 of the branch magnitude (north_star bf16 bar)."""
-    packed = E.pack_blocks(_same_blocks(64, n, 60))
-    x = torch.randn(batch, 32, 32, 64, generator=torch.Generator().manual_seed(batch + n)).to(DEV)
+    packed = E.pack_blocks(_same_blocks(c, n, 60))
+    x = torch.randn(batch, 32, 32, c, generator=torch.Generator().manual_seed(batch + n)).to(DEV)
+    # the tile kernels (per-block launches for C = 64, the tile chain for C = 128) as a second opinion
+    monkeypatch.setattr(E, "TRUNK_RESIDENT", False)
     h = x
     for pk in packed:
         h = E.fixup_forward_nhwc(pk, h, precision="bf16")
+    monkeypatch.setattr(E, "TRUNK_RESIDENT", True)
     y32 = E.run_blocks_nhwc(packed, x, "fp32")
     before = E.launch_count()
     y = E.run_blocks_nhwc(packed, x, "bf16")
@@ -175,23 +180,24 @@ def test_resident_trunk_vs_block_by_block_and_fp32(batch, n):
     lib = L.load()
     chain = E.PackedChain(packed, resident=True)
     L.check(lib.vqae_trunk_resident_bf16(E._ptr(xc), E._ptr(xc), E._ptr(chain.weights),
-                                         E._ptr(chain.scalars), chain.n, batch, 32, 32, 64,
+                                         E._ptr(chain.scalars), chain.n, batch, 32, 32, c,
                                          E._stream(xc.device)), "vqae_trunk_resident_bf16")
     torch.cuda.synchronize()
     assert torch.equal(xc, y)
 
 
-def test_resident_trunk_halo_and_wrap_exactness():
+@pytest.mark.parametrize("c", [64, 128])
+def test_resident_trunk_halo_and_wrap_exactness(c):
     """Identity-like weights make the 3x3 stage a pure circular shift: every pixel of the output must
     equal its shifted neighbour, which checks the halo rows pushed between CTAs, the wrap-around
     columns and the tap -> descriptor-shift mapping without any tolerance."""
-    blocks = _same_blocks(64, 1, 90)
+    blocks = _same_blocks(c, 1, 90)
     blk = blocks[0]
     with torch.no_grad():
         for name in ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4"):
             getattr(blk, name).zero_()
         blk.scale.fill_(1.0)
-        eye = torch.eye(64, device=DEV)
+        eye = torch.eye(c, device=DEV)
         blk.branch_conv1.weight.copy_(eye[:, :, None, None])
         blk.branch_conv3.weight.copy_(eye[:, :, None, None])
     for ky in range(3):
@@ -201,19 +207,19 @@ def test_resident_trunk_halo_and_wrap_exactness():
                 blk.branch_conv2.weight[:, :, ky, kx] = eye
             packed = E.pack_blocks([blk, blk])[:1]
             # positive bf16-exact inputs: ELU is the identity, bf16 rounding is exact
-            x = torch.randint(1, 200, (3, 32, 32, 64), device=DEV).float() / 8.0
+            x = torch.randint(1, 200, (3, 32, 32, c), device=DEV).float() / 8.0
             chain = E.PackedChain(packed, resident=True)
             out = torch.empty_like(x)
             L.check(L.load().vqae_trunk_resident_bf16(
                 E._ptr(x), E._ptr(out), E._ptr(chain.weights), E._ptr(chain.scalars), 1, 3, 32, 32,
-                64, E._stream(x.device)), "vqae_trunk_resident_bf16")
+                c, E._stream(x.device)), "vqae_trunk_resident_bf16")
             torch.cuda.synchronize()
             ref = x + torch.roll(x, shifts=(-(ky - 1), -(kx - 1)), dims=(1, 2))
             assert torch.equal(out, ref), (ky, kx, float((out - ref).abs().max()))
 
 
 @pytest.mark.parametrize("hw,batch,n", [(32, 3, 1), (32, 40, 3), (96, 1, 2), (64, 2, 2)])
-def test_c128_chain_kernel_vs_fp32_path(hw, batch, n):
+def test_c128_chain_kernel_vs_fp32_path(hw, batch, n, monkeypatch):
     """C = 128 'same' blocks (the trunk of the as-shipped n_down = 4 model) exist only in the
     persistent chain form (8-row tiles, one shared operand buffer): against the fp32 exact path,
     relative error of the bf16 branch < 1e-2; any batch and run length, deterministic."""
@@ -228,6 +234,7 @@ def test_c128_chain_kernel_vs_fp32_path(hw, batch, n):
         blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=40 + i, regime="perturbed",
                                               n_layers=12))
         blocks.append(blk.to(DEV))
+    monkeypatch.setattr(E, "TRUNK_RESIDENT", False)  # this test is about the tile-chain kernel
     packed = E.pack_blocks(blocks)
     assert all(pk.tc_ok(hw, hw) and pk.chain_only for pk in packed)
     x = torch.randn(batch, hw, hw, 128, device=DEV)
