@@ -169,11 +169,16 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
         float* t3 = reinterpret_cast<float*>(base + L.t3);
         rc = conv_f32(CONV_1x1, t1, p->w2, t2, nullptr, B, H, W, cb, cb, pre2, 1.f, 0.f, stream);
         if (rc) return rc;
-        rc = bicubic_up2_f32(t2, t3, B, H, W, cb, 0.f, stream);
-        if (rc) return rc;
-        // skip: conv1x1(inp + bias1c) at low res (into t1, now free), upsample, + bias1d
+        // skip: conv1x1(inp + bias1c) at low res (into t1, now free)
         rc = conv_f32(CONV_1x1, x, p->w_skip, t1, nullptr, B, H, W, ci, co, pre_skip, 1.f, 0.f,
                       stream);
+        if (rc) return rc;
+        // both upsamples, the pre-activation, branch_conv3 and the residual sum in ONE kernel: the
+        // upsampled tensors never reach HBM (same arithmetic as the three launches below)
+        if (up_tail_supported(B, H, W, cb, co))
+            return up_tail_f32(t2, t1, p->w3, out, B, H, W, cb, co, p->bias3a, p->bias3b, p->scale,
+                               p->bias4, p->bias1d, stream);
+        rc = bicubic_up2_f32(t2, t3, B, H, W, cb, 0.f, stream);
         if (rc) return rc;
         rc = bicubic_up2_f32(t1, skip, B, H, W, co, p->bias1d, stream);
         if (rc) return rc;

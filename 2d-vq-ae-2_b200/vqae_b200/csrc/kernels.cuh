@@ -15,6 +15,12 @@ int bicubic_up2_f32(const float* in, float* out, int64_t B, int H, int W, int C,
 int pack_conv_weight_f32(const float* w, float* packed, int O, int I, int taps,
                          cudaStream_t stream);
 
+// up_tail.cu (high-resolution half of an 'up' block in one kernel)
+bool up_tail_supported(int64_t B, int H, int W, int cb, int co);
+int up_tail_f32(const float* t2, const float* s1, const float* w3, float* out, int64_t B, int H, int W,
+                int cb, int co, float b3a, float b3b, float scale, float b4, float b1d,
+                cudaStream_t stream);
+
 // stems.cu
 int normalize_u8(const uint8_t* img, float* out, int64_t B, int H, int W, const float* mean,
                  const float* stdv, int out_layout, cudaStream_t stream);
