@@ -304,8 +304,8 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
             for (int ks = 0; ks < TQ_KK / 16; ++ks)
                 umma_bf16(tmem_base + b * TQ_K, dA + (uint64_t)((ks * 2 * Cfg::A_LBO) >> 4),
                           dB + (uint64_t)((ks * 2 * Cfg::B_LBO) >> 4), idesc, ks > 0, leader);
-            umma_commit(bar_acc_full + 8 * b, leader);
             umma_commit(bar_a_free, leader);
+            umma_commit(bar_acc_full + 8 * b, leader);
             __syncwarp();
         }
     } else if (warp < TQ_W_PROJ + 4) {
@@ -347,8 +347,6 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
                     xa[t] = *reinterpret_cast<const float4*>(src);
                     xb[t] = *reinterpret_cast<const float4*>(src + 32 * 128);
                 }
-                if (q == C / 16 - 1)
-                    mbar_arrive(bar_empty_x + 8 * s);          // release orders the reads before it
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const float xsa[4] = {xa[t].x, xa[t].y, xa[t].z, xa[t].w};
@@ -372,6 +370,10 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
                     }
                 }
             }
+            // hand the x stage back only after every value read from it has been consumed by the fmaf
+            // chains above (the arrive used to sit right behind the last group's loads)
+            fence_proxy_async_smem();
+            mbar_arrive(bar_empty_x + 8 * s);
             if ((pw & 1) == 0) TQ_PROF(3);
             uint4 hh[2][3], ll[2][3];
             float zz[2][8], TT[2];
@@ -406,10 +408,18 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
                     zo[1] = make_float4(z[4], z[5], z[6], z[7]);
                 }
             }
-            // A is single-buffered: wait for the previous tile's MMA; z/T slot b: wait for the
-            // epilogue of tile it - 2
-            if (it >= 1) mbar_wait(bar_a_free, (it - 1) & 1);
+            // z/T slot b: wait for the epilogue of tile it - 2; A is single-buffered: wait for the
+            // previous tile's MMA.  ORDER MATTERS: this warp pair only looks at every other phase of
+            // bar_a_free (the other pair takes the phases in between), and a parity wait cannot tell
+            // phase it - 1 from phase it - 3.  If this pair ran ahead while the MMA of tile it - 2 was
+            // still held up by a slow epilogue, the barrier would still be in phase it - 2, whose
+            // parity differs from the one waited for, and the wait would fall through -- A(it) would
+            // then overwrite A(it - 1) under the MMA's nose (observed: a handful of wrong codes in
+            // rows 0..31 of one tile in 2-4 % of launches).  The epilogue of tile it - 2 can only
+            // have finished after MMA(it - 2), so after the first wait the barrier is in phase
+            // it - 1 or later and the second wait means what it says.
             if (it >= 2) mbar_wait(bar_acc_free + 8 * b, ((it >> 1) - 1) & 1);
+            if (it >= 1) mbar_wait(bar_a_free, (it - 1) & 1);
             if ((pw & 1) == 0) TQ_PROF(4);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {

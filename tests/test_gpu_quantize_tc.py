@@ -89,6 +89,23 @@ def test_tc_bit_identical_to_cuda_core_kernel(batch, spatial):
     assert torch.equal(idx_a, idx_c)
 
 
+def test_tc_repeated_launches_stay_exact():
+    """Regression: 300 launches on the same 262 144 latents, every one bit-identical to the CUDA-core
+    kernel.  The x stage used to be handed back to the TMA producer right behind the last group of
+    shared-memory loads; in 2-4 % of launches the refill overwrote rows 0..31 of a tile before they
+    had been consumed and a handful of vectors got the code of someone else's latent
+    (profiles/determinism_quantizer.py)."""
+    pq = _module(seed=9)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(256, 1024, 64, generator=g).to(DEV)
+    _, idx_ref, _, _, z_ref = _run(pq, x, tc=False, want_out=False)
+    packed = pq.packed()
+    outs = [E.quantize(packed, x, True, True, 256, 1024, want_out=False, want_z=True) for _ in range(300)]
+    torch.cuda.synchronize()
+    bad = [i for i, o in enumerate(outs) if not (torch.equal(o[1], idx_ref) and torch.equal(o[4], z_ref))]
+    assert not bad, f"{len(bad)} of 300 launches differ from the exact kernel: {bad[:10]}"
+
+
 def test_tc_vs_oracle():
     import vqae_oracle as O
     pq = _module(seed=9)
