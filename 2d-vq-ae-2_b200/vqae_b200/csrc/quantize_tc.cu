@@ -413,10 +413,9 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
             // bar_a_free (the other pair takes the phases in between), and a parity wait cannot tell
             // phase it - 1 from phase it - 3.  If this pair ran ahead while the MMA of tile it - 2 was
             // still held up by a slow epilogue, the barrier would still be in phase it - 2, whose
-            // parity differs from the one waited for, and the wait would fall through -- A(it) would
-            // then overwrite A(it - 1) under the MMA's nose (observed: a handful of wrong codes in
-            // rows 0..31 of one tile in 2-4 % of launches).  The epilogue of tile it - 2 can only
-            // have finished after MMA(it - 2), so after the first wait the barrier is in phase
+            // parity differs from the one waited for, and the wait would fall through: A(it) could
+            // then overwrite A(it - 1) before the MMA has read it.  The epilogue of tile it - 2 can
+            // only have finished after MMA(it - 2), so after the first wait the barrier is in phase
             // it - 1 or later and the second wait means what it says.
             if (it >= 2) mbar_wait(bar_acc_free + 8 * b, ((it >> 1) - 1) & 1);
             if (it >= 1) mbar_wait(bar_a_free, (it - 1) & 1);

@@ -113,6 +113,50 @@ def test_fixup_block_vs_reference_golden(name, layout):
     assert H.rel_err(y.cpu(), torch.from_numpy(g[f"{name}_y"])) < 2e-5
 
 
+@pytest.mark.parametrize("c_in,hw,batch", [(16, 32, 3), (32, 64, 2), (64, 32, 5), (16, 128, 1)])
+def test_up_block_fused_tail_bit_identical_to_unfused(c_in, hw, batch):
+    """'up' block through vqae_fixup_block_f32 (high-resolution half fused in up_tail.cu: both bicubic
+    upsamples, pre-activation, branch_conv3, residual sum) against the same block composed from the
+    single-op entry points vqae_conv_f32 / vqae_bicubic_up2_f32 -- the unfused sequence the fused
+    kernel replaces.  Same tap weights, same fmaf order: bit-identical."""
+    from vqae_b200 import _lib as L
+    from vqae_b200 import engine as E
+    from vqae_b200.config import pre_activation_fixup
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blk = PreActFixupResBlock(in_channels=c_in, out_channels=c_in // 2, mode="up", **conf).eval()
+    blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=31, regime="perturbed", n_layers=12))
+    blk = blk.to(DEV)
+    pk = blk.packed()
+    x = torch.randn(batch, hw, hw, c_in, generator=torch.Generator().manual_seed(hw)).to(DEV)
+    y = E.fixup_forward_nhwc(pk, x, precision="fp32")
+    lib, st, sc = L.load(), E._stream(x.device), pk.scalars
+    cb, co = pk.c_branch, pk.c_out
+
+    def conv(inp, w, cin, cout, h, pre_add, pre_elu, post_add, scale, bias, res=None):
+        out = torch.empty(batch, h, h, cout, device=DEV)
+        L.check(lib.vqae_conv_f32(L.CONV_1x1, E._ptr(inp), E._ptr(w), E._ptr(out), E._ptr(res), batch, h, h,
+                                  cin, cout, pre_add, pre_elu, post_add, scale, bias, st), "conv")
+        return out
+
+    def up(inp, c, bias):
+        out = torch.empty(batch, 2 * hw, 2 * hw, c, device=DEV)
+        L.check(lib.vqae_bicubic_up2_f32(E._ptr(inp), E._ptr(out), batch, hw, hw, c, bias, st), "bicubic")
+        return out
+
+    t1 = conv(x, pk.w1, c_in, cb, hw, sc["bias1a"], 1, sc["bias1b"], 1.0, 0.0)
+    t2 = conv(t1, pk.w2, cb, cb, hw, sc["bias2a"], 1, sc["bias2b"], 1.0, 0.0)
+    t3 = up(t2, cb, 0.0)
+    s1 = conv(x, pk.w_skip, c_in, co, hw, sc["bias1c"], 0, 0.0, 1.0, 0.0)
+    skip = up(s1, co, sc["bias1d"])
+    ref = conv(t3, pk.w3, cb, co, 2 * hw, sc["bias3a"], 1, sc["bias3b"], sc["scale"], sc["bias4"], skip)
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape == (batch, 2 * hw, 2 * hw, co)
+    assert torch.equal(y, ref), float((y - ref).abs().max())
+
+
 def test_resize_conv_vs_oracle():
     from vqae_b200.layers.conv import ResizeConv2D
     conv = ResizeConv2D(16, 8, 1, bias=False).eval().to(DEV)
