@@ -39,10 +39,13 @@ struct UpTailCfg {
     static constexpr int OFF_S = UT_RY * UT_RX * PT;      // floats
     static constexpr int OFF_W = OFF_S + UT_RY * UT_RX * PS;
     static constexpr size_t SMEM = (size_t)(OFF_W + CB * CO) * sizeof(float);
+    // resident CTAs per SM the register allocation is tuned for (the kernel is latency-bound on
+    // shared-memory reads: more warps in flight matter more than a few spilled values)
+    static constexpr int MIN_CTAS = CB == 16 ? 4 : (CB == 32 ? 3 : 1);
 };
 
 template <int CB, int CO>
-__global__ void __launch_bounds__(UT_THREADS)
+__global__ void __launch_bounds__(UT_THREADS, UpTailCfg<CB, CO>::MIN_CTAS)
 up_tail_f32_kernel(UpTailArgs a) {
     using Cfg = UpTailCfg<CB, CO>;
     constexpr int PT = Cfg::PT, PS = Cfg::PS;
