@@ -37,31 +37,44 @@ namespace {
 
 using namespace tc;
 
-constexpr int RS_TH = 8, RS_W = 32, RS_H = 32, RS_CL = RS_H / RS_TH;
-constexpr int RS_PR = RS_TH + 2;                        // rows per stored column (with halo rows)
-constexpr int RS_NPIX = (RS_W + 2) * RS_PR;             // 340 stored pixels per operand buffer
-constexpr uint32_t RS_LBO = RS_NPIX * 16;               // k-chunk (8 channels) stride
-constexpr uint32_t RS_SBO = RS_PR * 16;                 // 8-row group stride = one column
+constexpr int RS_TH = 8;
 constexpr int RS_NW = 16;                               // worker warps
+constexpr int RS_PR = RS_TH + 2;                        // rows per stored column (with halo rows)
+constexpr uint32_t RS_SBO = RS_PR * 16;                 // 8-row group stride = one column
 
-// C = 64: two image slots per CTA (2 x (128 residual + 128 accumulator) TMEM columns), 8 KB weight
-// matrices, 8-deep ring per slot.  C = 128 (the trunk of the as-shipped n_down = 4 model): one slot
-// (256 + 256 columns), 32 KB matrices, 4-deep ring; the two M-tiles still pipeline against each other.
-template <int C>
+// Shapes (C channels, W x W pixels; a cluster of W / 8 CTAs owns an image, one CTA a strip of 8 rows =
+// W / 16 M-tiles, handled as two HALVES of MPH M-tiles each):
+//   C = 64,  W = 32  (256-model trunks)          2 M-tiles, 2 slots, cluster 4
+//   C = 128, W = 32  (512-model trunks)          2 M-tiles, 1 slot (256 + 256 TMEM columns), cluster 4
+//   C = 32,  W = 64  (the five-block 'same' runs of the 256-model pyramids)
+//                                                4 M-tiles, 2 slots, cluster 8
+//   (C = 16, W = 128 instantiates and is correct with clusters of 16, but at five blocks per run the
+//    image load / store and the few resident clusters leave it no faster than the tile kernel -- 1.03 vs
+//    1.00 ms at batch 256 -- so it is not dispatched)
+// In every case a slot's residual and accumulators take MT * C = 128 (256) TMEM columns each, an operand
+// buffer is (W + 2) * 10 pixels * C * 2 B ~ 42 (85) KB, and a worker unit (one half, one phase) is
+// 128 * MPH pixels x C channels = 8 192 (16 384) activations for the 16 worker warps.
+template <int C, int W>
 struct RsCfg {
-    static_assert(C == 64 || C == 128, "resident trunk kernel: C = 64 or 128");
-    static constexpr int NSLOT = C == 64 ? 2 : 1;
-    static constexpr int ISSUERS = 2 * NSLOT;           // one MMA issue warp per (slot, M-tile)
+    static_assert((C == 64 && W == 32) || (C == 128 && W == 32) || (C == 32 && W == 64) ||
+                  (C == 16 && W == 128), "resident trunk kernel: unsupported shape");
+    static constexpr int CL = W / RS_TH;                // cluster size (square images)
+    static constexpr int MT = W / 16, MPH = MT / 2;     // M-tiles per strip / per half
+    static constexpr int NSLOT = 2 * MT * C <= 256 ? 2 : 1;
+    static constexpr int ISSUERS = 2 * NSLOT;           // one MMA issue warp per (slot, half)
     static constexpr int THREADS = (RS_NW + ISSUERS + 1) * 32;   // + weight producer warp
-    static constexpr int RING = C == 64 ? 8 : 4;        // weight matrices in flight per slot
-    static constexpr uint32_t BUF = (C / 8) * RS_LBO;   // operand buffer of one slot
+    static constexpr int RING = C == 128 ? 4 : 8;       // weight matrices in flight per slot
+    static constexpr int NPIX = (W + 2) * RS_PR;        // stored pixels per operand buffer
+    static constexpr uint32_t LBO = NPIX * 16;          // k-chunk (8 channels) stride
+    static constexpr uint32_t BUF = (C / 8) * LBO;      // operand buffer of one slot
     static constexpr uint32_t WMAT = C * C * 2;
     static constexpr uint32_t WLBO = C * 16;
-    static constexpr uint32_t HALO_BYTES = (RS_W + 2) * C * 2;   // one halo row incl. wrap columns
+    static constexpr uint32_t HALO_BYTES = (W + 2) * C * 2;      // one halo row incl. wrap columns
     static constexpr uint32_t OFF_W = NSLOT * BUF;
     static constexpr uint32_t OFF_BAR = OFF_W + NSLOT * RING * WMAT;
     static constexpr uint32_t SMEM = OFF_BAR + 512;
-    static constexpr int CPT = C / 4;                   // TMEM columns (channels) per worker thread
+    static constexpr int CPT = C * MPH / 4;             // TMEM columns (channels) per worker thread
+    static_assert(CPT == 16 || CPT == 32, "16 or 32 channels per worker thread");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -212,15 +225,17 @@ __device__ __forceinline__ HalfRound half_round(int hr, int T0, int T1) {
     return h;
 }
 
-template <int C>
-__global__ void __cluster_dims__(RS_CL, 1, 1) __launch_bounds__(RsCfg<C>::THREADS, 1)
+template <int C, int W>
+__global__ void __cluster_dims__(RsCfg<C, W>::CL, 1, 1) __launch_bounds__(RsCfg<C, W>::THREADS, 1)
 trunk_resident_tc_kernel(ResidentArgs a) {
-    using Cfg = RsCfg<C>;
-    constexpr int RS_C = C, RS_RING = Cfg::RING, RS_ISSUERS = Cfg::ISSUERS, NSLOT = Cfg::NSLOT;
+    using Cfg = RsCfg<C, W>;
+    constexpr int RS_C = C, RS_W = W, RS_H = W, RS_CL = Cfg::CL, MPH = Cfg::MPH;
+    constexpr int RS_RING = Cfg::RING, RS_ISSUERS = Cfg::ISSUERS, NSLOT = Cfg::NSLOT;
     constexpr int CPT = Cfg::CPT, HC = CPT / 2;          // columns per thread / per half load
-    constexpr uint32_t RS_BUF = Cfg::BUF, RS_WMAT = Cfg::WMAT, RS_WLBO = Cfg::WLBO;
+    constexpr uint32_t RS_LBO = Cfg::LBO, RS_BUF = Cfg::BUF, RS_WMAT = Cfg::WMAT, RS_WLBO = Cfg::WLBO;
     constexpr uint32_t RS_HALO_BYTES = Cfg::HALO_BYTES, RS_OFF_W = Cfg::OFF_W, RS_OFF_BAR = Cfg::OFF_BAR;
-    constexpr uint32_t SLOT_COLS = 4 * C, ACC_COL = 2 * C;      // TMEM: per slot [R m0 | R m1 | D m0 | D m1]
+    // TMEM per slot: [R half 0 | R half 1 | D half 0 | D half 1], a half = MPH M-tiles of C columns
+    constexpr uint32_t HALF_COLS = MPH * C, ACC_COL = 2 * HALF_COLS, SLOT_COLS = 2 * ACC_COL;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sW = sbase + RS_OFF_W;
@@ -312,12 +327,15 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         const int iw = warp - RS_NW;
         const int slot = iw >> 1, m = iw & 1;
         const int T = slot ? T1 : T0;
-        const uint32_t R = slot * SLOT_COLS + m * RS_C, D = R + ACC_COL;
+        const uint32_t R = slot * SLOT_COLS + m * HALF_COLS, D = R + ACC_COL;
         int wcnt = 0;
         uint32_t wrk_par = 0;
         const uint64_t dW = make_desc(sW + slot * RS_RING * RS_WMAT, RS_WLBO, 128);
-        // A operand of this M-tile: own pixels start at stored column 16m + 1, row 1
-        const uint32_t a_base = sbase + (uint32_t)slot * RS_BUF + (uint32_t)(((16 * m + 1) * RS_PR + 1) * 16);
+        // A operand of this half's first M-tile: own pixels start at stored column 16 MPH m + 1, row 1;
+        // the next M-tile is 16 columns further
+        const uint32_t a_base = sbase + (uint32_t)slot * RS_BUF +
+                                (uint32_t)(((16 * MPH * m + 1) * RS_PR + 1) * 16);
+        constexpr uint32_t A_MT = 16 * RS_PR * 16;
         const uint32_t b_acc = bar_acc + 8 * iw, b_wrk = bar_wrk + 8 * iw, b_u = bar_u + 8 * slot;
         auto wait_wrk = [&]() {
             mbar_wait_wd(b_wrk, wrk_par);
@@ -333,12 +351,15 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             if (a.prof) ring_wait += clock64() - tw;
             tc_fence_after_sync();
             const uint64_t dWm = dW + (uint64_t)((rs * RS_WMAT) >> 4);
-            const uint64_t dA = make_desc(a_base + shift_px * 16, RS_LBO, RS_SBO);
 #pragma unroll
-            for (int ks = 0; ks < RS_C / 16; ++ks)
-                umma_bf16(tmem_base + d_col, dA + (uint64_t)((ks * 2 * RS_LBO) >> 4),
-                          dWm + (uint64_t)((ks * 2 * RS_WLBO) >> 4), idesc,
-                          (acc_first || ks > 0) ? 1u : 0u, leader);
+            for (int mi = 0; mi < MPH; ++mi) {
+                const uint64_t dA = make_desc(a_base + mi * A_MT + shift_px * 16, RS_LBO, RS_SBO);
+#pragma unroll
+                for (int ks = 0; ks < RS_C / 16; ++ks)
+                    umma_bf16(tmem_base + d_col + mi * RS_C, dA + (uint64_t)((ks * 2 * RS_LBO) >> 4),
+                              dWm + (uint64_t)((ks * 2 * RS_WLBO) >> 4), idesc,
+                              (acc_first || ks > 0) ? 1u : 0u, leader);
+            }
             umma_commit(bar_empty + 8 * (slot * RS_RING + rs), leader);
             ++wcnt;
         };
@@ -398,15 +419,16 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         // ---------------- workers: per unit (slot, M-tile, phase) one pixel x 16 channels per thread --
         // All 16 warps work on ONE M-tile at a time, so the MMA of M-tile 0 runs under the workers'
         // pass over M-tile 1 and the G3 / G1 round trips disappear from the chain.
-        const int q4 = warp & 3, cq = warp >> 2;         // TMEM lane quarter, 16-column quarter
-        const int col0 = 4 * q4 + (lane >> 3), row = lane & 7;     // pixel inside M-tile 0
-        const uint32_t t_off = ((uint32_t)(q4 * 32) << 16) + cq * CPT;
+        // TMEM lane quarter; M-tile inside the half; CPT-column group
+        const int q4 = warp & 3, mi = (warp >> 2) % MPH, cq = (warp >> 2) / MPH;
+        const int col0 = 16 * mi + 4 * q4 + (lane >> 3), row = lane & 7;   // pixel inside half 0
+        const uint32_t t_off = ((uint32_t)(q4 * 32) << 16) + mi * RS_C + cq * CPT;
         const uint32_t kc_off = (uint32_t)(cq * (CPT / 8)) * RS_LBO;
-        constexpr uint32_t M_PIX = 16 * RS_PR * 16;      // byte offset of M-tile 1's pixels (16 columns)
+        constexpr uint32_t M_PIX = 16 * MPH * RS_PR * 16;    // byte offset of half 1's pixels
         const uint32_t pix_own = (uint32_t)((col0 + 1) * RS_PR + row + 1) * 16 + kc_off;
         // wrap-around duplicates (circular padding): column 0 (M-tile 0) -> stored column 33,
         // column 31 (M-tile 1) -> stored column 0
-        const bool wrap0 = col0 == 0, wrap1 = col0 == 15;
+        const bool wrap0 = col0 == 0, wrap1 = col0 == 16 * MPH - 1;
         const uint32_t pix_wrap0 = (uint32_t)((RS_W + 1) * RS_PR + row + 1) * 16 + kc_off;
         const uint32_t pix_wrap1 = (uint32_t)(row + 1) * 16 + kc_off;
         // halo pushes: my row 0 is row 8 of the CTA above, my row 7 is row -1 of the CTA below
@@ -468,7 +490,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                     wait_acc(2 * b + m);                 // nine taps of step jprev complete
                     if (pf) pp[9 + m] = clock64();
                     float v[CPT];
-                    load_lo(tmem_base + b * SLOT_COLS + ACC_COL + m * RS_C + t_off, v);
+                    load_lo(tmem_base + b * SLOT_COLS + ACC_COL + m * HALF_COLS + t_off, v);
                     const uint32_t dst = buf + pix_own + m * M_PIX;
                     store_half(dst, v, 0, sp1.x, sp1.y);
                     tmem_ld_wait();
@@ -484,7 +506,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             if (h.g3 || h.g1) {
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
-                    const uint32_t Rm = tmem_base + b * SLOT_COLS + m * RS_C + t_off;
+                    const uint32_t Rm = tmem_base + b * SLOT_COLS + m * HALF_COLS + t_off;
                     float v[CPT];
                     if (h.g3) {
                         wait_acc(2 * b + m);             // G3 of step jprev complete
@@ -495,7 +517,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                         load_lo(Rm, v);
                         tmem_ld_wait();
                         float4* o = reinterpret_cast<float4*>(a.out + (size_t)img * RS_H * RS_W * RS_C +
-                                                              g_pix + m * 16 * RS_C);
+                                                              g_pix + m * 16 * MPH * RS_C);
 #pragma unroll
                         for (int k = 0; k < CPT / 4; ++k)
                             o[k] = make_float4(v[4 * k] + cum, v[4 * k + 1] + cum, v[4 * k + 2] + cum,
@@ -507,7 +529,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                         if (blk_n == 0) {
                             const int img = b ? img1 : img0;
                             const float4* s4 = reinterpret_cast<const float4*>(
-                                a.x + (size_t)img * RS_H * RS_W * RS_C + g_pix + m * 16 * RS_C);
+                                a.x + (size_t)img * RS_H * RS_W * RS_C + g_pix + m * 16 * MPH * RS_C);
 #pragma unroll
                             for (int k = 0; k < CPT / 4; ++k) {
                                 const float4 t = __ldg(s4 + k);
@@ -538,7 +560,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                     wait_acc(2 * b + m);                 // G1 of step j1 complete
                     if (pf) pp[15 + m] = clock64();
                     float v[CPT];
-                    load_lo(tmem_base + b * SLOT_COLS + ACC_COL + m * RS_C + t_off, v);
+                    load_lo(tmem_base + b * SLOT_COLS + ACC_COL + m * HALF_COLS + t_off, v);
                     constexpr int NCH = CPT / 8;         // 16-byte chunks per thread
                     uint4 u[NCH];
                     const uint32_t dst = buf + pix_own + m * M_PIX;
@@ -598,18 +620,21 @@ pack_resident_block_kernel(const float* __restrict__ w1, const float* __restrict
     out[i] = __float2bfloat16_rn(v);
 }
 
-template <int C>
+template <int C, int W>
 int launch_resident(const ResidentArgs& a, int64_t B, cudaStream_t stream) {
-    using Cfg = RsCfg<C>;
+    using Cfg = RsCfg<C, W>;
     static bool attr_set = false;
     if (!attr_set) {
-        VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<C>,
+        VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<C, W>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        if (Cfg::CL > 8)                                 // clusters of 16 CTAs are an opt-in size
+            VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<C, W>,
+                                               cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         attr_set = true;
     }
     const int64_t clusters = (B + Cfg::NSLOT - 1) / Cfg::NSLOT;      // one image per slot
-    if (clusters * RS_CL > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
-    trunk_resident_tc_kernel<C><<<(unsigned)clusters * RS_CL, Cfg::THREADS, Cfg::SMEM, stream>>>(a);
+    if (clusters * Cfg::CL > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
+    trunk_resident_tc_kernel<C, W><<<(unsigned)clusters * Cfg::CL, Cfg::THREADS, Cfg::SMEM, stream>>>(a);
     return check_launch();
 }
 
@@ -619,30 +644,31 @@ static long long* g_resident_prof = nullptr;
 void trunk_resident_set_prof(long long* dev_ptr) { g_resident_prof = dev_ptr; }
 
 bool trunk_resident_supported(int64_t B, int H, int W, int C) {
-    return B > 0 && H == RS_H && W == RS_W && (C == 64 || C == 128);
+    if (B <= 0 || H != W) return false;
+    return (W == 32 && (C == 64 || C == 128)) || (W == 64 && C == 32);
 }
 
 // resident clusters of the C = 64 kernel the device can hold at once (each runs one image pair)
 int trunk_resident_max_clusters(int* out) {
-    using Cfg = RsCfg<64>;
-    VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<64>,
+    using Cfg = RsCfg<64, 32>;
+    VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<64, 32>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(RS_CL * 64);
+    cfg.gridDim = dim3(Cfg::CL * 64);
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = RS_CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.x = Cfg::CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    VQAE_CUDA_TRY(cudaOccupancyMaxActiveClusters(out, trunk_resident_tc_kernel<64>, &cfg));
+    VQAE_CUDA_TRY(cudaOccupancyMaxActiveClusters(out, trunk_resident_tc_kernel<64, 32>, &cfg));
     return VQAE_OK;
 }
 
 int pack_resident_block_bf16(const float* w1, const float* w2, const float* w3, int C, float scale,
                              void* packed, cudaStream_t stream) {
     if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
-    if (C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
+    if (C != 32 && C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
     const int total = 11 * C * C;
     pack_resident_block_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(
         w1, w2, w3, C, scale, reinterpret_cast<__nv_bfloat16*>(packed));
@@ -659,7 +685,12 @@ int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, cons
     a.scal = scalars_dev;
     a.n_blocks = n_blocks; a.n_img = (int)B;
     a.prof = g_resident_prof;
-    return C == 64 ? launch_resident<64>(a, B, stream) : launch_resident<128>(a, B, stream);
+    switch (C) {
+        case 64: return launch_resident<64, 32>(a, B, stream);
+        case 128: return launch_resident<128, 32>(a, B, stream);
+        case 32: return launch_resident<32, 64>(a, B, stream);
+    }
+    return VQAE_ERR_UNSUPPORTED;
 }
 
 }  // namespace vqae

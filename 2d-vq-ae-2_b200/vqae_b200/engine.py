@@ -131,7 +131,7 @@ class PackedFixup:
             sc = self.scalars
             self.tc_scalars = (C.c_float * 8)(*[float(sc[k]) for k in (
                 "bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "scale")])
-            if self.c_in in (64, 128):
+            if self.c_in in (32, 64, 128):
                 # image-resident trunk kernel: branch_conv3 pre-multiplied by the Fixup scale
                 self.tc_weights_res = torch.empty(11 * cp * cp, dtype=torch.bfloat16, device=dev)
                 L.check(lib.vqae_pack_resident_block_bf16(
@@ -200,8 +200,9 @@ def pack_blocks(blocks: Sequence) -> List[PackedFixup]:
 # single calls
 # ----------------------------------------------------------------------------------------------
 PRECISIONS = ("fp32", "bf16")
-# C = 64 / 128 runs of 'same' blocks at 32 x 32 use the image-resident kernel (tc_resident.cu); False
-# selects the persistent tile-chain kernel (tc_chain.cu) for A/B measurements (profiles/step_breakdown.py)
+# Runs of 'same' blocks at C = 64 / 128 @ 32 x 32 and C = 32 @ 64 x 64 use the
+# image-resident kernel (tc_resident.cu); False selects the tile kernels (tc_chain.cu / tc_kernels.cu)
+# for A/B measurements (profiles/step_breakdown.py)
 TRUNK_RESIDENT = True
 
 

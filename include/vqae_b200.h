@@ -143,14 +143,14 @@ int vqae_same_chain_supported(int64_t batch, int height, int width, int c);
 int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void* w_packed_all,
                          const float* scalars_dev, void* flags, size_t flag_bytes, int n_blocks,
                          int64_t batch, int height, int width, int c, void* stream);
-/* The same run with the fp32 residual stream RESIDENT ON THE SM (c == 64, 32 x 32 latents: the
- * 50-block trunks model.py:150-153,240-263 plus the adjacent post/pre layers): a cluster of four
- * CTAs owns an image, the residual lives in tensor memory and branch_conv3 accumulates straight into
+/* The same run with the fp32 residual stream RESIDENT ON THE SM (c in {64, 128} at 32 x 32: the
+ * 50-block trunks model.py:150-153,240-263 plus the adjacent post/pre layers; c == 32 at 64 x 64: the
+ * five-block runs of the pyramids): a cluster of height / 8 CTAs owns an image, the residual lives in tensor memory and branch_conv3 accumulates straight into
  * it, halo rows travel through distributed shared memory; the only global traffic is the first load
  * and the last store of each image.  w_packed_all: vqae_pack_resident_block_bf16 outputs back to
- * back (11 * 64 * 64 bf16 per block, branch_conv3 pre-multiplied by the Fixup `scale`, so bias4 and
+ * back (11 * c * c bf16 per block, branch_conv3 pre-multiplied by the Fixup `scale`, so bias4 and
  * scale are applied as  x += (scale W3) v;  the bias4 terms are summed and added on the way out);
- * scalars_dev as for vqae_same_chain_bf16.  x, out: NHWC fp32 [B,32,32,64]; out may alias x.
+ * scalars_dev as for vqae_same_chain_bf16.  x, out: NHWC fp32 [B,H,W,c]; out may alias x.
  * Not bit-identical to vqae_same_block_bf16 (rounding of scale*W3, accumulation order): agrees
  * within the bf16 tolerance (tests/test_gpu_tc.py).                                            */
 /* profiling aid: DEVICE int64 [8][32] that CTA 0 fills with clock64() stamps of eight steady-state

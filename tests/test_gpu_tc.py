@@ -147,16 +147,20 @@ def _same_blocks(c, n, seed0):
     return blocks
 
 
+_RES_HW = {64: 32, 128: 32, 32: 64}
+
+
 @pytest.mark.parametrize("c,batch,n", [(64, 1, 2), (64, 2, 2), (64, 3, 5), (64, 8, 3), (64, 80, 6),
                                        (64, 151, 2), (64, 256, 11), (128, 1, 1), (128, 3, 2),
-                                       (128, 40, 3), (128, 70, 5)])
+                                       (128, 40, 3), (128, 70, 5), (32, 1, 2), (32, 5, 5), (32, 40, 3)])
 def test_resident_trunk_vs_block_by_block_and_fp32(c, batch, n, monkeypatch):
     """vqae_trunk_resident_bf16 (residual stream in tensor memory, 4-CTA clusters, halo rows through
     distributed shared memory, branch_conv3 accumulating into the residual) against n launches of
     vqae_same_block_bf16 (same bf16 operands up to the rounding of scale * W3) and against the fp32
     exact path.  Tolerance: 1e-2 of the branch magnitude (north_star bf16 bar)."""
+    hw = _RES_HW[c]
     packed = E.pack_blocks(_same_blocks(c, n, 60))
-    x = torch.randn(batch, 32, 32, c, generator=torch.Generator().manual_seed(batch + n)).to(DEV)
+    x = torch.randn(batch, hw, hw, c, generator=torch.Generator().manual_seed(batch + n)).to(DEV)
     # the tile kernels (per-block launches for C = 64, the tile chain for C = 128) as a second opinion
     monkeypatch.setattr(E, "TRUNK_RESIDENT", False)
     h = x
@@ -180,13 +184,13 @@ def test_resident_trunk_vs_block_by_block_and_fp32(c, batch, n, monkeypatch):
     lib = L.load()
     chain = E.PackedChain(packed, resident=True)
     L.check(lib.vqae_trunk_resident_bf16(E._ptr(xc), E._ptr(xc), E._ptr(chain.weights),
-                                         E._ptr(chain.scalars), chain.n, batch, 32, 32, c,
+                                         E._ptr(chain.scalars), chain.n, batch, hw, hw, c,
                                          E._stream(xc.device)), "vqae_trunk_resident_bf16")
     torch.cuda.synchronize()
     assert torch.equal(xc, y)
 
 
-@pytest.mark.parametrize("c", [64, 128])
+@pytest.mark.parametrize("c", [64, 128, 32])
 def test_resident_trunk_halo_and_wrap_exactness(c):
     """Identity-like weights make the 3x3 stage a pure circular shift: every pixel of the output must
     equal its shifted neighbour, which checks the halo rows pushed between CTAs, the wrap-around
@@ -207,11 +211,12 @@ def test_resident_trunk_halo_and_wrap_exactness(c):
                 blk.branch_conv2.weight[:, :, ky, kx] = eye
             packed = E.pack_blocks([blk, blk])[:1]
             # positive bf16-exact inputs: ELU is the identity, bf16 rounding is exact
-            x = torch.randint(1, 200, (3, 32, 32, c), device=DEV).float() / 8.0
+            hw = _RES_HW[c]
+            x = torch.randint(1, 200, (3, hw, hw, c), device=DEV).float() / 8.0
             chain = E.PackedChain(packed, resident=True)
             out = torch.empty_like(x)
             L.check(L.load().vqae_trunk_resident_bf16(
-                E._ptr(x), E._ptr(out), E._ptr(chain.weights), E._ptr(chain.scalars), 1, 3, 32, 32,
+                E._ptr(x), E._ptr(out), E._ptr(chain.weights), E._ptr(chain.scalars), 1, 3, hw, hw,
                 c, E._stream(x.device)), "vqae_trunk_resident_bf16")
             torch.cuda.synchronize()
             ref = x + torch.roll(x, shifts=(-(ky - 1), -(kx - 1)), dims=(1, 2))
