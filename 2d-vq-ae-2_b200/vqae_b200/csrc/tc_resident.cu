@@ -62,7 +62,7 @@ struct RsCfg {
     static constexpr int MT = W / 16, MPH = MT / 2;     // M-tiles per strip / per half
     static constexpr int NSLOT = 2 * MT * C <= 256 ? 2 : 1;
     static constexpr int ISSUERS = 2 * NSLOT;           // one MMA issue warp per (slot, half)
-    static constexpr int THREADS = (RS_NW + ISSUERS + 1) * 32;   // + weight producer warp
+    static constexpr int THREADS = (RS_NW + ISSUERS + NSLOT) * 32;   // + one weight producer warp per slot
     static constexpr int RING = C == 128 ? 4 : 8;       // weight matrices in flight per slot
     static constexpr int NPIX = (W + 2) * RS_PR;        // stored pixels per operand buffer
     static constexpr uint32_t LBO = NPIX * 16;          // k-chunk (8 channels) stride
@@ -203,7 +203,7 @@ __device__ __forceinline__ void tmem_st_wait() {
 
 // Issue order of the nine taps: the three dy = 0 taps need no halo row and go first, so the pushes of
 // the neighbours (DSMEM moves ~20 B/clk) overlap them; then dy = -1 (row from above), dy = +1 (below).
-__device__ __forceinline__ int tap_of(int i) { return i < 3 ? i + 3 : (i < 6 ? i - 3 : i); }
+__host__ __device__ constexpr int tap_of(int i) { return i < 3 ? i + 3 : (i < 6 ? i - 3 : i); }
 
 // The workers' static schedule.  Half-round hr (from -1): while slot a = hr & 1 runs the nine taps of
 // its step ja = hr >> 1, the workers serve the other slot b: E2 of step jprev, then P and E1 of step
@@ -286,38 +286,23 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint32_t idesc = make_idesc_bf16(128, C);
 
-    if (warp == RS_NW + RS_ISSUERS) {
-        // ---------------- weight producer: one ring per slot, each in its issuers' order ----------
-        // One thread serves both rings without ever blocking on either (a slot whose issuers wait for
-        // the workers must not starve the other slot's taps).
+    if (warp >= RS_NW + RS_ISSUERS) {
+        // ---------------- weight producers: one warp (one thread) per slot ------------------------
+        // Each slot streams its matrices through its own ring in its issuers' order.  A producer
+        // blocks on its own ring only (mbarrier.try_wait suspends the warp in hardware); a polling
+        // loop over both rings with __nanosleep delivered the last taps of every block ~1 k cycles late.
+        const int sl = warp - (RS_NW + RS_ISSUERS);
         if (lane == 0) {
-            int cnt[2] = {0, 0};
-            const int tot[2] = {T0 * 11, T1 * 11};
-            uint32_t spins = 0;
-            while (cnt[0] < tot[0] || cnt[1] < tot[1]) {
-                bool progress = false;
-#pragma unroll
-                for (int sl = 0; sl < 2; ++sl) {
-                    const int c = cnt[sl];
-                    if (c >= tot[sl]) continue;
-                    const int rs = c % RS_RING;
-                    const uint32_t be = bar_empty + 8 * (sl * RS_RING + rs);
-                    if (c >= RS_RING && !mbar_test(be, ((c / RS_RING) - 1) & 1)) continue;
-                    const int blk = (c / 11) % n, q = c % 11;
-                    const int m = q == 0 ? 0 : (q == 10 ? 10 : 1 + tap_of(q - 1));
-                    const uint32_t bf = bar_full + 8 * (sl * RS_RING + rs);
-                    mbar_arrive_expect_tx(bf, RS_WMAT);
-                    bulk_g2s(sW + (sl * RS_RING + rs) * RS_WMAT,
-                             reinterpret_cast<const uint8_t*>(a.w) + ((size_t)blk * 11 + m) * RS_WMAT,
-                             RS_WMAT, bf);
-                    cnt[sl] = c + 1;
-                    progress = true;
-                }
-                if (progress) spins = 0;
-                else {
-                    __nanosleep(64);                     // do not steal issue slots from the workers
-                    if (++spins > (1u << 24)) __trap();
-                }
+            const int tot = (sl ? T1 : T0) * 11;
+            for (int c = 0; c < tot; ++c) {
+                const int rs = c % RS_RING;
+                if (c >= RS_RING) mbar_wait_wd(bar_empty + 8 * (sl * RS_RING + rs), ((c / RS_RING) - 1) & 1);
+                const int blk = (c / 11) % n, q = c % 11;
+                const int m = q == 0 ? 0 : (q == 10 ? 10 : 1 + tap_of(q - 1));
+                const uint32_t bf = bar_full + 8 * (sl * RS_RING + rs);
+                mbar_arrive_expect_tx(bf, RS_WMAT);
+                bulk_g2s(sW + (sl * RS_RING + rs) * RS_WMAT,
+                         reinterpret_cast<const uint8_t*>(a.w) + ((size_t)blk * 11 + m) * RS_WMAT, RS_WMAT, bf);
             }
         }
     } else if (warp >= RS_NW) {
@@ -388,6 +373,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             mbar_wait_wd(b_u, hp);                       // U of both M-tiles written (E1)
             tc_fence_after_sync();
             if (pf) pp[3] = clock64();
+#pragma unroll
             for (int i = 0; i < 9; ++i) {
                 if (i == 3) mbar_wait_wd(hb, hp);        // halo row from the CTA above
                 if (i == 6) mbar_wait_wd(hb + 8, hp);    // halo row from the CTA below
