@@ -39,6 +39,7 @@ using namespace tc;
 
 constexpr int RS_TH = 8;
 constexpr int RS_NW = 16;                               // worker warps
+constexpr int RS_SCAL_BLOCKS = 128;                     // runs up to this length keep their scalars in shared memory
 constexpr int RS_PR = RS_TH + 2;                        // rows per stored column (with halo rows)
 constexpr uint32_t RS_SBO = RS_PR * 16;                 // 8-row group stride = one column
 
@@ -62,7 +63,8 @@ struct RsCfg {
     static constexpr int MT = W / 16, MPH = MT / 2;     // M-tiles per strip / per half
     static constexpr int NSLOT = 2 * MT * C <= 256 ? 2 : 1;
     static constexpr int ISSUERS = 2 * NSLOT;           // one MMA issue warp per (slot, half)
-    static constexpr int THREADS = (RS_NW + ISSUERS + NSLOT) * 32;   // + one weight producer warp per slot
+    // + one weight producer warp per slot + one halo pusher warp
+    static constexpr int THREADS = (RS_NW + ISSUERS + NSLOT + 1) * 32;
     static constexpr int RING = C == 128 ? 4 : 8;       // weight matrices in flight per slot
     static constexpr int NPIX = (W + 2) * RS_PR;        // stored pixels per operand buffer
     static constexpr uint32_t LBO = NPIX * 16;          // k-chunk (8 channels) stride
@@ -72,7 +74,8 @@ struct RsCfg {
     static constexpr uint32_t HALO_BYTES = (W + 2) * C * 2;      // one halo row incl. wrap columns
     static constexpr uint32_t OFF_W = NSLOT * BUF;
     static constexpr uint32_t OFF_BAR = OFF_W + NSLOT * RING * WMAT;
-    static constexpr uint32_t SMEM = OFF_BAR + 512;
+    static constexpr uint32_t OFF_SCAL = OFF_BAR + 512;      // per-block scalars of up to RS_SCAL_BLOCKS blocks
+    static constexpr uint32_t SMEM = OFF_SCAL + RS_SCAL_BLOCKS * 32;
     static constexpr int CPT = C * MPH / 4;             // TMEM columns (channels) per worker thread
     static_assert(CPT == 16 || CPT == 32, "16 or 32 channels per worker thread");
     static_assert(SMEM <= 232448, "shared memory budget");
@@ -246,12 +249,13 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     //   u[slot]       (2)  workers -> MMA: U of BOTH M-tiles written (the taps read across them)
     //   halo[slot][dir] (4) row data from a neighbour landed (dir 0 = from the CTA above)
     //   free[slot][dir] (4) the neighbour's taps have consumed my last push (dir 0 = the CTA above)
+    //   pushed[slot]  (2)  the pusher warp has read rows 0 / 7 of U: E2 may overwrite them with V
     //   full[2][RING] | empty[2][RING]   weight rings
     const uint32_t bar_acc = bar0, bar_wrk = bar0 + 32, bar_u = bar0 + 64, bar_halo = bar0 + 80;
-    const uint32_t bar_free = bar0 + 112;
-    const uint32_t bar_full = bar0 + 144, bar_empty = bar_full + 16 * RS_RING;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 144 + 32 * RS_RING);
-    static_assert(144 + 32 * RS_RING + 4 <= 512, "barrier region");
+    const uint32_t bar_free = bar0 + 112, bar_pushed = bar0 + 144;
+    const uint32_t bar_full = bar0 + 160, bar_empty = bar_full + 16 * RS_RING;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 160 + 32 * RS_RING);
+    static_assert(160 + 32 * RS_RING + 4 <= 512, "barrier region");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -272,6 +276,8 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         }
         mbar_init(bar_u, 2 * RS_NW);
         mbar_init(bar_u + 8, 2 * RS_NW);
+        mbar_init(bar_pushed, 1);
+        mbar_init(bar_pushed + 8, 1);
         for (int s = 0; s < 2 * RS_RING; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 2);             // both issue warps of the slot
@@ -279,6 +285,11 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         fence_mbar_init();
     }
     if (warp == RS_NW) tmem_alloc(smem_u32(tmem_slot), 512);
+    // the Fixup scalars of every block: a global load in front of a tcgen05 fence costs the workers an
+    // L2 round trip (~800 cycles) per half-round, a shared-memory read does not
+    float* scal_s = reinterpret_cast<float*>(smem + Cfg::OFF_SCAL);
+    for (int i = tid; i < 8 * (a.n_blocks < RS_SCAL_BLOCKS ? a.n_blocks : RS_SCAL_BLOCKS); i += Cfg::THREADS)
+        scal_s[i] = __ldg(a.scal + i);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -286,7 +297,41 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint32_t idesc = make_idesc_bf16(128, C);
 
-    if (warp >= RS_NW + RS_ISSUERS) {
+    if (warp == RS_NW + RS_ISSUERS + NSLOT) {
+        // ---------------- halo pusher: one warp, off the workers' critical path --------------------
+        // After E1 of (slot b, step j1) it copies stored rows 1 and 8 of the slot's U buffer (all W + 2
+        // stored columns, i.e. including the wrap-around duplicates E1 wrote) into stored row 9 of the
+        // CTA above and stored row 0 of the CTA below with st.async: the data travel in the async proxy
+        // the MMA reads operands with and complete bytes on the receiver's halo barrier (dir 0 = from
+        // above), so neither side needs a fence.  Distributed shared memory moves ~20 B/clk per SM:
+        // 8.7 KB per push is ~700 cycles, which used to stall the worker warps at every half-round.
+        const uint32_t up_rank = (rank + RS_CL - 1) % RS_CL, dn_rank = (rank + 1) % RS_CL;
+        const uint32_t up_base = mapa_u32(sbase, up_rank), dn_base = mapa_u32(sbase, dn_rank);
+        const uint32_t up_bar = mapa_u32(bar_halo + 8, up_rank);     // its "from below" barrier
+        const uint32_t dn_bar = mapa_u32(bar_halo, dn_rank);         // its "from above" barrier
+        constexpr int PIECES = (RS_W + 2) * (RS_C / 8);              // 16-byte pieces per row
+        for (int hr = -1; hr <= hr_last; ++hr) {
+            const HalfRound h = half_round(hr, T0, T1);
+            if (!h.g1) continue;
+            const int b = h.b, j1 = h.jprev + 1;
+            mbar_wait_wd(bar_u + 8 * b, j1 & 1);         // both halves of U written (E1)
+            if (j1 > 0) {                                // the neighbours' taps of the previous block
+                mbar_wait_cluster(bar_free + 16 * b, (j1 - 1) & 1);          // have read the old rows
+                mbar_wait_cluster(bar_free + 16 * b + 8, (j1 - 1) & 1);
+            }
+            const uint32_t buf = (uint32_t)b * RS_BUF;
+            for (int p = lane; p < PIECES; p += 32) {
+                const int kc = p / (RS_W + 2), cs = p - kc * (RS_W + 2);     // k-chunk, stored column
+                const uint32_t off = buf + kc * RS_LBO + (uint32_t)(cs * RS_PR) * 16;
+                const uint4 top = *reinterpret_cast<const uint4*>(smem + off + 1 * 16);       // my row 0
+                const uint4 bot = *reinterpret_cast<const uint4*>(smem + off + RS_TH * 16);   // my row 7
+                st_async_v4(up_base + off + (RS_TH + 1) * 16, top, up_bar + 16 * b);
+                st_async_v4(dn_base + off, bot, dn_bar + 16 * b);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_pushed + 8 * b);
+        }
+    } else if (warp >= RS_NW + RS_ISSUERS) {
         // ---------------- weight producers: one warp (one thread) per slot ------------------------
         // Each slot streams its matrices through its own ring in its issuers' order.  A producer
         // blocks on its own ring only (mbarrier.try_wait suspends the warp in hardware); a polling
@@ -417,15 +462,6 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         const bool wrap0 = col0 == 0, wrap1 = col0 == 16 * MPH - 1;
         const uint32_t pix_wrap0 = (uint32_t)((RS_W + 1) * RS_PR + row + 1) * 16 + kc_off;
         const uint32_t pix_wrap1 = (uint32_t)(row + 1) * 16 + kc_off;
-        // halo pushes: my row 0 is row 8 of the CTA above, my row 7 is row -1 of the CTA below
-        const bool push = row == 0 || row == RS_TH - 1;
-        const uint32_t nb_rank = row == 0 ? (rank + RS_CL - 1) % RS_CL : (rank + 1) % RS_CL;
-        const int nb_row = row == 0 ? RS_TH + 1 : 0;     // stored row index in the neighbour's buffer
-        const uint32_t nb_base = mapa_u32(sbase, nb_rank);
-        const uint32_t nb_own = (uint32_t)((col0 + 1) * RS_PR + nb_row) * 16 + kc_off;
-        const uint32_t nb_wrap0 = (uint32_t)((RS_W + 1) * RS_PR + nb_row) * 16 + kc_off;
-        const uint32_t nb_wrap1 = (uint32_t)nb_row * 16 + kc_off;
-        const uint32_t nb_bar = mapa_u32(bar_halo + (row == 0 ? 8 : 0), nb_rank);
         const size_t g_pix = ((size_t)(rank * RS_TH + row) * RS_W + col0) * RS_C + cq * CPT;
 
         uint32_t acc_par = 0;                            // bit 2s+m: parity of acc[s][m] to wait for next
@@ -467,8 +503,9 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             const uint32_t buf = sbase + (uint32_t)b * RS_BUF;
             // the scalars of both blocks this half-round touches, fetched ahead of the first wait
             const int blk_p = h.g3 ? h.jprev % n : 0, blk_n = h.g1 ? (h.jprev + 1) % n : 0;
-            const float4 sp1 = __ldg(reinterpret_cast<const float4*>(a.scal + blk_p * 8) + 1);
-            const float4 sn0 = __ldg(reinterpret_cast<const float4*>(a.scal + blk_n * 8));
+            const float* scal = n <= RS_SCAL_BLOCKS ? scal_s : a.scal;
+            const float4 sp1 = *(reinterpret_cast<const float4*>(scal + blk_p * 8) + 1);
+            const float4 sn0 = *reinterpret_cast<const float4*>(scal + blk_n * 8);
             if (h.g3) {
                 // ---- E2: V over U (own pixels), M-tile by M-tile ----
 #pragma unroll
@@ -477,6 +514,8 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                     if (pf) pp[9 + m] = clock64();
                     float v[CPT];
                     load_lo(tmem_base + b * SLOT_COLS + ACC_COL + m * HALF_COLS + t_off, v);
+                    // V goes over U in place: the pusher must have read rows 0 / 7 (long done)
+                    if (m == 0) mbar_wait_wd(bar_pushed + 8 * b, h.jprev & 1);
                     const uint32_t dst = buf + pix_own + m * M_PIX;
                     store_half(dst, v, 0, sp1.x, sp1.y);
                     tmem_ld_wait();
@@ -560,23 +599,6 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                         if (wrap) st_cta_v4(dw + k * RS_LBO, u[k]);
                     }
                     signal(bar_u + 8 * b);
-                    // halo pushes after the local hand-over: the dy = 0 taps run meanwhile.  My row 0
-                    // completes bytes on the upper CTA's "from below" barrier, my row 7 on the lower
-                    // CTA's "from above" barrier: halo[slot][dir], dir 0 = from above
-                    if (push) {
-                        // the neighbour's taps of the previous block must have read the old row
-                        if (j1 > 0 && m == 0)
-                            mbar_wait_cluster(bar_free + 16 * b + (row == 0 ? 0 : 8), (j1 - 1) & 1);
-                        const uint32_t nbar = nb_bar + 16 * b;
-                        const uint32_t nbuf = nb_base + (uint32_t)b * RS_BUF;
-                        const uint32_t dn = nbuf + nb_own + m * M_PIX;
-                        const uint32_t dnw = nbuf + (m ? nb_wrap1 : nb_wrap0);
-#pragma unroll
-                        for (int k = 0; k < NCH; ++k) {
-                            st_async_v4(dn + k * RS_LBO, u[k], nbar);
-                            if (wrap) st_async_v4(dnw + k * RS_LBO, u[k], nbar);
-                        }
-                    }
                 }
                 if (pf) pp[17] = clock64();
             }
