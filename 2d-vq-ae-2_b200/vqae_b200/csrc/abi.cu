@@ -135,6 +135,18 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
     const PreOp pre_skip{p->bias1c, 0.f, 0};
     int rc;
 
+    // 'up' block in two kernels: the three low-resolution 1x1 convs (up_head.cu: t2 and the low-res
+    // skip into t1), then both upsamples + branch_conv3 + residual sum (up_tail.cu); same arithmetic as
+    // the six launches further down
+    if (p->mode == VQAE_MODE_UP && p->w_skip && up_head_supported(B * H * W, ci, cb, co) &&
+        up_tail_supported(B, H, W, cb, co)) {
+        rc = up_head_f32(x, p->w1, p->w2, p->w_skip, t2, t1, B * H * W, ci, cb, co, p->bias1a,
+                         p->bias1b, p->bias2a, p->bias2b, p->bias1c, stream);
+        if (rc) return rc;
+        return up_tail_f32(t2, t1, p->w3, out, B, H, W, cb, co, p->bias3a, p->bias3b, p->scale,
+                           p->bias4, p->bias1d, stream);
+    }
+
     // branch_conv1(act(x + bias1a) + bias1b)                      conv_block.py:199-200
     rc = conv_f32(CONV_1x1, x, p->w1, t1, nullptr, B, H, W, ci, cb, pre1, 1.f, 0.f, stream);
     if (rc) return rc;
@@ -174,7 +186,8 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
                       stream);
         if (rc) return rc;
         // both upsamples, the pre-activation, branch_conv3 and the residual sum in ONE kernel: the
-        // upsampled tensors never reach HBM (same arithmetic as the three launches below)
+        // upsampled tensors never reach HBM (same arithmetic as the three launches below); reached
+        // when only the tail is built for the shape (c_branch = 64)
         if (up_tail_supported(B, H, W, cb, co))
             return up_tail_f32(t2, t1, p->w3, out, B, H, W, cb, co, p->bias3a, p->bias3b, p->scale,
                                p->bias4, p->bias1d, stream);

@@ -19,7 +19,7 @@ REPO = PKG.parent.parent
 LIB_PATH = PKG / "libvqae_b200.so"
 STAMP = PKG / ".libvqae_b200.stamp"
 
-SOURCES = ["abi.cu", "conv_f32.cu", "stems.cu", "quantize.cu", "quantize_tc.cu", "tc_kernels.cu", "tc_down.cu", "tc_chain.cu", "tc_resident.cu", "tc_bench.cu", "up_tail.cu"]
+SOURCES = ["abi.cu", "conv_f32.cu", "stems.cu", "quantize.cu", "quantize_tc.cu", "tc_kernels.cu", "tc_down.cu", "tc_chain.cu", "tc_resident.cu", "tc_bench.cu", "up_tail.cu", "up_head.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "tc_common.cuh"]
 
 NVCC_FLAGS = [

@@ -15,6 +15,12 @@ int bicubic_up2_f32(const float* in, float* out, int64_t B, int H, int W, int C,
 int pack_conv_weight_f32(const float* w, float* packed, int O, int I, int taps,
                          cudaStream_t stream);
 
+// up_head.cu (low-resolution half of an 'up' block: the three 1x1 convs in one pointwise kernel)
+bool up_head_supported(int64_t P, int ci, int cb, int co);
+int up_head_f32(const float* x, const float* w1, const float* w2, const float* ws, float* t2, float* s1,
+                int64_t P, int ci, int cb, int co, float b1a, float b1b, float b2a, float b2b, float b1c,
+                cudaStream_t stream);
+
 // up_tail.cu (high-resolution half of an 'up' block in one kernel)
 bool up_tail_supported(int64_t B, int H, int W, int cb, int co);
 int up_tail_f32(const float* t2, const float* s1, const float* w3, float* out, int64_t B, int H, int W,
