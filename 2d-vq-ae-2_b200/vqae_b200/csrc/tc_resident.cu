@@ -1,16 +1,19 @@
-// Image-resident tcgen05 kernel for a RUN of consecutive PreActFixupResBlocks in mode 'same' at the
-// latent resolution (C = 64, 32 x 32): the 50-block trunks (vq_ae/model.py:150-153,240-263) and the
-// post layers of the last DownBlock / first UpBlock (conv_block.py:18-91); block arithmetic
-// conv_block.py:196-216.
+// Image-resident tcgen05 kernel for a RUN of consecutive PreActFixupResBlocks in mode 'same' whose
+// image a thread-block cluster can own: the 50-block trunks (vq_ae/model.py:150-153,240-263) with the
+// adjacent post / pre layers of the pyramids (conv_block.py:18-91) at C = 64 or 128, 32 x 32, and the
+// five-block runs at C = 32, 64 x 64; block arithmetic conv_block.py:196-216.  (Written up for the
+// C = 64 shape; RsCfg below lists how the others map onto it.)
 //
 // The fp32 residual stream never leaves the SM: a cluster of four CTAs owns one image per *slot*,
 // CTA r holding rows 8r .. 8r+7 (256 pixels = two 128-lane M-tiles) of the residual in TENSOR MEMORY
 // (2 x 64 fp32 columns).  Per block and slot:
 //     P   workers: tcgen05.ld residual -> A1 = bf16(elu(x + b1a) + b1b) -> shared operand buffer
 //     G1  tcgen05.mma  D  = A1 . W1^T                      (2 M-tiles x 4 k-steps)
-//     E1  workers: U = bf16(elu(D + b2a) + b2b) -> operand buffer, wrap-around columns duplicated,
-//         first/last row pushed into the neighbour CTAs' halo rows through distributed shared memory
-//     G2  nine taps accumulate into D; a tap is a constant start-address shift of the A descriptor
+//     E1  workers: U = bf16(elu(D + b2a) + b2b) -> operand buffer, wrap-around columns duplicated;
+//         a pusher warp then copies the first / last row into the neighbour CTAs' halo rows through
+//         distributed shared memory (st.async, bytes counted on the receiver's mbarrier)
+//     G2  nine taps accumulate into D; a tap is a constant start-address shift of the A descriptor;
+//         the three dy = 0 taps need no halo row and go first
 //     E2  workers: V = bf16(elu(D + b3a) + b3b) -> operand buffer
 //     G3  tcgen05.mma  R += V . (scale W3)^T               accumulates straight into the residual
 // so the residual add costs nothing and there is no global-memory traffic between the first load and
@@ -21,13 +24,15 @@
 // multiplied -- and tap (dy, dx) is the shift (dx * 10 + dy) * 16 B.
 // Each CTA runs TWO slots (two different images, 2 x (128 residual + 128 accumulator) = 512 TMEM
 // columns) half a block out of phase: while the nine taps of one slot occupy the tensor pipe, the 16
-// worker warps run E2 -> P -> E1 of the other slot.  Every (slot, M-tile) has its OWN MMA issue warp:
-// one issuing thread only gets a 128 x 64 x 16 MMA every ~80 cycles out of the tensor pipe, several
-// streams together reach 48 (profiles/mma_bench_issuers.py).  Each slot streams its weight matrices
-// through its own ring of bulk copies, fed by one producer thread that never blocks on either ring.
+// worker warps run E2 -> P -> E1 of the other slot, half strip by half strip.  Every (slot, half strip)
+// has its OWN MMA issue warp: one issuing thread only gets a 128 x 64 x 16 MMA every ~80 cycles out of
+// the tensor pipe, several streams together reach 48 (profiles/mma_bench_issuers.py).  Each slot streams
+// its weight matrices through its own ring of bulk copies, fed by its own producer warp.
 // There is ONE operand buffer per slot (A1, U and V overwrite each other in place); a neighbour pushes
 // the halo rows of block i+1 only after this CTA has signalled that the taps of block i have read the
 // old rows (free barriers), which leaves 2 x 64 KB of shared memory for the weight rings.
+// Warp roles: 0-15 workers | MMA issue warps | weight producers | halo pusher.  Every wait carries a
+// watchdog (__trap after 2^26 polls): a protocol error faults instead of hanging the device.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -155,19 +160,6 @@ __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
             : "memory");
         if (!done && ++spins > (1u << 26)) __trap();
     } while (!done);
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done != 0;
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
