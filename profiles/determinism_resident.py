@@ -1,0 +1,35 @@
+"""Repeat the image-resident kernel on fixed inputs and count launches whose output differs bitwise
+from the first one.  usage: python profiles/determinism_resident.py [reps]"""
+import sys
+from pathlib import Path
+REPO = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(REPO / "2d-vq-ae-2_b200")]
+import torch  # noqa: E402
+from vqae_b200 import _lib as L  # noqa: E402
+from vqae_b200 import engine as E  # noqa: E402
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+dev = torch.device("cuda:0")
+lib = L.load()
+st = E._stream(dev)
+for C, HW, B, nblk in ((32, 64, 256, 5), (64, 32, 256, 6), (128, 32, 64, 4), (32, 64, 7, 5), (64, 32, 3, 9)):
+    gen = torch.Generator().manual_seed(7)
+    packs = []
+    for i in range(nblk):
+        ws = [(torch.randn(C, C, k, k, generator=gen) * 0.05).to(dev) for k in (1, 3, 1)]
+        pk = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
+        L.check(lib.vqae_pack_resident_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, 0.2,
+                                                  E._ptr(pk), st), "pack")
+        packs.append(pk)
+    w_all = torch.cat(packs)
+    scal = torch.tensor([[0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.2]] * nblk, dtype=torch.float32).to(dev)
+    x = torch.randn(B, HW, HW, C, device=dev)
+    outs = []
+    for i in range(reps + 1):
+        y = torch.empty_like(x)
+        L.check(lib.vqae_trunk_resident_bf16(E._ptr(x), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, HW, HW,
+                                             C, st), "resident")
+        outs.append(y)
+    torch.cuda.synchronize()
+    bad = [(i, int((o != outs[0]).sum())) for i, o in enumerate(outs[1:], 1) if not torch.equal(o, outs[0])]
+    print(f"C={C} {HW}x{HW} batch {B}, {nblk} blocks: {len(bad)}/{reps} launches differ from the first", bad[:8])

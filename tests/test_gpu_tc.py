@@ -190,6 +190,30 @@ def test_resident_trunk_vs_block_by_block_and_fp32(c, batch, n, monkeypatch):
     assert torch.equal(xc, y)
 
 
+@pytest.mark.parametrize("c,batch,n,reps", [(32, 256, 5, 150), (64, 256, 4, 100), (128, 70, 3, 60)])
+def test_resident_trunk_repeated_launches_bit_identical(c, batch, n, reps):
+    """Many launches on the same input must give the same bits: the kernel synchronises four (eight)
+    CTAs per image through mbarriers, distributed shared memory and tcgen05.commit, and a protocol
+    slip shows up as a rare bitwise difference, not as a tolerance failure (a variant with one weight
+    buffer shared by both slots failed this at C = 32, batch 256, in ~3 % of launches and was not
+    merged; profiles/determinism_resident.py)."""
+    hw = _RES_HW[c]
+    packed = E.pack_blocks(_same_blocks(c, n, 70))
+    chain = E.PackedChain(packed, resident=True)
+    x = torch.randn(batch, hw, hw, c, generator=torch.Generator().manual_seed(c + n)).to(DEV)
+    lib = L.load()
+    outs = []
+    for _ in range(reps + 1):
+        y = torch.empty_like(x)
+        L.check(lib.vqae_trunk_resident_bf16(E._ptr(x), E._ptr(y), E._ptr(chain.weights),
+                                             E._ptr(chain.scalars), chain.n, batch, hw, hw, c,
+                                             E._stream(x.device)), "vqae_trunk_resident_bf16")
+        outs.append(y)
+    torch.cuda.synchronize()
+    bad = [i for i, o in enumerate(outs[1:], 1) if not torch.equal(o, outs[0])]
+    assert not bad, f"{len(bad)} of {reps} launches differ from the first: {bad[:10]}"
+
+
 @pytest.mark.parametrize("c", [64, 128, 32])
 def test_resident_trunk_halo_and_wrap_exactness(c):
     """Identity-like weights make the 3x3 stage a pure circular shift: every pixel of the output must
