@@ -253,10 +253,20 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t leader = lane == 0;
     const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x / RS_CL;                 // one image per slot and cluster
+    // Persistent clusters: cluster k works through the image groups k, k + NCL, k + 2 NCL, ... (a group
+    // = one image per slot); the step counters of a slot simply run on across its images, so the next
+    // image's blocks follow the previous one's without re-launching the cluster (a re-launch costs
+    // ~20 us: all CTAs of the cluster must be free at once, TMEM allocation, barrier set-up, the
+    // half-block lead-in of slot 1 -- 40 % of the time of a five-block run).
+    const int cl_id = blockIdx.x / RS_CL, ncl = gridDim.x / RS_CL;
     const int n = a.n_blocks;
-    const int img0 = NSLOT * pair, img1 = NSLOT * pair + 1;
-    const int T0 = img0 < a.n_img ? n : 0, T1 = (NSLOT == 2 && img1 < a.n_img) ? n : 0;
+    const int n_groups = (a.n_img + NSLOT - 1) / NSLOT;
+    const int my_groups = cl_id < n_groups ? (n_groups - cl_id + ncl - 1) / ncl : 0;
+    // images of slot s: NSLOT * (cl_id + t * ncl) + s for t < cnt_s (the very last group may lack slot 1)
+    const int cnt0 = my_groups;
+    const int cnt1 = NSLOT == 2 ? my_groups - ((my_groups > 0 && NSLOT * (cl_id + (my_groups - 1) * ncl) + 1 >= a.n_img) ? 1 : 0) : 0;
+    const int T0 = n * cnt0, T1 = n * cnt1;
+    auto image_of = [&](int slot, int step) { return NSLOT * (cl_id + (step / n) * ncl) + slot; };
     const int hr_last = 2 * (T0 > T1 ? T0 : T1);
 
     if (tid == 0) {
@@ -530,7 +540,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                         if (pf) pp[12 + m] = clock64();
                     }
                     if (last) {
-                        const int img = b ? img1 : img0;
+                        const int img = image_of(b, h.jprev);
                         load_lo(Rm, v);
                         tmem_ld_wait();
                         float4* o = reinterpret_cast<float4*>(a.out + (size_t)img * RS_H * RS_W * RS_C +
@@ -544,7 +554,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                         // ---- P: A1 from the residual (first block of an image: from global memory) ----
                         float pre = sn0.x;
                         if (blk_n == 0) {
-                            const int img = b ? img1 : img0;
+                            const int img = image_of(b, h.jprev + 1);
                             const float4* s4 = reinterpret_cast<const float4*>(
                                 a.x + (size_t)img * RS_H * RS_W * RS_C + g_pix + m * 16 * MPH * RS_C);
 #pragma unroll
@@ -620,19 +630,41 @@ pack_resident_block_kernel(const float* __restrict__ w1, const float* __restrict
     out[i] = __float2bfloat16_rn(v);
 }
 
+// clusters of this instantiation the device holds at once (0 if the query fails)
+template <int C, int W>
+int resident_clusters() {
+    using Cfg = RsCfg<C, W>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(Cfg::CL * 64);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = Cfg::CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, trunk_resident_tc_kernel<C, W>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 template <int C, int W>
 int launch_resident(const ResidentArgs& a, int64_t B, cudaStream_t stream) {
     using Cfg = RsCfg<C, W>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<C, W>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         if (Cfg::CL > 8)                                 // clusters of 16 CTAs are an opt-in size
             VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<C, W>,
                                                cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
+        max_clusters = resident_clusters<C, W>();
     }
-    const int64_t clusters = (B + Cfg::NSLOT - 1) / Cfg::NSLOT;      // one image per slot
+    // one image per slot and group; persistent: no more clusters than the device holds at once
+    int64_t clusters = (B + Cfg::NSLOT - 1) / Cfg::NSLOT;
+    if (max_clusters > 0 && clusters > max_clusters) clusters = max_clusters;
     if (clusters * Cfg::CL > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
     trunk_resident_tc_kernel<C, W><<<(unsigned)clusters * Cfg::CL, Cfg::THREADS, Cfg::SMEM, stream>>>(a);
     return check_launch();
@@ -648,21 +680,13 @@ bool trunk_resident_supported(int64_t B, int H, int W, int C) {
     return (W == 32 && (C == 64 || C == 128)) || (W == 64 && C == 32);
 }
 
-// resident clusters of the C = 64 kernel the device can hold at once (each runs one image pair)
+// resident clusters of the C = 64 kernel the device can hold at once (each runs one image pair at a time)
 int trunk_resident_max_clusters(int* out) {
-    using Cfg = RsCfg<64, 32>;
     VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<64, 32>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(Cfg::CL * 64);
-    cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = Cfg::CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr; cfg.numAttrs = 1;
-    VQAE_CUDA_TRY(cudaOccupancyMaxActiveClusters(out, trunk_resident_tc_kernel<64, 32>, &cfg));
-    return VQAE_OK;
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)RsCfg<64, 32>::SMEM));
+    *out = resident_clusters<64, 32>();
+    return *out > 0 ? VQAE_OK : VQAE_ERR_CUDA;
 }
 
 int pack_resident_block_bf16(const float* w1, const float* w2, const float* w3, int C, float scale,
