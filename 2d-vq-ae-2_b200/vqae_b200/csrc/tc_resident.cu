@@ -495,6 +495,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             if (lane == 0) mbar_arrive(bar);
         };
 
+        int bn0 = 0, bn1 = 0, bp0 = 0, bp1 = 0;        // per slot: block of the next step to prepare / of the previous one
         for (int hr = -1; hr <= hr_last; ++hr) {
             const HalfRound h = half_round(hr, T0, T1);
             const int b = h.b;
@@ -504,7 +505,14 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             if (pf) pp[8] = clock64();
             const uint32_t buf = sbase + (uint32_t)b * RS_BUF;
             // the scalars of both blocks this half-round touches, fetched ahead of the first wait
-            const int blk_p = h.g3 ? h.jprev % n : 0, blk_n = h.g1 ? (h.jprev + 1) % n : 0;
+            // block indices of the two steps this half-round touches, kept as running counters (a run-time
+            // "% n" is a 30-instruction I2F / MUFU.RCP / F2I chain, twice, in front of the first wait of
+            // every half-round)
+            const int blk_n = b ? bn1 : bn0, blk_p = b ? bp1 : bp0;
+            if (h.g1) {
+                const int nx = blk_n + 1 == n ? 0 : blk_n + 1;
+                if (b) { bp1 = blk_n; bn1 = nx; } else { bp0 = blk_n; bn0 = nx; }
+            }
             const float* scal = n <= RS_SCAL_BLOCKS ? scal_s : a.scal;
             const float4 sp1 = *(reinterpret_cast<const float4*>(scal + blk_p * 8) + 1);
             const float4 sn0 = *reinterpret_cast<const float4*>(scal + blk_n * 8);

@@ -1,5 +1,5 @@
 """Launch the image-resident trunk kernel (vqae_trunk_resident_bf16) at the bench shape (timing / ncu).
-usage: python profiles/run_resident.py [n_blocks=54] [reps=3] [batch=256]"""
+usage: python profiles/run_resident.py [n_blocks=54] [reps=3] [batch=256] [C=64]"""
 import sys
 from pathlib import Path
 REPO = Path(__file__).resolve().parent.parent
@@ -8,10 +8,11 @@ import torch  # noqa: E402
 from vqae_b200 import _lib as L  # noqa: E402
 from vqae_b200 import engine as E  # noqa: E402
 
-H, W, C = 32, 32, 64
 nblk = int(sys.argv[1]) if len(sys.argv) > 1 else 54
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+C = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+H = W = {64: 32, 128: 32, 32: 64}[C]
 dev = torch.device("cuda:0")
 lib = L.load()
 st = E._stream(dev)
