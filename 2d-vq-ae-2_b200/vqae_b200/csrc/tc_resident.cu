@@ -520,7 +520,16 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                 // ---- E2: V over U (own pixels), M-tile by M-tile ----
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
-                    wait_acc(2 * b + m);                 // nine taps of step jprev complete
+                    // V overwrites U in place, and the taps of EACH half read one column of the other
+                    // half (dx = +-1 across the seam): both halves' taps must be complete before the
+                    // first store.  (Waiting per half let half 0's V land in column 16 MPH - 1 while
+                    // half 1's last taps were still reading it -- seven wrong pixels in the seam
+                    // column in ~1 % of launches once the tap phase got faster;
+                    // profiles/determinism_diffpos.py.)
+                    if (m == 0) {
+                        wait_acc(2 * b);                 // nine taps of step jprev complete, half 0
+                        wait_acc(2 * b + 1);             // ... and half 1
+                    }
                     if (pf) pp[9 + m] = clock64();
                     float v[CPT];
                     load_lo(tmem_base + b * SLOT_COLS + ACC_COL + m * HALF_COLS + t_off, v);
