@@ -68,9 +68,16 @@ struct RsCfg {
     static constexpr int MT = W / 16, MPH = MT / 2;     // M-tiles per strip / per half
     static constexpr int NSLOT = 2 * MT * C <= 256 ? 2 : 1;
     static constexpr int ISSUERS = 2 * NSLOT;           // one MMA issue warp per (slot, half)
-    // + one weight producer warp per slot + one halo pusher warp
-    static constexpr int THREADS = (RS_NW + ISSUERS + NSLOT + 1) * 32;
-    static constexpr int RING = C == 128 ? 4 : 8;       // weight matrices in flight per slot
+    // Weights.  C <= 64: ONE buffer of 11 matrices per CTA, entry q = matrix q of the current block, used
+    // by both slots (slot 1 half a block later) and refilled with the next block's matrix once all four
+    // issue warps have released it: ring position and descriptor offset of every MMA are compile-time
+    // constants (no R2UR traffic in front of the MMAs) and each block's weights are fetched once.
+    // C = 128 (32 KB matrices): a 4-deep ring in issue order with a run-time position.
+    static constexpr bool SHARED_W = C <= 64;
+    static constexpr int RING = SHARED_W ? 11 : 4;
+    static constexpr int NRING = SHARED_W ? 1 : NSLOT;  // rings (and producer warps) per CTA
+    // + one weight producer warp per ring + one halo pusher warp
+    static constexpr int THREADS = (RS_NW + ISSUERS + NRING + 1) * 32;
     static constexpr int NPIX = (W + 2) * RS_PR;        // stored pixels per operand buffer
     static constexpr uint32_t LBO = NPIX * 16;          // k-chunk (8 channels) stride
     static constexpr uint32_t BUF = (C / 8) * LBO;      // operand buffer of one slot
@@ -78,7 +85,7 @@ struct RsCfg {
     static constexpr uint32_t WLBO = C * 16;
     static constexpr uint32_t HALO_BYTES = (W + 2) * C * 2;      // one halo row incl. wrap columns
     static constexpr uint32_t OFF_W = NSLOT * BUF;
-    static constexpr uint32_t OFF_BAR = OFF_W + NSLOT * RING * WMAT;
+    static constexpr uint32_t OFF_BAR = OFF_W + NRING * RING * WMAT;
     static constexpr uint32_t OFF_SCAL = OFF_BAR + 512;      // per-block scalars of up to RS_SCAL_BLOCKS blocks
     static constexpr uint32_t SMEM = OFF_SCAL + RS_SCAL_BLOCKS * 32;
     static constexpr int CPT = C * MPH / 4;             // TMEM columns (channels) per worker thread
@@ -225,7 +232,8 @@ __global__ void __cluster_dims__(RsCfg<C, W>::CL, 1, 1) __launch_bounds__(RsCfg<
 trunk_resident_tc_kernel(ResidentArgs a) {
     using Cfg = RsCfg<C, W>;
     constexpr int RS_C = C, RS_W = W, RS_H = W, RS_CL = Cfg::CL, MPH = Cfg::MPH;
-    constexpr int RS_RING = Cfg::RING, RS_ISSUERS = Cfg::ISSUERS, NSLOT = Cfg::NSLOT;
+    constexpr int RS_RING = Cfg::RING, RS_ISSUERS = Cfg::ISSUERS, NSLOT = Cfg::NSLOT, NRING = Cfg::NRING;
+    constexpr bool SHARED_W = Cfg::SHARED_W;
     constexpr int CPT = Cfg::CPT, HC = CPT / 2;          // columns per thread / per half load
     constexpr uint32_t RS_LBO = Cfg::LBO, RS_BUF = Cfg::BUF, RS_WMAT = Cfg::WMAT, RS_WLBO = Cfg::WLBO;
     constexpr uint32_t RS_HALO_BYTES = Cfg::HALO_BYTES, RS_OFF_W = Cfg::OFF_W, RS_OFF_BAR = Cfg::OFF_BAR;
@@ -242,12 +250,12 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     //   halo[slot][dir] (4) row data from a neighbour landed (dir 0 = from the CTA above)
     //   free[slot][dir] (4) the neighbour's taps have consumed my last push (dir 0 = the CTA above)
     //   pushed[slot]  (2)  the pusher warp has read rows 0 / 7 of U: E2 may overwrite them with V
-    //   full[2][RING] | empty[2][RING]   weight rings
+    //   full[NRING][RING] | empty[NRING][RING]   weight ring(s)
     const uint32_t bar_acc = bar0, bar_wrk = bar0 + 32, bar_u = bar0 + 64, bar_halo = bar0 + 80;
     const uint32_t bar_free = bar0 + 112, bar_pushed = bar0 + 144;
-    const uint32_t bar_full = bar0 + 160, bar_empty = bar_full + 16 * RS_RING;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 160 + 32 * RS_RING);
-    static_assert(160 + 32 * RS_RING + 4 <= 512, "barrier region");
+    const uint32_t bar_full = bar0 + 160, bar_empty = bar_full + 8 * NRING * RS_RING;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_OFF_BAR + 160 + 16 * NRING * RS_RING);
+    static_assert(160 + 16 * NRING * RS_RING + 4 <= 512, "barrier region");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -280,9 +288,10 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         mbar_init(bar_u + 8, 2 * RS_NW);
         mbar_init(bar_pushed, 1);
         mbar_init(bar_pushed + 8, 1);
-        for (int s = 0; s < 2 * RS_RING; ++s) {
+        for (int s = 0; s < NRING * RS_RING; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 2);             // both issue warps of the slot
+            // every issue warp that reads the entry: both of a slot, of all active slots if shared
+            mbar_init(bar_empty + 8 * s, SHARED_W ? 2 * NSLOT : 2);
         }
         fence_mbar_init();
     }
@@ -299,7 +308,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint32_t idesc = make_idesc_bf16(128, C);
 
-    if (warp == RS_NW + RS_ISSUERS + NSLOT) {
+    if (warp == RS_NW + RS_ISSUERS + NRING) {
         // ---------------- halo pusher: one warp, off the workers' critical path --------------------
         // After E1 of (slot b, step j1) it copies stored rows 1 and 8 of the slot's U buffer (all W + 2
         // stored columns, i.e. including the wrap-around duplicates E1 wrote) into stored row 9 of the
@@ -334,13 +343,13 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             if (lane == 0) mbar_arrive(bar_pushed + 8 * b);
         }
     } else if (warp >= RS_NW + RS_ISSUERS) {
-        // ---------------- weight producers: one warp (one thread) per slot ------------------------
-        // Each slot streams its matrices through its own ring in its issuers' order.  A producer
-        // blocks on its own ring only (mbarrier.try_wait suspends the warp in hardware); a polling
-        // loop over both rings with __nanosleep delivered the last taps of every block ~1 k cycles late.
+        // ---------------- weight producer(s): one warp (one thread) per ring ------------------------
+        // Ring order = the issue order of a step: W1 | taps (tap_of) | scale * W3.  A producer blocks on
+        // its own ring only (mbarrier.try_wait suspends the warp in hardware); a polling loop over two
+        // rings with __nanosleep delivered the last taps of every block ~1 k cycles late.
         const int sl = warp - (RS_NW + RS_ISSUERS);
         if (lane == 0) {
-            const int tot = (sl ? T1 : T0) * 11;
+            const int tot = (SHARED_W ? (T0 > T1 ? T0 : T1) : (sl ? T1 : T0)) * 11;
             for (int c = 0; c < tot; ++c) {
                 const int rs = c % RS_RING;
                 if (c >= RS_RING) mbar_wait_wd(bar_empty + 8 * (sl * RS_RING + rs), ((c / RS_RING) - 1) & 1);
@@ -362,7 +371,8 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         const uint32_t R = slot * SLOT_COLS + m * HALF_COLS, D = R + ACC_COL;
         int wcnt = 0;
         uint32_t wrk_par = 0;
-        const uint64_t dW = make_desc(sW + slot * RS_RING * RS_WMAT, RS_WLBO, 128);
+        const int ring = SHARED_W ? 0 : slot;
+        const uint64_t dW = make_desc(sW + ring * RS_RING * RS_WMAT, RS_WLBO, 128);
         // A operand of this half's first M-tile: own pixels start at stored column 16 MPH m + 1, row 1;
         // the next M-tile is 16 columns further
         const uint32_t a_base = sbase + (uint32_t)slot * RS_BUF +
@@ -376,10 +386,14 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         };
         // one weight matrix against this M-tile: D(+)= A(shift) . W^T
         long long ring_wait = 0;
-        auto gemm = [&](int shift_px, uint32_t d_col, bool acc_first) {
-            const int rs = wcnt % RS_RING;
+        // q: position of the matrix inside a step (0 = W1, 1 + i = i-th tap issued, 10 = W3).  With the
+        // shared buffer q is also the ring position (a compile-time constant after unrolling) and the
+        // phase is the step's parity; with per-slot rings the position runs on with wcnt.
+        auto gemm = [&](int q, int j, int shift_px, uint32_t d_col, bool acc_first) {
+            const int rs = SHARED_W ? q : wcnt % RS_RING;
+            const uint32_t par = SHARED_W ? (uint32_t)(j & 1) : (uint32_t)((wcnt / RS_RING) & 1);
             const long long tw = a.prof ? clock64() : 0;
-            mbar_wait_wd(bar_full + 8 * (slot * RS_RING + rs), (wcnt / RS_RING) & 1);
+            mbar_wait_wd(bar_full + 8 * (ring * RS_RING + rs), par);
             if (a.prof) ring_wait += clock64() - tw;
             tc_fence_after_sync();
             const uint64_t dWm = dW + (uint64_t)((rs * RS_WMAT) >> 4);
@@ -392,7 +406,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                               dWm + (uint64_t)((ks * 2 * RS_WLBO) >> 4), idesc,
                               (acc_first || ks > 0) ? 1u : 0u, leader);
             }
-            umma_commit(bar_empty + 8 * (slot * RS_RING + rs), leader);
+            umma_commit(bar_empty + 8 * (ring * RS_RING + rs), leader);
             ++wcnt;
         };
         const uint32_t hb = bar_halo + 16 * slot;
@@ -408,7 +422,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             if (pf) pp[0] = clock64();
             wait_wrk();
             if (pf) pp[1] = clock64();
-            gemm(0, D, false);
+            gemm(0, j, 0, D, false);
             umma_commit(b_acc, leader);
             // ---- G2: nine taps; dy = 0 first, then the halo rows as they arrive ----
             const uint32_t hp = j & 1;
@@ -426,7 +440,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                 if (i == 6) mbar_wait_wd(hb + 8, hp);    // halo row from the CTA below
                 const int t = tap_of(i);
                 if (pf) pp[23 + i] = clock64();
-                gemm((t % 3 - 1) * RS_PR + (t / 3 - 1), D, i > 0);
+                gemm(1 + i, j, (t % 3 - 1) * RS_PR + (t / 3 - 1), D, i > 0);
             }
             umma_commit(b_acc, leader);
             if (pf) pp[4] = clock64();
@@ -443,10 +457,22 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             // ---- G3: R += V . (scale W3)^T ----
             wait_wrk();
             if (pf) pp[5] = clock64();
-            gemm(0, R, true);
+            gemm(10, j, 0, R, true);
             umma_commit(b_acc, leader);
             if (pf) pp[6] = clock64();
             __syncwarp();
+        }
+        // shared weight buffer: a slot with fewer steps than the other one (odd batch: the last image
+        // group has no slot 1) keeps releasing the entries it no longer reads, so that the producer's
+        // release count per entry stays 2 * NSLOT
+        if constexpr (SHARED_W) {
+            const int t_max = T0 > T1 ? T0 : T1;
+            for (int j = T; j < t_max; ++j)
+                for (int q = 0; q < RS_RING; ++q) {
+                    mbar_wait_wd(bar_full + 8 * q, (uint32_t)(j & 1));
+                    if (leader) mbar_arrive(bar_empty + 8 * q);
+                    __syncwarp();
+                }
         }
     } else {
         // ---------------- workers: per unit (slot, M-tile, phase) one pixel x 16 channels per thread --
