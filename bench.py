@@ -232,8 +232,8 @@ def time_dominant_kernel(dev, peaks, precision: str):
                 "with CUDA events on the launch stream, 4 rotating buffer pairs")
     achieved = flops / (ms * 1e-3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the committed
-    # ncu --set full capture (profiles/r1_trunk_resident_ncu_summary.txt): 72.1 MB + 22.1 MB
-    traffic = 94.12e6 if precision == "bf16" else None
+    # ncu --set full capture (profiles/r1_trunk_resident_ncu_summary.txt): 72.0 MB + 16.7 MB
+    traffic = 88.77e6 if precision == "bf16" else None
     return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops, "note": note}
