@@ -145,19 +145,23 @@ int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void*
                          int64_t batch, int height, int width, int c, void* stream);
 /* The same run with the fp32 residual stream RESIDENT ON THE SM (c in {64, 128} at 32 x 32: the
  * 50-block trunks model.py:150-153,240-263 plus the adjacent post/pre layers; c == 32 at 64 x 64: the
- * five-block runs of the pyramids): a cluster of height / 8 CTAs owns an image, the residual lives in tensor memory and branch_conv3 accumulates straight into
- * it, halo rows travel through distributed shared memory; the only global traffic is the first load
- * and the last store of each image.  w_packed_all: vqae_pack_resident_block_bf16 outputs back to
- * back (11 * c * c bf16 per block, branch_conv3 pre-multiplied by the Fixup `scale`, so bias4 and
+ * five-block runs of the pyramids): a cluster of height / 8 CTAs owns an image, the residual lives in
+ * tensor memory and branch_conv3 accumulates straight into it, halo rows travel through distributed
+ * shared memory; the only global traffic is the first load and the last store of each image.  The
+ * launch is persistent (at most as many clusters as the device holds at once; each works through
+ * its share of the batch), any batch size.  w_packed_all: vqae_pack_resident_block_bf16 outputs back
+ * to back (11 * c * c bf16 per block, branch_conv3 pre-multiplied by the Fixup `scale`, so bias4 and
  * scale are applied as  x += (scale W3) v;  the bias4 terms are summed and added on the way out);
  * scalars_dev as for vqae_same_chain_bf16.  x, out: NHWC fp32 [B,H,W,c]; out may alias x.
- * Not bit-identical to vqae_same_block_bf16 (rounding of scale*W3, accumulation order): agrees
- * within the bf16 tolerance (tests/test_gpu_tc.py).                                            */
+ * Deterministic (repeated launches are bit-identical).  Not bit-identical to vqae_same_block_bf16
+ * (rounding of scale*W3, accumulation order): agrees within the bf16 tolerance
+ * (tests/test_gpu_tc.py).                                                                       */
 /* profiling aid: DEVICE int64 [8][32] that CTA 0 fills with clock64() stamps of eight steady-state
  * half-rounds (MMA warp: slots 0-6, worker warp 0: slots 8-22); NULL switches it off          */
 void vqae_trunk_resident_set_profile(long long* phase_clocks);
-/* 4-CTA clusters of the resident kernel the current device holds at once (one image pair each);
- * -1 on error.  Batches that are a multiple of twice this number fill every wave.             */
+/* 4-CTA clusters of the c == 64 resident kernel the current device holds at once (one image pair
+ * each at a time); -1 on error.  Batches that are a multiple of twice this number keep every
+ * cluster busy to the end.                                                                      */
 int vqae_trunk_resident_max_clusters(void);
 int vqae_trunk_resident_supported(int64_t batch, int height, int width, int c);
 int vqae_pack_resident_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
