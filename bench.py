@@ -131,6 +131,14 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and is
+    # meant to use all the host threads it can
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     _, sd = build_model_and_state()
     cores = torch.get_num_threads()
     sample = 8
