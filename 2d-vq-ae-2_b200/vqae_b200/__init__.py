@@ -18,9 +18,10 @@ from ._instantiate import instantiate
 from .config import compose_vqae_conf
 from .layers import conv, conv_block, vq  # noqa: F401
 from .model import VQAE, Decoder, Encoder  # noqa: F401
+from .plan import accelerate  # noqa: F401
 
 __all__ = ["VQAE", "Encoder", "Decoder", "build_vqae", "compose_vqae_conf",
-           "install_as_vq_ae", "instantiate", "engine", "set_precision"]
+           "install_as_vq_ae", "instantiate", "engine", "set_precision", "accelerate"]
 
 
 def build_vqae(n_down: int = 4, **conf_overrides) -> VQAE:
@@ -34,11 +35,13 @@ def set_precision(module, precision: str):
     """Select the arithmetic of every Encoder/Decoder below ``module``: "fp32" (exact CUDA-core
     kernels, index parity with the reference) or "bf16" (tcgen05 tensor-core kernels with bf16
     operands, fp32 accumulation and an fp32 residual stream)."""
-    if precision not in engine.PRECISIONS:
-        raise ValueError(f"precision must be one of {engine.PRECISIONS}")
+    if precision is not None and precision not in engine.PRECISIONS:
+        raise ValueError(f"precision must be one of {engine.PRECISIONS} or None")
     for m in module.modules():
         if isinstance(m, (Encoder, Decoder)):
             m.precision = precision
+        elif "_b200" in m.__dict__:                    # reference modules bound by accelerate()
+            m.__dict__["_b200"].precision = precision
     return module
 
 

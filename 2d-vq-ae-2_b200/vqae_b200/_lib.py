@@ -75,6 +75,7 @@ SIGNATURES = {
                                   _vp, _vp, _sz, _i64, _i64, _vp]),
     "vqae_embed_codes_f32": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i64, _i64, _vp]),
     "vqae_codemap_place_u8": (_i, [_vp, _i64, _i, _i, _i64, _i, _vp, _i64, _i64, _vp]),
+    "vqae_codemap_place_i64": (_i, [_vp, _i64, _i, _i, _i64, _i, _vp, _i64, _i64, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

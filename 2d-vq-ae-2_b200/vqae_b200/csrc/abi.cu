@@ -37,11 +37,12 @@ static FixupScratch fixup_layout(const vqae_fixup_params* p, int64_t B, int H, i
         s.t2 = take(px / 4 * cb);
         s.skip = take(px / 4 * co);
     } else {
-        s.t1 = take(px * cb);        // branch_conv1 output, low res
+        // branch_conv1 output, low res; the low-res skip conv output (c_out channels) reuses it
+        // after branch_conv2 has consumed it, so it must hold the wider of the two
+        s.t1 = take(px * (cb > co ? cb : co));
         s.t2 = take(px * cb);        // 1x1 of branch_conv2 applied at low res
         s.t3 = take(px * 4 * cb);    // ... upsampled
         s.skip = take(px * 4 * co);  // upsampled skip
-        // the low-res skip conv output reuses t1 after branch_conv2 has consumed it
     }
     s.total = off;
     return s;
@@ -214,7 +215,8 @@ int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const 
 }  // extern "C"
 namespace vqae {
 int device_sm_count(int* out) {
-    static int sm_count = 0;
+    static PerDevice<int> sm_count_dev{};
+    int& sm_count = sm_count_dev.cur();
     if (sm_count == 0) {
         int dev = 0;
         VQAE_CUDA_TRY(cudaGetDevice(&dev));
@@ -238,12 +240,8 @@ int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packe
 int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c,
                          void* stream) {
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        VQAE_CUDA_TRY(cudaGetDevice(&dev));
-        VQAE_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
     return same_block_tc(x, out, w_packed, scalars8_host, batch, height, width, c, sm_count,
                          nullptr, (cudaStream_t)stream);
 }
@@ -374,6 +372,13 @@ int vqae_codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw,
                           int64_t map_cols, void* stream) {
     return codemap_place_u8(tiles, n_tiles, th, tw, first_patch, grid_cols, map, map_rows,
                             map_cols, (cudaStream_t)stream);
+}
+
+int vqae_codemap_place_i64(const int64_t* tiles, int64_t n_tiles, int th, int tw,
+                           int64_t first_patch, int grid_cols, int64_t* map, int64_t map_rows,
+                           int64_t map_cols, void* stream) {
+    return codemap_place_i64(tiles, n_tiles, th, tw, first_patch, grid_cols, map, map_rows,
+                             map_cols, (cudaStream_t)stream);
 }
 
 }  // extern "C"

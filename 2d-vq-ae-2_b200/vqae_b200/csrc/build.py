@@ -25,10 +25,11 @@ HEADERS = ["common.cuh", "kernels.cuh", "tc_common.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
+OBJ_DIR = CSRC / "build"            # git-ignored ("build/"); objects are rebuilt per file
 
 
 def _nvcc() -> str:
@@ -38,30 +39,63 @@ def _nvcc() -> str:
     raise FileNotFoundError("nvcc not found; cannot build libvqae_b200.so")
 
 
-def _digest() -> str:
+def _headers_digest() -> str:
     h = hashlib.sha256()
-    files = [CSRC / s for s in SOURCES + HEADERS if (CSRC / s).exists()]
-    files.append(REPO / "include" / "vqae_b200.h")
-    for f in files:
+    for f in [CSRC / s for s in HEADERS] + [REPO / "include" / "vqae_b200.h"]:
         h.update(f.name.encode())
         h.update(f.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
+def _digest() -> str:
+    h = hashlib.sha256(_headers_digest().encode())
+    for s in SOURCES:
+        h.update(s.encode())
+        h.update((CSRC / s).read_bytes())
+    return h.hexdigest()
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile if sources changed since the last build; return the library path."""
+    """Compile if sources changed since the last build; return the library path.  One nvcc -c per
+    changed .cu (in parallel), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     digest = _digest()
     if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text() == digest:
         return LIB_PATH
-    srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(REPO / "include"), "-I", str(CSRC),
-           "-o", str(LIB_PATH), *srcs]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
-    (PKG / "build.log").write_text(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
-        sys.stderr.write(log)
+    nvcc = _nvcc()
+    OBJ_DIR.mkdir(exist_ok=True)
+    hd = _headers_digest()
+    logs = []
+
+    def compile_one(src: str):
+        obj = OBJ_DIR / (src + ".o")
+        tag = OBJ_DIR / (src + ".sha")
+        want = hashlib.sha256(hd.encode() + (CSRC / src).read_bytes()).hexdigest()
+        if not force and obj.exists() and tag.exists() and tag.read_text() == want:
+            return obj, 0, ""
+        cmd = [nvcc, *NVCC_FLAGS, "-I", str(REPO / "include"), "-I", str(CSRC), "-c",
+               str(CSRC / src), "-o", str(obj)]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode == 0:
+            tag.write_text(want)
+        return obj, proc.returncode, " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    logs = [r[2] for r in results if r[2]]
+    failed = [r for r in results if r[1] != 0]
+    if not failed:
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB_PATH),
+               *[str(r[0]) for r in results]]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        logs.append(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        if proc.returncode != 0:
+            failed = [(None, proc.returncode, logs[-1])]
+    log = "\n".join(logs)
+    (PKG / "build.log").write_text(log)
+    if failed:
+        sys.stderr.write("\n".join(r[2] for r in failed))
         raise RuntimeError("nvcc failed building libvqae_b200.so (see output above)")
     if verbose:
         print(log)
@@ -70,4 +104,4 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -46,6 +46,20 @@ struct PreOp {
     }
 };
 
+// Per-device caches: function attributes, occupancy results and scratch allocations belong to ONE
+// device; a process that drives several GPUs must not reuse them across devices.
+constexpr int kMaxDevices = 64;
+inline int current_device_index() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return 0;
+    return d;
+}
+template <typename T>
+struct PerDevice {
+    T v[kMaxDevices];
+    T& cur() { return v[current_device_index()]; }
+};
+
 inline unsigned ceil_div_u(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
 }  // namespace vqae

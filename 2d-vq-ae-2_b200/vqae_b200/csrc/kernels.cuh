@@ -49,6 +49,9 @@ int embed_codes_f32(const void* indices, int idx_is_u8, const float* table, int 
 int codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw, int64_t first_patch,
                      int grid_cols, uint8_t* map, int64_t map_rows, int64_t map_cols,
                      cudaStream_t stream);
+int codemap_place_i64(const int64_t* tiles, int64_t n_tiles, int th, int tw, int64_t first_patch,
+                      int grid_cols, int64_t* map, int64_t map_rows, int64_t map_cols,
+                      cudaStream_t stream);
 
 // quantize_tc.cu (tcgen05 candidate filter + exact fp32 argmin)
 bool quantize_tc_supported(const vqae_quantizer_params* p, int x_layout, int out_layout,

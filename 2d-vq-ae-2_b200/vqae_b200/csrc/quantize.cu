@@ -297,9 +297,10 @@ embed_codes_kernel(const void* __restrict__ indices, const float* __restrict__ t
     }
 }
 
+template <typename MapT>
 __global__ void __launch_bounds__(256)
 codemap_place_kernel(const int64_t* __restrict__ tiles, int64_t total, int th, int tw,
-                     int64_t first_patch, int grid_cols, uint8_t* __restrict__ map,
+                     int64_t first_patch, int grid_cols, MapT* __restrict__ map,
                      int64_t map_cols) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -309,7 +310,7 @@ codemap_place_kernel(const int64_t* __restrict__ tiles, int64_t total, int th, i
     const int64_t t = r / th;
     const int64_t patch = first_patch + t;
     const int64_t prow = patch / grid_cols, pcol = patch % grid_cols;
-    map[(prow * th + y) * map_cols + pcol * tw + x] = (uint8_t)tiles[i];
+    map[(prow * th + y) * map_cols + pcol * tw + x] = (MapT)tiles[i];
 }
 
 }  // namespace
@@ -408,9 +409,10 @@ int embed_codes_f32(const void* indices, int idx_is_u8, const float* table, int 
     return check_launch();
 }
 
-int codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw, int64_t first_patch,
-                     int grid_cols, uint8_t* map, int64_t map_rows, int64_t map_cols,
-                     cudaStream_t stream) {
+template <typename MapT>
+static int codemap_place(const int64_t* tiles, int64_t n_tiles, int th, int tw, int64_t first_patch,
+                         int grid_cols, MapT* map, int64_t map_rows, int64_t map_cols,
+                         cudaStream_t stream) {
     if (!tiles || !map || n_tiles <= 0 || th <= 0 || tw <= 0 || grid_cols <= 0)
         return VQAE_ERR_BAD_ARG;
     const int64_t last = first_patch + n_tiles - 1;
@@ -418,10 +420,23 @@ int codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw, int6
         (int64_t)grid_cols * tw > map_cols)
         return VQAE_ERR_BAD_ARG;
     const int64_t total = n_tiles * th * tw;
-    codemap_place_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(tiles, total, th, tw,
-                                                                     first_patch, grid_cols, map,
-                                                                     map_cols);
+    codemap_place_kernel<MapT><<<ceil_div_u(total, 256), 256, 0, stream>>>(
+        tiles, total, th, tw, first_patch, grid_cols, map, map_cols);
     return check_launch();
+}
+
+int codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw, int64_t first_patch,
+                     int grid_cols, uint8_t* map, int64_t map_rows, int64_t map_cols,
+                     cudaStream_t stream) {
+    return codemap_place<uint8_t>(tiles, n_tiles, th, tw, first_patch, grid_cols, map, map_rows,
+                                  map_cols, stream);
+}
+
+int codemap_place_i64(const int64_t* tiles, int64_t n_tiles, int th, int tw, int64_t first_patch,
+                      int grid_cols, int64_t* map, int64_t map_rows, int64_t map_cols,
+                      cudaStream_t stream) {
+    return codemap_place<int64_t>(tiles, n_tiles, th, tw, first_patch, grid_cols, map, map_rows,
+                                  map_cols, stream);
 }
 
 }  // namespace vqae

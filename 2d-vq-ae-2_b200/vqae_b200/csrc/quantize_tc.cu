@@ -711,9 +711,10 @@ size_t quantize_tc_scratch_bytes(int64_t n) {
 // ring, so kernels of this library in flight on different streams never share one.
 static unsigned int* next_done_counter() {
     constexpr int SLOTS = 64;
-    static unsigned int* base = nullptr;
+    static PerDevice<unsigned int*> base_dev{};       // the ring lives on the device that uses it
     static std::atomic<unsigned> next{0};
     static std::mutex mu;
+    unsigned int*& base = base_dev.cur();
     if (base == nullptr) {
         std::lock_guard<std::mutex> g(mu);
         if (base == nullptr) {
@@ -756,11 +757,11 @@ int quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out, 
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return VQAE_ERR_UNSUPPORTED;
     auto kern = quantize_tc_kernel<C>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice<bool> attr_set{};
+    if (!attr_set.cur()) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)Cfg::SMEM));
-        attr_set = true;
+        attr_set.cur() = true;
     }
     const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
     a.partial = reinterpret_cast<float*>(scratch);

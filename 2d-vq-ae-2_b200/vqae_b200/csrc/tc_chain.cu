@@ -423,7 +423,8 @@ int launch_chain(ChainArgs a, int64_t B, int sm_count, cudaStream_t stream) {
     if (nt * a.n_blocks > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
     a.n_tiles = (int)nt;
     a.total = (int)(nt * a.n_blocks);
-    static int max_ctas = 0;
+    static PerDevice<int> max_ctas_dev{};
+    int& max_ctas = max_ctas_dev.cur();
     if (max_ctas == 0) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)Cfg::SMEM));

@@ -325,11 +325,11 @@ template <int CI, int CO>
 int launch_down(const DownArgs& a, int sm_count, cudaStream_t stream) {
     using Cfg = DownCfg<CI, CO>;
     auto kern = down_block_tc_kernel<CI, CO>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice<bool> attr_set{};
+    if (!attr_set.cur()) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)Cfg::SMEM));
-        attr_set = true;
+        attr_set.cur() = true;
     }
     const int cap = sm_count * Cfg::MIN_CTAS;
     const int grid = a.n_tiles < cap ? a.n_tiles : cap;

@@ -556,11 +556,11 @@ template <int CP, int CR>
 int launch_same_block(const SameBlockArgs& a, int sm_count, cudaStream_t stream) {
     using Cfg = SameCfg<CP, CR>;
     auto kern = same_block_tc_kernel<CP, CR>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice<bool> attr_set{};
+    if (!attr_set.cur()) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)Cfg::SMEM));
-        attr_set = true;
+        attr_set.cur() = true;
     }
     const int cap = sm_count * Cfg::MIN_CTAS;
     const int grid = a.n_tiles < cap ? a.n_tiles : cap;

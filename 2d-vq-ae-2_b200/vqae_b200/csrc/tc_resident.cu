@@ -696,8 +696,9 @@ int resident_clusters() {
 template <int C, int W>
 int launch_resident(const ResidentArgs& a, int64_t B, cudaStream_t stream) {
     using Cfg = RsCfg<C, W>;
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
+    static PerDevice<int> max_clusters_dev{};       // 0 = not queried yet on this device
+    int& max_clusters = max_clusters_dev.cur();
+    if (max_clusters == 0) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(trunk_resident_tc_kernel<C, W>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         if (Cfg::CL > 8)                                 // clusters of 16 CTAs are an opt-in size

@@ -132,11 +132,11 @@ up_head_f32_kernel(UpHeadArgs a) {
 template <int CB, int CO>
 int launch_up_head(const UpHeadArgs& a, cudaStream_t stream) {
     constexpr size_t smem = (size_t)(2 * CB * CB + CB * CO) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice<bool> attr_set{};
+    if (!attr_set.cur()) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(up_head_f32_kernel<CB, CO>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.cur() = true;
     }
     up_head_f32_kernel<CB, CO><<<ceil_div_u(a.P, UH_THREADS), UH_THREADS, smem, stream>>>(a);
     return check_launch();

@@ -163,11 +163,11 @@ up_tail_f32_kernel(UpTailArgs a) {
 template <int CB, int CO>
 int launch_up_tail(const UpTailArgs& a, int64_t B, cudaStream_t stream) {
     using Cfg = UpTailCfg<CB, CO>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice<bool> attr_set{};
+    if (!attr_set.cur()) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(up_tail_f32_kernel<CB, CO>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
+        attr_set.cur() = true;
     }
     dim3 grid(2 * a.W / UT_TX, 2 * a.H / UT_TY, (unsigned)B);
     up_tail_f32_kernel<CB, CO><<<grid, UT_THREADS, Cfg::SMEM, stream>>>(a);

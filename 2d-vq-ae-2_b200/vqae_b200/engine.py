@@ -90,13 +90,74 @@ _SCALARS = ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4",
             "bias1c", "bias1d")
 
 
+def infer_block_mode(block) -> str:
+    """'same' / 'down' / 'up' from the structure of a PreActFixupResBlock -- the reference's
+    class does not keep its ``mode`` argument (conv_block.py:136-194), so this also serves blocks
+    instantiated by the unmodified reference (vqae_b200.accelerate)."""
+    c2 = block.branch_conv2
+    k2, st = tuple(c2.kernel_size), tuple(c2.stride)
+    if hasattr(c2, "upsample") and k2 == (1, 1):
+        return "up"
+    if k2 == (2, 2) and st == (2, 2):
+        return "down"
+    if k2 == (3, 3) and st == (1, 1) and c2.padding_mode == "circular":
+        return "same"
+    raise NotImplementedError(f"PreActFixupResBlock with branch_conv2 {c2} is not built")
+
+
+def check_block_supported(block) -> None:
+    """Everything the kernels assume about a block, checked against the module itself
+    (conf/model/layers/conv_block/pre_activation_fixup.yaml)."""
+    from torch import nn
+    act = block.activation
+    if not (isinstance(act, nn.ELU) and act.alpha == 1.0):
+        raise NotImplementedError("only nn.ELU(alpha=1) activations are built "
+                                  "(conf/model/layers/activation/elu.yaml)")
+    convs = (block.branch_conv1, block.branch_conv2, block.branch_conv3, block.skip_conv)
+    for conv in convs:
+        if conv is None:
+            continue
+        if conv.bias is not None:
+            raise NotImplementedError("branch/skip convs with bias are not built "
+                                      "(pre_activation_fixup.yaml sets bias: False)")
+        if conv.groups != 1 or tuple(conv.dilation) != (1, 1):
+            raise NotImplementedError(f"grouped / dilated conv {conv} is not built")
+    for name in ("branch_conv1", "branch_conv3"):
+        conv = getattr(block, name)
+        if tuple(conv.kernel_size) != (1, 1) or tuple(conv.stride) != (1, 1) \
+                or hasattr(conv, "upsample"):
+            raise NotImplementedError(f"{name} {conv} is not a plain 1x1 conv")
+    mode = infer_block_mode(block)
+    declared = getattr(block, "mode", mode)
+    if declared != mode:
+        raise NotImplementedError(f"mode {declared!r} with branch_conv2 {block.branch_conv2} "
+                                  "is not built")
+    cb, ci, co = (block.branch_conv1.out_channels, block.branch_conv1.in_channels,
+                  block.branch_conv3.out_channels)
+    if block.branch_conv2.in_channels != cb or block.branch_conv2.out_channels != cb \
+            or block.branch_conv3.in_channels != cb:
+        raise NotImplementedError("branch convs with mismatched widths are not built")
+    sk = block.skip_conv
+    if mode == "same":
+        if sk is not None or ci != co:
+            raise NotImplementedError("'same' blocks that change the channel count are not built")
+    else:
+        if sk is None:
+            raise NotImplementedError(f"'{mode}' block without skip_conv is not built")
+        ks, ss = tuple(sk.kernel_size), tuple(sk.stride)
+        ok = (mode == "down" and ks == (2, 2) and ss == (2, 2)) or \
+             (mode == "up" and ks == (1, 1) and ss == (1, 1) and hasattr(sk, "upsample"))
+        if not ok or sk.in_channels != ci or sk.out_channels != co:
+            raise NotImplementedError(f"mode {mode!r} with skip_conv {sk} is not built")
+
+
 class PackedFixup:
     """Device-resident packed weights + the C struct of one PreActFixupResBlock."""
 
     def __init__(self, block, scalars: Sequence[float]):
         w2 = block.branch_conv2.weight
-        k2 = w2.shape[-1]
-        self.mode = {3: L.MODE_SAME, 2: L.MODE_DOWN, 1: L.MODE_UP}[k2]
+        self.mode = {"same": L.MODE_SAME, "down": L.MODE_DOWN, "up": L.MODE_UP}[
+            infer_block_mode(block)]
         self.c_in = block.branch_conv1.weight.shape[1]
         self.c_branch = block.branch_conv1.weight.shape[0]
         self.c_out = block.branch_conv3.weight.shape[0]
@@ -464,11 +525,26 @@ def codemap_place(tiles: Tensor, first_patch: int, grid_cols: int, code_map: Ten
     """Place int64 code tiles [P,th,tw] into the u8 map [rows*th, cols*tw] (row-major patches)."""
     lib = L.load()
     require_cuda(tiles, "codemap_place")
+    if code_map.dtype != torch.uint8:
+        raise ValueError("codemap_place writes uint8 maps (<= 256 codes); see codemap_place_i64")
     tiles = tiles.contiguous()
     p, th, tw = tiles.shape
     L.check(lib.vqae_codemap_place_u8(_ptr(tiles), p, th, tw, first_patch, grid_cols,
                                       _ptr(code_map), code_map.shape[0], code_map.shape[1],
                                       _stream(tiles.device)), "vqae_codemap_place_u8")
+
+
+def codemap_place_i64(tiles: Tensor, first_patch: int, grid_cols: int, code_map: Tensor) -> None:
+    """Like codemap_place, into an int64 map (any codebook size; narrowed on the host later)."""
+    lib = L.load()
+    require_cuda(tiles, "codemap_place_i64")
+    if code_map.dtype != torch.int64 or tiles.dtype != torch.int64:
+        raise ValueError("codemap_place_i64 expects int64 tiles and an int64 map")
+    tiles = tiles.contiguous()
+    p, th, tw = tiles.shape
+    L.check(lib.vqae_codemap_place_i64(_ptr(tiles), p, th, tw, first_patch, grid_cols,
+                                       _ptr(code_map), code_map.shape[0], code_map.shape[1],
+                                       _stream(tiles.device)), "vqae_codemap_place_i64")
 
 
 def launch_count() -> int:

@@ -1,21 +1,23 @@
 """The code-extraction caller on the B200 path (scope row f-1).
 
-Counterpart of ``run_eval`` / ``get_encodings`` in
-scripts/extract_embeddings/extract_embeddings.py:43-138: patches in, per-slide u8 code map
-out.  Differences by design: tiles arrive as raw uint8 NHWC (normalisation is fused into the
-stem kernel instead of running in DataLoader workers), the quantised tensor is never written
-(only indices are used, extract_embeddings.py:125-137), and tiles are placed into the slide
-map by a kernel instead of advanced indexing.
+Counterpart of ``run_eval`` / ``get_encodings`` / ``main`` in
+scripts/extract_embeddings/extract_embeddings.py:43-138,176-185: patches in, per-slide code map
+out, written as ``<ckpt>/encodings/<parent>/<stem>.npy``.  Differences by design: tiles may arrive
+as raw uint8 NHWC (normalisation is fused into the stem kernel instead of running in DataLoader
+workers), the quantised tensor is never written (only indices are used,
+extract_embeddings.py:125-137), and tiles are placed into the slide map by a kernel instead of
+advanced indexing.
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional, Tuple
+from pathlib import Path
+from typing import Dict, Iterable, Iterator, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import engine as E
-from .sharding import gather_code_tiles, shard_range, slide_grid
+from .sharding import gather_code_tiles, shard_range, slide_grid  # noqa: F401
 
 
 def cast_to_lowest_dtype(array: np.ndarray) -> np.ndarray:
@@ -26,6 +28,23 @@ def cast_to_lowest_dtype(array: np.ndarray) -> np.ndarray:
     return array.astype(np.result_type(np.min_scalar_type(amin), np.min_scalar_type(amax)))
 
 
+def extract_path(path: str) -> str:
+    """'<...>/<parent>/<name>.tif' -> '<parent>/<name>' (extract_embeddings.py:111-112)."""
+    return Path(path).parent.stem + '/' + Path(path).stem
+
+
+def encoding_path(ckpt_folder, array_name: str) -> Path:
+    """Where ``main`` stores a finished slide (extract_embeddings.py:183-185)."""
+    return Path(ckpt_folder) / 'encodings' / (array_name + '.npy')
+
+
+def save_encoding(ckpt_folder, array_name: str, array: np.ndarray) -> Path:
+    out_path = encoding_path(ckpt_folder, array_name)
+    out_path.parent.mkdir(parents=True, exist_ok=True)
+    np.save(str(out_path), array)
+    return out_path
+
+
 @torch.no_grad()
 def encode_patches(encoder, patches: torch.Tensor, mean=None, std=None) -> torch.Tensor:
     """patches: uint8 [B,H,W,3] or float [B,3,H,W] on a CUDA device -> int64 codes [B,h,w]."""
@@ -33,12 +52,21 @@ def encode_patches(encoder, patches: torch.Tensor, mean=None, std=None) -> torch
     return idx
 
 
+def _check_u8_codes(encoder) -> None:
+    k = int(encoder.vq_layers[0].num_embeddings)
+    if k > 256:
+        raise ValueError(f"uint8 code maps hold at most 256 codes, the quantiser has {k}; "
+                         "use get_encodings (narrowest dtype per slide) instead")
+
+
 @torch.no_grad()
 def compress_slide(encoder, batches: Iterable[Tuple[int, torch.Tensor]], grid: Tuple[int, int],
                    code_hw: Tuple[int, int], device: torch.device, mean=None, std=None
                    ) -> torch.Tensor:
     """Encode (first_patch_index, patch batch) pairs of one slide and place the code tiles into a
-    u8 map [rows*h, cols*w] on ``device`` (extract_embeddings.py:47-52,75-89)."""
+    u8 map [rows*h, cols*w] on ``device`` (extract_embeddings.py:47-52,75-89).  Needs a codebook of
+    at most 256 entries (the shipped K); wider codebooks go through ``get_encodings``."""
+    _check_u8_codes(encoder)
     rows, cols = grid
     th, tw = code_hw
     code_map = torch.zeros(rows * th, cols * tw, dtype=torch.uint8, device=device)
@@ -48,27 +76,88 @@ def compress_slide(encoder, batches: Iterable[Tuple[int, torch.Tensor]], grid: T
     return code_map
 
 
+@torch.no_grad()
+def get_encodings(encoder, batches: Iterable[Tuple[torch.Tensor, Sequence[str], Sequence[int],
+                                                   torch.Tensor]],
+                  lengths: Sequence[int], sizes: Sequence[Tuple[int, int]],
+                  device: Optional[torch.device] = None, mean=None, std=None
+                  ) -> Iterator[Tuple[str, np.ndarray]]:
+    """The slide-assembly loop of ``get_encodings`` (extract_embeddings.py:43-89) on the B200 path.
+
+    ``batches`` yields what the reference's DataLoader yields per step, minus the labels:
+    ``(imgs, img_paths, img_index, patch_index)`` with ``imgs`` uint8 [B,H,W,3] or float
+    [B,3,H,W], ``img_paths`` the slide path of every patch, ``img_index`` [B] the slide number and
+    ``patch_index`` [B,2] the (row, col) of the patch inside its slide grid.  ``lengths[i]`` /
+    ``sizes[i]`` are the dataset's ``_lengths`` / ``_sizes`` (patch count and (rows, cols) grid of
+    slide i, datamodules/camelyon16.py:160-168).  Yields ``(name, array)`` when the last patch of a
+    slide has been placed, ``name`` = ``extract_path(path)`` and ``array`` narrowed with
+    ``cast_to_lowest_dtype`` -- ready for ``save_encoding``."""
+    arrays: Dict[str, torch.Tensor] = {}
+    counts: Dict[str, int] = {}
+    for imgs, paths, img_index, patch_index in batches:
+        dev = device or imgs.device
+        idx = encode_patches(encoder, imgs.to(dev, non_blocking=True), mean, std)
+        th, tw = idx.shape[1:]
+        names = [extract_path(p) for p in paths]
+        img_index = torch.as_tensor(img_index).tolist()
+        patch_index = torch.as_tensor(patch_index).reshape(len(names), 2).tolist()
+        # group the batch by slide; runs of row-major consecutive patches go to the device in one
+        # placement call (the common case: the tiled dataset walks a slide in row-major order)
+        start = 0
+        n = len(names)
+        while start < n:
+            name, image_index = names[start], img_index[start]
+            rows, cols = (int(v) for v in sizes[image_index])
+            stop = start + 1
+            first = patch_index[start][0] * cols + patch_index[start][1]
+            while stop < n and names[stop] == name and \
+                    patch_index[stop][0] * cols + patch_index[stop][1] == first + (stop - start):
+                stop += 1
+            if name not in arrays:
+                counts[name] = int(lengths[image_index])
+                arrays[name] = torch.empty(rows * th, cols * tw, dtype=torch.int64, device=dev)
+            E.codemap_place_i64(idx[start:stop], first, cols, arrays[name])
+            counts[name] -= stop - start
+            if counts[name] == 0:
+                counts.pop(name)
+                yield name, cast_to_lowest_dtype(arrays.pop(name).cpu().numpy())
+            start = stop
+
+
+def extract_and_save(encoder, batches, lengths, sizes, ckpt_folder, **kw) -> Iterator[Path]:
+    """``main``'s inner loop (extract_embeddings.py:176-185): one ``.npy`` per finished slide."""
+    for name, array in get_encodings(encoder, batches, lengths, sizes, **kw):
+        yield save_encoding(ckpt_folder, name, array)
+
+
 class StreamingEncoder:
     """Double-buffered host -> device -> host code extraction.
 
     The copy of batch i+1 from pinned host memory runs on a side stream while batch i is encoded,
     and the code indices of batch i return to pinned host memory asynchronously -- the B200
     counterpart of the reference's DataLoader(pin_memory) + ``imgs.to(device, non_blocking=True)``
-    loop (extract_embeddings.py:95-101,118-122).  ``encode_stream`` yields one pinned int64
-    ``[B,h,w]`` tensor per input batch, in order; a yielded tensor is valid until two more
-    batches have been yielded."""
+    loop (extract_embeddings.py:95-101,118-122).  ``encode_stream`` yields one int64 ``[B,h,w]``
+    host tensor per input batch, in order.
+
+    By default every yielded tensor is an independent copy (safe to collect with ``list``).  With
+    ``reuse_buffers=True`` the pinned staging buffers themselves are yielded (no host copy): there
+    are ``N_OUT`` = 4 of them and results lag one batch behind submission, so a yielded tensor stays
+    valid only until the generator has been resumed ``N_OUT - 2`` = 2 more times."""
+
+    N_OUT = 4
 
     def __init__(self, encoder, device: torch.device, mean=None, std=None):
         self.encoder, self.device, self.mean, self.std = encoder, device, mean, std
         self.copy_stream = torch.cuda.Stream(device)
         self._dev_in = [None, None]
-        self._host_out = [None, None]
+        self._host_out = [None] * self.N_OUT
         self._h2d = [torch.cuda.Event() for _ in range(2)]
         self._free = [torch.cuda.Event() for _ in range(2)]     # device input buffer consumed
-        self._d2h = [torch.cuda.Event() for _ in range(2)]
+        self._d2h = [torch.cuda.Event() for _ in range(self.N_OUT)]
 
     def _stage(self, slot: int, host_batch: torch.Tensor, first_use: bool) -> None:
-        if self._dev_in[slot] is None or self._dev_in[slot].shape != host_batch.shape:
+        if self._dev_in[slot] is None or self._dev_in[slot].shape != host_batch.shape \
+                or self._dev_in[slot].dtype != host_batch.dtype:
             self._dev_in[slot] = torch.empty(host_batch.shape, dtype=host_batch.dtype,
                                              device=self.device)
             first_use = True
@@ -79,7 +168,7 @@ class StreamingEncoder:
             self._h2d[slot].record(self.copy_stream)
 
     @torch.no_grad()
-    def encode_stream(self, host_batches):
+    def encode_stream(self, host_batches, reuse_buffers: bool = False):
         main = torch.cuda.current_stream(self.device)
         it = iter(host_batches)
         nxt = next(it, None)
@@ -88,29 +177,30 @@ class StreamingEncoder:
         self._stage(0, nxt, True)
         i = 0
         pending = []
+
+        def result(oslot):
+            self._d2h[oslot].synchronize()
+            out = self._host_out[oslot]
+            return out if reuse_buffers else out.clone()
+
         while nxt is not None:
-            slot = i & 1
+            slot, oslot = i & 1, i % self.N_OUT
             cur, nxt = nxt, next(it, None)
             if nxt is not None:
                 self._stage(slot ^ 1, nxt, i == 0)
             main.wait_event(self._h2d[slot])
             idx = encode_patches(self.encoder, self._dev_in[slot], self.mean, self.std)
             self._free[slot].record(main)
-            if self._host_out[slot] is None or self._host_out[slot].shape != idx.shape:
-                self._host_out[slot] = torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
-            elif len(pending) == 2:
-                pass
-            self._host_out[slot].copy_(idx, non_blocking=True)
-            self._d2h[slot].record(main)
-            pending.append(slot)
+            if self._host_out[oslot] is None or self._host_out[oslot].shape != idx.shape:
+                self._host_out[oslot] = torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
+            self._host_out[oslot].copy_(idx, non_blocking=True)
+            self._d2h[oslot].record(main)
+            pending.append(oslot)
             if len(pending) == 2:                  # results lag one batch behind the submission
-                done = pending.pop(0)
-                self._d2h[done].synchronize()
-                yield self._host_out[done]
+                yield result(pending.pop(0))
             i += 1
-        for done in pending:
-            self._d2h[done].synchronize()
-            yield self._host_out[done]
+        for oslot in pending:
+            yield result(oslot)
 
 
 def tiles_to_map(tiles_u8: torch.Tensor, grid: Tuple[int, int]) -> torch.Tensor:

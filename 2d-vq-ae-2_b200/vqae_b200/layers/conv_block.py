@@ -16,6 +16,7 @@ import torch
 from torch import nn
 
 from .. import engine as E
+from .. import plan as P
 from .._instantiate import instantiate
 
 
@@ -137,44 +138,22 @@ class PreActFixupResBlock(nn.Module):
 
         if n_layers is not None:
             self.initialize_weights(n_layers)
-        self._packed = None
-        self._packed_key = None
 
     # -- B200 path -------------------------------------------------------------------------
     def check_supported(self) -> None:
-        act = self.activation
-        if not (isinstance(act, nn.ELU) and act.alpha == 1.0):
-            raise NotImplementedError("only nn.ELU(alpha=1) activations are built "
-                                      "(conf/model/layers/activation/elu.yaml)")
-        for conv in (self.branch_conv1, self.branch_conv2, self.branch_conv3, self.skip_conv):
-            if conv is not None and conv.bias is not None:
-                raise NotImplementedError("branch/skip convs with bias are not built "
-                                          "(pre_activation_fixup.yaml sets bias: False)")
-        k2 = tuple(self.branch_conv2.kernel_size)
-        ok = {
-            "same": k2 == (3, 3) and self.branch_conv2.padding_mode == "circular",
-            "down": k2 == (2, 2) and tuple(self.branch_conv2.stride) == (2, 2),
-            "up": k2 == (1, 1) and hasattr(self.branch_conv2, "upsample"),
-        }.get(self.mode, False)
-        if not ok:
-            raise NotImplementedError(f"mode {self.mode!r} with branch_conv2 "
-                                      f"{self.branch_conv2} is not built")
+        E.check_block_supported(self)
 
     def packed(self) -> E.PackedFixup:
+        st = P.state(self)
         key = E.block_version(self)
-        if self._packed is None or key != self._packed_key:
+        if st.packed is None or key != st.packed_key:
             self.check_supported()
-            self._packed = E.pack_blocks([self])[0]
-            self._packed_key = key
-        return self._packed
+            st.packed = E.pack_blocks([self])[0]
+            st.packed_key = key
+        return st.packed
 
     def forward(self, inp: torch.Tensor) -> torch.Tensor:
-        if self.training:
-            raise RuntimeError("PreActFixupResBlock: training-mode forward is outside the B200 "
-                               "inference path; call .eval()")
-        E.require_cuda(inp, "PreActFixupResBlock.forward")
-        x, cl = E.to_nhwc(inp)
-        return E.from_nhwc(E.fixup_forward_nhwc(self.packed(), x), cl)
+        return P.block_forward(self, inp)
 
     @torch.no_grad()
     def initialize_weights(self, num_layers):

@@ -15,6 +15,7 @@ import torch
 from torch import Tensor, nn
 
 from . import engine as E
+from . import plan as P
 from ._instantiate import instantiate
 
 
@@ -26,32 +27,7 @@ def maybe_repeat_layer(layer, repetitions: int):
     return layer
 
 
-def _flat_blocks(module: nn.Module) -> List[nn.Module]:
-    """All PreActFixupResBlocks below ``module`` in execution order."""
-    from .layers.conv_block import PreActFixupResBlock
-    return [m for m in module.modules() if isinstance(m, PreActFixupResBlock)]
-
-
-class _Plan:
-    """Packed blocks of one Sequential chain, re-packed when any parameter changes."""
-
-    def __init__(self):
-        self.key = None
-        self.packed: List[E.PackedFixup] = []
-        self.chains: dict = {}
-
-    def get(self, blocks: Sequence[nn.Module]) -> List[E.PackedFixup]:
-        key = tuple(E.block_version(b) for b in blocks)
-        if key != self.key:
-            for b in blocks:
-                b.check_supported()
-            self.packed = E.pack_blocks(blocks)
-            self.chains = {}
-            self.key = key
-        return self.packed
-
-    def run(self, blocks: Sequence[nn.Module], h: Tensor, precision: str = "fp32") -> Tensor:
-        return E.run_blocks_nhwc(self.get(blocks), h, precision, self.chains)
+_flat_blocks = P.flat_blocks      # kept under its round-1 name for profiles/ scripts
 
 
 class Encoder(nn.Module):
@@ -90,49 +66,18 @@ class Encoder(nn.Module):
         self.pre_enc_layers = nn.ModuleList(reversed(pre_enc_layers))
         self.shortcut_layers = nn.ModuleList(reversed(shortcut_layers))
         self.vq_layers = nn.ModuleList(reversed(vq_layers))
-        self._plan_down, self._plan_trunk = _Plan(), _Plan()
-        #: "fp32" (exact CUDA-core path) or "bf16" (tcgen05 kernels where built); see
-        #: vqae_b200.set_precision
-        self.precision = "fp32"
+        #: None = follow torch.autocast like the reference (fp32 unless autocast is active);
+        #: "fp32" / "bf16" / ... pin the arithmetic (vqae_b200.set_precision)
+        self.precision = None
 
     # -- B200 path -------------------------------------------------------------------------
-    def _check_topology(self) -> None:
-        if len(self.vq_layers) != 1 or any(s is not None for s in self.shortcut_layers):
-            raise NotImplementedError(
-                "the B200 plan covers the shipped single-level encoder "
-                "(conf/model/vq_ae.yaml); multi-level / shortcut hierarchies are not built")
-        if self.training:
-            raise RuntimeError("Encoder: training-mode forward is outside the B200 inference "
-                               "path; call .eval()")
-
     def encode(self, x: Tensor, mean=None, std=None, want_quantized: bool = True,
                want_latents: bool = False):
-        """Run the plan.  x: float [B,3,H,W] (NCHW or channels_last) or uint8 [B,H,W,3]
-        (normalised on the fly, a-N fused into the stem).  Returns
-        (enc or None, indices int64 [B,h,w], loss 0-dim, near_ties 0-dim int32, z or None)."""
-        self._check_topology()
-        E.require_cuda(x, "Encoder.forward")
-        cl = x.dtype == torch.uint8 or E.is_channels_last(x)
-        h = E.stem_in(x, self.in_stem.weight, self.in_stem.bias, mean, std)
-        # one plan over pyramid + trunk: the 'same' blocks that close the last DownBlock and the
-        # trunk are one run of equal-width blocks, i.e. ONE image-resident launch
-        h = self._plan_down.run(_flat_blocks(self.down_layers) + _flat_blocks(self.pre_enc_layers), h,
-                                self.precision)
-        vq = self.vq_layers[0]
-        pq = vq.packed()
-        b, hh, ww, c = h.shape
-        if c != pq.c:
-            raise NotImplementedError(
-                'VQ dim != channel dim not supported;'
-                f' found channel dim of {c}, expected {pq.c}')
-        out, idx, loss, ties, z = E.quantize(pq, h, True, cl, b, hh * ww,
-                                             want_out=want_quantized, want_z=want_latents)
-        vq.last_near_ties = ties
-        enc = None
-        if out is not None:
-            enc = (out.view(b, hh, ww, c).permute(0, 3, 1, 2) if cl else out.view(b, c, hh, ww))
-        return enc, idx.view(b, hh, ww), loss, ties, (z.view(b, hh, ww, -1) if z is not None
-                                                       else None)
+        """(enc or None, indices int64 [B,h,w], loss 0-dim, near_ties 0-dim int32, z or None);
+        x: float [B,3,H,W] (NCHW or channels_last) or uint8 [B,H,W,3] -- see plan.encoder_encode."""
+        out = P.encoder_encode(self, x, mean, std, want_quantized, want_latents)
+        self.vq_layers[0].last_near_ties = out[3]
+        return out
 
     def forward(self, x: Tensor) -> Tuple[Sequence[Tensor], Sequence[Tensor], Sequence[Tensor]]:
         """((enc,), (indices,), (loss,)) -- low-res to high-res order (model.py:189-217)."""
@@ -173,24 +118,10 @@ class Decoder(nn.Module):
         self.up_layers = nn.ModuleList(reversed(up_layers))
         self.post_enc_layers = nn.ModuleList(reversed(post_enc_layers))
         self.shortcut_layers = nn.ModuleList(reversed(shortcut_layers))
-        self._plan_trunk, self._plan_up = _Plan(), _Plan()
-        self.precision = "fp32"
+        self.precision = None
 
     def forward(self, x: Sequence[Tensor]) -> Tensor:
-        if len(x) != 1 or len(self.up_layers) != 1 or any(
-                s is not None for s in self.shortcut_layers):
-            raise NotImplementedError(
-                "the B200 plan covers the shipped single-level decoder "
-                "(conf/model/vq_ae.yaml); multi-level / shortcut hierarchies are not built")
-        if self.training:
-            raise RuntimeError("Decoder: training-mode forward is outside the B200 inference "
-                               "path; call .eval()")
-        enc = x[0]
-        E.require_cuda(enc, "Decoder.forward")
-        h, cl = E.to_nhwc(enc)
-        h = self._plan_trunk.run(_flat_blocks(self.post_enc_layers) + _flat_blocks(self.up_layers), h,
-                                 self.precision)
-        return E.stem_out(h, self.out_stem.weight, self.out_stem.bias, cl)
+        return P.decoder_forward(self, x)
 
 
 class VQAE(nn.Module):

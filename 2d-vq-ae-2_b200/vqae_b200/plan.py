@@ -1,0 +1,274 @@
+"""Execution plans of the hot path, written against *duck-typed* modules.
+
+Everything here reads a module only through the attributes the reference's classes define
+(``in_stem / down_layers / pre_enc_layers / vq_layers / shortcut_layers`` on an encoder
+(vq_ae/model.py:129-187), ``out_stem / up_layers / post_enc_layers`` on a decoder (:220-272),
+``embed / proj_in / proj_out / commitment_cost`` on a quantiser (layers/vq.py:17-42,168-187),
+``bias1a .. scale / branch_conv1..3 / skip_conv`` on a Fixup block (layers/conv_block.py:136-194)).
+So the same functions serve this package's mirrored classes (model.py, layers/*.py) and instances
+of the UNMODIFIED reference classes that ``vqae_b200.accelerate`` has bound to the B200 path.
+
+Per-module state (packed weights, selected precision, near-tie counter) lives in
+``module.__dict__['_b200']`` -- no parameters, no buffers, ``state_dict`` is untouched.
+"""
+from __future__ import annotations
+
+import types
+from math import prod
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import engine as E
+
+REDUCED = "bf16"        # what an active torch.autocast('cuda') selects
+
+
+def state(module) -> types.SimpleNamespace:
+    st = module.__dict__.get("_b200")
+    if st is None:
+        st = types.SimpleNamespace(precision=None, plan=None, packed=None, packed_key=None,
+                                   last_near_ties=None)
+        module.__dict__["_b200"] = st
+    return st
+
+
+def resolve_precision(module) -> str:
+    """Arithmetic of a plan run: an explicit ``set_precision`` wins; otherwise an active
+    ``torch.autocast('cuda')`` (the reference's extraction loop, extract_embeddings.py:124-125,
+    and eval.py:44) selects the reduced-precision tensor-core path, and plain calls run fp32 --
+    the same rule the reference's modules follow under PyTorch."""
+    p = getattr(module, "precision", None) or state(module).precision
+    if p is not None and p != "auto":
+        return p
+    return REDUCED if torch.is_autocast_enabled("cuda") else "fp32"
+
+
+def is_fixup_block(m) -> bool:
+    return all(hasattr(m, a) for a in ("branch_conv1", "branch_conv2", "branch_conv3", "bias1a",
+                                       "scale"))
+
+
+def flat_blocks(module: nn.Module) -> List[nn.Module]:
+    """All PreActFixupResBlocks below ``module`` in execution order."""
+    return [m for m in module.modules() if is_fixup_block(m)]
+
+
+class Plan:
+    """Packed blocks of one Sequential chain, re-packed when any parameter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.packed: List[E.PackedFixup] = []
+        self.chains: dict = {}
+
+    def get(self, blocks: Sequence[nn.Module]) -> List[E.PackedFixup]:
+        key = tuple(E.block_version(b) for b in blocks)
+        if key != self.key:
+            for b in blocks:
+                E.check_block_supported(b)
+            self.packed = E.pack_blocks(blocks)
+            self.chains = {}
+            self.key = key
+        return self.packed
+
+    def run(self, blocks: Sequence[nn.Module], h: Tensor, precision: str = "fp32") -> Tensor:
+        return E.run_blocks_nhwc(self.get(blocks), h, precision, self.chains)
+
+
+def _plan(module) -> Plan:
+    st = state(module)
+    if st.plan is None:
+        st.plan = Plan()
+    return st.plan
+
+
+# ---- quantiser (layers/vq.py) ------------------------------------------------------------------
+def packed_quantizer(vq) -> E.PackedQuantizer:
+    proj_in, proj_out = getattr(vq, "proj_in", None), getattr(vq, "proj_out", None)
+    tensors = [vq.embed] + ([proj_in.weight, proj_in.bias, proj_out.weight, proj_out.bias]
+                            if proj_in is not None else [])
+    key = tuple((t.data_ptr(), t._version) for t in tensors) + (float(vq.commitment_cost),)
+    st = state(vq)
+    if st.packed is None or key != st.packed_key:
+        st.packed = E.PackedQuantizer(vq.embed, vq.commitment_cost, proj_in, proj_out)
+        st.packed_key = key
+    return st.packed
+
+
+def check_quantizer_input(vq, inputs: Tensor) -> None:
+    """The argument checks of EMAVectorQuantizer.forward (vq.py:97-104) + what is built."""
+    channels = vq.proj_in.in_channels if getattr(vq, "proj_in", None) is not None \
+        else vq.embedding_dim
+    ndim = inputs.dim()
+    assert ndim >= 3                                                    # vq.py:98
+    if inputs.shape[1] != channels:                                     # vq.py:100-104
+        raise NotImplementedError(
+            'VQ dim != channel dim not supported;'
+            f' found channel dim of {inputs.shape[1]}, expected {channels}')
+    if ndim != 4:
+        # the reference passes p = inputs.dim() to cdist (vq.py:121-129); only p = 4 is built
+        raise NotImplementedError(f"only 4-D inputs (L4 distance) are supported, got {ndim}-D")
+    E.require_cuda(inputs, type(vq).__name__ + ".forward")
+
+
+def quantizer_forward(vq, inputs: Tensor, want_z: bool = False):
+    """(quantized, indices int64, loss 0-dim[, z]) of vq.py:96-154 / 185-192 in eval mode."""
+    check_quantizer_input(vq, inputs)
+    pq = packed_quantizer(vq)
+    b = inputs.shape[0]
+    s = prod(inputs.shape[2:])
+    cl = E.is_channels_last(inputs)
+    x = inputs if inputs.dtype == torch.float32 else inputs.float()
+    x = x.permute(0, 2, 3, 1).contiguous() if cl else x.contiguous()
+    out, idx, loss, ties, z = E.quantize(pq, x, cl, cl, b, s, want_out=True, want_z=want_z)
+    state(vq).last_near_ties = ties
+    sp = tuple(inputs.shape[2:])
+    quantized = out.view(b, *sp, pq.c).permute(0, 3, 1, 2) if cl else out.view(b, pq.c, *sp)
+    if inputs.dtype != torch.float32:
+        quantized = quantized.to(inputs.dtype)
+    return quantized, idx.view(b, *sp), loss, z
+
+
+def decode_codes(vq, embed_idx: Tensor, channels_last: bool = False) -> Tensor:
+    """proj_out(embed_code(idx)) for stored code maps: [B,H,W] int -> [B,C,H,W]."""
+    E.require_cuda(embed_idx, "decode_codes")
+    pq = packed_quantizer(vq)
+    b, h, w = embed_idx.shape
+    out = E.embed_codes(pq, embed_idx.reshape(-1), channels_last, b, h * w)
+    if channels_last:
+        return out.view(b, h, w, pq.c).permute(0, 3, 1, 2)
+    return out.view(b, pq.c, h, w)
+
+
+# ---- encoder / decoder (model.py) --------------------------------------------------------------
+def _check_single_level(levels: int, shortcuts, who: str) -> None:
+    if levels != 1 or any(s is not None for s in shortcuts):
+        raise NotImplementedError(
+            f"the B200 plan covers the shipped single-level {who} "
+            "(conf/model/vq_ae.yaml); multi-level / shortcut hierarchies are not built")
+
+
+def encoder_encode(enc, x: Tensor, mean=None, std=None, want_quantized: bool = True,
+                   want_latents: bool = False):
+    """Run the encoder plan.  x: float [B,3,H,W] (NCHW or channels_last) or uint8 [B,H,W,3]
+    (normalised on the fly, a-N fused into the stem).  Returns
+    (enc or None, indices int64 [B,h,w], loss 0-dim, near_ties 0-dim int32, z or None)."""
+    _check_single_level(len(enc.vq_layers), enc.shortcut_layers, "encoder")
+    if enc.training:
+        raise RuntimeError("Encoder: training-mode forward is outside the B200 inference "
+                           "path; call .eval()")
+    E.require_cuda(x, "Encoder.forward")
+    precision = resolve_precision(enc)
+    cl = x.dtype == torch.uint8 or E.is_channels_last(x)
+    h = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias, mean, std)
+    # one plan over pyramid + trunk: the 'same' blocks that close the last DownBlock and the
+    # trunk are one run of equal-width blocks, i.e. ONE image-resident launch
+    h = _plan(enc).run(flat_blocks(enc.down_layers) + flat_blocks(enc.pre_enc_layers), h, precision)
+    vq = enc.vq_layers[0]
+    pq = packed_quantizer(vq)
+    b, hh, ww, c = h.shape
+    if c != pq.c:
+        raise NotImplementedError(
+            'VQ dim != channel dim not supported;'
+            f' found channel dim of {c}, expected {pq.c}')
+    out, idx, loss, ties, z = E.quantize(pq, h, True, cl, b, hh * ww,
+                                         want_out=want_quantized, want_z=want_latents)
+    state(vq).last_near_ties = ties
+    enc_t = None
+    if out is not None:
+        enc_t = (out.view(b, hh, ww, c).permute(0, 3, 1, 2) if cl else out.view(b, c, hh, ww))
+    return enc_t, idx.view(b, hh, ww), loss, ties, (z.view(b, hh, ww, -1) if z is not None
+                                                     else None)
+
+
+def decoder_forward(dec, xs: Sequence[Tensor]) -> Tensor:
+    if len(xs) != 1:
+        raise NotImplementedError("the B200 plan covers the shipped single-level decoder")
+    _check_single_level(len(dec.up_layers), dec.shortcut_layers, "decoder")
+    if dec.training:
+        raise RuntimeError("Decoder: training-mode forward is outside the B200 inference "
+                           "path; call .eval()")
+    enc = xs[0]
+    E.require_cuda(enc, "Decoder.forward")
+    precision = resolve_precision(dec)
+    h, cl = E.to_nhwc(enc)
+    h = _plan(dec).run(flat_blocks(dec.post_enc_layers) + flat_blocks(dec.up_layers), h, precision)
+    return E.stem_out(h, dec.out_stem.weight, dec.out_stem.bias, cl)
+
+
+def block_forward(block, inp: Tensor) -> Tensor:
+    """One PreActFixupResBlock on an NCHW / channels_last tensor (conv_block.py:196-216)."""
+    if block.training:
+        raise RuntimeError("PreActFixupResBlock: training-mode forward is outside the B200 "
+                           "inference path; call .eval()")
+    E.require_cuda(inp, "PreActFixupResBlock.forward")
+    st = state(block)
+    key = E.block_version(block)
+    if st.packed is None or key != st.packed_key:
+        E.check_block_supported(block)
+        st.packed = E.pack_blocks([block])[0]
+        st.packed_key = key
+    x, cl = E.to_nhwc(inp)
+    return E.from_nhwc(E.fixup_forward_nhwc(st.packed, x, precision=resolve_precision(block)), cl)
+
+
+# ---- binding onto instantiated reference modules -------------------------------------------------
+def _bind(module, fast):
+    """Route eval-mode CUDA forwards of ``module`` to ``fast``; training mode and CPU tensors keep
+    the module's own (reference) forward."""
+    if "_b200_orig_forward" in module.__dict__:
+        return
+    orig = module.forward
+
+    def forward(self, *args, **kwargs):
+        first = args[0] if args else None
+        if isinstance(first, (list, tuple)) and first:
+            first = first[0]
+        if self.training or not (isinstance(first, Tensor) and first.is_cuda):
+            return orig(*args, **kwargs)
+        return fast(self, *args, **kwargs)
+
+    module.__dict__["_b200_orig_forward"] = orig
+    module.forward = types.MethodType(forward, module)
+
+
+def _enc_fast(enc, x):
+    e, idx, loss, _, _ = encoder_encode(enc, x)
+    return (e,), (idx,), (loss,)
+
+
+def _vq_fast(vq, inputs):
+    q, idx, loss, _ = quantizer_forward(vq, inputs)
+    return q, idx, loss
+
+
+def accelerate(model: nn.Module, precision: Optional[str] = None) -> nn.Module:
+    """Bind an instantiated model built from the reference's OWN classes (``vq_ae.model.VQAE`` /
+    ``Encoder`` / ``Decoder``, the quantisers of ``vq_ae.layers.vq``, ``PreActFixupResBlock``) to the
+    B200 path, in place: eval-mode forwards on CUDA tensors run the packed plans of this module,
+    everything else (training, CPU tensors, ``state_dict``, checkpoints, attributes) is the
+    reference's code, untouched.  ``precision``: "fp32", "bf16", ... or None = follow
+    ``torch.autocast`` like the reference does."""
+    if precision is not None and precision not in E.PRECISIONS:
+        raise ValueError(f"precision must be one of {E.PRECISIONS}")
+    n = 0
+    for m in model.modules():
+        if hasattr(m, "in_stem") and hasattr(m, "vq_layers") and hasattr(m, "pre_enc_layers"):
+            _bind(m, _enc_fast)
+            m.encode = types.MethodType(encoder_encode, m)
+        elif hasattr(m, "out_stem") and hasattr(m, "up_layers") and hasattr(m, "post_enc_layers"):
+            _bind(m, decoder_forward)
+        elif hasattr(m, "embed") and hasattr(m, "commitment_cost") and hasattr(m, "embed_code"):
+            _bind(m, _vq_fast)
+        elif is_fixup_block(m):
+            _bind(m, block_forward)
+        else:
+            continue
+        state(m).precision = precision
+        n += 1
+    if n == 0:
+        raise TypeError("accelerate(): no Encoder / Decoder / quantiser / Fixup block found below "
+                        f"{type(model).__name__}")
+    return model

@@ -265,6 +265,12 @@ int vqae_embed_codes_f32(const void* indices, int idx_is_u8, const float* table,
 int vqae_codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw,
                           int64_t first_patch, int grid_cols, uint8_t* map, int64_t map_rows,
                           int64_t map_cols, void* stream);
+/* the same into an int64 map: the reference assembles slides in the encoder's index dtype and
+ * narrows with cast_to_lowest_dtype only when a slide is complete (extract_embeddings.py:54-59,
+ * 75-89), which is what codebooks of more than 256 entries need.                            */
+int vqae_codemap_place_i64(const int64_t* tiles, int64_t n_tiles, int th, int tw,
+                           int64_t first_patch, int grid_cols, int64_t* map, int64_t map_rows,
+                           int64_t map_cols, void* stream);
 
 #ifdef __cplusplus
 }

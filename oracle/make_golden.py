@@ -112,6 +112,51 @@ def block_cases(cb_mod):
     return out
 
 
+# block cases at sizes the tcgen05 kernels tile (W % 32 == 0, H % 16 == 0): name -> (cin, cout, mode,
+# hw).  x is regenerated from its seed by the tests (helpers.tc_block_input); y is stored on a
+# sub-grid that contains both image borders.
+TC_BLOCK_CASES = {
+    "same8": (8, 8, "same", 32), "same16": (16, 16, "same", 32), "same32": (32, 32, "same", 32),
+    "same64": (64, 64, "same", 32), "same128": (128, 128, "same", 32),
+    "down8": (8, 16, "down", 32), "down16": (16, 32, "down", 32), "down32": (32, 64, "down", 32),
+    "down64": (64, 128, "down", 32),
+    "up16": (16, 8, "up", 16), "up32": (32, 16, "up", 16), "up64": (64, 32, "up", 16),
+    "up128": (128, 64, "up", 16),
+}
+
+
+def tc_sub_index(n: int):
+    return sorted(set(range(0, n, 3)) | {1, n - 2, n - 1})
+
+
+def tc_block_input(name: str) -> torch.Tensor:
+    cin, _, _, hw = TC_BLOCK_CASES[name]
+    g = torch.Generator().manual_seed(700 + cin + {"same": 0, "down": 1, "up": 2}[TC_BLOCK_CASES[name][2]])
+    return torch.randn(2, cin, hw, hw, generator=g)
+
+
+@torch.no_grad()
+def block_cases_tc(cb_mod):
+    out = {}
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    for name, (cin, cout, mode, hw) in TC_BLOCK_CASES.items():
+        blk = cb_mod.PreActFixupResBlock(in_channels=cin, out_channels=cout, mode=mode,
+                                         **conf).eval()
+        blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=13, regime="perturbed",
+                                              n_layers=12))
+        x = tc_block_input(name)
+        y = blk(x)
+        ii = torch.tensor(tc_sub_index(y.shape[-1]))
+        out[f"{name}_y_sub"] = _np(y[:, :, ii][:, :, :, ii])
+        out[f"{name}_y_stats"] = stats(y)
+        out[f"{name}_x_stats"] = stats(x)         # guards the regenerated input
+        out[f"{name}_branch_absmax"] = np.array(float((y - x).abs().max()) if mode == "same"
+                                                else float(y.abs().max()))
+    return out
+
+
 @torch.no_grad()
 def model_case(model_mod, n_down: int, regime: str, batch: int, size: int, seed: int):
     conf = compose_vqae_conf(n_down=n_down)
@@ -157,6 +202,7 @@ def main():
 
     np.savez_compressed(GOLDEN / "quantizer.npz", **quantizer_cases(vq_mod))
     np.savez_compressed(GOLDEN / "blocks.npz", **block_cases(cb_mod))
+    np.savez_compressed(GOLDEN / "blocks_tc.npz", **block_cases_tc(cb_mod))
     for tag, (n_down, regime, batch, size, seed) in {
         "model_nd3_perturbed": (3, "perturbed", 2, 256, 1),
         "model_nd3_fixup": (3, "fixup", 2, 256, 2),

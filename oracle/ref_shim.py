@@ -7,10 +7,12 @@ modules in ``sys.modules`` and puts the reference checkout on ``sys.path`` so th
 ``import vq_ae.model`` executes the reference's own source files.  No reference
 source is copied into this repository.
 
-Only ``oracle/make_golden.py`` and the container-only tests
-(``tests/test_oracle_vs_reference.py``) use this file.  /root/reference does not
-exist on the GPU box, so nothing in the ``-m gpu`` tests, ``smoke()`` or
-``bench.py`` may import it.
+Users: ``oracle/make_golden.py`` and ``tests/test_oracle_vs_reference.py`` (build
+container, against /root/reference); ``bench.py --impl reference`` and
+``tests/test_gpu_reference.py`` (GPU box, against the unmodified copy under the
+git-ignored ``oracle/_ref`` made by ``make -C oracle ref``; /root/reference itself
+does not exist there and is never read at run time).  The product package never
+imports this file.
 """
 from __future__ import annotations
 
@@ -21,7 +23,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("VQAE_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """VQAE_REFERENCE_ROOT, else the read-only checkout (build container), else the unmodified
+    copy that `make -C oracle ref` placed under oracle/_ref (travels to the GPU box)."""
+    env = os.environ.get("VQAE_REFERENCE_ROOT")
+    if env:
+        return env
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in ("/root/reference", os.path.join(here, "_ref")):
+        if os.path.isfile(os.path.join(cand, "vq_ae", "model.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
@@ -73,8 +88,8 @@ def install() -> None:
         return
     if not reference_available():
         raise FileNotFoundError(
-            f"reference checkout not found at {REFERENCE_ROOT}; the shim only works in "
-            "the build container"
+            f"reference not found at {REFERENCE_ROOT} (nor a copy under oracle/_ref); run "
+            "`make -C oracle ref` in the build container"
         )
     import torch
     from torch import nn

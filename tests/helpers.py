@@ -24,6 +24,15 @@ BLOCK_CASES = {
     "down8": (8, 16, "down", 16), "down32": (32, 64, "down", 8),
     "up16": (16, 8, "up", 8), "up64": (64, 32, "up", 4),
 }
+# blocks at sizes the tcgen05 kernels tile; goldens in blocks_tc.npz (oracle/make_golden.py, same table)
+TC_BLOCK_CASES = {
+    "same8": (8, 8, "same", 32), "same16": (16, 16, "same", 32), "same32": (32, 32, "same", 32),
+    "same64": (64, 64, "same", 32), "same128": (128, 128, "same", 32),
+    "down8": (8, 16, "down", 32), "down16": (16, 32, "down", 32), "down32": (32, 64, "down", 32),
+    "down64": (64, 128, "down", 32),
+    "up16": (16, 8, "up", 16), "up32": (32, 16, "up", 16), "up64": (64, 32, "up", 16),
+    "up128": (128, 64, "up", 16),
+}
 # the reference's near-tie rule: indices must match wherever the top-2 relative gap of the
 # un-rooted L4 sums exceeds this (SURVEY.md section 7 hard part 2)
 NEAR_TIE_REL_GAP = 16.0 * 2.0 ** -23
@@ -61,6 +70,38 @@ def make_block(name: str):
     blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=11, regime="perturbed",
                                           n_layers=12))
     return blk
+
+
+def tc_sub_index(n: int):
+    return sorted(set(range(0, n, 3)) | {1, n - 2, n - 1})
+
+
+def tc_block_input(name: str) -> torch.Tensor:
+    """The seeded input of a blocks_tc.npz case (checked against the golden's x_stats)."""
+    cin, _, mode, hw = TC_BLOCK_CASES[name]
+    g = torch.Generator().manual_seed(700 + cin + {"same": 0, "down": 1, "up": 2}[mode])
+    x = torch.randn(2, cin, hw, hw, generator=g)
+    want = golden("blocks_tc")[f"{name}_x_stats"]
+    got = np.array([x.double().mean().item(), x.double().std().item(), x.double().abs().sum().item()])
+    assert np.allclose(got, want, rtol=1e-9), "seeded input differs from the one the golden was made from"
+    return x
+
+
+def make_tc_block(name: str):
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    cin, cout, mode, hw = TC_BLOCK_CASES[name]
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blk = PreActFixupResBlock(in_channels=cin, out_channels=cout, mode=mode, **conf).eval()
+    blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=13, regime="perturbed",
+                                          n_layers=12))
+    return blk
+
+
+def sub_grid(y: torch.Tensor) -> torch.Tensor:
+    ii = torch.tensor(tc_sub_index(y.shape[-1]), device=y.device)
+    return y[:, :, ii][:, :, :, ii]
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:

@@ -1,0 +1,138 @@
+"""GPU: the REDUCED-PRECISION tensor-core path (the one bench.py times) pinned directly to the
+goldens written by the unmodified reference -- not to this repository's own fp32 path.
+
+What can and cannot be asserted (hard part 3): with bf16 GEMM operands the
+latents carry a relative error of a few 1e-3, so a vector whose two nearest codes are closer than
+that flips its code; the reference itself, run with bf16 convs, agrees with its fp32 run on ~96 %
+of codes.  A flipped code changes the decoded patch everywhere (54 circular 3x3 blocks at 32x32
+see the whole grid), so the 1e-2 reconstruction bar of north_star is checked where it is
+well-posed: on the decoder fed with the REFERENCE's codes, and on the quantised tensor at every
+position whose code agrees.  The encoder is held to: latent error, code agreement (bars set from
+the measured values in profiles/r2_reduced_vs_golden.txt), and "no flip where the reference's
+top-2 gap is large".
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import vqae_b200
+from vqae_b200 import engine as E
+from vqae_b200 import plan as P
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# tag -> (min code agreement, max relative latent error); measured on B200 (round 2):
+# agreement 0.9976 / 0.9922 / 0.9844 / 0.9863, latent error 3.6e-3 / 3.2e-3 / 2.3e-3 / 3.6e-3
+BF16_BARS = {
+    "model_nd3_fixup": (0.995, 6e-3),
+    "model_nd3_perturbed": (0.990, 6e-3),
+    "model_nd4_perturbed_256": (0.979, 6e-3),
+    "model_nd4_perturbed_512": (0.981, 6e-3),
+}
+
+
+def _pre_vq(m, x, precision):
+    enc = m.encoder
+    h = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias)
+    stem = h
+    blocks = P.flat_blocks(enc.down_layers) + P.flat_blocks(enc.pre_enc_layers)
+    h = P.Plan().run(blocks, h, precision)
+    return stem.permute(0, 3, 1, 2), h.permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("tag", sorted(H.MODEL_CASES))
+def test_bf16_model_vs_reference_golden(tag):
+    g = H.golden(tag)
+    min_agree, max_zerr = BF16_BARS[tag]
+    m, sd, x = H.model_and_state(tag)
+    m = vqae_b200.set_precision(m.to(DEV), "bf16")
+    try:
+        with torch.no_grad():
+            xd = x.to(DEV)
+            (enc,), (idx,), (loss,) = m.encoder(xd)
+            _, _, _, _, z = m.encoder.encode(xd, want_latents=True)
+            ref_codes = torch.from_numpy(g["idx"].astype(np.int64)).to(DEV)
+            dec_ref = m.decode_codes(ref_codes)              # decoder on the reference's codes
+            recon, _ = m(xd)
+            dec_own = m.decode_codes(idx)
+            stem, pre_vq = _pre_vq(m, xd, "bf16")
+        ref_idx = g["idx"].astype(np.int64).reshape(-1)
+        idx_np = idx.cpu().numpy().reshape(-1)
+        same = idx_np == ref_idx
+        # stem (fp32 CUDA-core kernel in every mode) and the pre-quantiser activations
+        assert H.rel_err(stem.cpu()[:, :, ::16, ::16], torch.from_numpy(g["in_stem_sub"])) < 1e-5
+        assert H.rel_err(pre_vq.cpu()[:, ::8, ::4, ::4], torch.from_numpy(g["pre_vq_sub"])) < 1e-2
+        # latents and codes
+        z_ref = torch.from_numpy(g["z"])
+        z_err = float((z.cpu().reshape(-1, 8) - z_ref).abs().max() / z_ref.abs().max())
+        assert z_err < max_zerr, z_err
+        assert same.mean() >= min_agree, same.mean()
+        assert not (~same & (g["gap"] >= 0.1)).any()         # flips only between near neighbours
+        assert int((~same & (g["gap"] >= 1e-2)).sum()) <= 12
+        assert abs(loss.item() - float(g["loss"])) < 1e-2 * abs(float(g["loss"]))
+        # quantised tensor: a table gather -- exact wherever the code agrees
+        msk = torch.from_numpy(same.reshape(g["idx"].shape))[:, ::4, ::4]
+        e_ref = torch.from_numpy(g["enc_sub"])
+        e_err = float(((enc.cpu()[:, ::8, ::4, ::4] - e_ref).abs() * msk[:, None]).max()
+                      / e_ref.abs().max())
+        assert e_err < 1e-6, e_err
+        # decoder: north_star's reduced-precision bar, on identical codes
+        assert H.rel_err(dec_ref.cpu()[:, :, ::8, ::8], torch.from_numpy(g["decode_codes_sub"])) < 1e-2
+        # the full forward is the composition of the two (same launches, same bits)
+        assert torch.equal(recon, dec_own)
+        print(f"{tag}: bf16 agreement {same.mean():.4f}, latent err {z_err:.2e}")
+    finally:
+        vqae_b200.set_precision(m, None)
+        m.cpu()
+
+
+@pytest.mark.parametrize("name", sorted(H.TC_BLOCK_CASES))
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_block_at_tensor_core_sizes_vs_reference_golden(name, precision):
+    """Every block shape of both shipped models at a size the tcgen05 kernels tile, against the
+    reference's output.  fp32: 2e-5.  bf16: 1e-2 of the output range (north_star) and 2e-2 of the
+    branch magnitude ('same' blocks: the part that actually went through bf16 GEMMs)."""
+    g = H.golden("blocks_tc")
+    blk = H.make_tc_block(name).to(DEV)
+    x = H.tc_block_input(name).to(DEV)
+    pk = blk.packed()
+    xn, _ = E.to_nhwc(x)
+    y = E.fixup_forward_nhwc(pk, xn, precision=precision).permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g[f"{name}_y_sub"])
+    got = H.sub_grid(y).cpu()
+    assert got.shape == ref.shape
+    err = float((got - ref).abs().max())
+    if precision == "fp32":
+        assert err / float(ref.abs().max()) < 2e-5
+    else:
+        assert err / float(ref.abs().max()) < 1e-2, err / float(ref.abs().max())
+        assert err / float(g[f"{name}_branch_absmax"]) < 2e-2, err / float(g[f"{name}_branch_absmax"])
+
+
+def test_autocast_selects_the_reduced_precision_path():
+    """The reference's extraction loop wraps the encoder in torch.autocast('cuda')
+    (extract_embeddings.py:124-125); with no explicit set_precision the drop-in follows it."""
+    tag = "model_nd3_perturbed"
+    m, sd, x = H.model_and_state(tag)
+    m = vqae_b200.set_precision(m.to(DEV), None)
+    try:
+        with torch.no_grad():
+            xd = x.to(DEV)
+            (_,), (i_plain,), _ = m.encoder(xd)
+            n0 = E.launch_count()
+            with torch.autocast("cuda"):
+                (_,), (i_auto,), _ = m.encoder(xd)
+            n_auto = E.launch_count() - n0
+            vqae_b200.set_precision(m, "bf16")
+            (_,), (i_bf16,), _ = m.encoder(xd)
+            vqae_b200.set_precision(m, "fp32")
+            (_,), (i_fp32,), _ = m.encoder(xd)
+        assert torch.equal(i_plain, i_fp32)                  # no autocast: fp32, like the reference
+        assert torch.equal(i_auto, i_bf16)                   # autocast: tensor-core path
+        assert n_auto < 40                                   # (the fp32 path needs > 200 launches)
+    finally:
+        vqae_b200.set_precision(m, None)
+        m.cpu()

@@ -12,7 +12,9 @@ import torch
 
 import helpers as H
 import vqae_oracle as O
+import vqae_b200
 from vqae_b200 import engine as E
+from vqae_b200 import plan as P
 from vqae_b200 import synthetic as S
 from vqae_b200.extract import compress_slide, encode_patches, tiles_to_map
 from vqae_b200.layers.vq import EMAVectorQuantizer, ProjectedEMAVectorQuantizer2d
@@ -169,13 +171,19 @@ def test_resize_conv_vs_oracle():
 def test_model_vs_reference_golden(tag):
     g = H.golden(tag)
     m, sd, x = H.model_and_state(tag)
-    m = m.to(DEV)
+    m = vqae_b200.set_precision(m.to(DEV), "fp32")
     try:
         with torch.no_grad():
             (enc,), (idx,), (loss,) = m.encoder(x.to(DEV))
             recon, (loss2,) = m(x.to(DEV))
             dec = m.decode_codes(idx)
+            dec_ref = m.decode_codes(torch.from_numpy(g["idx"].astype(np.int64)).to(DEV))
             _, _, _, ties, z = m.encoder.encode(x.to(DEV), want_latents=True)
+            enc_m = m.encoder
+            stem_nhwc = E.stem_in(x.to(DEV), enc_m.in_stem.weight, enc_m.in_stem.bias)
+            blocks = P.flat_blocks(enc_m.down_layers) + P.flat_blocks(enc_m.pre_enc_layers)
+            pre_vq = P.Plan().run(blocks, stem_nhwc, "fp32").permute(0, 3, 1, 2)
+            stem = stem_nhwc.permute(0, 3, 1, 2)
         assert idx.dtype == torch.int64 and tuple(idx.shape) == g["idx"].shape
         assert loss.dim() == 0 and torch.equal(loss, loss2)
         # latents against the reference's, then indices outside near-ties *scaled by the
@@ -189,12 +197,25 @@ def test_model_vs_reference_golden(tag):
         idx_np, ref_idx = idx.cpu().numpy().reshape(-1), g["idx"].astype(np.int64).reshape(-1)
         bad = (idx_np != ref_idx) & (g["gap"] >= thresh)
         assert int(bad.sum()) == 0, (int(bad.sum()), int((idx_np != ref_idx).sum()), z_err)
-        assert (idx_np != ref_idx).mean() < 2e-3
-        assert H.rel_err(enc.cpu()[:, ::8, ::4, ::4], torch.from_numpy(g["enc_sub"])) < 1e-4 \
-            or (idx_np != ref_idx).any()
-        assert H.rel_err(recon.cpu()[:, :, ::8, ::8], torch.from_numpy(g["recon_sub"])) < 1e-4 \
-            or (idx_np != ref_idx).any()
+        same = idx_np == ref_idx
+        assert (~same).mean() < 2e-3
+        # stem and pre-quantiser activations (the goldens carry both)
+        assert H.rel_err(stem.cpu()[:, :, ::16, ::16], torch.from_numpy(g["in_stem_sub"])) < 2e-5
+        assert H.rel_err(pre_vq.cpu()[:, ::8, ::4, ::4], torch.from_numpy(g["pre_vq_sub"])) < 1e-4
+        # quantised tensor: compared at every position whose code agrees (a near-tie flip changes
+        # that one position only -- it is masked, it does not switch the check off)
+        msk = torch.from_numpy(same.reshape(g["idx"].shape))[:, ::4, ::4]
+        e_ref = torch.from_numpy(g["enc_sub"])
+        e_err = float(((enc.cpu()[:, ::8, ::4, ::4] - e_ref).abs() * msk[:, None]).max() / e_ref.abs().max())
+        assert e_err < 1e-4, e_err
+        # decoder: on the REFERENCE's codes (well-posed whatever the encoder did), against both the
+        # decode-from-codes golden and the reference's reconstruction (identical codes there)
+        assert H.rel_err(dec_ref.cpu()[:, :, ::8, ::8], torch.from_numpy(g["decode_codes_sub"])) < 1e-4
+        assert H.rel_err(dec_ref.cpu()[:, :, ::8, ::8], torch.from_numpy(g["recon_sub"])) < 1e-4
+        # the model's own forward = decoder on its own codes; equals the golden when no code flipped
         assert H.rel_err(dec.cpu()[:, :, ::8, ::8], recon.cpu()[:, :, ::8, ::8]) < 1e-5
+        if same.all():
+            assert H.rel_err(recon.cpu()[:, :, ::8, ::8], torch.from_numpy(g["recon_sub"])) < 1e-4
         assert abs(loss.item() - float(g["loss"])) < 1e-4 * max(abs(float(g["loss"])), 1e-3)
     finally:
         m.cpu()
@@ -214,9 +235,15 @@ def test_encoder_channels_last_and_u8_inputs_agree_with_oracle():
             (enc_nc,), (idx_nc,), _ = m.encoder(x.to(DEV))
         assert E.is_channels_last(enc_cl) and enc_nc.is_contiguous()
         assert torch.equal(idx_u8, idx_nc) and torch.equal(idx_cl, idx_nc)
+        # The oracle here is torch-CPU fp32 on the same input, the CUDA path differs from it by fp32
+        # rounding only: the latent error is bounded like in test_model_vs_reference_golden
+        # (z_err < 1e-4 * max|z|, measured 4e-7), i.e. a relative change of the un-rooted L4 sums of at
+        # most 64 * z_err / d1 ~ 1e-4 for these weights, so codes may differ only where the top-2 gap
+        # is below that; 2 048 vectors with a gap density of ~1 per unit around 0 give < 1 such
+        # vector in expectation, so at most 2 are tolerated.
         bad, total_bad, _ = H.index_mismatches_outside_ties(idx_nc.cpu(), o_idx, gap.reshape(-1),
-                                                            thresh=1e-3)
-        assert bad == 0 and total_bad <= 4
+                                                            thresh=1e-4)
+        assert bad == 0 and total_bad <= 2
     finally:
         m.cpu()
 
