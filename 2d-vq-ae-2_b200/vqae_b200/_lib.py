@@ -16,7 +16,8 @@ LIB_NAME = "libvqae_b200.so"
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_DIM_MISMATCH, ERR_CUDA, ERR_SCRATCH = range(6)
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-DT_F32, DT_BF16, DT_U8 = 0, 1, 2
+DT_F32, DT_BF16, DT_U8, DT_F16 = 0, 1, 2, 3
+QUANT_AUTO, QUANT_CUDA_CORE, QUANT_TENSOR_CORE = 0, 1, 2
 MODE_SAME, MODE_DOWN, MODE_UP = 0, 1, 2
 CONV_1x1, CONV_2x2S2, CONV_3x3_CIRC = 0, 1, 2
 
@@ -39,6 +40,16 @@ class FixupParams(C.Structure):
     ]
 
 
+class PackDesc(C.Structure):
+    """struct vqae_pack_desc"""
+    _fields_ = [("kind", C.c_int32), ("c_in", C.c_int32), ("c_out", C.c_int32), ("taps", C.c_int32),
+                ("scale", C.c_float), ("n_elems", C.c_int32), ("src", C.c_void_p * 4),
+                ("dst", C.c_void_p)]
+
+
+PACK_F32_CONV, PACK_SAME_BF16, PACK_RESIDENT_BF16, PACK_DOWN_BF16, PACK_LO = 0, 1, 2, 3, 0x100
+
+
 class QuantizerParams(C.Structure):
     """struct vqae_quantizer_params"""
     _fields_ = [
@@ -59,6 +70,8 @@ SIGNATURES = {
     "vqae_launch_count": (C.c_uint64, []),
     "vqae_normalize_u8": (_i, [_vp, _vp, _i64, _i, _i, _fp, _fp, _i, _vp]),
     "vqae_pack_conv_weight_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "vqae_pack_elems": (_sz, [_i, _i, _i, _i]),
+    "vqae_pack_batched": (_i, [_vp, _i, _i, _vp]),
     "vqae_stem_in_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _fp, _fp, _vp]),
     "vqae_stem_out_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "vqae_conv_f32": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _i, _f, _f, _f, _vp]),
@@ -69,7 +82,9 @@ SIGNATURES = {
     "vqae_quantizer_scratch_bytes": (_sz, [_i64]),
     "vqae_quantize_f32": (_i, [C.POINTER(QuantizerParams), _vp, _i, _vp, _i, _vp, _vp, _vp, _f,
                                _vp, _vp, _sz, _i64, _i64, _vp]),
-    "vqae_quantize_tc_set_profile": (None, [_vp]),
+    "vqae_quantize_supported": (_i, [C.POINTER(QuantizerParams), _i, _i, _i, _i, _i, _i]),
+    "vqae_quantize": (_i, [C.POINTER(QuantizerParams), _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _f,
+                           _vp, _vp, _sz, _i64, _i64, _i, _vp]),
     "vqae_quantize_tc_supported": (_i, [C.POINTER(QuantizerParams), _i, _i, _i]),
     "vqae_quantize_tc_f32": (_i, [C.POINTER(QuantizerParams), _vp, _vp, _vp, _vp, _vp, _f, _vp,
                                   _vp, _vp, _sz, _i64, _i64, _vp]),
@@ -111,9 +126,29 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.vqae_abi_version() != 2:
-        raise RuntimeError(f"{path}: ABI version {lib.vqae_abi_version()} != 2")
+    if lib.vqae_abi_version() != 3:
+        raise RuntimeError(f"{path}: ABI version {lib.vqae_abi_version()} != 3")
     _lib = lib
+    return lib
+
+
+_aids: Optional[C.CDLL] = None
+
+
+def load_testaids() -> C.CDLL:
+    """libvqae_b200_testaids.so (include/vqae_b200_testaids.h): self test, MMA microbenchmarks and
+    profiling hooks -- for tests/ and profiles/, never used by the product path."""
+    global _aids
+    if _aids is not None:
+        return _aids
+    load()                                   # builds both libraries; the aids link against the first
+    from . import _lib_tc
+    lib = C.CDLL(str(PKG / "libvqae_b200_testaids.so"))
+    for name, (res, args) in _lib_tc.AIDS_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _aids = lib
     return lib
 
 

@@ -84,6 +84,14 @@ int vqae_pack_conv_weight_f32(const float* w_oihw, float* packed, int out_ch, in
     return pack_conv_weight_f32(w_oihw, packed, out_ch, in_ch, kh * kw, (cudaStream_t)stream);
 }
 
+size_t vqae_pack_elems(int kind, int c_in, int c_out, int taps) {
+    return pack_elems(kind, c_in, c_out, taps);
+}
+
+int vqae_pack_batched(const vqae_pack_desc* descs_device, int n_descs, int max_elems, void* stream) {
+    return pack_batched(descs_device, n_descs, max_elems, (cudaStream_t)stream);
+}
+
 int vqae_stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w_oihw,
                      const float* bias, float* out, int64_t batch, int height, int width,
                      int c_out, const float* mean_host, const float* std_host, void* stream) {
@@ -202,11 +210,6 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
     return VQAE_ERR_BAD_ARG;
 }
 
-int vqae_tc_selftest(const void* a_bf16, int a_rows, int row_shift, const void* b_bf16, float* d,
-                     void* stream) {
-    return tc_selftest(a_bf16, a_rows, row_shift, b_bf16, d, (cudaStream_t)stream);
-}
-
 int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                               int c, void* packed, void* stream) {
     return pack_same_block_bf16(w1_oihw, w2_oihw, w3_oihw, c, packed, (cudaStream_t)stream);
@@ -227,15 +230,6 @@ int device_sm_count(int* out) {
 }
 }  // namespace vqae
 extern "C" {
-
-int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packed,
-                                 const float* scalars8_host, int64_t batch, int height, int width,
-                                 int c, long long* phase_clocks, void* stream) {
-    int sm_count = 0;
-    if (int rc = device_sm_count(&sm_count)) return rc;
-    return same_block_tc(x, out, w_packed, scalars8_host, batch, height, width, c, sm_count,
-                         phase_clocks, (cudaStream_t)stream);
-}
 
 int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c,
@@ -265,8 +259,6 @@ int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void*
                          batch, height, width, c, sm_count, (cudaStream_t)stream);
 }
 
-void vqae_trunk_resident_set_profile(long long* phase_clocks) { trunk_resident_set_prof(phase_clocks); }
-
 int vqae_trunk_resident_max_clusters(void) {
     int n = 0;
     return trunk_resident_max_clusters(&n) == VQAE_OK ? n : -1;
@@ -287,16 +279,6 @@ int vqae_trunk_resident_bf16(const float* x, float* out, const void* w_packed_al
                              int width, int c, void* stream) {
     return trunk_resident_tc(x, out, w_packed_all, scalars_dev, n_blocks, batch, height, width, c,
                              (cudaStream_t)stream);
-}
-
-int vqae_tc_mma_bench(int n, int layout_type, int reps, int a_stride_rows, long long* out2,
-                      void* stream) {
-    return tc_mma_bench(n, layout_type, reps, a_stride_rows, out2, (cudaStream_t)stream);
-}
-
-int vqae_tc_mma_bench2(int m, int n, int reps, int n_issuers, int ctas_per_sm, int mode,
-                       long long* out_per_cta, void* stream) {
-    return tc_mma_bench2(m, n, reps, n_issuers, ctas_per_sm, mode, out_per_cta, (cudaStream_t)stream);
 }
 
 size_t vqae_down_block_pack_elems(int c_in) { return down_block_pack_elems(c_in); }
@@ -335,7 +317,19 @@ int vqae_quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layo
                         z_out, scratch, scratch_bytes, batch, spatial, (cudaStream_t)stream);
 }
 
-void vqae_quantize_tc_set_profile(long long* phase_clocks) { quantize_tc_set_prof(phase_clocks); }
+int vqae_quantize_supported(const vqae_quantizer_params* p, int x_dtype, int x_layout,
+                            int out_dtype, int out_layout, int has_out, int kernel) {
+    return quantize_supported(p, x_dtype, x_layout, out_dtype, out_layout, has_out != 0, kernel) ? 1 : 0;
+}
+
+int vqae_quantize(const vqae_quantizer_params* p, const void* x, int x_dtype, int x_layout,
+                  void* out, int out_dtype, int out_layout, int64_t* indices, float* loss,
+                  uint32_t* near_ties, float tie_rel_gap, float* z_out, void* scratch,
+                  size_t scratch_bytes, int64_t batch, int64_t spatial, int kernel, void* stream) {
+    return quantize_any(p, x, x_dtype, x_layout, out, out_dtype, out_layout, indices, loss,
+                        near_ties, tie_rel_gap, z_out, scratch, scratch_bytes, batch, spatial,
+                        kernel, (cudaStream_t)stream);
+}
 
 int vqae_quantize_tc_supported(const vqae_quantizer_params* p, int x_layout, int out_layout,
                                int has_out) {

@@ -19,7 +19,11 @@ REPO = PKG.parent.parent
 LIB_PATH = PKG / "libvqae_b200.so"
 STAMP = PKG / ".libvqae_b200.stamp"
 
-SOURCES = ["abi.cu", "conv_f32.cu", "stems.cu", "quantize.cu", "quantize_tc.cu", "tc_kernels.cu", "tc_down.cu", "tc_chain.cu", "tc_resident.cu", "tc_bench.cu", "up_tail.cu", "up_head.cu"]
+SOURCES = ["abi.cu", "conv_f32.cu", "stems.cu", "quantize.cu", "quantize_tc.cu", "tc_kernels.cu",
+           "tc_down.cu", "tc_chain.cu", "tc_resident.cu", "up_tail.cu", "up_head.cu", "pack.cu"]
+# test / measurement aids: a separate library that links against the product library
+AID_SOURCES = ["testaids.cu", "tc_bench.cu"]
+AIDS_PATH = PKG / "libvqae_b200_testaids.so"
 HEADERS = ["common.cuh", "kernels.cuh", "tc_common.cuh"]
 
 NVCC_FLAGS = [
@@ -41,7 +45,8 @@ def _nvcc() -> str:
 
 def _headers_digest() -> str:
     h = hashlib.sha256()
-    for f in [CSRC / s for s in HEADERS] + [REPO / "include" / "vqae_b200.h"]:
+    for f in [CSRC / s for s in HEADERS] + [REPO / "include" / "vqae_b200.h",
+                                            REPO / "include" / "vqae_b200_testaids.h"]:
         h.update(f.name.encode())
         h.update(f.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -50,7 +55,7 @@ def _headers_digest() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256(_headers_digest().encode())
-    for s in SOURCES:
+    for s in SOURCES + AID_SOURCES:
         h.update(s.encode())
         h.update((CSRC / s).read_bytes())
     return h.hexdigest()
@@ -61,7 +66,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     changed .cu (in parallel), then one link."""
     from concurrent.futures import ThreadPoolExecutor
     digest = _digest()
-    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text() == digest:
+    if not force and LIB_PATH.exists() and AIDS_PATH.exists() and STAMP.exists() \
+            and STAMP.read_text() == digest:
         return LIB_PATH
     nvcc = _nvcc()
     OBJ_DIR.mkdir(exist_ok=True)
@@ -81,17 +87,24 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
             tag.write_text(want)
         return obj, proc.returncode, " ".join(cmd) + "\n" + proc.stdout + proc.stderr
 
-    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
-        results = list(ex.map(compile_one, SOURCES))
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES + AID_SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, SOURCES + AID_SOURCES))
     logs = [r[2] for r in results if r[2]]
     failed = [r for r in results if r[1] != 0]
     if not failed:
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB_PATH),
-               *[str(r[0]) for r in results]]
-        proc = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-        if proc.returncode != 0:
-            failed = [(None, proc.returncode, logs[-1])]
+        main_objs = [str(r[0]) for r in results[:len(SOURCES)]]
+        aid_objs = [str(r[0]) for r in results[len(SOURCES):]]
+        for cmd in (
+            [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB_PATH),
+             *main_objs],
+            [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(AIDS_PATH),
+             *aid_objs, "-L", str(PKG), "-l:libvqae_b200.so", "-Xlinker", "-rpath=$ORIGIN"],
+        ):
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            logs.append(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+            if proc.returncode != 0:
+                failed = [(None, proc.returncode, logs[-1])]
+                break
     log = "\n".join(logs)
     (PKG / "build.log").write_text(log)
     if failed:

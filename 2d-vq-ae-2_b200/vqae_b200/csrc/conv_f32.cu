@@ -270,19 +270,6 @@ bicubic_up2_kernel(const float* __restrict__ in, float* __restrict__ out, int64_
     reinterpret_cast<float4*>(out)[i] = acc;
 }
 
-__global__ void __launch_bounds__(256)
-pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int O, int I,
-                        int taps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = O * I * taps;
-    if (i >= total) return;
-    // packed index i = (t * I + c) * O + o
-    const int o = i % O;
-    const int c = (i / O) % I;
-    const int t = i / (O * I);
-    packed[i] = w[((int64_t)o * I + c) * taps + t];
-}
-
 }  // namespace
 
 int conv_f32(int kind, const float* in, const float* w, float* out, const float* res, int64_t B,
@@ -316,14 +303,6 @@ int bicubic_up2_f32(const float* in, float* out, int64_t B, int H, int W, int C,
     const int64_t total4 = B * 2 * H * 2 * W * (C / 4);
     bicubic_up2_kernel<<<ceil_div_u(total4, 256), 256, 0, stream>>>(in, out, total4, H, W, C / 4,
                                                                     bias);
-    return check_launch();
-}
-
-int pack_conv_weight_f32(const float* w, float* packed, int O, int I, int taps,
-                         cudaStream_t stream) {
-    if (!w || !packed || O <= 0 || I <= 0 || taps <= 0) return VQAE_ERR_BAD_ARG;
-    const int total = O * I * taps;
-    pack_conv_weight_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(w, packed, O, I, taps);
     return check_launch();
 }
 

@@ -15,6 +15,11 @@ int bicubic_up2_f32(const float* in, float* out, int64_t B, int H, int W, int C,
 int pack_conv_weight_f32(const float* w, float* packed, int O, int I, int taps,
                          cudaStream_t stream);
 
+// pack.cu (every weight layout; one launch for a whole model's convs)
+size_t pack_elems(int kind, int c_in, int c_out, int taps);
+int pack_one(vqae_pack_desc d, cudaStream_t stream);
+int pack_batched(const vqae_pack_desc* descs_dev, int n_descs, int max_elems, cudaStream_t stream);
+
 // up_head.cu (low-resolution half of an 'up' block: the three 1x1 convs in one pointwise kernel)
 bool up_head_supported(int64_t P, int ci, int cb, int co);
 int up_head_f32(const float* x, const float* w1, const float* w2, const float* ws, float* t2, float* s1,
@@ -43,7 +48,13 @@ size_t quantizer_scratch_bytes(int64_t n);
 int quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layout, float* out,
                  int out_layout, int64_t* indices, float* loss, uint32_t* near_ties,
                  float tie_rel_gap, float* z_out, void* scratch, size_t scratch_bytes,
-                 int64_t B, int64_t S, cudaStream_t stream);
+                 int64_t B, int64_t S, cudaStream_t stream, int kernel = VQAE_QUANT_AUTO);
+bool quantize_supported(const vqae_quantizer_params* p, int x_dtype, int x_layout, int out_dtype,
+                        int out_layout, bool has_out, int kernel);
+int quantize_any(const vqae_quantizer_params* p, const void* x, int x_dtype, int x_layout, void* out,
+                 int out_dtype, int out_layout, int64_t* indices, float* loss, uint32_t* near_ties,
+                 float tie_rel_gap, float* z_out, void* scratch, size_t scratch_bytes, int64_t B,
+                 int64_t S, int kernel, cudaStream_t stream);
 int embed_codes_f32(const void* indices, int idx_is_u8, const float* table, int K, int C,
                     float* out, int out_layout, int64_t B, int64_t S, cudaStream_t stream);
 int codemap_place_u8(const int64_t* tiles, int64_t n_tiles, int th, int tw, int64_t first_patch,
@@ -64,8 +75,6 @@ void quantize_tc_set_prof(long long* dev_ptr);
 int device_sm_count(int* out);
 
 // tc_kernels.cu (tcgen05 bf16 path)
-int tc_selftest(const void* A, int a_rows, int row_shift, const void* B, float* D,
-                cudaStream_t stream);
 int same_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
                   int64_t B, int H, int W, int C, int sm_count, long long* prof,
                   cudaStream_t stream);
@@ -88,8 +97,6 @@ void trunk_resident_set_prof(long long* dev_ptr);
 int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, const float* scalars_dev,
                       int n_blocks, int64_t B, int H, int W, int C, cudaStream_t stream);
 
-int tc_mma_bench(int N, int layout_type, int reps, int a_stride_rows, long long* out,
-                 cudaStream_t stream);
 // tc_bench.cu
 int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, int mode, long long* out,
                   cudaStream_t stream);

@@ -1,0 +1,176 @@
+// Weight packing: OIHW fp32 conv weights of the reference's modules -> the layouts the kernels read.
+// One kernel serves every format; vqae_pack_batched packs ALL convs of a model (a table of
+// descriptors in device memory, one grid row per descriptor) in one launch, the single-matrix
+// entry points of the ABI pass one descriptor by value.
+//
+// Formats (include/vqae_b200.h, VQAE_PACK_*):
+//   F32_CONV      [tap][C_in][C_out] fp32                                  (conv_f32.cu)
+//   SAME_BF16     11 matrices [W1 | W2 tap 0..8 | W3], each UMMA canonical K-major [k-chunk][n][8],
+//                 zero padded from c to max(c, 16) channels               (tc_kernels.cu, tc_chain.cu)
+//   RESIDENT_BF16 the same with branch_conv3 pre-multiplied by the Fixup scale      (tc_resident.cu)
+//   DOWN_BF16     [W1 | W2 x4 planes | scale*W3 | Ws x4 planes], C_in zero padded to >= 16 (tc_down.cu)
+// The *_LO variants hold bf16(w - bf16(w)): the low half of the split-bf16 ("bf16x3") operands.
+#include "common.cuh"
+#include "kernels.cuh"
+
+#include <cuda_bf16.h>
+
+namespace vqae {
+namespace {
+
+__device__ __forceinline__ __nv_bfloat16 to_bf16(float v, bool lo) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    return lo ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+}
+
+// canonical [k-chunk][n][8] index r of an N-row matrix -> (n, k)
+__device__ __forceinline__ void canon(int r, int N, int& n, int& k) {
+    const int kc = r / (N * 8);
+    n = (r / 8) % N;
+    k = kc * 8 + (r % 8);
+}
+
+__device__ void pack_element(const vqae_pack_desc& d, int i) {
+    const float* w1 = reinterpret_cast<const float*>(d.src[0]);
+    const float* w2 = reinterpret_cast<const float*>(d.src[1]);
+    const float* w3 = reinterpret_cast<const float*>(d.src[2]);
+    const float* ws = reinterpret_cast<const float*>(d.src[3]);
+    const int kind = d.kind & 0xff;
+    const bool lo = (d.kind & VQAE_PACK_LO) != 0;
+    if (kind == VQAE_PACK_F32_CONV) {
+        // packed index i = (t * I + c) * O + o
+        const int O = d.c_out, I = d.c_in, taps = d.taps;
+        const int o = i % O, c = (i / O) % I, t = i / (O * I);
+        reinterpret_cast<float*>(d.dst)[i] = w1[((int64_t)o * I + c) * taps + t];
+        return;
+    }
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.dst);
+    if (kind == VQAE_PACK_SAME_BF16 || kind == VQAE_PACK_RESIDENT_BF16) {
+        const int CR = d.c_in, CP = CR < 16 ? 16 : CR;
+        const int per = CP * CP;
+        const int m = i / per;
+        int n, k;
+        canon(i % per, CP, n, k);
+        float v = 0.f;
+        if (n < CR && k < CR) {
+            if (m == 0) v = w1[n * CR + k];
+            else if (m == 10) v = w3[n * CR + k] * (kind == VQAE_PACK_RESIDENT_BF16 ? d.scale : 1.f);
+            else v = w2[((size_t)n * CR + k) * 9 + (m - 1)];
+        }
+        out[i] = to_bf16(v, lo);
+        return;
+    }
+    if (kind == VQAE_PACK_DOWN_BF16) {
+        const int CI = d.c_in, CIP = CI < 16 ? 16 : CI, CO = d.c_out;
+        const int n1 = CO * CIP, no = CO * CO;
+        int n, k, j = i;
+        float v = 0.f;
+        if (j < n1) {                                         // W1 [CO x CIP]  (OIHW 1x1)
+            canon(j, CO, n, k);
+            if (k < CI) v = w1[n * CI + k];
+        } else if ((j -= n1) < 4 * no) {                      // W2 planes: w2[n][k][ky][kx]
+            const int pl = j / no;
+            canon(j % no, CO, n, k);
+            v = w2[((size_t)n * CO + k) * 4 + pl];
+        } else if ((j -= 4 * no) < no) {                      // scale * W3
+            canon(j, CO, n, k);
+            v = w3[n * CO + k] * d.scale;
+        } else {                                              // Ws planes: ws[n][k][ky][kx], k < CI
+            j -= no;
+            const int pl = j / n1;
+            canon(j % n1, CO, n, k);
+            if (k < CI) v = ws[((size_t)n * CI + k) * 4 + pl];
+        }
+        out[i] = to_bf16(v, lo);
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_batched_kernel(const vqae_pack_desc* __restrict__ descs) {
+    const vqae_pack_desc d = descs[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_elems; i += gridDim.x * blockDim.x)
+        pack_element(d, i);
+}
+
+__global__ void __launch_bounds__(256) pack_one_kernel(const vqae_pack_desc d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.n_elems) pack_element(d, i);
+}
+
+}  // namespace
+
+size_t pack_elems(int kind, int c_in, int c_out, int taps) {
+    switch (kind & 0xff) {
+        case VQAE_PACK_F32_CONV: return (size_t)c_in * c_out * taps;
+        case VQAE_PACK_SAME_BF16:
+        case VQAE_PACK_RESIDENT_BF16: {
+            const size_t cp = c_in < 16 ? 16 : c_in;
+            return 11 * cp * cp;
+        }
+        case VQAE_PACK_DOWN_BF16: {
+            const size_t cip = c_in < 16 ? 16 : c_in, co = c_out;
+            return co * cip + 4 * co * co + co * co + 4 * co * cip;
+        }
+    }
+    return 0;
+}
+
+int pack_one(vqae_pack_desc d, cudaStream_t stream) {
+    if (!d.src[0] || !d.dst) return VQAE_ERR_BAD_ARG;
+    const size_t n = pack_elems(d.kind, d.c_in, d.c_out, d.taps);
+    if (n == 0 || n > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
+    d.n_elems = (int)n;
+    pack_one_kernel<<<ceil_div_u((int64_t)n, 256), 256, 0, stream>>>(d);
+    return check_launch();
+}
+
+int pack_batched(const vqae_pack_desc* descs_dev, int n_descs, int max_elems, cudaStream_t stream) {
+    if (!descs_dev || n_descs <= 0 || max_elems <= 0) return VQAE_ERR_BAD_ARG;
+    if (n_descs > 65535) return VQAE_ERR_UNSUPPORTED;
+    unsigned gx = ceil_div_u(max_elems, 256 * 4);
+    if (gx > 64) gx = 64;
+    pack_batched_kernel<<<dim3(gx, (unsigned)n_descs), 256, 0, stream>>>(descs_dev);
+    return check_launch();
+}
+
+// ---- single-matrix entry points (ABI v2 names) -------------------------------------------------
+static vqae_pack_desc make_desc(int kind, const float* a, const float* b, const float* c,
+                                const float* d, void* dst, int c_in, int c_out, int taps,
+                                float scale) {
+    vqae_pack_desc p{};
+    p.kind = kind; p.c_in = c_in; p.c_out = c_out; p.taps = taps; p.scale = scale;
+    p.src[0] = a; p.src[1] = b; p.src[2] = c; p.src[3] = d;
+    p.dst = dst;
+    return p;
+}
+
+int pack_conv_weight_f32(const float* w, float* packed, int O, int I, int taps,
+                         cudaStream_t stream) {
+    if (!w || !packed || O <= 0 || I <= 0 || taps <= 0) return VQAE_ERR_BAD_ARG;
+    return pack_one(make_desc(VQAE_PACK_F32_CONV, w, nullptr, nullptr, nullptr, packed, I, O, taps,
+                              1.f), stream);
+}
+
+int pack_same_block_bf16(const float* w1, const float* w2, const float* w3, int C, void* packed,
+                         cudaStream_t stream) {
+    if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
+    if (C != 8 && C != 16 && C != 32 && C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
+    return pack_one(make_desc(VQAE_PACK_SAME_BF16, w1, w2, w3, nullptr, packed, C, C, 9, 1.f), stream);
+}
+
+int pack_resident_block_bf16(const float* w1, const float* w2, const float* w3, int C, float scale,
+                             void* packed, cudaStream_t stream) {
+    if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
+    if (C != 32 && C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
+    return pack_one(make_desc(VQAE_PACK_RESIDENT_BF16, w1, w2, w3, nullptr, packed, C, C, 9, scale),
+                    stream);
+}
+
+int pack_down_block_bf16(const float* w1, const float* w2, const float* w3, const float* ws, int CI,
+                         float scale, void* packed, cudaStream_t stream) {
+    if (!w1 || !w2 || !w3 || !ws || !packed) return VQAE_ERR_BAD_ARG;
+    if (CI != 8 && CI != 16 && CI != 32 && CI != 64) return VQAE_ERR_UNSUPPORTED;
+    return pack_one(make_desc(VQAE_PACK_DOWN_BF16, w1, w2, w3, ws, packed, CI, 2 * CI, 4, scale),
+                    stream);
+}
+
+}  // namespace vqae

@@ -340,10 +340,36 @@ static int launch_q(const QArgs& a, size_t smem, unsigned grid, cudaStream_t str
     return check_launch();
 }
 
+bool quantize_supported(const vqae_quantizer_params* p, int x_dtype, int x_layout, int out_dtype,
+                        int out_layout, bool has_out, int kernel) {
+    if (!p) return false;
+    const bool f32 = x_dtype == VQAE_DT_F32 && (!has_out || out_dtype == VQAE_DT_F32);
+    const bool tc = f32 && quantize_tc_supported(p, x_layout, out_layout, has_out);
+    const bool cc = f32 && p->dim == QD && p->num_codes > 0 && p->num_codes <= 1024;
+    if (kernel == VQAE_QUANT_TENSOR_CORE) return tc;
+    if (kernel == VQAE_QUANT_CUDA_CORE) return cc;
+    return tc || cc;
+}
+
+int quantize_any(const vqae_quantizer_params* p, const void* x, int x_dtype, int x_layout, void* out,
+                 int out_dtype, int out_layout, int64_t* indices, float* loss, uint32_t* near_ties,
+                 float tie_rel_gap, float* z_out, void* scratch, size_t scratch_bytes, int64_t B,
+                 int64_t S, int kernel, cudaStream_t stream) {
+    if (!p) return VQAE_ERR_BAD_ARG;
+    if (kernel < VQAE_QUANT_AUTO || kernel > VQAE_QUANT_TENSOR_CORE) return VQAE_ERR_BAD_ARG;
+    if (x_dtype != VQAE_DT_F32 || (out && out_dtype != VQAE_DT_F32)) return VQAE_ERR_UNSUPPORTED;
+    if (kernel == VQAE_QUANT_TENSOR_CORE &&
+        !quantize_supported(p, x_dtype, x_layout, out_dtype, out_layout, out != nullptr, kernel))
+        return VQAE_ERR_UNSUPPORTED;
+    return quantize_f32(p, reinterpret_cast<const float*>(x), x_layout, reinterpret_cast<float*>(out),
+                        out_layout, indices, loss, near_ties, tie_rel_gap, z_out, scratch,
+                        scratch_bytes, B, S, stream, kernel);
+}
+
 int quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layout, float* out,
                  int out_layout, int64_t* indices, float* loss, uint32_t* near_ties,
                  float tie_rel_gap, float* z_out, void* scratch, size_t scratch_bytes, int64_t B,
-                 int64_t S, cudaStream_t stream) {
+                 int64_t S, cudaStream_t stream, int kernel) {
     if (!p || !x || !indices || !loss || !p->embed || B <= 0 || S <= 0) return VQAE_ERR_BAD_ARG;
     if (out && !p->table) return VQAE_ERR_BAD_ARG;
     if (p->dim != QD) return VQAE_ERR_UNSUPPORTED;
@@ -361,7 +387,7 @@ int quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layout, f
     a.b_in = p->b_in; a.table = p->table; a.N = N; a.S = S; a.K = p->num_codes; a.C = p->c;
     a.tie_rel_gap = tie_rel_gap;
 
-    if (quantize_tc_supported(p, x_layout, out_layout, out != nullptr)) {
+    if (kernel != VQAE_QUANT_CUDA_CORE && quantize_tc_supported(p, x_layout, out_layout, out != nullptr)) {
         // fused kernel: loss and near-tie totals are reduced by its last CTA (no memset / finalize)
         int sm_count = 0;
         if (int rc = device_sm_count(&sm_count)) return rc;

@@ -697,8 +697,6 @@ EncodeTiledFn encode_tiled_fn() {
 
 bool quantize_tc_supported(const vqae_quantizer_params* p, int x_layout, int out_layout,
                            bool has_out) {
-    if (const char* e = getenv("VQAE_QUANT_TC"))
-        if (atoi(e) == 0) return false;
     return p->w_in != nullptr && p->b_in != nullptr && p->num_codes == TQ_K && p->dim == TQ_D && p->c == 64 &&
            x_layout == VQAE_LAYOUT_NHWC && (!has_out || out_layout == VQAE_LAYOUT_NHWC);
 }

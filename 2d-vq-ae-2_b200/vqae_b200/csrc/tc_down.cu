@@ -285,42 +285,6 @@ down_block_tc_kernel(DownArgs a) {
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// canonical [k-chunk][n][8] bf16 pack of  [W1 | W2 x4 | scale*W3 | Ws x4]  with C_in zero padded
-__global__ void __launch_bounds__(256)
-pack_down_block_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
-                       const float* __restrict__ w3, const float* __restrict__ ws, int CI, int CIP,
-                       int CO, float scale, __nv_bfloat16* __restrict__ out) {
-    const int n1 = CO * CIP, no = CO * CO;
-    const int total = n1 + 4 * no + no + 4 * n1;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int idx = i;
-    float v = 0.f;
-    auto decode = [](int r, int N, int& n, int& k) {
-        const int kc = r / (N * 8);
-        n = (r / 8) % N;
-        k = kc * 8 + (r % 8);
-    };
-    int n, k;
-    if (i < n1) {                                         // W1 [CO x CIP]  (OIHW 1x1)
-        decode(i, CO, n, k);
-        if (k < CI) v = w1[n * CI + k];
-    } else if ((i -= n1) < 4 * no) {                      // W2 planes: w2[n][k][ky][kx]
-        const int pl = i / no;
-        decode(i % no, CO, n, k);
-        v = w2[((size_t)n * CO + k) * 4 + pl];
-    } else if ((i -= 4 * no) < no) {                      // scale * W3
-        decode(i, CO, n, k);
-        v = w3[n * CO + k] * scale;
-    } else {                                              // Ws planes: ws[n][k][ky][kx], k < CI
-        i -= no;
-        const int pl = i / n1;
-        decode(i % n1, CO, n, k);
-        if (k < CI) v = ws[((size_t)n * CI + k) * 4 + pl];
-    }
-    out[idx] = __float2bfloat16_rn(v);
-}
-
 template <int CI, int CO>
 int launch_down(const DownArgs& a, int sm_count, cudaStream_t stream) {
     using Cfg = DownCfg<CI, CO>;
@@ -342,17 +306,6 @@ int launch_down(const DownArgs& a, int sm_count, cudaStream_t stream) {
 size_t down_block_pack_elems(int CI) {
     const int CIP = CI < 16 ? 16 : CI, CO = 2 * CI;
     return (size_t)5 * CO * CIP + (size_t)5 * CO * CO;
-}
-
-int pack_down_block_bf16(const float* w1, const float* w2, const float* w3, const float* ws, int CI,
-                         float scale, void* packed, cudaStream_t stream) {
-    if (!w1 || !w2 || !w3 || !ws || !packed) return VQAE_ERR_BAD_ARG;
-    if (CI != 8 && CI != 16 && CI != 32) return VQAE_ERR_UNSUPPORTED;
-    const int CIP = CI < 16 ? 16 : CI, CO = 2 * CI;
-    const int total = (int)down_block_pack_elems(CI);
-    pack_down_block_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(
-        w1, w2, w3, ws, CI, CIP, CO, scale, reinterpret_cast<__nv_bfloat16*>(packed));
-    return check_launch();
 }
 
 int down_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,

@@ -19,8 +19,6 @@
 // pixel shift keeps the descriptor regular (tc_common.cuh).  W1/W3 stay resident in shared
 // memory, the nine 8 KB W2 taps stream through a 4-slot ring filled by bulk async copies
 // (UBLKCP) from L2.  Warps 0-7: prologue/epilogue math; warp 8: MMA issue; warp 9: W2 producer.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -29,126 +27,6 @@ namespace vqae {
 namespace {
 
 using namespace tc;
-
-// -----------------------------------------------------------------------------------------------
-// self test: D[128 x 64] = A[row_shift + m][k] . B[n][k], K = 64, operands staged in the canonical
-// layout with an odd pixel pitch -- validates descriptors, address shifts and the TMEM read-back
-// -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-tc_selftest_kernel(const __nv_bfloat16* __restrict__ A, int a_rows, int row_shift,
-                   const __nv_bfloat16* __restrict__ B, float* __restrict__ D) {
-    constexpr int K = 64, N = 64, KCH = K / 8;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int apix = a_rows | 1;                     // odd pitch, like the block kernel
-    const uint32_t a_lbo = apix * 16, b_lbo = N * 16;
-    uint8_t* sa = smem;
-    uint8_t* sb = sa + KCH * a_lbo;
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t tmem_base_s;
-
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // provably warp-uniform
-    const uint32_t leader = lane == 0;
-    for (int i = tid; i < a_rows * KCH; i += blockDim.x) {
-        const int r = i / KCH, kc = i % KCH;
-        *reinterpret_cast<uint4*>(sa + kc * a_lbo + r * 16) =
-            *reinterpret_cast<const uint4*>(A + (size_t)r * K + kc * 8);
-    }
-    for (int i = tid; i < N * KCH; i += blockDim.x) {
-        const int r = i / KCH, kc = i % KCH;
-        *reinterpret_cast<uint4*>(sb + kc * b_lbo + r * 16) =
-            *reinterpret_cast<const uint4*>(B + (size_t)r * K + kc * 8);
-    }
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 64);
-    if (tid == 0) {
-        mbar_init(smem_u32(&bar), 1);
-        fence_mbar_init();
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_base_s;
-
-    if (warp == 0) {                   // whole warp: umma_bf16 elects the issuing lane itself
-        const uint32_t idesc = make_idesc_bf16(128, N);
-#pragma unroll
-        for (int ks = 0; ks < K / 16; ++ks) {
-            const uint64_t ad = make_desc(smem_u32(sa) + row_shift * 16 + ks * 2 * a_lbo, a_lbo, 128);
-            const uint64_t bd = make_desc(smem_u32(sb) + ks * 2 * b_lbo, b_lbo, 128);
-            umma_bf16(tmem_base, ad, bd, idesc, ks > 0, 1u);
-        }
-        umma_commit(smem_u32(&bar), 1u);
-    }
-    __syncwarp();
-    mbar_wait(smem_u32(&bar), 0);
-    tc_fence_after_sync();
-    for (int h = 0; h < 2; ++h) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + h * 32, v);
-        tmem_ld_wait();
-        const int m = warp * 32 + lane;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) D[(size_t)m * N + h * 32 + j] = v[j];
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 64);
-}
-
-// -----------------------------------------------------------------------------------------------
-// MMA issue-rate microbenchmark (timing only, operand contents are arbitrary): `reps` back-to-back
-// tcgen05.mma of shape 128 x N x 16 (bf16) from shared memory, layout_type 0 (no swizzle, the
-// canonical layout used by the block kernels) or 2 (SWIZZLE_128B).  out[0] = cycles, out[1] = reps.
-// -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-tc_mma_bench_kernel(int N, int layout_type, int reps, int a_stride_rows, long long* out) {
-    const int nacc = layout_type >> 4 ? (layout_type >> 4) : 2;   // independent accumulators
-    layout_type &= 15;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < 160 * 1024 / 16; i += blockDim.x)
-        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
-    if (tid == 0) {
-        mbar_init(smem_u32(&bar), 1);
-        fence_mbar_init();
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_base_s;
-    if (warp == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, N);
-        const uint32_t sa = smem_u32(smem), sb = sa + 96 * 1024;
-        uint64_t ad, bd;
-        if (layout_type == 0) {
-            ad = make_desc(sa, 641 * 16, 128);
-            bd = make_desc(sb, N * 16, 128);
-        } else {   // SW128 K-major: rows of 128 B, 8-row groups 1024 B apart
-            ad = make_desc(sa, 16, 1024) | (2ull << 61);
-            bd = make_desc(sb, 16, 1024) | (2ull << 61);
-        }
-        const long long t0 = clock64();
-        for (int r = 0; r < reps; ++r) {
-            const uint32_t aoff = (uint32_t)((r % 5) * a_stride_rows * (layout_type == 0 ? 16 : 128)) >> 4;
-            umma_bf16(tmem_base + (r % nacc) * N, ad + aoff, bd + (uint64_t)((r & 3) * 2), idesc, 1u, 1u);
-        }
-        umma_commit(smem_u32(&bar), 1u);
-        mbar_wait(smem_u32(&bar), 0);
-        if (tid == 0) {
-            out[0] = clock64() - t0;
-            out[1] = reps;
-        }
-    }
-    __syncthreads();
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
-}
 
 // -----------------------------------------------------------------------------------------------
 // fused 'same' block on tcgen05, any H x W that tiles into 16 x 32 pixel tiles.
@@ -532,26 +410,6 @@ same_block_tc_kernel(SameBlockArgs a) {
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// OIHW fp32 weights of one 'same' block -> bf16 [11 matrices][k-chunk][n][8], zero padded from
-// CR to CP channels: matrix 0 = branch_conv1, 1..9 = branch_conv2 taps (ky*3+kx), 10 = branch_conv3
-__global__ void __launch_bounds__(256)
-pack_same_block_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
-                       const float* __restrict__ w3, int CR, int CP,
-                       __nv_bfloat16* __restrict__ out) {
-    const int per = CP * CP;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 11 * per) return;
-    const int m = i / per, r = i % per;
-    const int kc = r / (CP * 8), n = (r / 8) % CP, k = kc * 8 + (r % 8);
-    float v = 0.f;
-    if (n < CR && k < CR) {
-        if (m == 0) v = w1[n * CR + k];
-        else if (m == 10) v = w3[n * CR + k];
-        else v = w2[((size_t)n * CR + k) * 9 + (m - 1)];
-    }
-    out[i] = __float2bfloat16_rn(v);
-}
-
 template <int CP, int CR>
 int launch_same_block(const SameBlockArgs& a, int sm_count, cudaStream_t stream) {
     using Cfg = SameCfg<CP, CR>;
@@ -570,44 +428,6 @@ int launch_same_block(const SameBlockArgs& a, int sm_count, cudaStream_t stream)
 
 }  // namespace
 
-static inline int padded_channels(int C) { return C == 8 ? 16 : C; }
-
-int pack_same_block_bf16(const float* w1, const float* w2, const float* w3, int C, void* packed,
-                         cudaStream_t stream) {
-    if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
-    if (C != 8 && C != 16 && C != 32 && C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
-    const int CP = padded_channels(C);
-    const int total = 11 * CP * CP;
-    pack_same_block_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(
-        w1, w2, w3, C, CP, reinterpret_cast<__nv_bfloat16*>(packed));
-    return check_launch();
-}
-
-// -----------------------------------------------------------------------------------------------
-int tc_selftest(const void* A, int a_rows, int row_shift, const void* B, float* D,
-                cudaStream_t stream) {
-    if (!A || !B || !D || a_rows < 128 || row_shift < 0 || row_shift + 128 > a_rows)
-        return VQAE_ERR_BAD_ARG;
-    const size_t smem = (size_t)8 * ((a_rows | 1) * 16) + 8 * 64 * 16;
-    if (smem > 200 * 1024) return VQAE_ERR_UNSUPPORTED;
-    VQAE_CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_selftest_kernel<<<1, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A), a_rows,
-                                                 row_shift,
-                                                 reinterpret_cast<const __nv_bfloat16*>(B), D);
-    return check_launch();
-}
-
-int tc_mma_bench(int N, int layout_type, int reps, int a_stride_rows, long long* out,
-                 cudaStream_t stream) {
-    if (!out || reps <= 0 || N < 16 || N > 256 || N % 16) return VQAE_ERR_BAD_ARG;
-    const size_t smem = 160 * 1024;
-    VQAE_CUDA_TRY(cudaFuncSetAttribute(tc_mma_bench_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_mma_bench_kernel<<<1, 128, smem, stream>>>(N, layout_type, reps, a_stride_rows, out);
-    return check_launch();
-}
-
 int same_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
                   int64_t B, int H, int W, int C, int sm_count, long long* prof,
                   cudaStream_t stream) {
@@ -624,7 +444,6 @@ int same_block_tc(const float* x, float* out, const void* w_packed, const float*
     a.b3a = scalars8[4]; a.b3b = scalars8[5]; a.b4 = scalars8[6]; a.scale = scalars8[7];
     a.prof = prof;
     a.stagger_ns = (C == 64) ? 9000u : 0u;
-    if (const char* e = getenv("VQAE_STAGGER_NS")) a.stagger_ns = (unsigned)atoi(e);
     switch (C) {
         case 64: return launch_same_block<64, 64>(a, sm_count, stream);
         case 32: return launch_same_block<32, 32>(a, sm_count, stream);

@@ -656,23 +656,6 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     if (warp == RS_NW) tmem_dealloc(tmem_base, 512);
 }
 
-// like pack_same_block_kernel (tc_kernels.cu) with branch_conv3 pre-multiplied by the Fixup scale
-__global__ void __launch_bounds__(256)
-pack_resident_block_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
-                           const float* __restrict__ w3, int C, float scale,
-                           __nv_bfloat16* __restrict__ out) {
-    const int per = C * C;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 11 * per) return;
-    const int m = i / per, r = i % per;
-    const int kc = r / (C * 8), nn = (r / 8) % C, k = kc * 8 + (r % 8);
-    float v;
-    if (m == 0) v = w1[nn * C + k];
-    else if (m == 10) v = scale * w3[nn * C + k];
-    else v = w2[((size_t)nn * C + k) * 9 + (m - 1)];
-    out[i] = __float2bfloat16_rn(v);
-}
-
 // clusters of this instantiation the device holds at once (0 if the query fails)
 template <int C, int W>
 int resident_clusters() {
@@ -731,16 +714,6 @@ int trunk_resident_max_clusters(int* out) {
                                        (int)RsCfg<64, 32>::SMEM));
     *out = resident_clusters<64, 32>();
     return *out > 0 ? VQAE_OK : VQAE_ERR_CUDA;
-}
-
-int pack_resident_block_bf16(const float* w1, const float* w2, const float* w3, int C, float scale,
-                             void* packed, cudaStream_t stream) {
-    if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
-    if (C != 32 && C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
-    const int total = 11 * C * C;
-    pack_resident_block_kernel<<<ceil_div_u(total, 256), 256, 0, stream>>>(
-        w1, w2, w3, C, scale, reinterpret_cast<__nv_bfloat16*>(packed));
-    return check_launch();
 }
 
 int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, const float* scalars_dev,

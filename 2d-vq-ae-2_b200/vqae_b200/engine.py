@@ -152,7 +152,9 @@ def check_block_supported(block) -> None:
 
 
 class PackedFixup:
-    """Device-resident packed weights + the C struct of one PreActFixupResBlock."""
+    """Packed weights + the C struct of one PreActFixupResBlock.  Packing is lazy and batched:
+    ``ensure_packed`` fills the fp32 and/or tensor-core layouts of any number of blocks with ONE
+    launch of vqae_pack_batched."""
 
     def __init__(self, block, scalars: Sequence[float]):
         w2 = block.branch_conv2.weight
@@ -161,67 +163,96 @@ class PackedFixup:
         self.c_in = block.branch_conv1.weight.shape[1]
         self.c_branch = block.branch_conv1.weight.shape[0]
         self.c_out = block.branch_conv3.weight.shape[0]
-        self.w1 = pack_conv_weight(block.branch_conv1.weight)
-        self.w2 = pack_conv_weight(w2)
-        self.w3 = pack_conv_weight(block.branch_conv3.weight)
-        self.w_skip = (pack_conv_weight(block.skip_conv.weight)
-                       if block.skip_conv is not None else None)
+        self.device = w2.device
+        # fp32 contiguous sources, kept alive until (and after) the asynchronous pack has read them
+        self.src = [t.detach().float().contiguous() for t in
+                    (block.branch_conv1.weight, w2, block.branch_conv3.weight)]
+        self.src.append(block.skip_conv.weight.detach().float().contiguous()
+                        if block.skip_conv is not None else None)
         self.scalars = dict(zip(_SCALARS, scalars))
+        sc = self.scalars
         p = L.FixupParams()
         p.mode, p.c_in, p.c_out, p.c_branch = self.mode, self.c_in, self.c_out, self.c_branch
-        p.w1, p.w2, p.w3 = self.w1.data_ptr(), self.w2.data_ptr(), self.w3.data_ptr()
-        p.w_skip = self.w_skip.data_ptr() if self.w_skip is not None else None
-        for name, val in self.scalars.items():
+        for name, val in sc.items():
             setattr(p, name, float(val))
         self.params = p
-        # tcgen05 path: bf16 operand pack of a 'same' block at the trunk width (C = 64)
-        self.tc_weights = None
-        self.tc_weights_res = None
+        self.w1 = self.w2 = self.w3 = self.w_skip = None           # fp32 [tap][I][O] packs
+        # tcgen05 path: bf16 operand packs
+        self.tc_weights = self.tc_weights_res = None
         self.tc_scalars = None
+        self.tc_kind = None
         if self.mode == L.MODE_SAME and self.c_in in (8, 16, 32, 64, 128) and \
                 self.c_branch == self.c_in and self.c_out == self.c_in:
-            lib = L.load()
-            dev = w2.device
-            cp = 16 if self.c_in == 8 else self.c_in          # C = 8 runs zero-padded as 16
-            self.tc_weights = torch.empty(11 * cp * cp, dtype=torch.bfloat16, device=dev)
-            ws = [t.detach().float().contiguous() for t in
-                  (block.branch_conv1.weight, w2, block.branch_conv3.weight)]
-            L.check(lib.vqae_pack_same_block_bf16(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]),
-                                                  self.c_in, _ptr(self.tc_weights), _stream(dev)),
-                    "vqae_pack_same_block_bf16")
-            sc = self.scalars
+            self.tc_kind = "same"
             self.tc_scalars = (C.c_float * 8)(*[float(sc[k]) for k in (
                 "bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "scale")])
-            if self.c_in in (32, 64, 128):
-                # image-resident trunk kernel: branch_conv3 pre-multiplied by the Fixup scale
-                self.tc_weights_res = torch.empty(11 * cp * cp, dtype=torch.bfloat16, device=dev)
-                L.check(lib.vqae_pack_resident_block_bf16(
-                    _ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), self.c_in, float(sc["scale"]),
-                    _ptr(self.tc_weights_res), _stream(dev)), "vqae_pack_resident_block_bf16")
-
-        if self.mode == L.MODE_DOWN and self.c_in in (8, 16, 32) and \
+        elif self.mode == L.MODE_DOWN and self.c_in in (8, 16, 32) and \
                 self.c_branch == 2 * self.c_in and self.c_out == 2 * self.c_in:
-            lib = L.load()
-            dev = w2.device
-            sc = self.scalars
-            n = lib.vqae_down_block_pack_elems(self.c_in)
-            self.tc_weights = torch.empty(n, dtype=torch.bfloat16, device=dev)
-            ws = [t.detach().float().contiguous() for t in
-                  (block.branch_conv1.weight, w2, block.branch_conv3.weight,
-                   block.skip_conv.weight)]
-            L.check(lib.vqae_pack_down_block_bf16(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]),
-                                                  _ptr(ws[3]), self.c_in, float(sc["scale"]),
-                                                  _ptr(self.tc_weights), _stream(dev)),
-                    "vqae_pack_down_block_bf16")
+            self.tc_kind = "down"
             self.tc_scalars = (C.c_float * 8)(*(
                 [float(sc[k]) for k in ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a",
                                         "bias3b", "bias1c")]
                 + [float(sc["bias4"]) + float(sc["bias1d"])]))
 
+    @property
+    def has_resident(self) -> bool:
+        return self.tc_kind == "same" and self.c_in in (32, 64, 128)
+
+    # -- descriptors of the packs that are still missing ----------------------------------------
+    def _desc(self, kind, dst, c_in, c_out, taps, srcs, scale=1.0):
+        d = L.PackDesc()
+        d.kind, d.c_in, d.c_out, d.taps, d.scale = kind, c_in, c_out, taps, float(scale)
+        d.n_elems = dst.numel()
+        for i, t in enumerate(srcs):
+            d.src[i] = t.data_ptr() if t is not None else None
+        d.dst = dst.data_ptr()
+        return d
+
+    def descs_f32(self) -> List["L.PackDesc"]:
+        if self.w1 is not None:
+            return []
+        out, packs = [], []
+        for t in self.src:
+            if t is None:
+                packs.append(None)
+                continue
+            o, i, kh, kw = t.shape
+            dst = torch.empty(kh * kw, i, o, dtype=torch.float32, device=self.device)
+            out.append(self._desc(L.PACK_F32_CONV, dst, i, o, kh * kw, [t]))
+            packs.append(dst)
+        self.w1, self.w2, self.w3, self.w_skip = packs
+        p = self.params
+        p.w1, p.w2, p.w3 = self.w1.data_ptr(), self.w2.data_ptr(), self.w3.data_ptr()
+        p.w_skip = self.w_skip.data_ptr() if self.w_skip is not None else None
+        return out
+
+    def descs_tc(self) -> List["L.PackDesc"]:
+        if self.tc_kind is None or self.tc_weights is not None:
+            return []
+        lib = L.load()
+        out = []
+        sc = self.scalars
+        if self.tc_kind == "same":
+            n = lib.vqae_pack_elems(L.PACK_SAME_BF16, self.c_in, self.c_in, 9)
+            self.tc_weights = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            out.append(self._desc(L.PACK_SAME_BF16, self.tc_weights, self.c_in, self.c_in, 9,
+                                  self.src[:3]))
+            if self.has_resident:
+                # image-resident trunk kernel: branch_conv3 pre-multiplied by the Fixup scale
+                self.tc_weights_res = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+                out.append(self._desc(L.PACK_RESIDENT_BF16, self.tc_weights_res, self.c_in,
+                                      self.c_in, 9, self.src[:3], sc["scale"]))
+        else:
+            n = lib.vqae_pack_elems(L.PACK_DOWN_BF16, self.c_in, self.c_out, 4)
+            self.tc_weights = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            out.append(self._desc(L.PACK_DOWN_BF16, self.tc_weights, self.c_in, self.c_out, 4,
+                                  self.src, sc["scale"]))
+        return out
+
     def tc_ok(self, h: int, w: int) -> bool:
         """a tcgen05 kernel is built for this block at this size (16 x 32 pixel tiles; 8 x 32 for
         the C = 128 'same' blocks, which only exist in the persistent chain form)"""
-        if self.tc_weights is None or self.mode not in (L.MODE_SAME, L.MODE_DOWN) or w % 32:
+        if self.tc_kind is None or w % 32:
             return False
         return h % 8 == 0 if self.chain_only else h % 16 == 0
 
@@ -257,6 +288,36 @@ def pack_blocks(blocks: Sequence) -> List[PackedFixup]:
     return [PackedFixup(b, host[i * n:(i + 1) * n]) for i, b in enumerate(blocks)]
 
 
+def ensure_packed(packed: Sequence[PackedFixup], f32: Sequence[bool], tc: Sequence[bool]) -> None:
+    """Pack whatever is still missing for the requested layouts -- one vqae_pack_batched launch."""
+    descs, keep = [], []
+    for pk, want_f32, want_tc in zip(packed, f32, tc):
+        if want_f32:
+            descs += pk.descs_f32()
+        if want_tc:
+            descs += pk.descs_tc()
+    if not descs:
+        return
+    dev = packed[0].device
+    arr = (L.PackDesc * len(descs))(*descs)
+    table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+    L.check(L.load().vqae_pack_batched(_ptr(table), len(descs), max(d.n_elems for d in descs),
+                                       _stream(dev)), "vqae_pack_batched")
+    # the table is read by the kernel asynchronously: keep it until the stream has passed it
+    table.record_stream(torch.cuda.current_stream(dev))
+
+
+def _plan_layouts(packed: Sequence[PackedFixup], h: int, w: int, precision: str):
+    """(needs fp32 pack, needs tensor-core pack) per block for an input of h x w."""
+    f32, tc = [], []
+    for pk in packed:
+        use_tc = precision != "fp32" and pk.tc_ok(h, w)
+        tc.append(use_tc)
+        f32.append(not use_tc)
+        h, w = pk.out_hw(h, w)
+    return f32, tc
+
+
 # ----------------------------------------------------------------------------------------------
 # single calls
 # ----------------------------------------------------------------------------------------------
@@ -279,6 +340,7 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
     if c != pk.c_in:
         raise ValueError(f"fixup block expects {pk.c_in} input channels, got {c}")
     ho, wo = pk.out_hw(h, w)
+    ensure_packed([pk], *_plan_layouts([pk], h, w, precision))
     if out is None:
         out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
     if precision == "bf16" and pk.tc_ok(h, w) and pk.mode == L.MODE_DOWN:
@@ -303,7 +365,8 @@ class PackedChain:
     """Back-to-back bf16 weight packs + device scalar table of a run of tcgen05 'same' blocks."""
 
     def __init__(self, run: Sequence[PackedFixup], resident: bool = False):
-        dev = run[0].tc_weights.device
+        ensure_packed(run, [False] * len(run), [True] * len(run))
+        dev = run[0].device
         self.n = len(run)
         self.c = run[0].c_in
         self.resident = resident
@@ -327,7 +390,7 @@ def _chain_runs(packed: Sequence[PackedFixup], h: int, w: int, batch: int = 1 <<
             while j < n and packed[j].mode == L.MODE_SAME and packed[j].c_in == pk.c_in \
                     and packed[j].tc_ok(hh, ww):
                 j += 1
-            resident = TRUNK_RESIDENT and pk.tc_weights_res is not None and \
+            resident = TRUNK_RESIDENT and pk.has_resident and \
                 lib.vqae_trunk_resident_supported(batch, hh, ww, pk.c_in)
             if (j - i >= 2 or pk.chain_only) and \
                     (resident or lib.vqae_same_chain_supported(batch, hh, ww, pk.c_in)):
@@ -344,6 +407,7 @@ def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "
     """A Sequential chain of PreActFixupResBlocks on an NHWC fp32 tensor.  In "bf16" mode runs of
     consecutive tcgen05 'same' blocks execute as ONE launch: image-resident (vqae_trunk_resident_bf16)
     for C = 64 at 32 x 32, the persistent tile chain (vqae_same_chain_bf16) otherwise."""
+    ensure_packed(packed, *_plan_layouts(packed, h.shape[1], h.shape[2], precision))
     if precision != "bf16":
         for pk in packed:
             h = fixup_forward_nhwc(pk, h, precision=precision)
@@ -481,27 +545,68 @@ class PackedQuantizer:
         self.params = p
 
 
+_TORCH_DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16}
+_KERNEL = {"auto": L.QUANT_AUTO, "cuda_core": L.QUANT_CUDA_CORE, "tensor_core": L.QUANT_TENSOR_CORE}
+
+
 def quantize(pq: PackedQuantizer, x: Tensor, x_nhwc: bool, out_nhwc: bool, batch: int,
-             spatial: int, want_out: bool = True, want_z: bool = False
+             spatial: int, want_out: bool = True, want_z: bool = False, kernel: str = "auto",
+             out_dtype: Optional[torch.dtype] = None
              ) -> Tuple[Optional[Tensor], Tensor, Tensor, Tensor, Optional[Tensor]]:
-    """x: contiguous fp32, [B,S,c] if x_nhwc else [B,c,S].  Returns
-    (out or None, indices int64 [B*S], loss 0-dim, near_ties uint32 0-dim, z or None)."""
+    """x: contiguous fp32 / bf16 / fp16, [B,S,c] if x_nhwc else [B,c,S].  Returns
+    (out or None, indices int64 [B*S], loss 0-dim, near_ties uint32 0-dim, z or None).
+    kernel: "auto", "cuda_core" (the exact CUDA-core kernel) or "tensor_core" (tcgen05)."""
     lib = L.load()
     dev = x.device
     n = batch * spatial
-    out = torch.empty(n * pq.c, dtype=torch.float32, device=dev) if want_out else None
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty(n * pq.c, dtype=out_dtype, device=dev) if want_out else None
     idx = torch.empty(n, dtype=torch.int64, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     ties = torch.empty((), dtype=torch.int32, device=dev)
     z = torch.empty(n, pq.d, dtype=torch.float32, device=dev) if want_z else None
     need = lib.vqae_quantizer_scratch_bytes(n)
     ws = workspace(dev, need)
-    L.check(lib.vqae_quantize_f32(
-        C.byref(pq.params), _ptr(x), L.LAYOUT_NHWC if x_nhwc else L.LAYOUT_NCHW, _ptr(out),
-        L.LAYOUT_NHWC if out_nhwc else L.LAYOUT_NCHW, _ptr(idx), _ptr(loss), _ptr(ties),
-        NEAR_TIE_REL_GAP, _ptr(z), _ptr(ws), ws.numel(), batch, spatial, _stream(dev)),
-        "vqae_quantize_f32")
+    L.check(lib.vqae_quantize(
+        C.byref(pq.params), _ptr(x), _TORCH_DT[x.dtype], L.LAYOUT_NHWC if x_nhwc else L.LAYOUT_NCHW,
+        _ptr(out), _TORCH_DT[out_dtype], L.LAYOUT_NHWC if out_nhwc else L.LAYOUT_NCHW, _ptr(idx),
+        _ptr(loss), _ptr(ties), NEAR_TIE_REL_GAP, _ptr(z), _ptr(ws), ws.numel(), batch, spatial,
+        _KERNEL[kernel], _stream(dev)), "vqae_quantize")
     return out, idx, loss, ties, z
+
+
+# I/O dtypes of the quantiser call for which a kernel is built (config 2 cells)
+QUANT_IO_DTYPES = ("fp32",)
+
+
+class QuantizeBuffers:
+    """Preallocated outputs + scratch of one quantiser call shape (steady-state callers, bench)."""
+
+    def __init__(self, pq: PackedQuantizer, n: int, dtype: torch.dtype, dev: torch.device):
+        lib = L.load()
+        self.n, self.dtype = n, dtype
+        self.out = torch.empty(n * pq.c, dtype=dtype, device=dev)
+        self.idx = torch.empty(n, dtype=torch.int64, device=dev)
+        self.loss = torch.empty((), dtype=torch.float32, device=dev)
+        self.ties = torch.empty((), dtype=torch.int32, device=dev)
+        self.ws = workspace(dev, lib.vqae_quantizer_scratch_bytes(n))
+        dt = _TORCH_DT[dtype]
+        tc = bool(lib.vqae_quantize_supported(C.byref(pq.params), dt, L.LAYOUT_NHWC, dt,
+                                              L.LAYOUT_NHWC, 1, L.QUANT_TENSOR_CORE))
+        self.kernel_name = ("quantize_tc_kernel (tcgen05 L4 filter + exact fp32 argmin + gather, "
+                            "fused loss)" if tc else "quantize_kernel (CUDA-core)")
+
+
+def quantize_into(pq: PackedQuantizer, x: Tensor, bufs: QuantizeBuffers, batch: int, spatial: int
+                  ) -> None:
+    """The quantiser call on NHWC input into preallocated buffers (no allocation, no sync)."""
+    lib = L.load()
+    dt = _TORCH_DT[x.dtype]
+    L.check(lib.vqae_quantize(
+        C.byref(pq.params), _ptr(x), dt, L.LAYOUT_NHWC, _ptr(bufs.out), _TORCH_DT[bufs.dtype],
+        L.LAYOUT_NHWC, _ptr(bufs.idx), _ptr(bufs.loss), _ptr(bufs.ties), NEAR_TIE_REL_GAP, None,
+        _ptr(bufs.ws), bufs.ws.numel(), batch, spatial, L.QUANT_AUTO, _stream(x.device)),
+        "vqae_quantize")
 
 
 def embed_codes(pq: PackedQuantizer, idx: Tensor, out_nhwc: bool, batch: int, spatial: int

@@ -168,7 +168,9 @@ class StreamingEncoder:
             self._h2d[slot].record(self.copy_stream)
 
     @torch.no_grad()
-    def encode_stream(self, host_batches, reuse_buffers: bool = False):
+    def encode_stream(self, host_batches, reuse_buffers: bool = False, to_host: bool = True):
+        """``to_host=False`` keeps the codes on the device (freshly allocated int64 tensors, e.g. for
+        a code-tile gather): the host -> device staging still overlaps the encode."""
         main = torch.cuda.current_stream(self.device)
         it = iter(host_batches)
         nxt = next(it, None)
@@ -191,6 +193,10 @@ class StreamingEncoder:
             main.wait_event(self._h2d[slot])
             idx = encode_patches(self.encoder, self._dev_in[slot], self.mean, self.std)
             self._free[slot].record(main)
+            if not to_host:
+                yield idx
+                i += 1
+                continue
             if self._host_out[oslot] is None or self._host_out[oslot].shape != idx.shape:
                 self._host_out[oslot] = torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
             self._host_out[oslot].copy_(idx, non_blocking=True)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VQAE_ABI_VERSION 2
+#define VQAE_ABI_VERSION 3
 
 enum {
     VQAE_OK = 0,
@@ -38,7 +38,7 @@ enum {
 /* layouts of tensors crossing the boundary */
 enum { VQAE_LAYOUT_NCHW = 0, VQAE_LAYOUT_NHWC = 1 };
 /* element types crossing the boundary */
-enum { VQAE_DT_F32 = 0, VQAE_DT_BF16 = 1, VQAE_DT_U8 = 2 };
+enum { VQAE_DT_F32 = 0, VQAE_DT_BF16 = 1, VQAE_DT_U8 = 2, VQAE_DT_F16 = 3 };
 /* PreActFixupResBlock modes (layers/conv_block.py:147) */
 enum { VQAE_MODE_SAME = 0, VQAE_MODE_DOWN = 1, VQAE_MODE_UP = 2 };
 
@@ -60,6 +60,26 @@ int vqae_normalize_u8(const uint8_t* img, float* out, int64_t batch, int height,
  * OIHW fp32 conv weight -> [KH*KW][I][O] fp32 ("tap-major, output-channel fastest").        */
 int vqae_pack_conv_weight_f32(const float* w_oihw, float* packed, int out_ch, int in_ch, int kh,
                               int kw, void* stream);
+
+/* Batched form: every weight layout of this library, any number of matrices / blocks, ONE launch.
+ * A descriptor names the OIHW fp32 sources of one conv (F32_CONV: src[0]) or of one
+ * PreActFixupResBlock (SAME / RESIDENT: src = {branch_conv1, branch_conv2, branch_conv3};
+ * DOWN: + skip_conv) and the destination; c_in / c_out are the block's channel counts (F32_CONV:
+ * the conv's, with `taps` = kh*kw); `scale` is the Fixup scale folded into branch_conv3 by the
+ * RESIDENT and DOWN layouts.  kind | VQAE_PACK_LO writes bf16(w - bf16(w)), the low half of the
+ * split-bf16 operands of precision "bf16x3".  n_elems = vqae_pack_elems(kind, c_in, c_out, taps).
+ * descs_device: the table in DEVICE memory; max_elems: the largest n_elems in it.             */
+enum { VQAE_PACK_F32_CONV = 0, VQAE_PACK_SAME_BF16 = 1, VQAE_PACK_RESIDENT_BF16 = 2,
+       VQAE_PACK_DOWN_BF16 = 3, VQAE_PACK_LO = 0x100 };
+typedef struct vqae_pack_desc {
+    int32_t kind, c_in, c_out, taps;
+    float scale;
+    int32_t n_elems;
+    const void* src[4];
+    void* dst;
+} vqae_pack_desc;
+size_t vqae_pack_elems(int kind, int c_in, int c_out, int taps);
+int vqae_pack_batched(const vqae_pack_desc* descs_device, int n_descs, int max_elems, void* stream);
 
 /* ---- a-S  stems --------------------------------------------------------------------------
  * in_stem  (vq_ae/model.py:141,198; conv_layer/same2d.yaml: 3x3, zero pad, bias) 3 -> c_out.
@@ -156,9 +176,6 @@ int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void*
  * Deterministic (repeated launches are bit-identical).  Not bit-identical to vqae_same_block_bf16
  * (rounding of scale*W3, accumulation order): agrees within the bf16 tolerance
  * (tests/test_gpu_tc.py).                                                                       */
-/* profiling aid: DEVICE int64 [8][32] that CTA 0 fills with clock64() stamps of eight steady-state
- * half-rounds (MMA warp: slots 0-6, worker warp 0: slots 8-22); NULL switches it off          */
-void vqae_trunk_resident_set_profile(long long* phase_clocks);
 /* 4-CTA clusters of the c == 64 resident kernel the current device holds at once (one image pair
  * each at a time); -1 on error.  Batches that are a multiple of twice this number keep every
  * cluster busy to the end.                                                                      */
@@ -182,25 +199,6 @@ int vqae_pack_down_block_bf16(const float* w1_oihw, const float* w2_oihw, const 
 int vqae_down_block_bf16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c_in,
                          void* stream);
-/* same call, additionally writing clock64() at the 8 phase boundaries of every CTA's first tile
- * to phase_clocks[grid][8] (device memory, >= 8 * 4 * SM-count int64) -- profiling aid        */
-int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packed,
-                                 const float* scalars8_host, int64_t batch, int height, int width,
-                                 int c, long long* phase_clocks, void* stream);
-/* tcgen05.mma issue-rate microbenchmark (timing aid): `reps` MMAs of 128 x n x 16 bf16 from shared
- * memory in layout_type 0 (un-swizzled K-major) or 2 (128-byte swizzle); out2[0] = cycles, [1] = reps */
-int vqae_tc_mma_bench(int n, int layout_type, int reps, int a_stride_rows, long long* out2,
-                      void* stream);
-/* the same measurement with n_issuers warps per CTA issuing concurrently (own accumulators) and
- * ctas_per_sm CTAs resident per SM; m in {64, 128}; mode bit 0: every issuer has its own A and B
- * regions, bit 1: A row groups 160 B apart (the resident kernel's tile layout); out_per_cta: DEVICE int64 [SMs * ctas_per_sm]
- * cycles until every issuer's `reps` MMAs have completed                                       */
-int vqae_tc_mma_bench2(int m, int n, int reps, int n_issuers, int ctas_per_sm, int mode,
-                       long long* out_per_cta, void* stream);
-/* descriptor/TMEM self test: d[128][64] = a[row_shift + m][0..63] . b[n][0..63] (bf16 in, fp32 out),
- * a: [a_rows][64] bf16 row-major, b: [64][64] bf16 row-major (device pointers)                */
-int vqae_tc_selftest(const void* a_bf16, int a_rows, int row_shift, const void* b_bf16, float* d,
-                     void* stream);
 
 /* ---- a-P / a-Q / a-G  quantiser -------------------------------------------------------------
  * ProjectedEMAVectorQuantizer2d.forward + EMAVectorQuantizer.forward in eval mode
@@ -243,11 +241,21 @@ int vqae_quantize_f32(const vqae_quantizer_params* p, const float* x, int x_layo
  * near-tie count come from the same exact fp32 evaluation as the CUDA-core kernel and are
  * bit-identical to it.  diag (may be NULL): fp32 [N][4] = {min approximate distance (offset by
  * -sum z^4), error scale T, number of candidates, 1 if the row took the full exact scan}.      */
-/* profiling aid: while non-NULL, CTA 0 of every tcgen05 quantiser launch writes clock64() stamps of
- * its tiles 10..13 to phase_clocks[4][16] (device memory, 64 int64); NULL switches it off      */
-void vqae_quantize_tc_set_profile(long long* phase_clocks);
 int vqae_quantize_tc_supported(const vqae_quantizer_params* p, int x_layout, int out_layout,
                                int has_out);
+/* General form: x / out in x_dtype / out_dtype (VQAE_DT_F32, VQAE_DT_BF16 or VQAE_DT_F16 -- the
+ * distance arithmetic is fp32 whatever the I/O type, like torch.cdist under autocast), and an
+ * explicit kernel choice instead of any environment switch: VQAE_QUANT_AUTO takes the tcgen05
+ * kernel where vqae_quantize_supported(..., VQAE_QUANT_TENSOR_CORE) is 1 and the CUDA-core kernel
+ * (fp32 I/O only) elsewhere; the other two values force one of them (VQAE_ERR_UNSUPPORTED if it
+ * is not built for the shape).                                                                 */
+enum { VQAE_QUANT_AUTO = 0, VQAE_QUANT_CUDA_CORE = 1, VQAE_QUANT_TENSOR_CORE = 2 };
+int vqae_quantize_supported(const vqae_quantizer_params* p, int x_dtype, int x_layout,
+                            int out_dtype, int out_layout, int has_out, int kernel);
+int vqae_quantize(const vqae_quantizer_params* p, const void* x, int x_dtype, int x_layout,
+                  void* out, int out_dtype, int out_layout, int64_t* indices, float* loss,
+                  uint32_t* near_ties, float tie_rel_gap, float* z_out, void* scratch,
+                  size_t scratch_bytes, int64_t batch, int64_t spatial, int kernel, void* stream);
 int vqae_quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out,
                          int64_t* indices, float* loss, uint32_t* near_ties, float tie_rel_gap,
                          float* z_out, float* diag, void* scratch, size_t scratch_bytes,

@@ -16,7 +16,7 @@ for n in (64, 128, 256):
             if nacc * n > 512:
                 continue
             reps = 1000
-            L.check(lib.vqae_tc_mma_bench(n, layout | (nacc << 4), reps, 128, E._ptr(out), E._stream(dev)), "bench")
+            L.check(L.load_testaids().vqae_tc_mma_bench(n, layout | (nacc << 4), reps, 128, E._ptr(out), E._stream(dev)), "bench")
             torch.cuda.synchronize()
             c, r = out.tolist()
             print(f"{n:4d} {layout:3d} {nacc:5d} {reps:5d} {c / r:8.1f} {128 * n / 256:6.0f}")

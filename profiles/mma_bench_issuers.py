@@ -14,7 +14,7 @@ print("M N issuers ctas/SM mode(1: own A/B per issuer, 2: 160 B row groups) : cy
 for m, n in ((128, 64), (128, 16), (128, 128), (64, 64), (64, 128), (64, 256), (128, 256)):
     for iss, cps in ((1, 1), (2, 1), (4, 1), (1, 2), (2, 2), (1, 4)):
         for mode in (0, 1, 3, 7):
-            rc = lib.vqae_tc_mma_bench2(m, n, reps, iss, cps, mode, E._ptr(out), E._stream(dev))
+            rc = L.load_testaids().vqae_tc_mma_bench2(m, n, reps, iss, cps, mode, E._ptr(out), E._stream(dev))
             if rc != 0:
                 continue
             torch.cuda.synchronize()

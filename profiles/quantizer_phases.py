@@ -19,10 +19,10 @@ prof = torch.zeros(64, dtype=torch.int64, device=dev)
 lib = L.load()
 for _ in range(3):
     E.quantize(packed, x, True, True, 512, 1024)
-lib.vqae_quantize_tc_set_profile(prof.data_ptr())
+L.load_testaids().vqae_quantize_tc_set_profile(prof.data_ptr())
 E.quantize(packed, x, True, True, 512, 1024)
 torch.cuda.synchronize()
-lib.vqae_quantize_tc_set_profile(None)
+L.load_testaids().vqae_quantize_tc_set_profile(None)
 p = prof.view(4, 16).cpu()
 t0 = int(p[0][p[0] > 0].min())
 names = ["mma_go", "proj_top", "proj_x_ready", "proj_z_done", "proj_bufs_free", "proj_done",

@@ -42,10 +42,10 @@ for i in range(reps):
 
 # phase clocks of CTA 0, eight steady-state half-rounds
 prof = torch.zeros(8 * 32, dtype=torch.int64, device=dev)
-lib.vqae_trunk_resident_set_profile(E._ptr(prof))
+L.load_testaids().vqae_trunk_resident_set_profile(E._ptr(prof))
 L.check(lib.vqae_trunk_resident_bf16(E._ptr(xs[0]), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, H, W, C, st), "resident")
 torch.cuda.synchronize()
-lib.vqae_trunk_resident_set_profile(None)
+L.load_testaids().vqae_trunk_resident_set_profile(None)
 p = prof.cpu().view(8, 32)
 t0 = int(p[0, 0])
 print("issuer (slot 0, M-tile 0), even rows: step_start  A1wait_done  G1_issued  Uwait_done  taps_issued  Vwait_done  G3_issued")

@@ -35,23 +35,14 @@ def _module(seed=5, embed_scale=1.0, embed=None):
 
 
 def _run(pq, x_nhwc, tc: bool, want_out=True):
-    """x_nhwc: [B,S,64] contiguous.  Returns (out, idx, loss, ties, z)."""
-    old = os.environ.get("VQAE_QUANT_TC")
-    os.environ["VQAE_QUANT_TC"] = "1" if tc else "0"
-    try:
-        b, s, _ = x_nhwc.shape
-        packed = pq.packed()
-        lib = L.load()
-        sup = lib.vqae_quantize_tc_supported(C.byref(packed.params), L.LAYOUT_NHWC, L.LAYOUT_NHWC, 1)
-        assert sup == (1 if tc else 0)
-        res = E.quantize(packed, x_nhwc, True, True, b, s, want_out=want_out, want_z=True)
-        torch.cuda.synchronize()
-        return res
-    finally:
-        if old is None:
-            os.environ.pop("VQAE_QUANT_TC", None)
-        else:
-            os.environ["VQAE_QUANT_TC"] = old
+    """x_nhwc: [B,S,64] contiguous.  Returns (out, idx, loss, ties, z) of the tcgen05 kernel (tc) or
+    of the exact CUDA-core kernel -- an explicit ABI argument, no environment switch."""
+    b, s, _ = x_nhwc.shape
+    packed = pq.packed()
+    res = E.quantize(packed, x_nhwc, True, True, b, s, want_out=want_out, want_z=True,
+                     kernel="tensor_core" if tc else "cuda_core")
+    torch.cuda.synchronize()
+    return res
 
 
 def _diag(pq, x_nhwc):
@@ -175,9 +166,7 @@ def test_module_forward_uses_tc_path_channels_last():
     out, idx, loss = pq(x)
     torch.cuda.synchronize()
     assert E.launch_count() - before == 1                 # one fused kernel, nothing else
-    os.environ["VQAE_QUANT_TC"] = "0"
-    try:
-        out2, idx2, loss2 = pq(x)
-    finally:
-        os.environ.pop("VQAE_QUANT_TC")
-    assert torch.equal(idx, idx2) and torch.equal(out, out2)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    out2, idx2, loss2, _, _ = E.quantize(pq.packed(), xn, True, True, 4, 1024, kernel="cuda_core")
+    assert torch.equal(idx.reshape(-1), idx2) and torch.equal(
+        out.permute(0, 2, 3, 1).reshape(-1), out2)

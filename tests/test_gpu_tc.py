@@ -24,7 +24,7 @@ def test_tc_selftest_descriptor_shift(a_rows, shift):
     a = torch.randn(a_rows, 64, generator=g).to(DEV).bfloat16()
     b = torch.randn(64, 64, generator=g).to(DEV).bfloat16()
     d = torch.zeros(128, 64, device=DEV)
-    L.check(lib.vqae_tc_selftest(E._ptr(a), a_rows, shift, E._ptr(b), E._ptr(d), E._stream(d.device)),
+    L.check(L.load_testaids().vqae_tc_selftest(E._ptr(a), a_rows, shift, E._ptr(b), E._ptr(d), E._stream(d.device)),
             "vqae_tc_selftest")
     torch.cuda.synchronize()
     ref = a[shift:shift + 128].float() @ b.float().t()
@@ -117,6 +117,7 @@ def test_persistent_chain_bit_identical_to_block_by_block(c, hw, batch, n, monke
         blocks.append(blk.to(DEV))
     monkeypatch.setattr(E, "TRUNK_RESIDENT", False)  # this test is about the tile-chain kernel
     packed = E.pack_blocks(blocks)
+    E.ensure_packed(packed, [True] * len(packed), [True] * len(packed))   # not part of the launch counts
     x = torch.randn(batch, hw, hw, c, device=DEV)
     h = x
     for pk in packed:
@@ -160,6 +161,7 @@ def test_resident_trunk_vs_block_by_block_and_fp32(c, batch, n, monkeypatch):
     exact path.  Tolerance: 1e-2 of the branch magnitude (north_star bf16 bar)."""
     hw = _RES_HW[c]
     packed = E.pack_blocks(_same_blocks(c, n, 60))
+    E.ensure_packed(packed, [True] * len(packed), [True] * len(packed))   # not part of the launch counts
     x = torch.randn(batch, hw, hw, c, generator=torch.Generator().manual_seed(batch + n)).to(DEV)
     # the tile kernels (per-block launches for C = 64, the tile chain for C = 128) as a second opinion
     monkeypatch.setattr(E, "TRUNK_RESIDENT", False)
@@ -199,6 +201,7 @@ def test_resident_trunk_repeated_launches_bit_identical(c, batch, n, reps):
     merged; profiles/determinism_resident.py)."""
     hw = _RES_HW[c]
     packed = E.pack_blocks(_same_blocks(c, n, 70))
+    E.ensure_packed(packed, [True] * len(packed), [True] * len(packed))   # not part of the launch counts
     chain = E.PackedChain(packed, resident=True)
     x = torch.randn(batch, hw, hw, c, generator=torch.Generator().manual_seed(c + n)).to(DEV)
     lib = L.load()
@@ -265,6 +268,7 @@ def test_c128_chain_kernel_vs_fp32_path(hw, batch, n, monkeypatch):
         blocks.append(blk.to(DEV))
     monkeypatch.setattr(E, "TRUNK_RESIDENT", False)  # this test is about the tile-chain kernel
     packed = E.pack_blocks(blocks)
+    E.ensure_packed(packed, [True] * len(packed), [True] * len(packed))   # not part of the launch counts
     assert all(pk.tc_ok(hw, hw) and pk.chain_only for pk in packed)
     x = torch.randn(batch, hw, hw, 128, device=DEV)
     y32 = E.run_blocks_nhwc(packed, x, "fp32")

@@ -28,7 +28,15 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/vqae_b200.h but not exported"
     from vqae_b200 import _lib_tc
     assert declared == set(_lib.SIGNATURES) | set(_lib_tc.SIGNATURES)
-    assert lib.vqae_abi_version() == 2
+    # test / measurement aids live in their own library and header, outside the product ABI
+    aid_header = re.sub(r"/\*.*?\*/", "", (REPO / "include" / "vqae_b200_testaids.h").read_text(),
+                        flags=re.S)
+    aid_declared = set(re.findall(r"\b(vqae_[a-z0-9_]+)\s*\(", aid_header))
+    aids = _lib.load_testaids()
+    assert aid_declared == set(_lib_tc.AIDS_SIGNATURES) and not (aid_declared & declared)
+    for name in sorted(aid_declared):
+        assert hasattr(aids, name) and not hasattr(lib, name), name
+    assert lib.vqae_abi_version() == 3
     assert lib.vqae_error_string(3).decode().startswith("VQ dim != channel dim")
 
 
