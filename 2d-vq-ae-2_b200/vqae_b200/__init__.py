@@ -33,7 +33,7 @@ def build_vqae(n_down: int = 4, **conf_overrides) -> VQAE:
 
 def set_precision(module, precision: str):
     """Select the arithmetic of every Encoder/Decoder below ``module``: "fp32" (exact CUDA-core
-    kernels, index parity with the reference) or "bf16" (tcgen05 tensor-core kernels with bf16
+    kernels, index parity with the reference) or "fp16" (tcgen05 tensor-core kernels with bf16
     operands, fp32 accumulation and an fp32 residual stream)."""
     if precision is not None and precision not in engine.PRECISIONS:
         raise ValueError(f"precision must be one of {engine.PRECISIONS} or None")

@@ -11,18 +11,18 @@ _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _fp = C.POINTER(C.c_float)
 
 SIGNATURES: dict = {
-    "vqae_pack_same_block_bf16": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
-    "vqae_same_block_bf16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
+    "vqae_pack_same_block_f16": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "vqae_same_block_f16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
     "vqae_same_chain_flag_bytes": (C.c_size_t, [_i, _i64]),
     "vqae_same_chain_supported": (_i, [_i64, _i, _i, _i]),
-    "vqae_same_chain_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i, _i64, _i, _i, _i, _vp]),
+    "vqae_same_chain_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i, _i64, _i, _i, _i, _vp]),
     "vqae_trunk_resident_max_clusters": (_i, []),
     "vqae_trunk_resident_supported": (_i, [_i64, _i, _i, _i]),
-    "vqae_pack_resident_block_bf16": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp]),
-    "vqae_trunk_resident_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
+    "vqae_pack_resident_block_f16": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp]),
+    "vqae_trunk_resident_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "vqae_down_block_pack_elems": (C.c_size_t, [_i]),
-    "vqae_pack_down_block_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
-    "vqae_down_block_bf16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
+    "vqae_pack_down_block_f16": (_i, [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
+    "vqae_down_block_f16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
 }
 
 # include/vqae_b200_testaids.h (libvqae_b200_testaids.so): tests/ and profiles/ only

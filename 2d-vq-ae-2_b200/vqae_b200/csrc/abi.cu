@@ -210,9 +210,9 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
     return VQAE_ERR_BAD_ARG;
 }
 
-int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+int vqae_pack_same_block_f16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                               int c, void* packed, void* stream) {
-    return pack_same_block_bf16(w1_oihw, w2_oihw, w3_oihw, c, packed, (cudaStream_t)stream);
+    return pack_same_block_f16(w1_oihw, w2_oihw, w3_oihw, c, packed, (cudaStream_t)stream);
 }
 
 }  // extern "C"
@@ -231,7 +231,7 @@ int device_sm_count(int* out) {
 }  // namespace vqae
 extern "C" {
 
-int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
+int vqae_same_block_f16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c,
                          void* stream) {
     int sm_count = 0;
@@ -250,7 +250,7 @@ int vqae_same_chain_supported(int64_t batch, int height, int width, int c) {
     return same_chain_supported(batch, height, width, c, sm_count) ? 1 : 0;
 }
 
-int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void* w_packed_all,
+int vqae_same_chain_f16(const float* x, float* buf_a, float* buf_b, const void* w_packed_all,
                          const float* scalars_dev, void* flags, size_t flag_bytes, int n_blocks,
                          int64_t batch, int height, int width, int c, void* stream) {
     int sm_count = 0;
@@ -268,13 +268,13 @@ int vqae_trunk_resident_supported(int64_t batch, int height, int width, int c) {
     return trunk_resident_supported(batch, height, width, c) ? 1 : 0;
 }
 
-int vqae_pack_resident_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+int vqae_pack_resident_block_f16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                                   int c, float scale, void* packed, void* stream) {
-    return pack_resident_block_bf16(w1_oihw, w2_oihw, w3_oihw, c, scale, packed,
+    return pack_resident_block_f16(w1_oihw, w2_oihw, w3_oihw, c, scale, packed,
                                     (cudaStream_t)stream);
 }
 
-int vqae_trunk_resident_bf16(const float* x, float* out, const void* w_packed_all,
+int vqae_trunk_resident_f16(const float* x, float* out, const void* w_packed_all,
                              const float* scalars_dev, int n_blocks, int64_t batch, int height,
                              int width, int c, void* stream) {
     return trunk_resident_tc(x, out, w_packed_all, scalars_dev, n_blocks, batch, height, width, c,
@@ -283,14 +283,14 @@ int vqae_trunk_resident_bf16(const float* x, float* out, const void* w_packed_al
 
 size_t vqae_down_block_pack_elems(int c_in) { return down_block_pack_elems(c_in); }
 
-int vqae_pack_down_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+int vqae_pack_down_block_f16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                               const float* wskip_oihw, int c_in, float scale, void* packed,
                               void* stream) {
-    return pack_down_block_bf16(w1_oihw, w2_oihw, w3_oihw, wskip_oihw, c_in, scale, packed,
+    return pack_down_block_f16(w1_oihw, w2_oihw, w3_oihw, wskip_oihw, c_in, scale, packed,
                                 (cudaStream_t)stream);
 }
 
-int vqae_down_block_bf16(const float* x, float* out, const void* w_packed,
+int vqae_down_block_f16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c_in,
                          void* stream) {
     int sm_count = 0;

@@ -78,7 +78,7 @@ int device_sm_count(int* out);
 int same_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
                   int64_t B, int H, int W, int C, int sm_count, long long* prof,
                   cudaStream_t stream);
-int pack_same_block_bf16(const float* w1, const float* w2, const float* w3, int C, void* packed,
+int pack_same_block_f16(const float* w1, const float* w2, const float* w3, int C, void* packed,
                          cudaStream_t stream);
 
 // tc_chain.cu (persistent multi-block 'same' chain)
@@ -90,7 +90,7 @@ int same_chain_tc(const float* x, float* buf_a, float* buf_b, const void* w_pack
 
 // tc_resident.cu (image-resident trunk: residual stream in tensor memory, 4-CTA clusters)
 bool trunk_resident_supported(int64_t B, int H, int W, int C);
-int pack_resident_block_bf16(const float* w1, const float* w2, const float* w3, int C, float scale,
+int pack_resident_block_f16(const float* w1, const float* w2, const float* w3, int C, float scale,
                              void* packed, cudaStream_t stream);
 int trunk_resident_max_clusters(int* out);
 void trunk_resident_set_prof(long long* dev_ptr);
@@ -102,7 +102,7 @@ int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, int mo
                   cudaStream_t stream);
 // tc_down.cu
 size_t down_block_pack_elems(int CI);
-int pack_down_block_bf16(const float* w1, const float* w2, const float* w3, const float* ws, int CI,
+int pack_down_block_f16(const float* w1, const float* w2, const float* w3, const float* ws, int CI,
                          float scale, void* packed, cudaStream_t stream);
 int down_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
                   int64_t B, int H, int W, int CI, int sm_count, cudaStream_t stream);

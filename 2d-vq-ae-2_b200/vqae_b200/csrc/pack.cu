@@ -13,14 +13,25 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace vqae {
 namespace {
 
-__device__ __forceinline__ __nv_bfloat16 to_bf16(float v, bool lo) {
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    return lo ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+// fp32 -> operand element (tc_common.cuh: fp16, or bf16 when VQAE_OPERAND_F16 == 0); lo = the
+// rounding remainder, again rounded to the operand type
+#if VQAE_OPERAND_F16
+using op_t = __half;
+__device__ __forceinline__ op_t op_round(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float op_float(op_t v) { return __half2float(v); }
+#else
+using op_t = __nv_bfloat16;
+__device__ __forceinline__ op_t op_round(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float op_float(op_t v) { return __bfloat162float(v); }
+#endif
+__device__ __forceinline__ op_t to_bf16(float v, bool lo) {
+    const op_t hi = op_round(v);
+    return lo ? op_round(v - op_float(hi)) : hi;
 }
 
 // canonical [k-chunk][n][8] index r of an N-row matrix -> (n, k)
@@ -44,8 +55,8 @@ __device__ void pack_element(const vqae_pack_desc& d, int i) {
         reinterpret_cast<float*>(d.dst)[i] = w1[((int64_t)o * I + c) * taps + t];
         return;
     }
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.dst);
-    if (kind == VQAE_PACK_SAME_BF16 || kind == VQAE_PACK_RESIDENT_BF16) {
+    op_t* out = reinterpret_cast<op_t*>(d.dst);
+    if (kind == VQAE_PACK_SAME_F16 || kind == VQAE_PACK_RESIDENT_F16) {
         const int CR = d.c_in, CP = CR < 16 ? 16 : CR;
         const int per = CP * CP;
         const int m = i / per;
@@ -54,13 +65,13 @@ __device__ void pack_element(const vqae_pack_desc& d, int i) {
         float v = 0.f;
         if (n < CR && k < CR) {
             if (m == 0) v = w1[n * CR + k];
-            else if (m == 10) v = w3[n * CR + k] * (kind == VQAE_PACK_RESIDENT_BF16 ? d.scale : 1.f);
+            else if (m == 10) v = w3[n * CR + k] * (kind == VQAE_PACK_RESIDENT_F16 ? d.scale : 1.f);
             else v = w2[((size_t)n * CR + k) * 9 + (m - 1)];
         }
         out[i] = to_bf16(v, lo);
         return;
     }
-    if (kind == VQAE_PACK_DOWN_BF16) {
+    if (kind == VQAE_PACK_DOWN_F16) {
         const int CI = d.c_in, CIP = CI < 16 ? 16 : CI, CO = d.c_out;
         const int n1 = CO * CIP, no = CO * CO;
         int n, k, j = i;
@@ -101,12 +112,12 @@ __global__ void __launch_bounds__(256) pack_one_kernel(const vqae_pack_desc d) {
 size_t pack_elems(int kind, int c_in, int c_out, int taps) {
     switch (kind & 0xff) {
         case VQAE_PACK_F32_CONV: return (size_t)c_in * c_out * taps;
-        case VQAE_PACK_SAME_BF16:
-        case VQAE_PACK_RESIDENT_BF16: {
+        case VQAE_PACK_SAME_F16:
+        case VQAE_PACK_RESIDENT_F16: {
             const size_t cp = c_in < 16 ? 16 : c_in;
             return 11 * cp * cp;
         }
-        case VQAE_PACK_DOWN_BF16: {
+        case VQAE_PACK_DOWN_F16: {
             const size_t cip = c_in < 16 ? 16 : c_in, co = c_out;
             return co * cip + 4 * co * co + co * co + 4 * co * cip;
         }
@@ -150,26 +161,26 @@ int pack_conv_weight_f32(const float* w, float* packed, int O, int I, int taps,
                               1.f), stream);
 }
 
-int pack_same_block_bf16(const float* w1, const float* w2, const float* w3, int C, void* packed,
+int pack_same_block_f16(const float* w1, const float* w2, const float* w3, int C, void* packed,
                          cudaStream_t stream) {
     if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
     if (C != 8 && C != 16 && C != 32 && C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
-    return pack_one(make_desc(VQAE_PACK_SAME_BF16, w1, w2, w3, nullptr, packed, C, C, 9, 1.f), stream);
+    return pack_one(make_desc(VQAE_PACK_SAME_F16, w1, w2, w3, nullptr, packed, C, C, 9, 1.f), stream);
 }
 
-int pack_resident_block_bf16(const float* w1, const float* w2, const float* w3, int C, float scale,
+int pack_resident_block_f16(const float* w1, const float* w2, const float* w3, int C, float scale,
                              void* packed, cudaStream_t stream) {
     if (!w1 || !w2 || !w3 || !packed) return VQAE_ERR_BAD_ARG;
     if (C != 32 && C != 64 && C != 128) return VQAE_ERR_UNSUPPORTED;
-    return pack_one(make_desc(VQAE_PACK_RESIDENT_BF16, w1, w2, w3, nullptr, packed, C, C, 9, scale),
+    return pack_one(make_desc(VQAE_PACK_RESIDENT_F16, w1, w2, w3, nullptr, packed, C, C, 9, scale),
                     stream);
 }
 
-int pack_down_block_bf16(const float* w1, const float* w2, const float* w3, const float* ws, int CI,
+int pack_down_block_f16(const float* w1, const float* w2, const float* w3, const float* ws, int CI,
                          float scale, void* packed, cudaStream_t stream) {
     if (!w1 || !w2 || !w3 || !ws || !packed) return VQAE_ERR_BAD_ARG;
     if (CI != 8 && CI != 16 && CI != 32 && CI != 64) return VQAE_ERR_UNSUPPORTED;
-    return pack_one(make_desc(VQAE_PACK_DOWN_BF16, w1, w2, w3, ws, packed, CI, 2 * CI, 4, scale),
+    return pack_one(make_desc(VQAE_PACK_DOWN_F16, w1, w2, w3, ws, packed, CI, 2 * CI, 4, scale),
                     stream);
 }
 

@@ -143,10 +143,10 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
         h[i] = bf16_hi_as_float(v[i]);
         l[i] = v[i] - h[i];
     }
-    hi = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]),
-                    pack_bf16(h[6], h[7]));
-    lo = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]),
-                    pack_bf16(l[6], l[7]));
+    hi = make_uint4(pack_true_bf16(h[0], h[1]), pack_true_bf16(h[2], h[3]), pack_true_bf16(h[4], h[5]),
+                    pack_true_bf16(h[6], h[7]));
+    lo = make_uint4(pack_true_bf16(l[0], l[1]), pack_true_bf16(l[2], l[3]), pack_true_bf16(l[4], l[5]),
+                    pack_true_bf16(l[6], l[7]));
 }
 
 #define TQ_PROF(slot)                                                                   \
@@ -268,7 +268,7 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
         const float c1 = bf16_hi_as_float(e4 - c0);
         const float c2 = (e4 - c0) - c1;
         *reinterpret_cast<uint4*>(brow + 9 * Cfg::B_LBO) =
-            make_uint4(pack_bf16(c0, c1), pack_bf16(c2, 0.f), 0u, 0u);
+            make_uint4(pack_true_bf16(c0, c1), pack_true_bf16(c2, 0.f), 0u, 0u);
     } else if (tid < TQ_K + TQ_D) {
         const int d = tid - TQ_K;
         float m = 0.f;
@@ -291,7 +291,7 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
         }
     } else if (warp == TQ_W_MMA) {
         // ================= MMA warp =================
-        const uint32_t idesc = make_idesc_bf16(128, TQ_K);
+        const uint32_t idesc = make_idesc_true_bf16(128, TQ_K);
         const uint64_t dA = make_desc(sbase + Cfg::OFF_A, Cfg::A_LBO, 128);
         const uint64_t dB = make_desc(sbase + Cfg::OFF_B, Cfg::B_LBO, 128);
         for (int it = 0; it < my_tiles; ++it) {

@@ -3,7 +3,17 @@
 // descriptor for the un-swizzled K-major canonical layout.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
+
+// GEMM operand element type of the reduced-precision conv kernels: IEEE fp16 (11-bit significand).
+// The reference's own inference runs under torch.autocast('cuda') = fp16
+// (scripts/extract_embeddings/extract_embeddings.py:124), and with fp16 operands the encoder flips
+// ~5x fewer codes against the reference's fp32 run than with bf16 operands (8-bit significand) at the
+// same tensor-core rate.  0 selects bf16 (wider exponent range) for the whole library.
+#ifndef VQAE_OPERAND_F16
+#define VQAE_OPERAND_F16 1
+#endif
 
 namespace vqae {
 namespace tc {
@@ -129,7 +139,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // instruction descriptor: kind::f16, A = B = bf16 (K-major), D = fp32, shape M x N x 16
+// (a_format / b_format: 0 = F16, 1 = BF16)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (VQAE_OPERAND_F16 ? 0u : ((1u << 7) | (1u << 10))) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// always bf16 operands (the quantiser's split-bf16 filter GEMM, the self test)
+__host__ __device__ constexpr uint32_t make_idesc_true_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
@@ -162,8 +178,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
         : "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+// two fp32 -> two bf16, whatever the conv operand type (the quantiser's split-bf16 filter GEMM)
+__device__ __forceinline__ uint32_t pack_true_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// two fp32 -> two operand elements (fp16, or bf16 when VQAE_OPERAND_F16 == 0)
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+#if VQAE_OPERAND_F16
+    __half2 v = __floats2half2_rn(lo, hi);
+#else
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+#endif
     return *reinterpret_cast<uint32_t*>(&v);
 }
 

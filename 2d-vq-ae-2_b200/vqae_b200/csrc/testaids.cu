@@ -53,7 +53,7 @@ tc_selftest_kernel(const __nv_bfloat16* __restrict__ A, int a_rows, int row_shif
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {                   // whole warp: umma_bf16 elects the issuing lane itself
-        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint32_t idesc = make_idesc_true_bf16(128, N);
 #pragma unroll
         for (int ks = 0; ks < K / 16; ++ks) {
             const uint64_t ad = make_desc(smem_u32(sa) + row_shift * 16 + ks * 2 * a_lbo, a_lbo, 128);

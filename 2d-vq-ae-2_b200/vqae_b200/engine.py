@@ -233,19 +233,19 @@ class PackedFixup:
         out = []
         sc = self.scalars
         if self.tc_kind == "same":
-            n = lib.vqae_pack_elems(L.PACK_SAME_BF16, self.c_in, self.c_in, 9)
-            self.tc_weights = torch.empty(n, dtype=torch.bfloat16, device=self.device)
-            out.append(self._desc(L.PACK_SAME_BF16, self.tc_weights, self.c_in, self.c_in, 9,
+            n = lib.vqae_pack_elems(L.PACK_SAME_F16, self.c_in, self.c_in, 9)
+            self.tc_weights = torch.empty(n, dtype=torch.float16, device=self.device)
+            out.append(self._desc(L.PACK_SAME_F16, self.tc_weights, self.c_in, self.c_in, 9,
                                   self.src[:3]))
             if self.has_resident:
                 # image-resident trunk kernel: branch_conv3 pre-multiplied by the Fixup scale
-                self.tc_weights_res = torch.empty(n, dtype=torch.bfloat16, device=self.device)
-                out.append(self._desc(L.PACK_RESIDENT_BF16, self.tc_weights_res, self.c_in,
+                self.tc_weights_res = torch.empty(n, dtype=torch.float16, device=self.device)
+                out.append(self._desc(L.PACK_RESIDENT_F16, self.tc_weights_res, self.c_in,
                                       self.c_in, 9, self.src[:3], sc["scale"]))
         else:
-            n = lib.vqae_pack_elems(L.PACK_DOWN_BF16, self.c_in, self.c_out, 4)
-            self.tc_weights = torch.empty(n, dtype=torch.bfloat16, device=self.device)
-            out.append(self._desc(L.PACK_DOWN_BF16, self.tc_weights, self.c_in, self.c_out, 4,
+            n = lib.vqae_pack_elems(L.PACK_DOWN_F16, self.c_in, self.c_out, 4)
+            self.tc_weights = torch.empty(n, dtype=torch.float16, device=self.device)
+            out.append(self._desc(L.PACK_DOWN_F16, self.tc_weights, self.c_in, self.c_out, 4,
                                   self.src, sc["scale"]))
         return out
 
@@ -321,7 +321,7 @@ def _plan_layouts(packed: Sequence[PackedFixup], h: int, w: int, precision: str)
 # ----------------------------------------------------------------------------------------------
 # single calls
 # ----------------------------------------------------------------------------------------------
-PRECISIONS = ("fp32", "bf16")
+PRECISIONS = ("fp32", "fp16")
 # Runs of 'same' blocks at C = 64 / 128 @ 32 x 32 and C = 32 @ 64 x 64 use the
 # image-resident kernel (tc_resident.cu); False selects the tile kernels (tc_chain.cu / tc_kernels.cu)
 # for A/B measurements (profiles/step_breakdown.py)
@@ -332,7 +332,7 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
                        precision: str = "fp32") -> Tensor:
     """x: contiguous NHWC fp32 [B,H,W,c_in] -> NHWC fp32 [B,H',W',c_out].
 
-    precision "fp32": CUDA-core exact path.  "bf16": tcgen05 kernels (bf16 operands, fp32
+    precision "fp32": CUDA-core exact path.  "fp16": tcgen05 kernels (bf16 operands, fp32
     accumulation and fp32 residual stream) wherever one is built for the block's shape, the
     fp32 kernels elsewhere."""
     lib = L.load()
@@ -343,15 +343,15 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
     ensure_packed([pk], *_plan_layouts([pk], h, w, precision))
     if out is None:
         out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
-    if precision == "bf16" and pk.tc_ok(h, w) and pk.mode == L.MODE_DOWN:
-        L.check(lib.vqae_down_block_bf16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
-                                         b, h, w, c, _stream(x.device)), "vqae_down_block_bf16")
+    if precision == "fp16" and pk.tc_ok(h, w) and pk.mode == L.MODE_DOWN:
+        L.check(lib.vqae_down_block_f16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
+                                         b, h, w, c, _stream(x.device)), "vqae_down_block_f16")
         return out
-    if precision == "bf16" and pk.tc_ok(h, w) and pk.chain_only:
-        return run_blocks_nhwc([pk], x, "bf16")
-    if precision == "bf16" and pk.tc_ok(h, w):
-        L.check(lib.vqae_same_block_bf16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
-                                         b, h, w, c, _stream(x.device)), "vqae_same_block_bf16")
+    if precision == "fp16" and pk.tc_ok(h, w) and pk.chain_only:
+        return run_blocks_nhwc([pk], x, "fp16")
+    if precision == "fp16" and pk.tc_ok(h, w):
+        L.check(lib.vqae_same_block_f16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
+                                         b, h, w, c, _stream(x.device)), "vqae_same_block_f16")
         return out
     need = lib.vqae_fixup_block_scratch_bytes(C.byref(pk.params), b, h, w)
     ws = workspace(x.device, need)
@@ -404,11 +404,11 @@ def _chain_runs(packed: Sequence[PackedFixup], h: int, w: int, batch: int = 1 <<
 
 def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "fp32",
                     chain_cache: Optional[dict] = None) -> Tensor:
-    """A Sequential chain of PreActFixupResBlocks on an NHWC fp32 tensor.  In "bf16" mode runs of
-    consecutive tcgen05 'same' blocks execute as ONE launch: image-resident (vqae_trunk_resident_bf16)
-    for C = 64 at 32 x 32, the persistent tile chain (vqae_same_chain_bf16) otherwise."""
+    """A Sequential chain of PreActFixupResBlocks on an NHWC fp32 tensor.  In "fp16" mode runs of
+    consecutive tcgen05 'same' blocks execute as ONE launch: image-resident (vqae_trunk_resident_f16)
+    for C = 64 at 32 x 32, the persistent tile chain (vqae_same_chain_f16) otherwise."""
     ensure_packed(packed, *_plan_layouts(packed, h.shape[1], h.shape[2], precision))
-    if precision != "bf16":
+    if precision != "fp16":
         for pk in packed:
             h = fixup_forward_nhwc(pk, h, precision=precision)
         return h
@@ -430,18 +430,18 @@ def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "
             chain = cache[key] = PackedChain(packed[i:j], resident)
         if resident:
             out = torch.empty_like(h)
-            L.check(lib.vqae_trunk_resident_bf16(
+            L.check(lib.vqae_trunk_resident_f16(
                 _ptr(h), _ptr(out), _ptr(chain.weights), _ptr(chain.scalars), chain.n, b, hh, ww, c,
-                _stream(h.device)), "vqae_trunk_resident_bf16")
+                _stream(h.device)), "vqae_trunk_resident_f16")
             h = out
             i = j
             continue
         bufs = [torch.empty_like(h), torch.empty_like(h)]
         fbytes = lib.vqae_same_chain_flag_bytes(chain.n, b)
         flags = torch.empty(fbytes, dtype=torch.uint8, device=h.device)
-        L.check(lib.vqae_same_chain_bf16(
+        L.check(lib.vqae_same_chain_f16(
             _ptr(h), _ptr(bufs[0]), _ptr(bufs[1]), _ptr(chain.weights), _ptr(chain.scalars),
-            _ptr(flags), fbytes, chain.n, b, hh, ww, c, _stream(h.device)), "vqae_same_chain_bf16")
+            _ptr(flags), fbytes, chain.n, b, hh, ww, c, _stream(h.device)), "vqae_same_chain_f16")
         h = bufs[(chain.n - 1) & 1]
         i = j
     return h

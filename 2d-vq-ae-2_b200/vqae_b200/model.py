@@ -67,7 +67,7 @@ class Encoder(nn.Module):
         self.shortcut_layers = nn.ModuleList(reversed(shortcut_layers))
         self.vq_layers = nn.ModuleList(reversed(vq_layers))
         #: None = follow torch.autocast like the reference (fp32 unless autocast is active);
-        #: "fp32" / "bf16" / ... pin the arithmetic (vqae_b200.set_precision)
+        #: "fp32" / "fp16" / ... pin the arithmetic (vqae_b200.set_precision)
         self.precision = None
 
     # -- B200 path -------------------------------------------------------------------------

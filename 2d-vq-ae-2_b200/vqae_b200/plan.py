@@ -22,7 +22,7 @@ from torch import Tensor, nn
 
 from . import engine as E
 
-REDUCED = "bf16"        # what an active torch.autocast('cuda') selects
+REDUCED = "fp16"        # what an active torch.autocast('cuda') selects
 
 
 def state(module) -> types.SimpleNamespace:
@@ -249,7 +249,7 @@ def accelerate(model: nn.Module, precision: Optional[str] = None) -> nn.Module:
     ``Encoder`` / ``Decoder``, the quantisers of ``vq_ae.layers.vq``, ``PreActFixupResBlock``) to the
     B200 path, in place: eval-mode forwards on CUDA tensors run the packed plans of this module,
     everything else (training, CPU tensors, ``state_dict``, checkpoints, attributes) is the
-    reference's code, untouched.  ``precision``: "fp32", "bf16", ... or None = follow
+    reference's code, untouched.  ``precision``: "fp32", "fp16", ... or None = follow
     ``torch.autocast`` like the reference does."""
     if precision is not None and precision not in E.PRECISIONS:
         raise ValueError(f"precision must be one of {E.PRECISIONS}")

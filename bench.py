@@ -280,9 +280,9 @@ def time_trunk_kernel(dev, peaks, model, C: int, B: int):
     assert lib.vqae_trunk_resident_supported(B, H, W, C)
 
     def launch(i):
-        L.check(lib.vqae_trunk_resident_bf16(E._ptr(xs[i % nbuf]), E._ptr(ys[i % nbuf]),
+        L.check(lib.vqae_trunk_resident_f16(E._ptr(xs[i % nbuf]), E._ptr(ys[i % nbuf]),
                                              E._ptr(chain.weights), E._ptr(chain.scalars), nblk, B,
-                                             H, W, C, st), "vqae_trunk_resident_bf16")
+                                             H, W, C, st), "vqae_trunk_resident_f16")
     ms = _event_time(launch, 5, dev)
     flops = 2.0 * B * H * W * C * C * 11 * nblk
     achieved = flops / (ms * 1e-3) / 1e12
@@ -537,7 +537,7 @@ def run_gpu(args):
             "metric": w["metric"], "value": value, "unit": "patches/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16",
             "data": "synthetic",
             "config": {"workload": w["text"]},
             "detail": {"precision": args.precision,
@@ -604,7 +604,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="encode256", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--precision", default="fp16")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the side measurements (other precisions, config 2, CPU baseline)")
     args = ap.parse_args()

@@ -69,8 +69,8 @@ int vqae_pack_conv_weight_f32(const float* w_oihw, float* packed, int out_ch, in
  * RESIDENT and DOWN layouts.  kind | VQAE_PACK_LO writes bf16(w - bf16(w)), the low half of the
  * split-bf16 operands of precision "bf16x3".  n_elems = vqae_pack_elems(kind, c_in, c_out, taps).
  * descs_device: the table in DEVICE memory; max_elems: the largest n_elems in it.             */
-enum { VQAE_PACK_F32_CONV = 0, VQAE_PACK_SAME_BF16 = 1, VQAE_PACK_RESIDENT_BF16 = 2,
-       VQAE_PACK_DOWN_BF16 = 3, VQAE_PACK_LO = 0x100 };
+enum { VQAE_PACK_F32_CONV = 0, VQAE_PACK_SAME_F16 = 1, VQAE_PACK_RESIDENT_F16 = 2,
+       VQAE_PACK_DOWN_F16 = 3, VQAE_PACK_LO = 0x100 };
 typedef struct vqae_pack_desc {
     int32_t kind, c_in, c_out, taps;
     float scale;
@@ -139,28 +139,28 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
  * convs and their pre-activations fused in one kernel; c in {8, 16, 32, 64} (8 runs zero-padded
  * as 16), height % 16 == 0, width % 32 == 0 -- every 'same' block of the shipped encoder and
  * decoder (DownBlock/UpBlock pre/post layers and the 50-block trunks, model.py:150-153,240-263).
- * w_packed comes from vqae_pack_same_block_bf16 (11 * cp * cp bf16, cp = max(c, 16));
+ * w_packed comes from vqae_pack_same_block_f16 (11 * cp * cp bf16, cp = max(c, 16));
  * scalars8_host = {bias1a, bias1b, bias2a, bias2b, bias3a, bias3b, bias4, scale} on the HOST.
  * x, out: NHWC fp32 [B,H,W,c], must not alias.                                               */
-int vqae_pack_same_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+int vqae_pack_same_block_f16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                               int c, void* packed, void* stream);
-int vqae_same_block_bf16(const float* x, float* out, const void* w_packed,
+int vqae_same_block_f16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c,
                          void* stream);
 /* A run of n_blocks consecutive 'same' blocks of equal width in ONE persistent launch (the 50-block
  * trunks model.py:150-153,240-263 and the post layers of DownBlock/UpBlock): every (block, tile)
  * task is scheduled round-robin over the resident CTAs and ordered by per-(block, image) completion
  * counters, so no SM idles at block boundaries.  Results are bit-identical to n_blocks calls of
- * vqae_same_block_bf16.  w_packed_all: the blocks' vqae_pack_same_block_bf16 outputs back to back;
+ * vqae_same_block_f16.  w_packed_all: the blocks' vqae_pack_same_block_f16 outputs back to back;
  * scalars_dev: DEVICE float [n_blocks][8] in the order of scalars8_host above; block i reads
  * (i ? buf[(i-1)&1] : x) and writes buf[i&1] with buf = {buf_a, buf_b}: the result is in
  * buf[(n_blocks-1)&1]; flags: DEVICE scratch of vqae_same_chain_flag_bytes(n_blocks, batch).    */
 size_t vqae_same_chain_flag_bytes(int n_blocks, int64_t batch);
 /* 1 if the persistent form is built for this shape on the current device: c == 64 and at least
  * SM-count + tiles-per-image tiles per block (the scheduling argument in csrc/tc_chain.cu needs
- * that); otherwise run the blocks one by one with vqae_same_block_bf16.                       */
+ * that); otherwise run the blocks one by one with vqae_same_block_f16.                       */
 int vqae_same_chain_supported(int64_t batch, int height, int width, int c);
-int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void* w_packed_all,
+int vqae_same_chain_f16(const float* x, float* buf_a, float* buf_b, const void* w_packed_all,
                          const float* scalars_dev, void* flags, size_t flag_bytes, int n_blocks,
                          int64_t batch, int height, int width, int c, void* stream);
 /* The same run with the fp32 residual stream RESIDENT ON THE SM (c in {64, 128} at 32 x 32: the
@@ -169,11 +169,11 @@ int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void*
  * tensor memory and branch_conv3 accumulates straight into it, halo rows travel through distributed
  * shared memory; the only global traffic is the first load and the last store of each image.  The
  * launch is persistent (at most as many clusters as the device holds at once; each works through
- * its share of the batch), any batch size.  w_packed_all: vqae_pack_resident_block_bf16 outputs back
+ * its share of the batch), any batch size.  w_packed_all: vqae_pack_resident_block_f16 outputs back
  * to back (11 * c * c bf16 per block, branch_conv3 pre-multiplied by the Fixup `scale`, so bias4 and
  * scale are applied as  x += (scale W3) v;  the bias4 terms are summed and added on the way out);
- * scalars_dev as for vqae_same_chain_bf16.  x, out: NHWC fp32 [B,H,W,c]; out may alias x.
- * Deterministic (repeated launches are bit-identical).  Not bit-identical to vqae_same_block_bf16
+ * scalars_dev as for vqae_same_chain_f16.  x, out: NHWC fp32 [B,H,W,c]; out may alias x.
+ * Deterministic (repeated launches are bit-identical).  Not bit-identical to vqae_same_block_f16
  * (rounding of scale*W3, accumulation order): agrees within the bf16 tolerance
  * (tests/test_gpu_tc.py).                                                                       */
 /* 4-CTA clusters of the c == 64 resident kernel the current device holds at once (one image pair
@@ -181,22 +181,22 @@ int vqae_same_chain_bf16(const float* x, float* buf_a, float* buf_b, const void*
  * cluster busy to the end.                                                                      */
 int vqae_trunk_resident_max_clusters(void);
 int vqae_trunk_resident_supported(int64_t batch, int height, int width, int c);
-int vqae_pack_resident_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+int vqae_pack_resident_block_f16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                                   int c, float scale, void* packed, void* stream);
-int vqae_trunk_resident_bf16(const float* x, float* out, const void* w_packed_all,
+int vqae_trunk_resident_f16(const float* x, float* out, const void* w_packed_all,
                              const float* scalars_dev, int n_blocks, int64_t batch, int height,
                              int width, int c, void* stream);
 /* PreActFixupResBlock in mode 'down' (conv specs pre_activation_fixup.yaml:35-45): c_in ->
  * 2*c_in, stride 2, branch + skip fused in one tcgen05 kernel; c_in in {8, 16, 32},
  * height % 16 == 0, width % 32 == 0.  w_packed: vqae_down_block_pack_elems(c_in) bf16 from
- * vqae_pack_down_block_bf16 (scale is folded into branch_conv3 there);
+ * vqae_pack_down_block_f16 (scale is folded into branch_conv3 there);
  * scalars8_host = {bias1a, bias1b, bias2a, bias2b, bias3a, bias3b, bias1c, bias4 + bias1d}.
  * x: NHWC fp32 [B,H,W,c_in];  out: NHWC fp32 [B,H/2,W/2,2*c_in].                             */
 size_t vqae_down_block_pack_elems(int c_in);
-int vqae_pack_down_block_bf16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
+int vqae_pack_down_block_f16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                               const float* wskip_oihw, int c_in, float scale, void* packed,
                               void* stream);
-int vqae_down_block_bf16(const float* x, float* out, const void* w_packed,
+int vqae_down_block_f16(const float* x, float* out, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c_in,
                          void* stream);
 

@@ -15,7 +15,7 @@ from vqae_b200.model import _flat_blocks  # noqa: E402
 
 
 def main():
-    precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+    precision = sys.argv[1] if len(sys.argv) > 1 else "fp16"
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     n_down = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     dev = torch.device("cuda:0")
@@ -39,7 +39,7 @@ def main():
                 ev.append((label, e))
         mark("start")
         h = enc
-        runs = dict(E._chain_runs(packed, h.shape[1], h.shape[2], h.shape[0])) if precision == "bf16" else {}
+        runs = dict(E._chain_runs(packed, h.shape[1], h.shape[2], h.shape[0])) if precision == "fp16" else {}
         i = 0
         while i < len(packed):
             pk = packed[i]

@@ -11,7 +11,7 @@ if len(sys.argv) > 2 and sys.argv[2] == "chain":
 dev = torch.device("cuda:0")
 model = vqae_b200.build_vqae(n_down=3).eval()
 model.load_state_dict(S.make_state_dict(model.state_dict(), seed=1, regime="perturbed"))
-m = vqae_b200.set_precision(model.to(dev), sys.argv[1] if len(sys.argv) > 1 else "bf16")
+m = vqae_b200.set_precision(model.to(dev), sys.argv[1] if len(sys.argv) > 1 else "fp16")
 enc = m.encoder
 NB = 24
 batches = [device_patches(256 * k, 256, dev) for k in range(NB)]

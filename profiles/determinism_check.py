@@ -13,7 +13,7 @@ from vqae_b200 import synthetic as S  # noqa: E402
 from vqae_b200.model import _flat_blocks  # noqa: E402
 
 dev = torch.device("cuda:0")
-precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+precision = sys.argv[1] if len(sys.argv) > 1 else "fp16"
 # leave different garbage in freed device memory from run to run
 junk = torch.empty(int(sys.argv[2]) if len(sys.argv) > 2 else 1, 1 << 20, device=dev).normal_()
 del junk
@@ -35,7 +35,7 @@ names = {0: "same", 1: "down", 2: "up"}
 with torch.no_grad():
     a = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias)
     print("stem_in", h(a))
-    runs = dict(E._chain_runs(packed, a.shape[1], a.shape[2], a.shape[0])) if precision == "bf16" else {}
+    runs = dict(E._chain_runs(packed, a.shape[1], a.shape[2], a.shape[0])) if precision == "fp16" else {}
     i = 0
     while i < len(packed):
         pk = packed[i]

@@ -10,7 +10,7 @@ packs = []
 for i in range(nblk):
     ws = [(torch.randn(C, C, k, k, generator=gen) * 0.05).to(dev) for k in (1, 3, 1)]
     pk = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
-    L.check(lib.vqae_pack_resident_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, 0.2, E._ptr(pk), st), "pack")
+    L.check(lib.vqae_pack_resident_block_f16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, 0.2, E._ptr(pk), st), "pack")
     packs.append(pk)
 w_all = torch.cat(packs)
 scal = torch.tensor([[0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.2]] * nblk, dtype=torch.float32).to(dev)
@@ -18,7 +18,7 @@ x = torch.randn(B, HW, HW, C, device=dev)
 outs = []
 for i in range(401):
     y = torch.empty_like(x)
-    L.check(lib.vqae_trunk_resident_bf16(E._ptr(x), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, HW, HW, C, st), "r")
+    L.check(lib.vqae_trunk_resident_f16(E._ptr(x), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, HW, HW, C, st), "r")
     outs.append(y)
 torch.cuda.synchronize()
 for i, o in enumerate(outs[1:], 1):

@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 m = vqae_b200.build_vqae(n_down=3).eval()
 m.load_state_dict(S.make_state_dict(m.state_dict(), seed=1, regime="perturbed"))
-m = vqae_b200.set_precision(m.to(dev), "bf16")
+m = vqae_b200.set_precision(m.to(dev), "fp16")
 enc = m.encoder
 x = S.synthetic_patches_u8(256, 256, 42).to(dev)
 with torch.no_grad():
@@ -25,7 +25,7 @@ pq = enc.vq_layers[0].packed()
 from vqae_b200.model import _flat_blocks  # noqa: E402
 with torch.no_grad():
     h = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias)
-    h = E.run_blocks_nhwc(E.pack_blocks(_flat_blocks(enc.down_layers) + _flat_blocks(enc.pre_enc_layers)), h, "bf16")
+    h = E.run_blocks_nhwc(E.pack_blocks(_flat_blocks(enc.down_layers) + _flat_blocks(enc.pre_enc_layers)), h, "fp16")
 b, hh, ww, c = h.shape
 os.environ["VQAE_QUANT_TC"] = "0"
 _r = E.quantize(pq, h, True, True, b, hh * ww, want_out=False, want_z=True)

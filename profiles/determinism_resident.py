@@ -18,7 +18,7 @@ for C, HW, B, nblk in ((32, 64, 256, 5), (64, 32, 256, 6), (128, 32, 64, 4), (32
     for i in range(nblk):
         ws = [(torch.randn(C, C, k, k, generator=gen) * 0.05).to(dev) for k in (1, 3, 1)]
         pk = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
-        L.check(lib.vqae_pack_resident_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, 0.2,
+        L.check(lib.vqae_pack_resident_block_f16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, 0.2,
                                                   E._ptr(pk), st), "pack")
         packs.append(pk)
     w_all = torch.cat(packs)
@@ -27,7 +27,7 @@ for C, HW, B, nblk in ((32, 64, 256, 5), (64, 32, 256, 6), (128, 32, 64, 4), (32
     outs = []
     for i in range(reps + 1):
         y = torch.empty_like(x)
-        L.check(lib.vqae_trunk_resident_bf16(E._ptr(x), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, HW, HW,
+        L.check(lib.vqae_trunk_resident_f16(E._ptr(x), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, HW, HW,
                                              C, st), "resident")
         outs.append(y)
     torch.cuda.synchronize()

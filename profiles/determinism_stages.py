@@ -11,7 +11,7 @@ from vqae_b200 import synthetic as S  # noqa: E402
 from vqae_b200.model import _flat_blocks  # noqa: E402
 
 dev = torch.device("cuda:0")
-precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+precision = sys.argv[1] if len(sys.argv) > 1 else "fp16"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 m = vqae_b200.build_vqae(n_down=3).eval()
 m.load_state_dict(S.make_state_dict(m.state_dict(), seed=1, regime="perturbed"))
@@ -39,7 +39,7 @@ def repeat(label, fn):
 
 with torch.no_grad():
     a = repeat("stem_in", lambda: E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias))
-    runs = dict(E._chain_runs(packed, a.shape[1], a.shape[2], a.shape[0])) if precision == "bf16" else {}
+    runs = dict(E._chain_runs(packed, a.shape[1], a.shape[2], a.shape[0])) if precision == "fp16" else {}
     i = 0
     while i < len(packed):
         pk = packed[i]

@@ -29,7 +29,7 @@ for n_down, size, batch in ((3, 256, 64), (4, 512, 16)):
     m.load_state_dict(S.make_state_dict(m.state_dict(), seed=1, regime="perturbed"))
     m = m.to(dev)
     x = S.synthetic_patches(batch, size, 7).to(dev)
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "fp16"):
         vqae_b200.set_precision(m, prec)
         with torch.no_grad():
             (enc,), (idx,), _ = m.encoder(x)

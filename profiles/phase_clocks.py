@@ -22,7 +22,7 @@ ws = [torch.randn(C, C, k, k, device=dev) * 0.05 for k in (1, 3, 1)]
 cp = max(C, 16)
 packed = torch.empty(11 * cp * cp, dtype=torch.bfloat16, device=dev)
 st = E._stream(dev)
-L.check(lib.vqae_pack_same_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, E._ptr(packed), st), "pack")
+L.check(lib.vqae_pack_same_block_f16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, E._ptr(packed), st), "pack")
 sc = (ctypes.c_float * 8)(0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.9)
 prof = torch.zeros(148 * 4, 8, dtype=torch.int64, device=dev)
 for _ in range(3):

@@ -13,7 +13,7 @@ import helpers as H  # noqa: E402
 import vqae_b200  # noqa: E402
 
 DEV = "cuda:0"
-precisions = sys.argv[1:] or ["bf16"]
+precisions = sys.argv[1:] or ["fp16"]
 for prec in precisions:
     for tag in sorted(H.MODEL_CASES):
         g = H.golden(tag)

@@ -1,4 +1,4 @@
-"""Launch the persistent 50-block trunk kernel (vqae_same_chain_bf16) at the bench shape (for ncu)."""
+"""Launch the persistent 50-block trunk kernel (vqae_same_chain_f16) at the bench shape (for ncu)."""
 import sys
 from pathlib import Path
 REPO = Path(__file__).resolve().parent.parent
@@ -18,7 +18,7 @@ packs = []
 for i in range(nblk):
     ws = [(torch.randn(C, C, k, k, generator=gen) * 0.05).to(dev) for k in (1, 3, 1)]
     pk = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
-    L.check(lib.vqae_pack_same_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, E._ptr(pk), st), "pack")
+    L.check(lib.vqae_pack_same_block_f16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, E._ptr(pk), st), "pack")
     packs.append(pk)
 w_all = torch.cat(packs)
 scal = torch.tensor([[0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.2]] * nblk, dtype=torch.float32).to(dev)
@@ -29,7 +29,7 @@ ys = [torch.empty(B, H, W, C, device=dev) for _ in range(2)]
 for i in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    L.check(lib.vqae_same_chain_bf16(E._ptr(xs[i % 2]), E._ptr(ys[0]), E._ptr(ys[1]), E._ptr(w_all), E._ptr(scal),
+    L.check(lib.vqae_same_chain_f16(E._ptr(xs[i % 2]), E._ptr(ys[0]), E._ptr(ys[1]), E._ptr(w_all), E._ptr(scal),
                                      E._ptr(flags), fbytes, nblk, B, H, W, C, st), "chain")
     e1.record()
     torch.cuda.synchronize()

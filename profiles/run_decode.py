@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 m = vqae_b200.build_vqae(n_down=3).eval()
 m.load_state_dict(S.make_state_dict(m.state_dict(), seed=1, regime="perturbed"))
-m = vqae_b200.set_precision(m.to(dev), "bf16")
+m = vqae_b200.set_precision(m.to(dev), "fp16")
 enc = torch.randn(batch, 64, 32, 32, device=dev)
 with torch.no_grad():
     for _ in range(3):

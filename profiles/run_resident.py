@@ -1,4 +1,4 @@
-"""Launch the image-resident trunk kernel (vqae_trunk_resident_bf16) at the bench shape (timing / ncu).
+"""Launch the image-resident trunk kernel (vqae_trunk_resident_f16) at the bench shape (timing / ncu).
 usage: python profiles/run_resident.py [n_blocks=54] [reps=3] [batch=256] [C=64]"""
 import sys
 from pathlib import Path
@@ -21,7 +21,7 @@ packs = []
 for i in range(nblk):
     ws = [(torch.randn(C, C, k, k, generator=gen) * 0.05).to(dev) for k in (1, 3, 1)]
     pk = torch.empty(11 * C * C, dtype=torch.bfloat16, device=dev)
-    L.check(lib.vqae_pack_resident_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, 0.2,
+    L.check(lib.vqae_pack_resident_block_f16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, 0.2,
                                               E._ptr(pk), st), "pack")
     packs.append(pk)
 w_all = torch.cat(packs)
@@ -32,7 +32,7 @@ y = torch.empty(B, H, W, C, device=dev)
 for i in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    L.check(lib.vqae_trunk_resident_bf16(E._ptr(xs[i % 2]), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B,
+    L.check(lib.vqae_trunk_resident_f16(E._ptr(xs[i % 2]), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B,
                                          H, W, C, st), "resident")
     e1.record()
     torch.cuda.synchronize()
@@ -43,7 +43,7 @@ for i in range(reps):
 # phase clocks of CTA 0, eight steady-state half-rounds
 prof = torch.zeros(8 * 32, dtype=torch.int64, device=dev)
 L.load_testaids().vqae_trunk_resident_set_profile(E._ptr(prof))
-L.check(lib.vqae_trunk_resident_bf16(E._ptr(xs[0]), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, H, W, C, st), "resident")
+L.check(lib.vqae_trunk_resident_f16(E._ptr(xs[0]), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, H, W, C, st), "resident")
 torch.cuda.synchronize()
 L.load_testaids().vqae_trunk_resident_set_profile(None)
 p = prof.cpu().view(8, 32)

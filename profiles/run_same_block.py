@@ -21,9 +21,9 @@ ws = [torch.randn(C, C, k, k, device=dev) * 0.05 for k in (1, 3, 1)]
 cp = max(C, 16)
 packed = torch.empty(11 * cp * cp, dtype=torch.bfloat16, device=dev)
 st = E._stream(dev)
-L.check(lib.vqae_pack_same_block_bf16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, E._ptr(packed), st), "pack")
+L.check(lib.vqae_pack_same_block_f16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2]), C, E._ptr(packed), st), "pack")
 sc = (ctypes.c_float * 8)(0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.9)
 for i in range(8):
-    L.check(lib.vqae_same_block_bf16(E._ptr(xs[i % 2]), E._ptr(ys[i % 2]), E._ptr(packed), sc, B, HW, HW, C, st), "run")
+    L.check(lib.vqae_same_block_f16(E._ptr(xs[i % 2]), E._ptr(ys[i % 2]), E._ptr(packed), sc, B, HW, HW, C, st), "run")
 torch.cuda.synchronize()
 print("ok")

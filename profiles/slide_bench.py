@@ -50,7 +50,7 @@ def main():
     lo, hi = shard_range(n_total, rank, world)
     model = vqae_b200.build_vqae(n_down=3).eval()
     model.load_state_dict(S.make_state_dict(model.state_dict(), seed=1, regime="perturbed"))
-    model = vqae_b200.set_precision(model.to(dev), "bf16")
+    model = vqae_b200.set_precision(model.to(dev), "fp16")
     enc = model.encoder
     # inputs are generated before the timed region (H2D / generation reported separately)
     t0 = time.perf_counter()

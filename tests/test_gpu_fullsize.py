@@ -96,7 +96,7 @@ def test_encode_stream_collected_equals_per_batch_encodes():
     recycled internally); with reuse_buffers=True the documented validity window holds."""
     tag = "model_nd3_perturbed"
     m, sd, _ = H.model_and_state(tag)
-    m = vqae_b200.set_precision(m.to(DEV), "bf16")
+    m = vqae_b200.set_precision(m.to(DEV), "fp16")
     try:
         batches = [S.synthetic_patches_u8(3, 256, 900 + i).pin_memory() for i in range(7)]
         ref = [X.encode_patches(m.encoder, b.to(DEV)).cpu() for b in batches]

@@ -1,10 +1,10 @@
 """GPU: the REDUCED-PRECISION tensor-core path (the one bench.py times) pinned directly to the
 goldens written by the unmodified reference -- not to this repository's own fp32 path.
 
-What can and cannot be asserted (hard part 3): with bf16 GEMM operands the
-latents carry a relative error of a few 1e-3, so a vector whose two nearest codes are closer than
-that flips its code; the reference itself, run with bf16 convs, agrees with its fp32 run on ~96 %
-of codes.  A flipped code changes the decoded patch everywhere (54 circular 3x3 blocks at 32x32
+What can and cannot be asserted (hard part 3): with 16-bit GEMM operands the
+latents carry a relative error of a few 1e-4 (fp16 operands; a few 1e-3 with bf16 operands, which
+round 1 used), so a vector whose two nearest codes are closer than that flips its code; the
+reference itself, run with bf16 convs, agrees with its fp32 run on ~96 % of codes.  A flipped code changes the decoded patch everywhere (54 circular 3x3 blocks at 32x32
 see the whole grid), so the 1e-2 reconstruction bar of north_star is checked where it is
 well-posed: on the decoder fed with the REFERENCE's codes, and on the quantised tensor at every
 position whose code agrees.  The encoder is held to: latent error, code agreement (bars set from
@@ -23,13 +23,14 @@ from vqae_b200 import plan as P
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-# tag -> (min code agreement, max relative latent error); measured on B200 (round 2):
-# agreement 0.9976 / 0.9922 / 0.9844 / 0.9863, latent error 3.6e-3 / 3.2e-3 / 2.3e-3 / 3.6e-3
+# tag -> (min code agreement, max relative latent error); measured on B200 (round 2, fp16 operands,
+# profiles/r2_reduced_vs_golden.txt): agreement 1.0000 / 0.9985 / 0.9980 / 1.0000, latent error
+# 4.1e-4 / 3.9e-4 / 3.2e-4 / 4.9e-4  (bf16 operands: 0.9976 / 0.9922 / 0.9844 / 0.9863, ~3e-3)
 BF16_BARS = {
-    "model_nd3_fixup": (0.995, 6e-3),
-    "model_nd3_perturbed": (0.990, 6e-3),
-    "model_nd4_perturbed_256": (0.979, 6e-3),
-    "model_nd4_perturbed_512": (0.981, 6e-3),
+    "model_nd3_fixup": (0.998, 1e-3),
+    "model_nd3_perturbed": (0.995, 1e-3),
+    "model_nd4_perturbed_256": (0.994, 1e-3),
+    "model_nd4_perturbed_512": (0.997, 1e-3),
 }
 
 
@@ -43,11 +44,11 @@ def _pre_vq(m, x, precision):
 
 
 @pytest.mark.parametrize("tag", sorted(H.MODEL_CASES))
-def test_bf16_model_vs_reference_golden(tag):
+def test_reduced_precision_model_vs_reference_golden(tag):
     g = H.golden(tag)
     min_agree, max_zerr = BF16_BARS[tag]
     m, sd, x = H.model_and_state(tag)
-    m = vqae_b200.set_precision(m.to(DEV), "bf16")
+    m = vqae_b200.set_precision(m.to(DEV), "fp16")
     try:
         with torch.no_grad():
             xd = x.to(DEV)
@@ -57,7 +58,7 @@ def test_bf16_model_vs_reference_golden(tag):
             dec_ref = m.decode_codes(ref_codes)              # decoder on the reference's codes
             recon, _ = m(xd)
             dec_own = m.decode_codes(idx)
-            stem, pre_vq = _pre_vq(m, xd, "bf16")
+            stem, pre_vq = _pre_vq(m, xd, "fp16")
         ref_idx = g["idx"].astype(np.int64).reshape(-1)
         idx_np = idx.cpu().numpy().reshape(-1)
         same = idx_np == ref_idx
@@ -69,8 +70,7 @@ def test_bf16_model_vs_reference_golden(tag):
         z_err = float((z.cpu().reshape(-1, 8) - z_ref).abs().max() / z_ref.abs().max())
         assert z_err < max_zerr, z_err
         assert same.mean() >= min_agree, same.mean()
-        assert not (~same & (g["gap"] >= 0.1)).any()         # flips only between near neighbours
-        assert int((~same & (g["gap"] >= 1e-2)).sum()) <= 12
+        assert not (~same & (g["gap"] >= 1e-2)).any()        # flips only between near neighbours
         assert abs(loss.item() - float(g["loss"])) < 1e-2 * abs(float(g["loss"]))
         # quantised tensor: a table gather -- exact wherever the code agrees
         msk = torch.from_numpy(same.reshape(g["idx"].shape))[:, ::4, ::4]
@@ -79,17 +79,18 @@ def test_bf16_model_vs_reference_golden(tag):
                       / e_ref.abs().max())
         assert e_err < 1e-6, e_err
         # decoder: north_star's reduced-precision bar, on identical codes
-        assert H.rel_err(dec_ref.cpu()[:, :, ::8, ::8], torch.from_numpy(g["decode_codes_sub"])) < 1e-2
+        # (north_star: 1e-2; measured <= 3.1e-4 with fp16 operands)
+        assert H.rel_err(dec_ref.cpu()[:, :, ::8, ::8], torch.from_numpy(g["decode_codes_sub"])) < 2e-3
         # the full forward is the composition of the two (same launches, same bits)
         assert torch.equal(recon, dec_own)
-        print(f"{tag}: bf16 agreement {same.mean():.4f}, latent err {z_err:.2e}")
+        print(f"{tag}: fp16-operand agreement {same.mean():.4f}, latent err {z_err:.2e}")
     finally:
         vqae_b200.set_precision(m, None)
         m.cpu()
 
 
 @pytest.mark.parametrize("name", sorted(H.TC_BLOCK_CASES))
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_block_at_tensor_core_sizes_vs_reference_golden(name, precision):
     """Every block shape of both shipped models at a size the tcgen05 kernels tile, against the
     reference's output.  fp32: 2e-5.  bf16: 1e-2 of the output range (north_star) and 2e-2 of the
@@ -126,7 +127,7 @@ def test_autocast_selects_the_reduced_precision_path():
             with torch.autocast("cuda"):
                 (_,), (i_auto,), _ = m.encoder(xd)
             n_auto = E.launch_count() - n0
-            vqae_b200.set_precision(m, "bf16")
+            vqae_b200.set_precision(m, "fp16")
             (_,), (i_bf16,), _ = m.encoder(xd)
             vqae_b200.set_precision(m, "fp32")
             (_,), (i_fp32,), _ = m.encoder(xd)

@@ -47,7 +47,7 @@ def test_same_block_bf16_vs_fp32_path(c, hw, batch):
     assert pk.tc_ok(hw, hw)
     x = torch.randn(batch, hw, hw, c, device=DEV)
     y32 = E.fixup_forward_nhwc(pk, x, precision="fp32")
-    y16 = E.fixup_forward_nhwc(pk, x, precision="bf16")
+    y16 = E.fixup_forward_nhwc(pk, x, precision="fp16")
     torch.cuda.synchronize()
     branch = (y32 - x)
     err = float((y16 - y32).abs().max() / branch.abs().max())
@@ -70,7 +70,7 @@ def test_down_block_bf16_vs_fp32_path(c, hw, batch):
     assert pk.tc_ok(hw, hw)
     x = torch.randn(batch, hw, hw, c, device=DEV)
     y32 = E.fixup_forward_nhwc(pk, x, precision="fp32")
-    y16 = E.fixup_forward_nhwc(pk, x, precision="bf16")
+    y16 = E.fixup_forward_nhwc(pk, x, precision="fp16")
     torch.cuda.synchronize()
     assert y16.shape == (batch, hw // 2, hw // 2, 2 * c)
     assert H.rel_err(y16, y32) < 1e-2, H.rel_err(y16, y32)
@@ -85,7 +85,7 @@ def test_encoder_bf16_agreement_with_fp32():
             vqae_b200.set_precision(m, "fp32")
             (e32,), (i32,), (l32,) = m.encoder(x.to(DEV))
             r32 = m.decoder((e32,))
-            vqae_b200.set_precision(m, "bf16")
+            vqae_b200.set_precision(m, "fp16")
             (e16,), (i16,), (l16,) = m.encoder(x.to(DEV))
             r16 = m.decoder((e16,))
         agree = float((i32 == i16).float().mean())
@@ -102,8 +102,8 @@ def test_encoder_bf16_agreement_with_fp32():
 @pytest.mark.parametrize("c,hw,batch,n", [(64, 32, 80, 6), (64, 32, 75, 3), (64, 32, 200, 11),
                                           (64, 64, 20, 4), (64, 32, 3, 5), (32, 64, 4, 3)])
 def test_persistent_chain_bit_identical_to_block_by_block(c, hw, batch, n, monkeypatch):
-    """vqae_same_chain_bf16 (one persistent launch, tiles of block i+1 ordered after their producers
-    in block i by release/acquire counters) against n launches of vqae_same_block_bf16."""
+    """vqae_same_chain_f16 (one persistent launch, tiles of block i+1 ordered after their producers
+    in block i by release/acquire counters) against n launches of vqae_same_block_f16."""
     from vqae_b200.config import pre_activation_fixup
     from vqae_b200.layers.conv_block import PreActFixupResBlock
     conf = pre_activation_fixup(n_layers=12)
@@ -121,10 +121,10 @@ def test_persistent_chain_bit_identical_to_block_by_block(c, hw, batch, n, monke
     x = torch.randn(batch, hw, hw, c, device=DEV)
     h = x
     for pk in packed:
-        h = E.fixup_forward_nhwc(pk, h, precision="bf16")
+        h = E.fixup_forward_nhwc(pk, h, precision="fp16")
     for _ in range(3):                               # repeated: flags are re-zeroed every launch
         before = E.launch_count()
-        hc = E.run_blocks_nhwc(packed, x, "bf16")
+        hc = E.run_blocks_nhwc(packed, x, "fp16")
         torch.cuda.synchronize()
         chained = bool(L.load().vqae_same_chain_supported(batch, hw, hw, c))
         assert chained == (c == 64 and batch * (hw // 16) * (hw // 32) - (hw // 16) * (hw // 32) >= 148)
@@ -155,9 +155,9 @@ _RES_HW = {64: 32, 128: 32, 32: 64}
                                        (64, 151, 2), (64, 256, 11), (128, 1, 1), (128, 3, 2),
                                        (128, 40, 3), (128, 70, 5), (32, 1, 2), (32, 5, 5), (32, 40, 3)])
 def test_resident_trunk_vs_block_by_block_and_fp32(c, batch, n, monkeypatch):
-    """vqae_trunk_resident_bf16 (residual stream in tensor memory, 4-CTA clusters, halo rows through
+    """vqae_trunk_resident_f16 (residual stream in tensor memory, 4-CTA clusters, halo rows through
     distributed shared memory, branch_conv3 accumulating into the residual) against n launches of
-    vqae_same_block_bf16 (same bf16 operands up to the rounding of scale * W3) and against the fp32
+    vqae_same_block_f16 (same bf16 operands up to the rounding of scale * W3) and against the fp32
     exact path.  Tolerance: 1e-2 of the branch magnitude (north_star bf16 bar)."""
     hw = _RES_HW[c]
     packed = E.pack_blocks(_same_blocks(c, n, 60))
@@ -167,11 +167,11 @@ def test_resident_trunk_vs_block_by_block_and_fp32(c, batch, n, monkeypatch):
     monkeypatch.setattr(E, "TRUNK_RESIDENT", False)
     h = x
     for pk in packed:
-        h = E.fixup_forward_nhwc(pk, h, precision="bf16")
+        h = E.fixup_forward_nhwc(pk, h, precision="fp16")
     monkeypatch.setattr(E, "TRUNK_RESIDENT", True)
     y32 = E.run_blocks_nhwc(packed, x, "fp32")
     before = E.launch_count()
-    y = E.run_blocks_nhwc(packed, x, "bf16")
+    y = E.run_blocks_nhwc(packed, x, "fp16")
     torch.cuda.synchronize()
     assert E.launch_count() - before == 1
     branch = float((y32 - x).abs().max())
@@ -180,14 +180,14 @@ def test_resident_trunk_vs_block_by_block_and_fp32(c, batch, n, monkeypatch):
     assert float((y - y32).abs().max()) / branch < 1e-2
     assert H.rel_err(y, y32) < 5e-3
     for _ in range(2):                               # deterministic, no state left behind
-        assert torch.equal(y, E.run_blocks_nhwc(packed, x, "bf16"))
+        assert torch.equal(y, E.run_blocks_nhwc(packed, x, "fp16"))
     # in place (out aliases x) gives the same bits
     xc = x.clone()
     lib = L.load()
     chain = E.PackedChain(packed, resident=True)
-    L.check(lib.vqae_trunk_resident_bf16(E._ptr(xc), E._ptr(xc), E._ptr(chain.weights),
+    L.check(lib.vqae_trunk_resident_f16(E._ptr(xc), E._ptr(xc), E._ptr(chain.weights),
                                          E._ptr(chain.scalars), chain.n, batch, hw, hw, c,
-                                         E._stream(xc.device)), "vqae_trunk_resident_bf16")
+                                         E._stream(xc.device)), "vqae_trunk_resident_f16")
     torch.cuda.synchronize()
     assert torch.equal(xc, y)
 
@@ -208,9 +208,9 @@ def test_resident_trunk_repeated_launches_bit_identical(c, batch, n, reps):
     outs = []
     for _ in range(reps + 1):
         y = torch.empty_like(x)
-        L.check(lib.vqae_trunk_resident_bf16(E._ptr(x), E._ptr(y), E._ptr(chain.weights),
+        L.check(lib.vqae_trunk_resident_f16(E._ptr(x), E._ptr(y), E._ptr(chain.weights),
                                              E._ptr(chain.scalars), chain.n, batch, hw, hw, c,
-                                             E._stream(x.device)), "vqae_trunk_resident_bf16")
+                                             E._stream(x.device)), "vqae_trunk_resident_f16")
         outs.append(y)
     torch.cuda.synchronize()
     bad = [i for i, o in enumerate(outs[1:], 1) if not torch.equal(o, outs[0])]
@@ -242,9 +242,9 @@ def test_resident_trunk_halo_and_wrap_exactness(c):
             x = torch.randint(1, 200, (3, hw, hw, c), device=DEV).float() / 8.0
             chain = E.PackedChain(packed, resident=True)
             out = torch.empty_like(x)
-            L.check(L.load().vqae_trunk_resident_bf16(
+            L.check(L.load().vqae_trunk_resident_f16(
                 E._ptr(x), E._ptr(out), E._ptr(chain.weights), E._ptr(chain.scalars), 1, 3, hw, hw,
-                c, E._stream(x.device)), "vqae_trunk_resident_bf16")
+                c, E._stream(x.device)), "vqae_trunk_resident_f16")
             torch.cuda.synchronize()
             ref = x + torch.roll(x, shifts=(-(ky - 1), -(kx - 1)), dims=(1, 2))
             assert torch.equal(out, ref), (ky, kx, float((out - ref).abs().max()))
@@ -273,17 +273,17 @@ def test_c128_chain_kernel_vs_fp32_path(hw, batch, n, monkeypatch):
     x = torch.randn(batch, hw, hw, 128, device=DEV)
     y32 = E.run_blocks_nhwc(packed, x, "fp32")
     before = E.launch_count()
-    y16 = E.run_blocks_nhwc(packed, x, "bf16")
+    y16 = E.run_blocks_nhwc(packed, x, "fp16")
     torch.cuda.synchronize()
     assert E.launch_count() - before == 1
     branch = y32 - x
     assert float((y16 - y32).abs().max() / branch.abs().max()) < 1e-2
     assert H.rel_err(y16, y32) < 5e-3
-    assert torch.equal(y16, E.run_blocks_nhwc(packed, x, "bf16"))
+    assert torch.equal(y16, E.run_blocks_nhwc(packed, x, "fp16"))
     # block by block through the same kernel (n_blocks = 1 each) gives the same bits
     h = x
     for pk in packed:
-        h = E.fixup_forward_nhwc(pk, h, precision="bf16")
+        h = E.fixup_forward_nhwc(pk, h, precision="fp16")
     assert torch.equal(h, y16)
 
 
@@ -298,7 +298,7 @@ def test_encoder_nd4_512_bf16_agreement_with_fp32():
         with torch.no_grad():
             vqae_b200.set_precision(m, "fp32")
             (e32,), (i32,), (l32,) = m.encoder(x.to(DEV))
-            vqae_b200.set_precision(m, "bf16")
+            vqae_b200.set_precision(m, "fp16")
             before = E.launch_count()
             (e16,), (i16,), (l16,) = m.encoder(x.to(DEV))
             launches = E.launch_count() - before
