@@ -70,6 +70,10 @@ bool quantize_tc_supported(const vqae_quantizer_params* p, int x_layout, int out
 int quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out, int64_t* indices,
                     float* loss, void* scratch, uint32_t* near_ties, float tie_rel_gap,
                     float* z_out, float* diag, int64_t N, int sm_count, cudaStream_t stream);
+int quantize_tc(const vqae_quantizer_params* p, const void* x, void* out, int dtype,
+                int64_t* indices, float* loss, void* scratch, uint32_t* near_ties,
+                float tie_rel_gap, float* z_out, float* diag, int64_t N, int sm_count,
+                cudaStream_t stream);
 size_t quantize_tc_scratch_bytes(int64_t n);
 void quantize_tc_set_prof(long long* dev_ptr);
 int device_sm_count(int* out);

@@ -344,7 +344,9 @@ bool quantize_supported(const vqae_quantizer_params* p, int x_dtype, int x_layou
                         int out_layout, bool has_out, int kernel) {
     if (!p) return false;
     const bool f32 = x_dtype == VQAE_DT_F32 && (!has_out || out_dtype == VQAE_DT_F32);
-    const bool tc = f32 && quantize_tc_supported(p, x_layout, out_layout, has_out);
+    const bool io_ok = (x_dtype == VQAE_DT_F32 || x_dtype == VQAE_DT_BF16 || x_dtype == VQAE_DT_F16) &&
+                       (!has_out || out_dtype == x_dtype);
+    const bool tc = io_ok && quantize_tc_supported(p, x_layout, out_layout, has_out);
     const bool cc = f32 && p->dim == QD && p->num_codes > 0 && p->num_codes <= 1024;
     if (kernel == VQAE_QUANT_TENSOR_CORE) return tc;
     if (kernel == VQAE_QUANT_CUDA_CORE) return cc;
@@ -357,10 +359,19 @@ int quantize_any(const vqae_quantizer_params* p, const void* x, int x_dtype, int
                  int64_t S, int kernel, cudaStream_t stream) {
     if (!p) return VQAE_ERR_BAD_ARG;
     if (kernel < VQAE_QUANT_AUTO || kernel > VQAE_QUANT_TENSOR_CORE) return VQAE_ERR_BAD_ARG;
-    if (x_dtype != VQAE_DT_F32 || (out && out_dtype != VQAE_DT_F32)) return VQAE_ERR_UNSUPPORTED;
-    if (kernel == VQAE_QUANT_TENSOR_CORE &&
-        !quantize_supported(p, x_dtype, x_layout, out_dtype, out_layout, out != nullptr, kernel))
+    if (!quantize_supported(p, x_dtype, x_layout, out_dtype, out_layout, out != nullptr, kernel))
         return VQAE_ERR_UNSUPPORTED;
+    if (x_dtype != VQAE_DT_F32) {
+        // 16-bit I/O exists on the tcgen05 kernel only (fp32 distance arithmetic inside)
+        if (!x || !indices || !loss || !p->embed || B <= 0 || S <= 0) return VQAE_ERR_BAD_ARG;
+        if (out && !p->table) return VQAE_ERR_BAD_ARG;
+        const int64_t N = B * S;
+        if (!scratch || scratch_bytes < quantizer_scratch_bytes(N)) return VQAE_ERR_SCRATCH;
+        int sm_count = 0;
+        if (int rc = device_sm_count(&sm_count)) return rc;
+        return quantize_tc(p, x, out, x_dtype, indices, loss, scratch, near_ties, tie_rel_gap, z_out,
+                           nullptr, N, sm_count, stream);
+    }
     return quantize_f32(p, reinterpret_cast<const float*>(x), x_layout, reinterpret_cast<float*>(out),
                         out_layout, indices, loss, near_ties, tie_rel_gap, z_out, scratch,
                         scratch_bytes, B, S, stream, kernel);

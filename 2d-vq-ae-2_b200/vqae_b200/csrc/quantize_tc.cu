@@ -1,4 +1,6 @@
-// Fused projected quantiser on tcgen05: HBM-bound form of quantize.cu for NHWC fp32 latents.
+// Fused projected quantiser on tcgen05: HBM-bound form of quantize.cu for NHWC latents, C = 64 or 128
+// channels, fp32 / bf16 / fp16 input and output (the distance arithmetic is fp32 in every case,
+// like torch.cdist under autocast -- SURVEY.md section 0, finding 3).
 //
 // Reference: ProjectedEMAVectorQuantizer2d.forward / EMAVectorQuantizer.forward in eval mode
 // (vq_ae/layers/vq.py:96-154,185-192).  Per tile of 128 latent vectors, all on chip:
@@ -25,6 +27,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -47,14 +50,20 @@ constexpr int TQ_THREADS = 512;
 constexpr int TQ_W_PROJ = 0, TQ_W_MMA = 4, TQ_W_COPY = 5, TQ_W_EPI = 8;
 constexpr float TQ_ERR_C = 1.0f / 32768.0f;     // c = 2^-15: bound on |D_k - exact| / T
 
-template <int C>
+template <int C, typename XT>
 struct TqCfg {
-    static constexpr int XH = C / 32;                         // 128-byte column slabs per row
-    static constexpr uint32_t X_SLAB = TQ_M * 128;            // one TMA box: 128 rows x 32 fp32
+    static constexpr int XB = sizeof(XT);                     // bytes per x / out element
+    static constexpr int CPS = 128 / XB;                      // channels per 128-byte slab
+    static constexpr int XH = C / CPS;                        // 128-byte column slabs per row
+    static constexpr uint32_t X_SLAB = TQ_M * 128;            // one TMA box: 128 rows x 128 bytes
     static constexpr uint32_t X_STAGE = XH * X_SLAB;
     static constexpr uint32_t OFF_X = 0;
     static constexpr uint32_t OFF_TAB = OFF_X + TQ_XS * X_STAGE;
-    static constexpr uint32_t TAB_BYTES = TQ_K * C * 4;
+    // E' table in the OUTPUT element type; it lives in shared memory when that fits next to the
+    // x stages (<= 64 KB: every cell but C = 128 fp32, whose rows are gathered through L1/L2)
+    static constexpr bool TAB_SMEM = TQ_K * C * XB <= 64 * 1024;
+    static constexpr bool TAB_CONVERT = XB != 4;              // fp32 table -> XT while loading
+    static constexpr uint32_t TAB_BYTES = TAB_SMEM ? TQ_K * C * XB : 0;
     static constexpr uint32_t OFF_B = OFF_TAB + TAB_BYTES;
     static constexpr uint32_t B_LBO = TQ_K * 16;
     static constexpr uint32_t OFF_A = OFF_B + TQ_CH * B_LBO;
@@ -70,10 +79,10 @@ struct TqCfg {
     static constexpr uint32_t SMEM = OFF_BAR + 160 + 1024;      // + slack to align the base to 1024 B
 };
 
-template <int C>
+template <int C, typename XT>
 struct TqArgs {
-    const float* x;          // [N][C]
-    float* out;              // [N][C] or null
+    const XT* x;             // [N][C]
+    XT* out;                 // [N][C] or null
     int64_t* idx;            // [N]
     float* partial;          // [gridDim.x] per-CTA sums of |z - e|^2
     uint32_t* tie_partial;   // [gridDim.x] per-CTA near-tie counts
@@ -155,10 +164,49 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
             a.prof[(it - 10) * 16 + (slot)] = clock64();                                \
     } while (0)
 
-template <int C>
+// 16 consecutive channels of one x row (128-byte-swizzled stage) as fp32
+template <typename XT>
+__device__ __forceinline__ void load_x16(const uint8_t* xr, uint32_t slab_bytes, int q, int sw,
+                                         float (&v)[16]) {
+    if constexpr (sizeof(XT) == 4) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = q * 4 + t;                          // 16-byte chunk of the row
+            const float4 f = *reinterpret_cast<const float4*>(xr + (j >> 3) * slab_bytes +
+                                                              (((j & 7) << 4) ^ sw));
+            v[4 * t] = f.x; v[4 * t + 1] = f.y; v[4 * t + 2] = f.z; v[4 * t + 3] = f.w;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int j = q * 2 + t;
+            const uint4 u = *reinterpret_cast<const uint4*>(xr + (j >> 3) * slab_bytes +
+                                                            (((j & 7) << 4) ^ sw));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float2 f;
+                if constexpr (std::is_same<XT, __half>::value)
+                    f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                else
+                    f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                v[8 * t + 2 * i] = f.x; v[8 * t + 2 * i + 1] = f.y;
+            }
+        }
+    }
+}
+
+template <typename XT>
+__device__ __forceinline__ XT from_float(float v) {
+    if constexpr (std::is_same<XT, __half>::value) return __float2half_rn(v);
+    else if constexpr (std::is_same<XT, __nv_bfloat16>::value) return __float2bfloat16_rn(v);
+    else return v;
+}
+
+template <int C, typename XT>
 __global__ void __launch_bounds__(TQ_THREADS, 1)
-quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ CUtensorMap tmap) {
-    using Cfg = TqCfg<C>;
+quantize_tc_kernel(const __grid_constant__ TqArgs<C, XT> a, const __grid_constant__ CUtensorMap tmap) {
+    using Cfg = TqCfg<C, XT>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B destinations must sit on the 1024-byte swizzle pattern
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -190,8 +238,8 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
             mbar_arrive_expect_tx(bar_full_x + 8 * s, Cfg::X_STAGE);
 #pragma unroll
             for (int h = 0; h < Cfg::XH; ++h)
-                tma_load_2d(sbase + Cfg::OFF_X + s * Cfg::X_STAGE + h * Cfg::X_SLAB, &tmap, h * 32,
-                            (int)n0, bar_full_x + 8 * s);
+                tma_load_2d(sbase + Cfg::OFF_X + s * Cfg::X_STAGE + h * Cfg::X_SLAB, &tmap,
+                            h * Cfg::CPS, (int)n0, bar_full_x + 8 * s);
         }
         __syncwarp();
     };
@@ -203,7 +251,7 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
         mbar_init(bar_a_full, 64);     mbar_init(bar_a_free, 1);
         mbar_init(bar_acc_full, 1);    mbar_init(bar_acc_full + 8, 1);
         mbar_init(bar_acc_free, 128);  mbar_init(bar_acc_free + 8, 128);
-        mbar_init(bar_table, 1);
+        mbar_init(bar_table, Cfg::TAB_CONVERT ? 64 : 1);
         fence_mbar_init();
     }
     if (warp == TQ_W_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -214,7 +262,7 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
     for (int i = tid; i < TQ_K * TQ_D / 4; i += TQ_THREADS)
         *reinterpret_cast<float4*>(cb + (i >> 1) * Cfg::CBP + (i & 1) * 4) =
             __ldg(reinterpret_cast<const float4*>(a.embed) + i);
-    if (a.out != nullptr && warp == TQ_W_COPY && lane == 0) {
+    if (Cfg::TAB_SMEM && !Cfg::TAB_CONVERT && a.out != nullptr && warp == TQ_W_COPY && lane == 0) {
         // E' table (64 KB) -> shared memory as 16 bulk async copies that complete on their own
         // barrier: the epilogue only needs it at its first output phase, so the load is off the
         // start-up path.  Every CTA reads the same bytes: each one starts at a different chunk,
@@ -283,6 +331,28 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
 
     float sq_acc = 0.f;                    // epilogue threads: sum over own vectors of |z - e|^2
 
+    if (Cfg::TAB_SMEM && Cfg::TAB_CONVERT && a.out != nullptr && (warp == 6 || warp == 7)) {
+        // 16-bit outputs: the E' table is rounded to the output type once, on its way into shared
+        // memory, by the two otherwise idle warps (off the start-up path of every other role)
+        const int t64 = tid - 6 * 32;
+        XT* tab = reinterpret_cast<XT*>(smem + Cfg::OFF_TAB);
+        constexpr int NV = TQ_K * C / 4;               // float4 groups
+        for (int i0 = t64; i0 < NV; i0 += 64 * 8) {
+            float4 f[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i0 + u * 64 < NV) f[u] = __ldg(reinterpret_cast<const float4*>(a.table) + i0 + u * 64);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i0 + u * 64 < NV) {
+                    XT* d = tab + (size_t)(i0 + u * 64) * 4;
+                    d[0] = from_float<XT>(f[u].x); d[1] = from_float<XT>(f[u].y);
+                    d[2] = from_float<XT>(f[u].z); d[3] = from_float<XT>(f[u].w);
+                }
+        }
+        mbar_arrive(bar_table);
+    }
+
     if (warp == TQ_W_COPY) {
         // ================= copy warp =================
         for (int it = TQ_XS; it < my_tiles; ++it) {
@@ -339,35 +409,25 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
                 for (int d = 0; d < 4; ++d) zp[r][d] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < C / 16; ++q) {                 // 16 channels at a time
-                float4 xa[4], xb[4];
+                float xsa[16], xsb[16];
+                load_x16<XT>(xr, Cfg::X_SLAB, q, sw, xsa);
+                load_x16<XT>(xr + 32 * 128, Cfg::X_SLAB, q, sw, xsb);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int j = q * 4 + t;
-                    const uint8_t* src = xr + (j >> 3) * Cfg::X_SLAB + (((j & 7) << 4) ^ sw);
-                    xa[t] = *reinterpret_cast<const float4*>(src);
-                    xb[t] = *reinterpret_cast<const float4*>(src + 32 * 128);
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float xsa[4] = {xa[t].x, xa[t].y, xa[t].z, xa[t].w};
-                    const float xsb[4] = {xb[t].x, xb[t].y, xb[t].z, xb[t].w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int c = (q * 4 + t) * 4 + u;
-                        const float4 wa = wsm4[c * 2], wb = wsm4[c * 2 + 1];
-                        const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
-                        const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
-                        const float2 xx = make_float2(xsa[u], xsa[u]);
-                        const float2 yy = make_float2(xsb[u], xsb[u]);
-                        zp[0][0] = __ffma2_rn(xx, w0, zp[0][0]);
-                        zp[1][0] = __ffma2_rn(yy, w0, zp[1][0]);
-                        zp[0][1] = __ffma2_rn(xx, w1, zp[0][1]);
-                        zp[1][1] = __ffma2_rn(yy, w1, zp[1][1]);
-                        zp[0][2] = __ffma2_rn(xx, w2, zp[0][2]);
-                        zp[1][2] = __ffma2_rn(yy, w2, zp[1][2]);
-                        zp[0][3] = __ffma2_rn(xx, w3, zp[0][3]);
-                        zp[1][3] = __ffma2_rn(yy, w3, zp[1][3]);
-                    }
+                for (int u = 0; u < 16; ++u) {
+                    const int c = q * 16 + u;
+                    const float4 wa = wsm4[c * 2], wb = wsm4[c * 2 + 1];
+                    const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
+                    const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+                    const float2 xx = make_float2(xsa[u], xsa[u]);
+                    const float2 yy = make_float2(xsb[u], xsb[u]);
+                    zp[0][0] = __ffma2_rn(xx, w0, zp[0][0]);
+                    zp[1][0] = __ffma2_rn(yy, w0, zp[1][0]);
+                    zp[0][1] = __ffma2_rn(xx, w1, zp[0][1]);
+                    zp[1][1] = __ffma2_rn(yy, w1, zp[1][1]);
+                    zp[0][2] = __ffma2_rn(xx, w2, zp[0][2]);
+                    zp[1][2] = __ffma2_rn(yy, w2, zp[1][2]);
+                    zp[0][3] = __ffma2_rn(xx, w3, zp[0][3]);
+                    zp[1][3] = __ffma2_rn(yy, w3, zp[1][3]);
                 }
             }
             // hand the x stage back only after every value read from it has been consumed by the fmaf
@@ -597,31 +657,36 @@ quantize_tc_kernel(const __grid_constant__ TqArgs<C> a, const __grid_constant__ 
             // out rows = table[idx]: 32 / (C/4) rows per warp instruction, 128-bit, line-coalesced;
             // shuffles, table reads and stores are issued in batches of 8 (memory-level parallelism)
             if (a.out != nullptr) {
-                if (!table_ready) {                    // first output phase of this warp
+                if (Cfg::TAB_SMEM && !table_ready) {   // first output phase of this warp
                     mbar_wait(bar_table, 0);
                     table_ready = true;
                 }
-                constexpr int LPR = C / 4;             // lanes per row
+                constexpr int LPR = C * Cfg::XB / 16;  // lanes per row (16 bytes each)
                 constexpr int RPI = 32 / LPR;          // rows per iteration
                 constexpr int NIT = 32 / RPI;
+                constexpr int EPL = 16 / Cfg::XB;      // elements per lane
                 const int sub = lane / LPR, c4 = lane % LPR;
-                float* obase = a.out + (n0 + wq * 32 + sub) * C + c4 * 4;
+                XT* obase = a.out + (n0 + wq * 32 + sub) * C + c4 * EPL;
                 const int64_t rows_left = a.N - (n0 + wq * 32 + sub);
 #pragma unroll
                 for (int i0 = 0; i0 < NIT; i0 += 8) {
                     int kk[8];
-                    float4 val[8];
+                    uint4 val[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         kk[u] = __shfl_sync(0xffffffffu, bidx, (i0 + u) * RPI + sub);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        val[u] = *reinterpret_cast<const float4*>(smem + Cfg::OFF_TAB +
-                                                                  (kk[u] * C + c4 * 4) * 4);
+                    for (int u = 0; u < 8; ++u) {
+                        if constexpr (Cfg::TAB_SMEM)
+                            val[u] = *reinterpret_cast<const uint4*>(
+                                smem + Cfg::OFF_TAB + (kk[u] * C + c4 * EPL) * Cfg::XB);
+                        else                            // fp32 rows of the 128 KB table through L1/L2
+                            val[u] = __ldg(reinterpret_cast<const uint4*>(a.table + kk[u] * C + c4 * EPL));
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         if ((i0 + u) * RPI < rows_left)
-                            *reinterpret_cast<float4*>(obase + (size_t)(i0 + u) * RPI * C) = val[u];
+                            *reinterpret_cast<uint4*>(obase + (size_t)(i0 + u) * RPI * C) = val[u];
                 }
             }
             if (wq == 0) TQ_PROF(11);
@@ -697,8 +762,9 @@ EncodeTiledFn encode_tiled_fn() {
 
 bool quantize_tc_supported(const vqae_quantizer_params* p, int x_layout, int out_layout,
                            bool has_out) {
-    return p->w_in != nullptr && p->b_in != nullptr && p->num_codes == TQ_K && p->dim == TQ_D && p->c == 64 &&
-           x_layout == VQAE_LAYOUT_NHWC && (!has_out || out_layout == VQAE_LAYOUT_NHWC);
+    return p->w_in != nullptr && p->b_in != nullptr && p->num_codes == TQ_K && p->dim == TQ_D &&
+           (p->c == 64 || p->c == 128) && x_layout == VQAE_LAYOUT_NHWC &&
+           (!has_out || out_layout == VQAE_LAYOUT_NHWC);
 }
 
 size_t quantize_tc_scratch_bytes(int64_t n) {
@@ -728,33 +794,35 @@ static unsigned int* next_done_counter() {
 static long long* g_tq_prof = nullptr;
 void quantize_tc_set_prof(long long* dev_ptr) { g_tq_prof = dev_ptr; }
 
-int quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out, int64_t* indices,
-                    float* loss, void* scratch, uint32_t* near_ties, float tie_rel_gap,
-                    float* z_out, float* diag, int64_t N, int sm_count, cudaStream_t stream) {
-    constexpr int C = 64;
-    using Cfg = TqCfg<C>;
+template <int C, typename XT>
+static int launch_quantize_tc(const vqae_quantizer_params* p, const void* x, void* out,
+                              int64_t* indices, float* loss, void* scratch, uint32_t* near_ties,
+                              float tie_rel_gap, float* z_out, float* diag, int64_t N, int sm_count,
+                              CUtensorMapDataType tm_dtype, cudaStream_t stream) {
+    using Cfg = TqCfg<C, XT>;
     if (N > 0x7fffff00ll) return VQAE_ERR_UNSUPPORTED;        // TMA row coordinate is an int32
-    TqArgs<C> a;
-    a.x = x; a.out = out; a.idx = indices; a.near_ties = near_ties;
+    TqArgs<C, XT> a;
+    a.x = reinterpret_cast<const XT*>(x); a.out = reinterpret_cast<XT*>(out);
+    a.idx = indices; a.near_ties = near_ties;
     a.z_out = z_out; a.diag = diag; a.prof = g_tq_prof;
     a.embed = p->embed; a.table = p->table; a.N = N;
     a.num_tiles = (int)((N + TQ_M - 1) / TQ_M);
     a.tie_rel_gap = tie_rel_gap;
     a.margin = 4.f * TQ_ERR_C + 2.f * tie_rel_gap;
     a.w_in = p->w_in; a.b_in = p->b_in;
-    // [N][C] fp32 viewed as a 2-D tensor; box = 128 rows x 32 channels (128 bytes), 128B swizzle
+    // [N][C] viewed as a 2-D tensor; box = 128 rows x 128 bytes of channels, 128B swizzle
     EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return VQAE_ERR_UNSUPPORTED;
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)N};
-    const cuuint64_t gstride[1] = {(cuuint64_t)C * sizeof(float)};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)TQ_M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)C * sizeof(XT)};
+    const cuuint32_t box[2] = {(cuuint32_t)Cfg::CPS, (cuuint32_t)TQ_M};
     const cuuint32_t estr[2] = {1u, 1u};
-    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstride, box,
-               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    if (encode(&tmap, tm_dtype, 2, const_cast<void*>(x), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return VQAE_ERR_UNSUPPORTED;
-    auto kern = quantize_tc_kernel<C>;
+    auto kern = quantize_tc_kernel<C, XT>;
     static PerDevice<bool> attr_set{};
     if (!attr_set.cur()) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -771,6 +839,34 @@ int quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out, 
     a.commitment_cost = p->commitment_cost;
     kern<<<grid, TQ_THREADS, Cfg::SMEM, stream>>>(a, tmap);
     return check_launch();
+}
+
+// x / out: NHWC, both of element type `dtype` (VQAE_DT_F32 / VQAE_DT_BF16 / VQAE_DT_F16)
+int quantize_tc(const vqae_quantizer_params* p, const void* x, void* out, int dtype,
+                int64_t* indices, float* loss, void* scratch, uint32_t* near_ties,
+                float tie_rel_gap, float* z_out, float* diag, int64_t N, int sm_count,
+                cudaStream_t stream) {
+#define TQ_LAUNCH(CC, T, TM)                                                                      \
+    return launch_quantize_tc<CC, T>(p, x, out, indices, loss, scratch, near_ties, tie_rel_gap,   \
+                                     z_out, diag, N, sm_count, TM, stream)
+    if (p->c == 64) {
+        if (dtype == VQAE_DT_F32) TQ_LAUNCH(64, float, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        if (dtype == VQAE_DT_BF16) TQ_LAUNCH(64, __nv_bfloat16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        if (dtype == VQAE_DT_F16) TQ_LAUNCH(64, __half, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    } else if (p->c == 128) {
+        if (dtype == VQAE_DT_F32) TQ_LAUNCH(128, float, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        if (dtype == VQAE_DT_BF16) TQ_LAUNCH(128, __nv_bfloat16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        if (dtype == VQAE_DT_F16) TQ_LAUNCH(128, __half, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    }
+#undef TQ_LAUNCH
+    return VQAE_ERR_UNSUPPORTED;
+}
+
+int quantize_tc_f32(const vqae_quantizer_params* p, const float* x, float* out, int64_t* indices,
+                    float* loss, void* scratch, uint32_t* near_ties, float tie_rel_gap,
+                    float* z_out, float* diag, int64_t N, int sm_count, cudaStream_t stream) {
+    return quantize_tc(p, x, out, VQAE_DT_F32, indices, loss, scratch, near_ties, tie_rel_gap, z_out,
+                       diag, N, sm_count, stream);
 }
 
 }  // namespace vqae

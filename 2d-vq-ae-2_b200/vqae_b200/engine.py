@@ -576,7 +576,7 @@ def quantize(pq: PackedQuantizer, x: Tensor, x_nhwc: bool, out_nhwc: bool, batch
 
 
 # I/O dtypes of the quantiser call for which a kernel is built (config 2 cells)
-QUANT_IO_DTYPES = ("fp32",)
+QUANT_IO_DTYPES = ("fp32", "bf16", "fp16")
 
 
 class QuantizeBuffers:

@@ -12,8 +12,10 @@ from vqae_b200.layers.vq import ProjectedEMAVectorQuantizer2d  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-pq = ProjectedEMAVectorQuantizer2d(256, 64, 1.0, 0.99, 1e-5, 8).eval().to(dev)
-x = torch.randn(512, 1024, 64, device=dev)
+C = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+DT = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[sys.argv[2] if len(sys.argv) > 2 else "fp32"]
+pq = ProjectedEMAVectorQuantizer2d(256, C, 1.0, 0.99, 1e-5, 8).eval().to(dev)
+x = torch.randn(512, 1024, C, device=dev).to(DT)
 packed = pq.packed()
 prof = torch.zeros(64, dtype=torch.int64, device=dev)
 lib = L.load()

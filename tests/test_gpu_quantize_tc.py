@@ -170,3 +170,51 @@ def test_module_forward_uses_tc_path_channels_last():
     out2, idx2, loss2, _, _ = E.quantize(pq.packed(), xn, True, True, 4, 1024, kernel="cuda_core")
     assert torch.equal(idx.reshape(-1), idx2) and torch.equal(
         out.permute(0, 2, 3, 1).reshape(-1), out2)
+
+
+_IO = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+@pytest.mark.parametrize("c", [64, 128])
+@pytest.mark.parametrize("io", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("batch,spatial", [(3, 1024), (1, 200), (37, 1024)])
+def test_tc_cells_bit_identical_to_cuda_core_kernel(c, io, batch, spatial):
+    """Every (C, I/O dtype) cell of config 2 on the tcgen05 kernel against the exact CUDA-core kernel
+    fed the same values in fp32 (a 16-bit input converts to fp32 exactly; the distance arithmetic
+    is fp32 in both): indices, loss, near-tie count and latents bit-identical, the output rows equal
+    to the fp32 rows rounded to the output type."""
+    pq = ProjectedEMAVectorQuantizer2d(256, c, 1.0, 0.99, 1e-5, 8).eval()
+    sd = S.make_state_dict(pq.state_dict(), seed=9, regime="perturbed")
+    pq.load_state_dict(sd)
+    pq = pq.to(DEV)
+    packed = pq.packed()
+    dt = _IO[io]
+    g = torch.Generator().manual_seed(batch * 7 + spatial + c)
+    x = torch.randn(batch, spatial, c, generator=g).to(DEV).to(dt)
+    out, idx, loss, ties, z = E.quantize(packed, x, True, True, batch, spatial, want_z=True,
+                                         kernel="tensor_core")
+    out2, idx2, loss2, ties2, z2 = E.quantize(packed, x.float(), True, True, batch, spatial,
+                                              want_z=True, kernel="cuda_core")
+    torch.cuda.synchronize()
+    assert out.dtype == dt
+    assert torch.equal(idx, idx2) and torch.equal(z, z2)
+    # the two kernels sum the same per-vector terms over different partitions (per CTA / per tile)
+    assert abs(loss.item() - loss2.item()) <= 2e-6 * abs(loss2.item()) and int(ties) == int(ties2)
+    assert torch.equal(out, out2.to(dt))
+    # repeated launches: same bits
+    for _ in range(3):
+        o3, i3, l3, t3, _ = E.quantize(packed, x, True, True, batch, spatial, kernel="tensor_core")
+        assert torch.equal(i3, idx) and torch.equal(o3, out) and torch.equal(l3, loss)
+
+
+def test_forced_kernel_choice_is_reported_not_silently_replaced():
+    """kernel="tensor_core" on a shape the tcgen05 kernel is not built for is an error, and 16-bit
+    I/O on the CUDA-core kernel is refused (no silent substitution)."""
+    pq = ProjectedEMAVectorQuantizer2d(256, 32, 1.0, 0.99, 1e-5, 8).eval().to(DEV)
+    x = torch.randn(2, 64, 32, device=DEV)
+    with pytest.raises(L.VqaeError):
+        E.quantize(pq.packed(), x, True, True, 2, 64, kernel="tensor_core")
+    pq64 = _module()
+    with pytest.raises(L.VqaeError):
+        E.quantize(pq64.packed(), torch.randn(2, 64, 64, device=DEV).half(), True, True, 2, 64,
+                   kernel="cuda_core")
