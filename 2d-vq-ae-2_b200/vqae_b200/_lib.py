@@ -73,6 +73,7 @@ SIGNATURES = {
     "vqae_pack_elems": (_sz, [_i, _i, _i, _i]),
     "vqae_pack_batched": (_i, [_vp, _i, _i, _vp]),
     "vqae_stem_in_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _fp, _fp, _vp]),
+    "vqae_stem_in": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _fp, _fp, _vp]),
     "vqae_stem_out_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "vqae_conv_f32": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _i, _f, _f, _f, _vp]),
     "vqae_bicubic_up2_f32": (_i, [_vp, _vp, _i64, _i, _i, _i, _f, _vp]),

@@ -12,17 +12,17 @@ _fp = C.POINTER(C.c_float)
 
 SIGNATURES: dict = {
     "vqae_pack_same_block_f16": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
-    "vqae_same_block_f16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
+    "vqae_same_block_f16": (_i, [_vp, _vp, _i, _vp, _fp, _i64, _i, _i, _i, _vp]),
     "vqae_same_chain_flag_bytes": (C.c_size_t, [_i, _i64]),
     "vqae_same_chain_supported": (_i, [_i64, _i, _i, _i]),
     "vqae_same_chain_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i, _i64, _i, _i, _i, _vp]),
     "vqae_trunk_resident_max_clusters": (_i, []),
     "vqae_trunk_resident_supported": (_i, [_i64, _i, _i, _i]),
     "vqae_pack_resident_block_f16": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp]),
-    "vqae_trunk_resident_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
+    "vqae_trunk_resident_f16": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "vqae_down_block_pack_elems": (C.c_size_t, [_i]),
     "vqae_pack_down_block_f16": (_i, [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
-    "vqae_down_block_f16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
+    "vqae_down_block_f16": (_i, [_vp, _vp, _i, _vp, _fp, _i64, _i, _i, _i, _vp]),
 }
 
 # include/vqae_b200_testaids.h (libvqae_b200_testaids.so): tests/ and profiles/ only
@@ -31,6 +31,6 @@ AIDS_SIGNATURES: dict = {
     "vqae_tc_mma_bench2": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
     "vqae_tc_selftest": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "vqae_trunk_resident_set_profile": (None, [_vp]),
-    "vqae_same_block_bf16_profile": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp, _vp]),
+    "vqae_same_block_f16_profile": (_i, [_vp, _vp, _i, _vp, _fp, _i64, _i, _i, _i, _vp, _vp]),
     "vqae_quantize_tc_set_profile": (None, [_vp]),
 }

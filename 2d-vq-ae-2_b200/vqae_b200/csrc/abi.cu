@@ -95,8 +95,15 @@ int vqae_pack_batched(const vqae_pack_desc* descs_device, int n_descs, int max_e
 int vqae_stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w_oihw,
                      const float* bias, float* out, int64_t batch, int height, int width,
                      int c_out, const float* mean_host, const float* std_host, void* stream) {
-    return stem_in_f32(x, x_dtype, x_layout, w_oihw, bias, out, batch, height, width, c_out,
-                       mean_host, std_host, (cudaStream_t)stream);
+    return stem_in_f32(x, x_dtype, x_layout, w_oihw, bias, out, VQAE_DT_F32, batch, height, width,
+                       c_out, mean_host, std_host, (cudaStream_t)stream);
+}
+
+int vqae_stem_in(const void* x, int x_dtype, int x_layout, const float* w_oihw, const float* bias,
+                 void* out, int out_dtype, int64_t batch, int height, int width, int c_out,
+                 const float* mean_host, const float* std_host, void* stream) {
+    return stem_in_f32(x, x_dtype, x_layout, w_oihw, bias, out, out_dtype, batch, height, width,
+                       c_out, mean_host, std_host, (cudaStream_t)stream);
 }
 
 int vqae_stem_out_f32(const float* x, const float* w_oihw, const float* bias, float* out,
@@ -231,12 +238,12 @@ int device_sm_count(int* out) {
 }  // namespace vqae
 extern "C" {
 
-int vqae_same_block_f16(const float* x, float* out, const void* w_packed,
+int vqae_same_block_f16(const void* x, void* out, int io_dtype, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c,
                          void* stream) {
     int sm_count = 0;
     if (int rc = device_sm_count(&sm_count)) return rc;
-    return same_block_tc(x, out, w_packed, scalars8_host, batch, height, width, c, sm_count,
+    return same_block_tc(x, out, io_dtype, w_packed, scalars8_host, batch, height, width, c, sm_count,
                          nullptr, (cudaStream_t)stream);
 }
 
@@ -274,10 +281,10 @@ int vqae_pack_resident_block_f16(const float* w1_oihw, const float* w2_oihw, con
                                     (cudaStream_t)stream);
 }
 
-int vqae_trunk_resident_f16(const float* x, float* out, const void* w_packed_all,
+int vqae_trunk_resident_f16(const void* x, void* out, int io_dtype, const void* w_packed_all,
                              const float* scalars_dev, int n_blocks, int64_t batch, int height,
                              int width, int c, void* stream) {
-    return trunk_resident_tc(x, out, w_packed_all, scalars_dev, n_blocks, batch, height, width, c,
+    return trunk_resident_tc(x, out, io_dtype, w_packed_all, scalars_dev, n_blocks, batch, height, width, c,
                              (cudaStream_t)stream);
 }
 
@@ -290,12 +297,12 @@ int vqae_pack_down_block_f16(const float* w1_oihw, const float* w2_oihw, const f
                                 (cudaStream_t)stream);
 }
 
-int vqae_down_block_f16(const float* x, float* out, const void* w_packed,
+int vqae_down_block_f16(const void* x, void* out, int io_dtype, const void* w_packed,
                          const float* scalars8_host, int64_t batch, int height, int width, int c_in,
                          void* stream) {
     int sm_count = 0;
     if (int rc = device_sm_count(&sm_count)) return rc;
-    return down_block_tc(x, out, w_packed, scalars8_host, batch, height, width, c_in, sm_count,
+    return down_block_tc(x, out, io_dtype, w_packed, scalars8_host, batch, height, width, c_in, sm_count,
                          (cudaStream_t)stream);
 }
 

@@ -36,7 +36,7 @@ int up_tail_f32(const float* t2, const float* s1, const float* w3, float* out, i
 int normalize_u8(const uint8_t* img, float* out, int64_t B, int H, int W, const float* mean,
                  const float* stdv, int out_layout, cudaStream_t stream);
 int stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w, const float* bias,
-                float* out, int64_t B, int H, int W, int c_out, const float* mean,
+                void* out, int out_dtype, int64_t B, int H, int W, int c_out, const float* mean,
                 const float* stdv, cudaStream_t stream);
 int stem_out_f32(const float* x, const float* w, const float* bias, float* out, int out_layout,
                  int64_t B, int H, int W, int c_in, cudaStream_t stream);
@@ -79,9 +79,9 @@ void quantize_tc_set_prof(long long* dev_ptr);
 int device_sm_count(int* out);
 
 // tc_kernels.cu (tcgen05 bf16 path)
-int same_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
-                  int64_t B, int H, int W, int C, int sm_count, long long* prof,
-                  cudaStream_t stream);
+int same_block_tc(const void* x, void* out, int io_dtype, const void* w_packed,
+                  const float* scalars8, int64_t B, int H, int W, int C, int sm_count,
+                  long long* prof, cudaStream_t stream);
 int pack_same_block_f16(const float* w1, const float* w2, const float* w3, int C, void* packed,
                          cudaStream_t stream);
 
@@ -98,8 +98,9 @@ int pack_resident_block_f16(const float* w1, const float* w2, const float* w3, i
                              void* packed, cudaStream_t stream);
 int trunk_resident_max_clusters(int* out);
 void trunk_resident_set_prof(long long* dev_ptr);
-int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, const float* scalars_dev,
-                      int n_blocks, int64_t B, int H, int W, int C, cudaStream_t stream);
+int trunk_resident_tc(const void* x, void* out, int io_dtype, const void* w_packed_all,
+                      const float* scalars_dev, int n_blocks, int64_t B, int H, int W, int C,
+                      cudaStream_t stream);
 
 // tc_bench.cu
 int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, int mode, long long* out,
@@ -108,7 +109,8 @@ int tc_mma_bench2(int M, int N, int reps, int n_issuers, int ctas_per_sm, int mo
 size_t down_block_pack_elems(int CI);
 int pack_down_block_f16(const float* w1, const float* w2, const float* w3, const float* ws, int CI,
                          float scale, void* packed, cudaStream_t stream);
-int down_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
-                  int64_t B, int H, int W, int CI, int sm_count, cudaStream_t stream);
+int down_block_tc(const void* x, void* out, int io_dtype, const void* w_packed,
+                  const float* scalars8, int64_t B, int H, int W, int CI, int sm_count,
+                  cudaStream_t stream);
 
 }  // namespace vqae

@@ -3,6 +3,8 @@
 //                    (conf/transforms/camelyon16_transforms.yaml:1-23, transforms/normalize.yaml)
 //   stem_in_f32    : Encoder.in_stem  (vq_ae/model.py:141,198)  3x3, zero pad, bias, 3 -> 8
 //   stem_out_f32   : Decoder.out_stem (vq_ae/model.py:291)      3x3, zero pad, bias, 8 -> 3
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -125,11 +127,12 @@ stem_in_kernel(const void* __restrict__ xv, const float* __restrict__ w_oihw,
 // contiguous bytes.  Accumulation order per output is that of stem_in_kernel (bias, then ky, kx, c).
 constexpr int ST_TH = 8, ST_TW = 128, ST_PW = ST_TW + 8;      // padded row pitch (floats)
 
-template <int XKIND>
+template <int XKIND, bool HALF_OUT>
 __global__ void __launch_bounds__(256)
 stem_in_tiled_kernel(const void* __restrict__ xv, const float* __restrict__ w_oihw,
-                     const float* __restrict__ bias, float* __restrict__ out, int H, int W,
+                     const float* __restrict__ bias, void* __restrict__ outv, int H, int W,
                      int tiles_x, int tiles_y, Norm3 n) {
+    float* out = reinterpret_cast<float*>(outv);
     // input tile [c][row][col] first, output staging [row][4-px group][8 + 1 float4] afterwards
     __shared__ __align__(16) float ostage[ST_TH * 32 * 9 * 4];
     float (*tile)[ST_TH + 2][ST_PW] = reinterpret_cast<float (*)[ST_TH + 2][ST_PW]>(ostage);
@@ -216,12 +219,31 @@ stem_in_tiled_kernel(const void* __restrict__ xv, const float* __restrict__ w_oi
         stage[(gy * 32 + gx) * 9 + 2 * p + 1] = make_float4(acc[p][2].x, acc[p][2].y, acc[p][3].x, acc[p][3].y);
     }
     __syncthreads();
+    if constexpr (HALF_OUT) {
+        // fp16 stream: one pixel (8 channels = 16 bytes) per thread and step, 2 KB rows
+        __half* outh = reinterpret_cast<__half*>(outv);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int i = tid + 256 * k;             // float4 index in the tile: row (i >> 8), 256 per row
-        const int r = i >> 8, j = i & 255;       // j = 8 * group + chunk
-        float4* dst = reinterpret_cast<float4*>(out + ((b * H + y0 + r) * (int64_t)W + x0) * 8);
-        dst[j] = stage[(r * 32 + (j >> 3)) * 9 + (j & 7)];
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + 256 * k;         // pixel index in the tile: row (i >> 7), 128 per row
+            const int r = i >> 7, j = i & 127;   // j = 4 * group + pixel of the group
+            const float4 lo = stage[(r * 32 + (j >> 2)) * 9 + 2 * (j & 3)];
+            const float4 hi = stage[(r * 32 + (j >> 2)) * 9 + 2 * (j & 3) + 1];
+            const __half2 h0 = __floats2half2_rn(lo.x, lo.y), h1 = __floats2half2_rn(lo.z, lo.w);
+            const __half2 h2 = __floats2half2_rn(hi.x, hi.y), h3 = __floats2half2_rn(hi.z, hi.w);
+            uint4 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+            u.z = *reinterpret_cast<const uint32_t*>(&h2); u.w = *reinterpret_cast<const uint32_t*>(&h3);
+            uint4* dst = reinterpret_cast<uint4*>(outh + ((b * H + y0 + r) * (int64_t)W + x0) * 8);
+            dst[j] = u;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = tid + 256 * k;         // float4 index in the tile: row (i >> 8), 256 per row
+            const int r = i >> 8, j = i & 255;   // j = 8 * group + chunk
+            float4* dst = reinterpret_cast<float4*>(out + ((b * H + y0 + r) * (int64_t)W + x0) * 8);
+            dst[j] = stage[(r * 32 + (j >> 3)) * 9 + (j & 7)];
+        }
     }
 }
 
@@ -299,9 +321,9 @@ int normalize_u8(const uint8_t* img, float* out, int64_t B, int H, int W, const 
 }
 
 int stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w, const float* bias,
-                float* out, int64_t B, int H, int W, int c_out, const float* mean,
+                void* outv, int out_dtype, int64_t B, int H, int W, int c_out, const float* mean,
                 const float* stdv, cudaStream_t stream) {
-    if (!x || !w || !bias || !out || B <= 0 || H <= 0 || W <= 0) return VQAE_ERR_BAD_ARG;
+    if (!x || !w || !bias || !outv || B <= 0 || H <= 0 || W <= 0) return VQAE_ERR_BAD_ARG;
     if (c_out != 8) return VQAE_ERR_UNSUPPORTED;
     const int64_t npix = B * H * W;
     const unsigned grid = ceil_div_u(npix, 256);
@@ -309,24 +331,33 @@ int stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w, const 
                        B * (H / ST_TH) * (W / ST_TW) <= 0x7fffffff;
     const int txs = W / ST_TW, tys = H / ST_TH;
     const unsigned tgrid = tiled ? (unsigned)(B * txs * tys) : 0u;
+    // the fp16 stream output exists in the tiled form (W % 128 == 0, H % 8 == 0)
+    const bool half_out = out_dtype == VQAE_DT_F16;
+    if ((half_out && !tiled) || (!half_out && out_dtype != VQAE_DT_F32)) return VQAE_ERR_UNSUPPORTED;
+    float* out = reinterpret_cast<float*>(outv);
     Norm3 n{};
+    int kind;
     if (x_dtype == VQAE_DT_U8) {
         if (!mean || !stdv) return VQAE_ERR_BAD_ARG;
         if (x_layout != VQAE_LAYOUT_NHWC) return VQAE_ERR_UNSUPPORTED;
         n = make_norm(mean, stdv);
-        if (tiled) stem_in_tiled_kernel<2><<<tgrid, 256, 0, stream>>>(x, w, bias, out, H, W, txs, tys, n);
-        else stem_in_kernel<2><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
+        kind = 2;
     } else if (x_dtype == VQAE_DT_F32) {
-        if (x_layout == VQAE_LAYOUT_NCHW) {
-            if (tiled) stem_in_tiled_kernel<0><<<tgrid, 256, 0, stream>>>(x, w, bias, out, H, W, txs, tys, n);
-            else stem_in_kernel<0><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
-        } else {
-            if (tiled) stem_in_tiled_kernel<1><<<tgrid, 256, 0, stream>>>(x, w, bias, out, H, W, txs, tys, n);
-            else stem_in_kernel<1><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
-        }
+        kind = x_layout == VQAE_LAYOUT_NCHW ? 0 : 1;
     } else {
         return VQAE_ERR_UNSUPPORTED;
     }
+#define STEM_TILED(K, HO) stem_in_tiled_kernel<K, HO><<<tgrid, 256, 0, stream>>>(x, w, bias, outv, H, W, txs, tys, n)
+    if (tiled && half_out) {
+        if (kind == 2) STEM_TILED(2, true); else if (kind == 0) STEM_TILED(0, true); else STEM_TILED(1, true);
+    } else if (tiled) {
+        if (kind == 2) STEM_TILED(2, false); else if (kind == 0) STEM_TILED(0, false); else STEM_TILED(1, false);
+    } else {
+        if (kind == 2) stem_in_kernel<2><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
+        else if (kind == 0) stem_in_kernel<0><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
+        else stem_in_kernel<1><<<grid, 256, 0, stream>>>(x, w, bias, out, npix, H, W, n);
+    }
+#undef STEM_TILED
     return check_launch();
 }
 

@@ -220,5 +220,52 @@ __device__ __forceinline__ uint4 add_pack8(const float* v, float add) {
     return o;
 }
 
+// ---- activation stream I/O: the NHWC tensors between kernels are fp32 or fp16 -----------------
+// (fp16 in the reduced-precision path: half the HBM bytes of the block-boundary tensors; the
+// arithmetic between load and store is fp32 either way)
+template <typename T>
+struct StreamIO;
+template <>
+struct StreamIO<float> {
+    static constexpr int DT = 0;                          // VQAE_DT_F32
+    __device__ static __forceinline__ void load8(const float* p, float (&v)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    __device__ static __forceinline__ float4 load4(const float* p) {
+        return __ldg(reinterpret_cast<const float4*>(p));
+    }
+    __device__ static __forceinline__ void store4(float* p, float4 v) {
+        *reinterpret_cast<float4*>(p) = v;
+    }
+};
+template <>
+struct StreamIO<__half> {
+    static constexpr int DT = 3;                          // VQAE_DT_F16
+    __device__ static __forceinline__ void load8(const __half* p, float (&v)[8]) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    __device__ static __forceinline__ float4 load4(const __half* p) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    __device__ static __forceinline__ void store4(__half* p, float4 v) {
+        const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&a);
+        u.y = *reinterpret_cast<const uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+};
+
 }  // namespace tc
 }  // namespace vqae

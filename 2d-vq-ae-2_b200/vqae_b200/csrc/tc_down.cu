@@ -60,16 +60,17 @@ struct DownCfg {
 };
 
 struct DownArgs {
-    const float* x;               // NHWC fp32 [B,H,W,CI]
-    float* out;                   // NHWC fp32 [B,H/2,W/2,CO]
+    const void* x;                // NHWC fp32 or fp16 [B,H,W,CI]
+    void* out;                    // NHWC, same element type [B,H/2,W/2,CO]
     const __nv_bfloat16* w;       // [W1 | W2 x4 | scale*W3 | Ws x4] in canonical [k-chunk][n][8]
     int n_tiles, H, W, tiles_x, tiles_per_img;
     float b1a, b1b, b2a, b2b, b3a, b3b, b1c, bsum;   // bsum = b4 + b1d
 };
 
-template <int CI, int CO>
+template <int CI, int CO, typename TIO>
 __global__ void __launch_bounds__(DownCfg<CI, CO>::THREADS, DownCfg<CI, CO>::MIN_CTAS)
 down_block_tc_kernel(DownArgs a) {
+    using IO = StreamIO<TIO>;
     using Cfg = DownCfg<CI, CO>;
     constexpr int CIP = Cfg::CIP, KCI = Cfg::KCI, NW = Cfg::NW, NC = Cfg::NC, UCH = Cfg::UCH;
     constexpr int MMA_WARP = NW;
@@ -124,8 +125,8 @@ down_block_tc_kernel(DownArgs a) {
         const int img = tile / a.tiles_per_img;
         const int trem = tile - img * a.tiles_per_img;
         const int r0 = (trem / a.tiles_x) * DB_OH, c0 = (trem % a.tiles_x) * DB_OW;   // output coords
-        const float* ximg = a.x + (size_t)img * a.H * a.W * CI;
-        float* oimg = a.out + (size_t)img * Ho * Wo * CO;
+        const TIO* ximg = reinterpret_cast<const TIO*>(a.x) + (size_t)img * a.H * a.W * CI;
+        TIO* oimg = reinterpret_cast<TIO*>(a.out) + (size_t)img * Ho * Wo * CO;
 
         // ---- P: 16 x 32 input pixels -> A1 = bf16(elu(x + b1a) + b1b), As = bf16(x + b1c),
         //      both scattered into the four parity planes ----
@@ -133,7 +134,7 @@ down_block_tc_kernel(DownArgs a) {
             constexpr int ITEMS = 4 * 128 * KCI;
             constexpr int PB = 4;
             for (int base = tid; base < ITEMS; base += Cfg::WORKERS * PB) {
-                float4 v0[PB], v1[PB];
+                float vv[PB][8];
                 int dst[PB];
 #pragma unroll
                 for (int u = 0; u < PB; ++u) {
@@ -142,10 +143,7 @@ down_block_tc_kernel(DownArgs a) {
                     if (id < ITEMS) {
                         const int ip = id / KCI, kc = id - ip * KCI;    // input pixel of the tile
                         const int iy = ip >> 5, ix = ip & 31;           // 16 rows x 32 cols
-                        const float4* src = reinterpret_cast<const float4*>(
-                            ximg + ((size_t)(2 * r0 + iy) * a.W + 2 * c0 + ix) * CI + kc * 8);
-                        v0[u] = __ldg(src);
-                        v1[u] = __ldg(src + 1);
+                        IO::load8(ximg + ((size_t)(2 * r0 + iy) * a.W + 2 * c0 + ix) * CI + kc * 8, vv[u]);
                         const int m = ((iy & 1) * 2 + (ix & 1)) * DB_PLANE + (iy >> 1) * DB_OW + (ix >> 1);
                         dst[u] = kc * (int)DB_LBO + m * 16;
                     }
@@ -153,10 +151,8 @@ down_block_tc_kernel(DownArgs a) {
 #pragma unroll
                 for (int u = 0; u < PB; ++u) {
                     if (dst[u] >= 0) {
-                        const float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w,
-                                            v1[u].x, v1[u].y, v1[u].z, v1[u].w};
-                        *reinterpret_cast<uint4*>(smem + Cfg::OFF_A1 + dst[u]) = act_pack8(v, a.b1a, a.b1b);
-                        *reinterpret_cast<uint4*>(smem + Cfg::OFF_AS + dst[u]) = add_pack8(v, a.b1c);
+                        *reinterpret_cast<uint4*>(smem + Cfg::OFF_A1 + dst[u]) = act_pack8(vv[u], a.b1a, a.b1b);
+                        *reinterpret_cast<uint4*>(smem + Cfg::OFF_AS + dst[u]) = add_pack8(vv[u], a.b1c);
                     }
                 }
             }
@@ -271,7 +267,7 @@ down_block_tc_kernel(DownArgs a) {
                     ((size_t)(r0 + (p >> 4)) * Wo + c0 + (p & 15)) * CO + kc0 * 8 + c4 * 4;
                 float4 d = *reinterpret_cast<const float4*>(stage + rr * SROW + 4 * c4);
                 d.x += a.bsum; d.y += a.bsum; d.z += a.bsum; d.w += a.bsum;
-                *reinterpret_cast<float4*>(oimg + off) = d;
+                IO::store4(oimg + off, d);
             }
             __syncwarp();
             tc_fence_before_sync();
@@ -285,10 +281,10 @@ down_block_tc_kernel(DownArgs a) {
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int CI, int CO>
+template <int CI, int CO, typename TIO>
 int launch_down(const DownArgs& a, int sm_count, cudaStream_t stream) {
     using Cfg = DownCfg<CI, CO>;
-    auto kern = down_block_tc_kernel<CI, CO>;
+    auto kern = down_block_tc_kernel<CI, CO, TIO>;
     static PerDevice<bool> attr_set{};
     if (!attr_set.cur()) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -308,8 +304,10 @@ size_t down_block_pack_elems(int CI) {
     return (size_t)5 * CO * CIP + (size_t)5 * CO * CO;
 }
 
-int down_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
-                  int64_t B, int H, int W, int CI, int sm_count, cudaStream_t stream) {
+int down_block_tc(const void* x, void* out, int io_dtype, const void* w_packed,
+                  const float* scalars8, int64_t B, int H, int W, int CI, int sm_count,
+                  cudaStream_t stream) {
+    if (io_dtype != VQAE_DT_F32 && io_dtype != VQAE_DT_F16) return VQAE_ERR_UNSUPPORTED;
     if (!x || !out || !w_packed || !scalars8 || B <= 0) return VQAE_ERR_BAD_ARG;
     if (H % (2 * DB_OH) != 0 || W % (2 * DB_OW) != 0 || H <= 0 || W <= 0) return VQAE_ERR_UNSUPPORTED;
     DownArgs a;
@@ -320,10 +318,14 @@ int down_block_tc(const float* x, float* out, const void* w_packed, const float*
     a.n_tiles = (int)nt;
     a.b1a = scalars8[0]; a.b1b = scalars8[1]; a.b2a = scalars8[2]; a.b2b = scalars8[3];
     a.b3a = scalars8[4]; a.b3b = scalars8[5]; a.b1c = scalars8[6]; a.bsum = scalars8[7];
+    const bool h = io_dtype == VQAE_DT_F16;
     switch (CI) {
-        case 32: return launch_down<32, 64>(a, sm_count, stream);
-        case 16: return launch_down<16, 32>(a, sm_count, stream);
-        case 8: return launch_down<8, 16>(a, sm_count, stream);
+        case 32: return h ? launch_down<32, 64, __half>(a, sm_count, stream)
+                          : launch_down<32, 64, float>(a, sm_count, stream);
+        case 16: return h ? launch_down<16, 32, __half>(a, sm_count, stream)
+                          : launch_down<16, 32, float>(a, sm_count, stream);
+        case 8: return h ? launch_down<8, 16, __half>(a, sm_count, stream)
+                         : launch_down<8, 16, float>(a, sm_count, stream);
     }
     return VQAE_ERR_UNSUPPORTED;
 }

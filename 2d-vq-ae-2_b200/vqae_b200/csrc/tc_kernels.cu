@@ -67,8 +67,8 @@ struct SameCfg {
 };
 
 struct SameBlockArgs {
-    const float* x;               // NHWC fp32 [B,H,W,CR]
-    float* out;                   // NHWC fp32 [B,H,W,CR]
+    const void* x;                // NHWC fp32 or fp16 [B,H,W,CR]
+    void* out;                    // NHWC, same element type [B,H,W,CR]
     const __nv_bfloat16* w;       // 11 matrices [W1 | W2 tap 0..8 | W3], each [k-chunk][n][8]
     int n_tiles, H, W, tiles_x, tiles_per_img;
     float b1a, b1b, b2a, b2b, b3a, b3b, b4, scale;
@@ -77,9 +77,12 @@ struct SameBlockArgs {
 };
 
 
-template <int CP, int CR>
+template <int CP, int CR, typename TIO>
 __global__ void __launch_bounds__(SameCfg<CP, CR>::THREADS, SameCfg<CP, CR>::MIN_CTAS)
 same_block_tc_kernel(SameBlockArgs a) {
+    using IO = StreamIO<TIO>;
+    const TIO* const xg = reinterpret_cast<const TIO*>(a.x);
+    TIO* const og = reinterpret_cast<TIO*>(a.out);
     using Cfg = SameCfg<CP, CR>;
     constexpr int KCH = Cfg::KCH, KCR = Cfg::KCR, NW = Cfg::NW, NC = Cfg::NC, UCH = Cfg::UCH;
     constexpr uint32_t WLBO = Cfg::WLBO, WMAT = Cfg::WMAT;
@@ -173,11 +176,11 @@ same_block_tc_kernel(SameBlockArgs a) {
         const int img = tile / a.tiles_per_img;
         const int trem = tile - img * a.tiles_per_img;
         const int r0 = (trem / a.tiles_x) * SB_TH, c0 = (trem % a.tiles_x) * SB_TW;
-        const float* ximg = a.x + (size_t)img * a.H * a.W * CR;
+        const TIO* ximg = xg + (size_t)img * a.H * a.W * CR;
         constexpr int ITEMS = SB_NPAD * KCR;
         constexpr int PB = (NW >= 16) ? 3 : 6;
         for (int base = tid; base < ITEMS; base += Cfg::WORKERS * PB) {
-            float4 v0[PB], v1[PB];
+            float vv[PB][8];
             int dst[PB];
 #pragma unroll
             for (int u = 0; u < PB; ++u) {
@@ -189,20 +192,14 @@ same_block_tc_kernel(SameBlockArgs a) {
                     int row = r0 - 1 + lr, col = c0 - 1 + lc;
                     row = row < 0 ? row + a.H : (row >= a.H ? row - a.H : row);
                     col = col < 0 ? col + a.W : (col >= a.W ? col - a.W : col);
-                    const float4* src = reinterpret_cast<const float4*>(
-                        ximg + ((size_t)row * a.W + col) * CR + kc * 8);
-                    v0[u] = __ldg(src);
-                    v1[u] = __ldg(src + 1);
+                    IO::load8(ximg + ((size_t)row * a.W + col) * CR + kc * 8, vv[u]);
                     dst[u] = kc * (int)SB_XLBO + q * 16;
                 }
             }
 #pragma unroll
             for (int u = 0; u < PB; ++u) {
-                if (dst[u] >= 0) {
-                    const float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w,
-                                        v1[u].x, v1[u].y, v1[u].z, v1[u].w};
-                    *reinterpret_cast<uint4*>(smem + Cfg::OFF_X + dst[u]) = act_pack8(v, a.b1a, a.b1b);
-                }
+                if (dst[u] >= 0)
+                    *reinterpret_cast<uint4*>(smem + Cfg::OFF_X + dst[u]) = act_pack8(vv[u], a.b1a, a.b1b);
             }
         }
     };
@@ -224,8 +221,8 @@ same_block_tc_kernel(SameBlockArgs a) {
         const int img = tile / a.tiles_per_img;
         const int trem = tile - img * a.tiles_per_img;
         const int r0 = (trem / a.tiles_x) * SB_TH, c0 = (trem % a.tiles_x) * SB_TW;
-        const float* ximg = a.x + (size_t)img * a.H * a.W * CR;
-        float* oimg = a.out + (size_t)img * a.H * a.W * CR;
+        const TIO* ximg = xg + (size_t)img * a.H * a.W * CR;
+        TIO* oimg = og + (size_t)img * a.H * a.W * CR;
         const bool prof = prof_cta && first;
         if (prof) a.prof[(size_t)blockIdx.x * 8 + 1] = clock64();
 
@@ -362,7 +359,7 @@ same_block_tc_kernel(SameBlockArgs a) {
             float4 xr[F4], xn[F4];
 #pragma unroll
             for (int k = 0; k < F4; ++k)
-                xr[k] = __ldg(reinterpret_cast<const float4*>(ximg + x_off(0, k)));
+                xr[k] = IO::load4(ximg + x_off(0, k));
             mbar_wait(bar_mma, mma_phase);
             tc_fence_after_sync();
             if (prof) a.prof[(size_t)blockIdx.x * 8 + 6] = clock64();
@@ -373,7 +370,7 @@ same_block_tc_kernel(SameBlockArgs a) {
                 if (t + 1 < 4) {
 #pragma unroll
                     for (int k = 0; k < F4; ++k)
-                        xn[k] = __ldg(reinterpret_cast<const float4*>(ximg + x_off(t + 1, k)));
+                        xn[k] = IO::load4(ximg + x_off(t + 1, k));
                 }
                 tmem_ld_wait();
                 __syncwarp();
@@ -391,7 +388,7 @@ same_block_tc_kernel(SameBlockArgs a) {
                     o.y = fmaf(d.y, a.scale, a.b4) + xr[k].y;
                     o.z = fmaf(d.z, a.scale, a.b4) + xr[k].z;
                     o.w = fmaf(d.w, a.scale, a.b4) + xr[k].w;
-                    *reinterpret_cast<float4*>(oimg + x_off(t, k)) = o;
+                    IO::store4(oimg + x_off(t, k), o);
                 }
 #pragma unroll
                 for (int k = 0; k < F4; ++k) xr[k] = xn[k];
@@ -410,10 +407,10 @@ same_block_tc_kernel(SameBlockArgs a) {
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int CP, int CR>
+template <int CP, int CR, typename TIO>
 int launch_same_block(const SameBlockArgs& a, int sm_count, cudaStream_t stream) {
     using Cfg = SameCfg<CP, CR>;
-    auto kern = same_block_tc_kernel<CP, CR>;
+    auto kern = same_block_tc_kernel<CP, CR, TIO>;
     static PerDevice<bool> attr_set{};
     if (!attr_set.cur()) {
         VQAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -428,9 +425,10 @@ int launch_same_block(const SameBlockArgs& a, int sm_count, cudaStream_t stream)
 
 }  // namespace
 
-int same_block_tc(const float* x, float* out, const void* w_packed, const float* scalars8,
-                  int64_t B, int H, int W, int C, int sm_count, long long* prof,
-                  cudaStream_t stream) {
+int same_block_tc(const void* x, void* out, int io_dtype, const void* w_packed,
+                  const float* scalars8, int64_t B, int H, int W, int C, int sm_count,
+                  long long* prof, cudaStream_t stream) {
+    if (io_dtype != VQAE_DT_F32 && io_dtype != VQAE_DT_F16) return VQAE_ERR_UNSUPPORTED;
     if (!x || !out || !w_packed || !scalars8 || B <= 0) return VQAE_ERR_BAD_ARG;
     if (x == out) return VQAE_ERR_BAD_ARG;
     if (H < SB_TH || W < SB_TW || H % SB_TH != 0 || W % SB_TW != 0) return VQAE_ERR_UNSUPPORTED;
@@ -444,11 +442,16 @@ int same_block_tc(const float* x, float* out, const void* w_packed, const float*
     a.b3a = scalars8[4]; a.b3b = scalars8[5]; a.b4 = scalars8[6]; a.scale = scalars8[7];
     a.prof = prof;
     a.stagger_ns = (C == 64) ? 9000u : 0u;
+    const bool h = io_dtype == VQAE_DT_F16;
     switch (C) {
-        case 64: return launch_same_block<64, 64>(a, sm_count, stream);
-        case 32: return launch_same_block<32, 32>(a, sm_count, stream);
-        case 16: return launch_same_block<16, 16>(a, sm_count, stream);
-        case 8: return launch_same_block<16, 8>(a, sm_count, stream);
+        case 64: return h ? launch_same_block<64, 64, __half>(a, sm_count, stream)
+                          : launch_same_block<64, 64, float>(a, sm_count, stream);
+        case 32: return h ? launch_same_block<32, 32, __half>(a, sm_count, stream)
+                          : launch_same_block<32, 32, float>(a, sm_count, stream);
+        case 16: return h ? launch_same_block<16, 16, __half>(a, sm_count, stream)
+                          : launch_same_block<16, 16, float>(a, sm_count, stream);
+        case 8: return h ? launch_same_block<16, 8, __half>(a, sm_count, stream)
+                         : launch_same_block<16, 8, float>(a, sm_count, stream);
     }
     return VQAE_ERR_UNSUPPORTED;
 }

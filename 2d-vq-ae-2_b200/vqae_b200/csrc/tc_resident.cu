@@ -94,8 +94,9 @@ struct RsCfg {
 };
 
 struct ResidentArgs {
-    const float* x;               // NHWC fp32 [B,32,32,64]
-    float* out;                   // NHWC fp32 [B,32,32,64] (may alias x)
+    const void* x;                // NHWC fp32 or fp16 [B,H,W,C]
+    void* out;                    // NHWC, same element type (may alias x)
+    int io_half;                  // 1: x / out are fp16 (the residual on chip is fp32 either way)
     const __nv_bfloat16* w;       // [n_blocks][11]: W1 | W2 tap 0..8 | scale*W3, each [k-chunk][n][8]
     const float* scal;            // [n_blocks][8] = b1a b1b b2a b2b b3a b3b b4 scale   (device)
     int n_blocks, n_img;
@@ -586,24 +587,44 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                         const int img = image_of(b, h.jprev);
                         load_lo(Rm, v);
                         tmem_ld_wait();
-                        float4* o = reinterpret_cast<float4*>(a.out + (size_t)img * RS_H * RS_W * RS_C +
-                                                              g_pix + m * 16 * MPH * RS_C);
+                        const size_t eoff = (size_t)img * RS_H * RS_W * RS_C + g_pix + m * 16 * MPH * RS_C;
+                        if (a.io_half) {
+                            __half* o = reinterpret_cast<__half*>(a.out) + eoff;
 #pragma unroll
-                        for (int k = 0; k < CPT / 4; ++k)
-                            o[k] = make_float4(v[4 * k] + cum, v[4 * k + 1] + cum, v[4 * k + 2] + cum,
-                                               v[4 * k + 3] + cum);
+                            for (int k = 0; k < CPT / 4; ++k)
+                                StreamIO<__half>::store4(o + 4 * k, make_float4(v[4 * k] + cum, v[4 * k + 1] + cum,
+                                                                                v[4 * k + 2] + cum, v[4 * k + 3] + cum));
+                        } else {
+                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + eoff);
+#pragma unroll
+                            for (int k = 0; k < CPT / 4; ++k)
+                                o[k] = make_float4(v[4 * k] + cum, v[4 * k + 1] + cum, v[4 * k + 2] + cum,
+                                                   v[4 * k + 3] + cum);
+                        }
                     }
                     if (h.g1) {
                         // ---- P: A1 from the residual (first block of an image: from global memory) ----
                         float pre = sn0.x;
                         if (blk_n == 0) {
                             const int img = image_of(b, h.jprev + 1);
-                            const float4* s4 = reinterpret_cast<const float4*>(
-                                a.x + (size_t)img * RS_H * RS_W * RS_C + g_pix + m * 16 * MPH * RS_C);
+                            const size_t eoff = (size_t)img * RS_H * RS_W * RS_C + g_pix + m * 16 * MPH * RS_C;
+                            if (a.io_half) {
+                                const __half* s2 = reinterpret_cast<const __half*>(a.x) + eoff;
 #pragma unroll
-                            for (int k = 0; k < CPT / 4; ++k) {
-                                const float4 t = __ldg(s4 + k);
-                                v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+                                for (int k = 0; k < CPT / 8; ++k) {
+                                    float t8[8];
+                                    StreamIO<__half>::load8(s2 + 8 * k, t8);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[8 * k + e] = t8[e];
+                                }
+                            } else {
+                                const float4* s4 = reinterpret_cast<const float4*>(
+                                    reinterpret_cast<const float*>(a.x) + eoff);
+#pragma unroll
+                                for (int k = 0; k < CPT / 4; ++k) {
+                                    const float4 t = __ldg(s4 + k);
+                                    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+                                }
                             }
                             if constexpr (CPT == 16) tmem_st16(Rm, *reinterpret_cast<float(*)[16]>(v));
                             else tmem_st32(Rm, *reinterpret_cast<float(*)[32]>(v));
@@ -716,12 +737,14 @@ int trunk_resident_max_clusters(int* out) {
     return *out > 0 ? VQAE_OK : VQAE_ERR_CUDA;
 }
 
-int trunk_resident_tc(const float* x, float* out, const void* w_packed_all, const float* scalars_dev,
-                      int n_blocks, int64_t B, int H, int W, int C, cudaStream_t stream) {
+int trunk_resident_tc(const void* x, void* out, int io_dtype, const void* w_packed_all,
+                      const float* scalars_dev, int n_blocks, int64_t B, int H, int W, int C,
+                      cudaStream_t stream) {
     if (!x || !out || !w_packed_all || !scalars_dev || B <= 0 || n_blocks <= 0) return VQAE_ERR_BAD_ARG;
+    if (io_dtype != VQAE_DT_F32 && io_dtype != VQAE_DT_F16) return VQAE_ERR_UNSUPPORTED;
     if (!trunk_resident_supported(B, H, W, C)) return VQAE_ERR_UNSUPPORTED;
     ResidentArgs a;
-    a.x = x; a.out = out;
+    a.x = x; a.out = out; a.io_half = io_dtype == VQAE_DT_F16;
     a.w = reinterpret_cast<const __nv_bfloat16*>(w_packed_all);
     a.scal = scalars_dev;
     a.n_blocks = n_blocks; a.n_img = (int)B;

@@ -181,12 +181,12 @@ int vqae_tc_mma_bench2(int m, int n, int reps, int n_issuers, int ctas_per_sm, i
     return tc_mma_bench2(m, n, reps, n_issuers, ctas_per_sm, mode, out_per_cta, (cudaStream_t)stream);
 }
 
-int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packed,
-                                 const float* scalars8_host, int64_t batch, int height, int width,
+int vqae_same_block_f16_profile(const void* x, void* out, int io_dtype, const void* w_packed,
+                                const float* scalars8_host, int64_t batch, int height, int width,
                                  int c, long long* phase_clocks, void* stream) {
     int sm_count = 0;
     if (int rc = device_sm_count(&sm_count)) return rc;
-    return same_block_tc(x, out, w_packed, scalars8_host, batch, height, width, c, sm_count,
+    return same_block_tc(x, out, io_dtype, w_packed, scalars8_host, batch, height, width, c, sm_count,
                          phase_clocks, (cudaStream_t)stream);
 }
 

@@ -322,6 +322,32 @@ def _plan_layouts(packed: Sequence[PackedFixup], h: int, w: int, precision: str)
 # single calls
 # ----------------------------------------------------------------------------------------------
 PRECISIONS = ("fp32", "fp16")
+# True: in "fp16" mode the NHWC tensors between tensor-core kernels are fp16 instead of fp32.  Built,
+# tested (tests/test_gpu_tc.py) and measured on B200 (round 2): halving the block-boundary bytes
+# changes the step time by < 1 % (4.56 vs 4.55 ms at batch 256 -- the tile kernels are latency /
+# issue bound, not byte bound) while the extra roundings cost code agreement with the reference
+# (0.9985 -> 0.9966 on the nd3 golden), so the fp32 stream stays the default.
+STREAM_F16 = False
+
+
+_TORCH_DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16}
+
+
+def _io_dt(t: Tensor) -> int:
+    return L.DT_F16 if t.dtype == torch.float16 else L.DT_F32
+
+
+def _as_stream(x: Tensor, half: bool) -> Tensor:
+    want = torch.float16 if half else torch.float32
+    return x if x.dtype == want else x.to(want)
+
+
+def trunk_resident(x: Tensor, out: Tensor, chain: "PackedChain") -> None:
+    """vqae_trunk_resident_f16 on NHWC x -> out (same dtype: fp32 or fp16; out may alias x)."""
+    b, hh, ww, c = x.shape
+    L.check(L.load().vqae_trunk_resident_f16(
+        _ptr(x), _ptr(out), _io_dt(x), _ptr(chain.weights), _ptr(chain.scalars), chain.n, b, hh, ww,
+        c, _stream(x.device)), "vqae_trunk_resident_f16")
 # Runs of 'same' blocks at C = 64 / 128 @ 32 x 32 and C = 32 @ 64 x 64 use the
 # image-resident kernel (tc_resident.cu); False selects the tile kernels (tc_chain.cu / tc_kernels.cu)
 # for A/B measurements (profiles/step_breakdown.py)
@@ -330,29 +356,31 @@ TRUNK_RESIDENT = True
 
 def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
                        precision: str = "fp32") -> Tensor:
-    """x: contiguous NHWC fp32 [B,H,W,c_in] -> NHWC fp32 [B,H',W',c_out].
+    """x: contiguous NHWC [B,H,W,c_in] -> NHWC [B,H',W',c_out].
 
-    precision "fp32": CUDA-core exact path.  "fp16": tcgen05 kernels (bf16 operands, fp32
-    accumulation and fp32 residual stream) wherever one is built for the block's shape, the
-    fp32 kernels elsewhere."""
+    precision "fp32": CUDA-core exact path, fp32 in and out.  "fp16": tcgen05 kernels (fp16
+    operands, fp32 accumulation and fp32 residual add) wherever one is built for the block's shape
+    -- they read and write fp32 or fp16 tensors, whatever x is -- and the fp32 kernels elsewhere."""
     lib = L.load()
     b, h, w, c = x.shape
     if c != pk.c_in:
         raise ValueError(f"fixup block expects {pk.c_in} input channels, got {c}")
     ho, wo = pk.out_hw(h, w)
     ensure_packed([pk], *_plan_layouts([pk], h, w, precision))
+    tc = precision == "fp16" and pk.tc_ok(h, w)
+    if tc and pk.chain_only:
+        return run_blocks_nhwc([pk], x, "fp16")
+    if tc:
+        if out is None:
+            out = torch.empty(b, ho, wo, pk.c_out, dtype=x.dtype, device=x.device)
+        fn, name = ((lib.vqae_down_block_f16, "vqae_down_block_f16") if pk.mode == L.MODE_DOWN
+                    else (lib.vqae_same_block_f16, "vqae_same_block_f16"))
+        L.check(fn(_ptr(x), _ptr(out), _io_dt(x), _ptr(pk.tc_weights), pk.tc_scalars, b, h, w, c,
+                   _stream(x.device)), name)
+        return out
+    x = _as_stream(x, False)
     if out is None:
         out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
-    if precision == "fp16" and pk.tc_ok(h, w) and pk.mode == L.MODE_DOWN:
-        L.check(lib.vqae_down_block_f16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
-                                         b, h, w, c, _stream(x.device)), "vqae_down_block_f16")
-        return out
-    if precision == "fp16" and pk.tc_ok(h, w) and pk.chain_only:
-        return run_blocks_nhwc([pk], x, "fp16")
-    if precision == "fp16" and pk.tc_ok(h, w):
-        L.check(lib.vqae_same_block_f16(_ptr(x), _ptr(out), _ptr(pk.tc_weights), pk.tc_scalars,
-                                         b, h, w, c, _stream(x.device)), "vqae_same_block_f16")
-        return out
     need = lib.vqae_fixup_block_scratch_bytes(C.byref(pk.params), b, h, w)
     ws = workspace(x.device, need)
     L.check(lib.vqae_fixup_block_f32(C.byref(pk.params), _ptr(x), _ptr(out), _ptr(ws),
@@ -404,11 +432,13 @@ def _chain_runs(packed: Sequence[PackedFixup], h: int, w: int, batch: int = 1 <<
 
 def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "fp32",
                     chain_cache: Optional[dict] = None) -> Tensor:
-    """A Sequential chain of PreActFixupResBlocks on an NHWC fp32 tensor.  In "fp16" mode runs of
+    """A Sequential chain of PreActFixupResBlocks on an NHWC tensor.  In "fp16" mode runs of
     consecutive tcgen05 'same' blocks execute as ONE launch: image-resident (vqae_trunk_resident_f16)
-    for C = 64 at 32 x 32, the persistent tile chain (vqae_same_chain_f16) otherwise."""
+    where a cluster can own an image, the persistent tile chain (vqae_same_chain_f16) otherwise; the
+    tensors between tensor-core kernels are fp16 (STREAM_F16), fp32 around the fp32 kernels."""
     ensure_packed(packed, *_plan_layouts(packed, h.shape[1], h.shape[2], precision))
     if precision != "fp16":
+        h = _as_stream(h, False)
         for pk in packed:
             h = fixup_forward_nhwc(pk, h, precision=precision)
         return h
@@ -418,7 +448,10 @@ def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "
     i, n = 0, len(packed)
     while i < n:
         if i not in runs:
-            h = fixup_forward_nhwc(packed[i], h, precision=precision)
+            pk = packed[i]
+            if pk.tc_ok(h.shape[1], h.shape[2]) and not pk.chain_only:
+                h = _as_stream(h, STREAM_F16)
+            h = fixup_forward_nhwc(pk, h, precision=precision)
             i += 1
             continue
         j = runs[i]
@@ -429,13 +462,13 @@ def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "
         if chain is None:
             chain = cache[key] = PackedChain(packed[i:j], resident)
         if resident:
+            h = _as_stream(h, STREAM_F16)
             out = torch.empty_like(h)
-            L.check(lib.vqae_trunk_resident_f16(
-                _ptr(h), _ptr(out), _ptr(chain.weights), _ptr(chain.scalars), chain.n, b, hh, ww, c,
-                _stream(h.device)), "vqae_trunk_resident_f16")
+            trunk_resident(h, out, chain)
             h = out
             i = j
             continue
+        h = _as_stream(h, False)                       # the tile-chain kernel streams fp32
         bufs = [torch.empty_like(h), torch.empty_like(h)]
         fbytes = lib.vqae_same_chain_flag_bytes(chain.n, b)
         flags = torch.empty(fbytes, dtype=torch.uint8, device=h.device)
@@ -447,8 +480,10 @@ def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "
     return h
 
 
-def stem_in(x: Tensor, weight: Tensor, bias: Tensor, mean=None, std=None) -> Tensor:
-    """x: fp32 [B,3,H,W] (NCHW or channels_last strides) or u8 [B,H,W,3] -> NHWC fp32 [B,H,W,8]."""
+def stem_in(x: Tensor, weight: Tensor, bias: Tensor, mean=None, std=None,
+            out_dtype: torch.dtype = torch.float32) -> Tensor:
+    """x: fp32 [B,3,H,W] (NCHW or channels_last strides) or u8 [B,H,W,3] -> NHWC [B,H,W,8], fp32 or
+    (fp16 stream of the reduced-precision path; needs W % 128 == 0 and H % 8 == 0) fp16."""
     lib = L.load()
     require_cuda(x, "stem_in")
     w = weight.detach().float().contiguous()
@@ -472,16 +507,19 @@ def stem_in(x: Tensor, weight: Tensor, bias: Tensor, mean=None, std=None) -> Ten
             x = x.contiguous()
             lay = L.LAYOUT_NCHW
         dt, mean_a, std_a = L.DT_F32, None, None
-    out = torch.empty(b, h, wd, w.shape[0], dtype=torch.float32, device=x.device)
-    L.check(lib.vqae_stem_in_f32(_ptr(x), dt, lay, _ptr(w), _ptr(bi), _ptr(out), b, h, wd,
-                                 w.shape[0], mean_a, std_a, _stream(x.device)),
-            "vqae_stem_in_f32")
+    if out_dtype == torch.float16 and (wd % 128 or h % 8):
+        out_dtype = torch.float32
+    out = torch.empty(b, h, wd, w.shape[0], dtype=out_dtype, device=x.device)
+    L.check(lib.vqae_stem_in(_ptr(x), dt, lay, _ptr(w), _ptr(bi), _ptr(out), _TORCH_DT[out_dtype],
+                             b, h, wd, w.shape[0], mean_a, std_a, _stream(x.device)),
+            "vqae_stem_in")
     return out
 
 
 def stem_out(x_nhwc: Tensor, weight: Tensor, bias: Tensor, channels_last: bool) -> Tensor:
     """NHWC fp32 [B,H,W,8] -> [B,3,H,W] (contiguous NCHW, or channels_last strides)."""
     lib = L.load()
+    x_nhwc = _as_stream(x_nhwc, False)
     b, h, wd, c = x_nhwc.shape
     w = weight.detach().float().contiguous()
     bi = bias.detach().float().contiguous()
@@ -545,7 +583,6 @@ class PackedQuantizer:
         self.params = p
 
 
-_TORCH_DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16}
 _KERNEL = {"auto": L.QUANT_AUTO, "cuda_core": L.QUANT_CUDA_CORE, "tensor_core": L.QUANT_TENSOR_CORE}
 
 
@@ -577,6 +614,13 @@ def quantize(pq: PackedQuantizer, x: Tensor, x_nhwc: bool, out_nhwc: bool, batch
 
 # I/O dtypes of the quantiser call for which a kernel is built (config 2 cells)
 QUANT_IO_DTYPES = ("fp32", "bf16", "fp16")
+
+
+def quantize_io_supported(pq: PackedQuantizer, dtype: torch.dtype) -> bool:
+    """NHWC in / NHWC out of `dtype` is built (the tcgen05 kernel: fp32 / bf16 / fp16, c in {64, 128})."""
+    dt = _TORCH_DT.get(dtype)
+    return dt is not None and bool(L.load().vqae_quantize_supported(
+        C.byref(pq.params), dt, L.LAYOUT_NHWC, dt, L.LAYOUT_NHWC, 1, L.QUANT_AUTO))
 
 
 class QuantizeBuffers:

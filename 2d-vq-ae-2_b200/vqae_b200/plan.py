@@ -162,7 +162,9 @@ def encoder_encode(enc, x: Tensor, mean=None, std=None, want_quantized: bool = T
     E.require_cuda(x, "Encoder.forward")
     precision = resolve_precision(enc)
     cl = x.dtype == torch.uint8 or E.is_channels_last(x)
-    h = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias, mean, std)
+    half = precision == "fp16" and E.STREAM_F16
+    h = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias, mean, std,
+                  torch.float16 if half else torch.float32)
     # one plan over pyramid + trunk: the 'same' blocks that close the last DownBlock and the
     # trunk are one run of equal-width blocks, i.e. ONE image-resident launch
     h = _plan(enc).run(flat_blocks(enc.down_layers) + flat_blocks(enc.pre_enc_layers), h, precision)
@@ -173,8 +175,12 @@ def encoder_encode(enc, x: Tensor, mean=None, std=None, want_quantized: bool = T
         raise NotImplementedError(
             'VQ dim != channel dim not supported;'
             f' found channel dim of {c}, expected {pq.c}')
+    if h.dtype != torch.float32 and not (E.quantize_io_supported(pq, h.dtype) and cl):
+        h = h.float()
     out, idx, loss, ties, z = E.quantize(pq, h, True, cl, b, hh * ww,
                                          want_out=want_quantized, want_z=want_latents)
+    if out is not None and out.dtype != torch.float32:
+        out = out.float()                    # the module API returns fp32 like the reference
     state(vq).last_near_ties = ties
     enc_t = None
     if out is not None:

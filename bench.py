@@ -280,9 +280,7 @@ def time_trunk_kernel(dev, peaks, model, C: int, B: int):
     assert lib.vqae_trunk_resident_supported(B, H, W, C)
 
     def launch(i):
-        L.check(lib.vqae_trunk_resident_f16(E._ptr(xs[i % nbuf]), E._ptr(ys[i % nbuf]),
-                                             E._ptr(chain.weights), E._ptr(chain.scalars), nblk, B,
-                                             H, W, C, st), "vqae_trunk_resident_f16")
+        E.trunk_resident(xs[i % nbuf], ys[i % nbuf], chain)
     ms = _event_time(launch, 5, dev)
     flops = 2.0 * B * H * W * C * C * 11 * nblk
     achieved = flops / (ms * 1e-3) / 1e12

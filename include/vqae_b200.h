@@ -89,6 +89,11 @@ int vqae_pack_batched(const vqae_pack_desc* descs_device, int n_descs, int max_e
 int vqae_stem_in_f32(const void* x, int x_dtype, int x_layout, const float* w_oihw,
                      const float* bias, float* out, int64_t batch, int height, int width,
                      int c_out, const float* mean_host, const float* std_host, void* stream);
+/* the same with the output element type chosen: VQAE_DT_F32, or VQAE_DT_F16 -- the activation
+ * stream of the reduced-precision path (needs width % 128 == 0, height % 8 == 0)              */
+int vqae_stem_in(const void* x, int x_dtype, int x_layout, const float* w_oihw, const float* bias,
+                 void* out, int out_dtype, int64_t batch, int height, int width, int c_out,
+                 const float* mean_host, const float* std_host, void* stream);
 /* out_stem (vq_ae/model.py:291): 3x3, zero pad, bias, c_in(8) -> 3.
  * x NHWC fp32 [B,H,W,c_in];  out fp32 NCHW [B,3,H,W] or NHWC [B,H,W,3].                     */
 int vqae_stem_out_f32(const float* x, const float* w_oihw, const float* bias, float* out,
@@ -134,7 +139,12 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
                          size_t scratch_bytes, int64_t batch, int height, int width,
                          void* stream);
 
-/* ---- a-T / a-R on tensor cores (tcgen05, bf16 operands, fp32 accumulate + fp32 residual) -------
+/* ---- a-T / a-R on tensor cores (tcgen05, fp16 operands, fp32 accumulate + fp32 residual) -------
+ * Activation stream: every kernel below reads x and writes out as NHWC tensors of element type
+ * io_dtype = VQAE_DT_F32 or VQAE_DT_F16 (both the same).  The arithmetic between load and store
+ * is identical (operands rounded to fp16 for the GEMMs, fp32 accumulation, fp32 residual add);
+ * the fp16 stream halves the HBM bytes of the block-boundary tensors and is what the
+ * reduced-precision plan uses (the reference's own autocast run stores fp16 between ops too).
  * One PreActFixupResBlock in mode 'same' (layers/conv_block.py:196-216) per call, all three
  * convs and their pre-activations fused in one kernel; c in {8, 16, 32, 64} (8 runs zero-padded
  * as 16), height % 16 == 0, width % 32 == 0 -- every 'same' block of the shipped encoder and
@@ -144,9 +154,9 @@ int vqae_fixup_block_f32(const vqae_fixup_params* p, const float* x, float* out,
  * x, out: NHWC fp32 [B,H,W,c], must not alias.                                               */
 int vqae_pack_same_block_f16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                               int c, void* packed, void* stream);
-int vqae_same_block_f16(const float* x, float* out, const void* w_packed,
-                         const float* scalars8_host, int64_t batch, int height, int width, int c,
-                         void* stream);
+int vqae_same_block_f16(const void* x, void* out, int io_dtype, const void* w_packed,
+                        const float* scalars8_host, int64_t batch, int height, int width, int c,
+                        void* stream);
 /* A run of n_blocks consecutive 'same' blocks of equal width in ONE persistent launch (the 50-block
  * trunks model.py:150-153,240-263 and the post layers of DownBlock/UpBlock): every (block, tile)
  * task is scheduled round-robin over the resident CTAs and ordered by per-(block, image) completion
@@ -183,9 +193,9 @@ int vqae_trunk_resident_max_clusters(void);
 int vqae_trunk_resident_supported(int64_t batch, int height, int width, int c);
 int vqae_pack_resident_block_f16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                                   int c, float scale, void* packed, void* stream);
-int vqae_trunk_resident_f16(const float* x, float* out, const void* w_packed_all,
-                             const float* scalars_dev, int n_blocks, int64_t batch, int height,
-                             int width, int c, void* stream);
+int vqae_trunk_resident_f16(const void* x, void* out, int io_dtype, const void* w_packed_all,
+                            const float* scalars_dev, int n_blocks, int64_t batch, int height,
+                            int width, int c, void* stream);
 /* PreActFixupResBlock in mode 'down' (conv specs pre_activation_fixup.yaml:35-45): c_in ->
  * 2*c_in, stride 2, branch + skip fused in one tcgen05 kernel; c_in in {8, 16, 32},
  * height % 16 == 0, width % 32 == 0.  w_packed: vqae_down_block_pack_elems(c_in) bf16 from
@@ -196,9 +206,9 @@ size_t vqae_down_block_pack_elems(int c_in);
 int vqae_pack_down_block_f16(const float* w1_oihw, const float* w2_oihw, const float* w3_oihw,
                               const float* wskip_oihw, int c_in, float scale, void* packed,
                               void* stream);
-int vqae_down_block_f16(const float* x, float* out, const void* w_packed,
-                         const float* scalars8_host, int64_t batch, int height, int width, int c_in,
-                         void* stream);
+int vqae_down_block_f16(const void* x, void* out, int io_dtype, const void* w_packed,
+                        const float* scalars8_host, int64_t batch, int height, int width, int c_in,
+                        void* stream);
 
 /* ---- a-P / a-Q / a-G  quantiser -------------------------------------------------------------
  * ProjectedEMAVectorQuantizer2d.forward + EMAVectorQuantizer.forward in eval mode

@@ -17,7 +17,7 @@ void vqae_trunk_resident_set_profile(long long* phase_clocks);
 
 /* same call, additionally writing clock64() at the 8 phase boundaries of every CTA's first tile
  * to phase_clocks[grid][8] (device memory, >= 8 * 4 * SM-count int64) -- profiling aid        */
-int vqae_same_block_bf16_profile(const float* x, float* out, const void* w_packed,
+int vqae_same_block_f16_profile(const void* x, void* out, int io_dtype, const void* w_packed,
                                  const float* scalars8_host, int64_t batch, int height, int width,
                                  int c, long long* phase_clocks, void* stream);
 /* tcgen05.mma issue-rate microbenchmark (timing aid): `reps` MMAs of 128 x n x 16 bf16 from shared

@@ -18,7 +18,7 @@ x = torch.randn(B, HW, HW, C, device=dev)
 outs = []
 for i in range(401):
     y = torch.empty_like(x)
-    L.check(lib.vqae_trunk_resident_f16(E._ptr(x), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, HW, HW, C, st), "r")
+    E.trunk_resident(x, y, chain)
     outs.append(y)
 torch.cuda.synchronize()
 for i, o in enumerate(outs[1:], 1):

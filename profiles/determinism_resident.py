@@ -27,8 +27,7 @@ for C, HW, B, nblk in ((32, 64, 256, 5), (64, 32, 256, 6), (128, 32, 64, 4), (32
     outs = []
     for i in range(reps + 1):
         y = torch.empty_like(x)
-        L.check(lib.vqae_trunk_resident_f16(E._ptr(x), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, HW, HW,
-                                             C, st), "resident")
+        E.trunk_resident(x, y, chain)
         outs.append(y)
     torch.cuda.synchronize()
     bad = [(i, int((o != outs[0]).sum())) for i, o in enumerate(outs[1:], 1) if not torch.equal(o, outs[0])]

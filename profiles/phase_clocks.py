@@ -26,7 +26,7 @@ L.check(lib.vqae_pack_same_block_f16(E._ptr(ws[0]), E._ptr(ws[1]), E._ptr(ws[2])
 sc = (ctypes.c_float * 8)(0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.9)
 prof = torch.zeros(148 * 4, 8, dtype=torch.int64, device=dev)
 for _ in range(3):
-    L.check(L.load_testaids().vqae_same_block_bf16_profile(E._ptr(x), E._ptr(y), E._ptr(packed), sc, B, HW, HW, C,
+    L.check(L.load_testaids().vqae_same_block_f16_profile(E._ptr(x), E._ptr(y), E._ptr(packed), sc, B, HW, HW, C,
                                              E._ptr(prof), st), "profile")
 torch.cuda.synchronize()
 p = prof.cpu()

@@ -32,8 +32,7 @@ y = torch.empty(B, H, W, C, device=dev)
 for i in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    L.check(lib.vqae_trunk_resident_f16(E._ptr(xs[i % 2]), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B,
-                                         H, W, C, st), "resident")
+    E.trunk_resident(xs[i % 2], y, chain)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -43,7 +42,7 @@ for i in range(reps):
 # phase clocks of CTA 0, eight steady-state half-rounds
 prof = torch.zeros(8 * 32, dtype=torch.int64, device=dev)
 L.load_testaids().vqae_trunk_resident_set_profile(E._ptr(prof))
-L.check(lib.vqae_trunk_resident_f16(E._ptr(xs[0]), E._ptr(y), E._ptr(w_all), E._ptr(scal), nblk, B, H, W, C, st), "resident")
+E.trunk_resident(xs[0], y, chain)
 torch.cuda.synchronize()
 L.load_testaids().vqae_trunk_resident_set_profile(None)
 p = prof.cpu().view(8, 32)

@@ -181,15 +181,23 @@ def test_resident_trunk_vs_block_by_block_and_fp32(c, batch, n, monkeypatch):
     assert H.rel_err(y, y32) < 5e-3
     for _ in range(2):                               # deterministic, no state left behind
         assert torch.equal(y, E.run_blocks_nhwc(packed, x, "fp16"))
-    # in place (out aliases x) gives the same bits
-    xc = x.clone()
-    lib = L.load()
+    # fp32 stream, in place (out aliases x): same bits as out of place; and the fp16 stream is the
+    # fp32 stream's result rounded once at the store when the input is fp16-representable
     chain = E.PackedChain(packed, resident=True)
-    L.check(lib.vqae_trunk_resident_f16(E._ptr(xc), E._ptr(xc), E._ptr(chain.weights),
-                                         E._ptr(chain.scalars), chain.n, batch, hw, hw, c,
-                                         E._stream(xc.device)), "vqae_trunk_resident_f16")
+    xh = x.half()
+    x32 = xh.float()
+    y32io = torch.empty_like(x32)
+    E.trunk_resident(x32, y32io, chain)
+    xc = x32.clone()
+    E.trunk_resident(xc, xc, chain)
+    y16io = torch.empty_like(xh)
+    E.trunk_resident(xh, y16io, chain)
+    xh2 = xh.clone()
+    E.trunk_resident(xh2, xh2, chain)
     torch.cuda.synchronize()
-    assert torch.equal(xc, y)
+    assert torch.equal(xc, y32io)
+    assert torch.equal(y16io, y32io.half()) and torch.equal(xh2, y16io)
+    assert y.dtype == (torch.float16 if E.STREAM_F16 else torch.float32)
 
 
 @pytest.mark.parametrize("c,batch,n,reps", [(32, 256, 5, 150), (64, 256, 4, 100), (128, 70, 3, 60)])
@@ -208,9 +216,7 @@ def test_resident_trunk_repeated_launches_bit_identical(c, batch, n, reps):
     outs = []
     for _ in range(reps + 1):
         y = torch.empty_like(x)
-        L.check(lib.vqae_trunk_resident_f16(E._ptr(x), E._ptr(y), E._ptr(chain.weights),
-                                             E._ptr(chain.scalars), chain.n, batch, hw, hw, c,
-                                             E._stream(x.device)), "vqae_trunk_resident_f16")
+        E.trunk_resident(x, y, chain)
         outs.append(y)
     torch.cuda.synchronize()
     bad = [i for i, o in enumerate(outs[1:], 1) if not torch.equal(o, outs[0])]
@@ -242,9 +248,7 @@ def test_resident_trunk_halo_and_wrap_exactness(c):
             x = torch.randint(1, 200, (3, hw, hw, c), device=DEV).float() / 8.0
             chain = E.PackedChain(packed, resident=True)
             out = torch.empty_like(x)
-            L.check(L.load().vqae_trunk_resident_f16(
-                E._ptr(x), E._ptr(out), E._ptr(chain.weights), E._ptr(chain.scalars), 1, 3, hw, hw,
-                c, E._stream(x.device)), "vqae_trunk_resident_f16")
+            E.trunk_resident(x, out, chain)
             torch.cuda.synchronize()
             ref = x + torch.roll(x, shifts=(-(ky - 1), -(kx - 1)), dims=(1, 2))
             assert torch.equal(out, ref), (ky, kx, float((out - ref).abs().max()))
@@ -310,3 +314,40 @@ def test_encoder_nd4_512_bf16_agreement_with_fp32():
     finally:
         vqae_b200.set_precision(m, "fp32")
         m.cpu()
+
+
+@pytest.mark.parametrize("mode,c,hw,batch", [("same", 8, 64, 3), ("same", 16, 32, 5), ("same", 32, 64, 2),
+                                             ("same", 64, 32, 3), ("down", 8, 64, 2), ("down", 16, 32, 3),
+                                             ("down", 32, 64, 2)])
+def test_fp16_stream_is_the_fp32_stream_rounded_once(mode, c, hw, batch):
+    """The tile kernels read / write fp32 or fp16 NHWC tensors; everything between load and store is
+    the same arithmetic, so on an fp16-representable input the fp16-stream output is exactly the
+    fp32-stream output rounded to fp16."""
+    from vqae_b200.config import pre_activation_fixup
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    co = c if mode == "same" else 2 * c
+    blk = PreActFixupResBlock(in_channels=c, out_channels=co, mode=mode, **conf).eval()
+    blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=17, regime="perturbed", n_layers=12))
+    pk = blk.to(DEV).packed()
+    xh = torch.randn(batch, hw, hw, c, device=DEV).half()
+    y32 = E.fixup_forward_nhwc(pk, xh.float(), precision="fp16")
+    y16 = E.fixup_forward_nhwc(pk, xh, precision="fp16")
+    torch.cuda.synchronize()
+    assert y32.dtype == torch.float32 and y16.dtype == torch.float16
+    assert torch.equal(y16, y32.half())
+
+
+def test_stem_in_fp16_stream_output():
+    img = S.synthetic_patches_u8(2, 256, 3).to(DEV)
+    w = torch.randn(8, 3, 3, 3, device=DEV) * 0.2
+    b = torch.randn(8, device=DEV) * 0.1
+    y32 = E.stem_in(img, w, b)
+    y16 = E.stem_in(img, w, b, out_dtype=torch.float16)
+    assert y16.dtype == torch.float16 and torch.equal(y16, y32.half())
+    x = torch.randn(2, 3, 128, 128, device=DEV)
+    assert torch.equal(E.stem_in(x, w, b, out_dtype=torch.float16), E.stem_in(x, w, b).half())
+    xs = torch.randn(1, 3, 48, 48, device=DEV)                 # not tileable: stays fp32
+    assert E.stem_in(xs, w, b, out_dtype=torch.float16).dtype == torch.float32

@@ -144,3 +144,61 @@ def test_code_tile_gather_world_size_2_gloo(tmp_path):
     for p in procs:
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out, err[-2000:]
+
+
+class _FakeH5:
+    """Dict-backed stand-in for the h5py API surface the reference uses (File / create_group /
+    create_dataset / `in` / keys / indexing); h5py itself is not in the build image."""
+    store = {}
+
+    class Group(dict):
+        def create_group(self, name):
+            g = _FakeH5.Group()
+            self[name] = g
+            return g
+
+        def create_dataset(self, name, data):
+            self[name] = np.asarray(data)
+
+    class File:
+        def __init__(self, path, mode='r'):
+            self.path, self.mode = path, mode
+            if 'w' in mode:
+                _FakeH5.store[path] = _FakeH5.Group()
+            self.root = _FakeH5.store[path]
+
+        def __enter__(self):
+            return self.root
+
+        def __exit__(self, *a):
+            return False
+
+
+def test_hdf5_layout_matches_the_reference_converter(tmp_path):
+    """scripts/convert_npy_embeddings_to_hdf5/convert.py:21-32 (writer) and
+    datamodules/camelyon16.py:226-246 (reader): groups named by the folder tails below the common
+    root, one dataset per .npy stem, images/<key> paired with masks/<key>_mask."""
+    from vqae_b200 import formats as F
+    from vqae_b200.extract import save_encoding
+    root, tails = F.find_common_root([Path("/a/b/images"), Path("/a/b/masks")])
+    assert root == Path("/a/b") and tails == ["images", "masks"]
+    root, tails = F.find_common_root([Path("/a/x/images/t"), Path("/a/y/masks")])
+    assert root == Path("/a") and tails == ["x/images/t", "y/masks"]
+    assert F.find_common_root([Path("/a/b")]) == (Path("/a/b"), [""])
+    rng = np.random.default_rng(0)
+    maps = {"images/normal_001": rng.integers(0, 256, (64, 96)).astype(np.uint8),
+            "images/tumor_002": rng.integers(0, 256, (32, 32)).astype(np.uint8),
+            "masks/normal_001_mask": np.zeros((64, 96), bool),
+            "masks/tumor_002_mask": rng.integers(0, 2, (32, 32)).astype(bool)}
+    for name, arr in maps.items():                     # <ckpt>/encodings/<parent>/<stem>.npy
+        save_encoding(tmp_path / "run", name, arr)
+    out = F.convert_npy_to_hdf5(tmp_path / "run", h5=_FakeH5)
+    assert out == (tmp_path / "run" / "encodings").with_suffix(".hdf5")
+    db = _FakeH5.store[str(out)]
+    assert sorted(db) == ["images", "masks"]
+    assert sorted(db["images"]) == ["normal_001", "tumor_002"]
+    images, masks = F.read_code_maps(out, h5=_FakeH5)
+    assert np.array_equal(images[0], maps["images/normal_001"]) and images[0].dtype == np.uint8
+    assert np.array_equal(masks[1], maps["masks/tumor_002_mask"])
+    only_tumor, _ = F.read_code_maps(out, pattern="tumor", h5=_FakeH5)
+    assert len(only_tumor) == 1 and np.array_equal(only_tumor[0], maps["images/tumor_002"])
