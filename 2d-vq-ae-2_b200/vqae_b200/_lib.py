@@ -47,7 +47,8 @@ class PackDesc(C.Structure):
                 ("dst", C.c_void_p)]
 
 
-PACK_F32_CONV, PACK_SAME_F16, PACK_RESIDENT_F16, PACK_DOWN_F16, PACK_LO = 0, 1, 2, 3, 0x100
+PACK_F32_CONV, PACK_SAME_F16, PACK_RESIDENT_F16, PACK_DOWN_F16, PACK_SAME_MMA_F16 = 0, 1, 2, 3, 4
+PACK_LO = 0x100
 
 
 class QuantizerParams(C.Structure):

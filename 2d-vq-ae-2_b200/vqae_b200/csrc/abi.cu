@@ -247,6 +247,19 @@ int vqae_same_block_f16(const void* x, void* out, int io_dtype, const void* w_pa
                          nullptr, (cudaStream_t)stream);
 }
 
+int vqae_same_block_mma_supported(int height, int width, int c) {
+    return same_block_mma_supported(height, width, c) ? 1 : 0;
+}
+
+int vqae_same_block_mma_f16(const float* x, float* out, const void* w_packed,
+                            const float* scalars8_host, int64_t batch, int height, int width, int c,
+                            void* stream) {
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return same_block_mma(x, out, w_packed, scalars8_host, batch, height, width, c, sm_count,
+                          (cudaStream_t)stream);
+}
+
 size_t vqae_same_chain_flag_bytes(int n_blocks, int64_t batch) {
     return same_chain_flag_bytes(n_blocks, batch);
 }

@@ -85,6 +85,11 @@ int same_block_tc(const void* x, void* out, int io_dtype, const void* w_packed,
 int pack_same_block_f16(const float* w1, const float* w2, const float* w3, int C, void* packed,
                          cudaStream_t stream);
 
+// mma_same.cu (low-channel 'same' blocks on warp-level MMAs)
+bool same_block_mma_supported(int H, int W, int C);
+int same_block_mma(const float* x, float* out, const void* w_packed, const float* scalars8,
+                   int64_t B, int H, int W, int C, int sm_count, cudaStream_t stream);
+
 // tc_chain.cu (persistent multi-block 'same' chain)
 size_t same_chain_flag_bytes(int n_blocks, int64_t B);
 bool same_chain_supported(int64_t B, int H, int W, int C, int sm_count);

@@ -71,6 +71,26 @@ __device__ void pack_element(const vqae_pack_desc& d, int i) {
         out[i] = to_bf16(v, lo);
         return;
     }
+    if (kind == VQAE_PACK_SAME_MMA_F16) {
+        // [11][n][k] row-major: W1 | W2 tap 0..8 | W3 (mma_same.cu reads B fragments from rows n)
+        // For c >= 16 the kernel reads x and writes out with one 128-bit access per lane: lane
+        // (g, t) holds channels 4t .. 4t + 3 of a 16-channel group in fragment slots 2t, 2t + 1,
+        // 2t + 8, 2t + 9.  Slot i of a group therefore stands for channel perm(i); W1's input (k)
+        // order and W3's output (n) order are stored in slot order.
+        const int Cc = d.c_in, per = Cc * Cc;
+        const int m = i / per, n = (i % per) / Cc, k = i % Cc;
+        auto perm = [Cc](int s) {
+            if (Cc < 16) return s;
+            const int r = s & 15;
+            return (s & ~15) + 4 * ((r & 7) >> 1) + 2 * (r >> 3) + (r & 1);
+        };
+        float v;
+        if (m == 0) v = w1[n * Cc + perm(k)];
+        else if (m == 10) v = w3[perm(n) * Cc + k];
+        else v = w2[((size_t)n * Cc + k) * 9 + (m - 1)];
+        out[i] = to_bf16(v, lo);
+        return;
+    }
     if (kind == VQAE_PACK_DOWN_F16) {
         const int CI = d.c_in, CIP = CI < 16 ? 16 : CI, CO = d.c_out;
         const int n1 = CO * CIP, no = CO * CO;
@@ -117,6 +137,7 @@ size_t pack_elems(int kind, int c_in, int c_out, int taps) {
             const size_t cp = c_in < 16 ? 16 : c_in;
             return 11 * cp * cp;
         }
+        case VQAE_PACK_SAME_MMA_F16: return (size_t)11 * c_in * c_in;
         case VQAE_PACK_DOWN_F16: {
             const size_t cip = c_in < 16 ? 16 : c_in, co = c_out;
             return co * cip + 4 * co * co + co * co + 4 * co * cip;

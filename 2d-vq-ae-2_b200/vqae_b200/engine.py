@@ -178,7 +178,7 @@ class PackedFixup:
         self.params = p
         self.w1 = self.w2 = self.w3 = self.w_skip = None           # fp32 [tap][I][O] packs
         # tcgen05 path: bf16 operand packs
-        self.tc_weights = self.tc_weights_res = None
+        self.tc_weights = self.tc_weights_res = self.mma_weights = None
         self.tc_scalars = None
         self.tc_kind = None
         if self.mode == L.MODE_SAME and self.c_in in (8, 16, 32, 64, 128) and \
@@ -237,6 +237,12 @@ class PackedFixup:
             self.tc_weights = torch.empty(n, dtype=torch.float16, device=self.device)
             out.append(self._desc(L.PACK_SAME_F16, self.tc_weights, self.c_in, self.c_in, 9,
                                   self.src[:3]))
+            if self.c_in in (8, 16, 32):
+                # low-channel form on warp-level MMAs (mma_same.cu): plain [11][n][k]
+                self.mma_weights = torch.empty(11 * self.c_in * self.c_in, dtype=torch.float16,
+                                               device=self.device)
+                out.append(self._desc(L.PACK_SAME_MMA_F16, self.mma_weights, self.c_in, self.c_in, 9,
+                                      self.src[:3]))
             if self.has_resident:
                 # image-resident trunk kernel: branch_conv3 pre-multiplied by the Fixup scale
                 self.tc_weights_res = torch.empty(n, dtype=torch.float16, device=self.device)
@@ -322,6 +328,11 @@ def _plan_layouts(packed: Sequence[PackedFixup], h: int, w: int, precision: str)
 # single calls
 # ----------------------------------------------------------------------------------------------
 PRECISIONS = ("fp32", "fp16")
+# 'same' blocks of these widths run on warp-level MMAs (mma_same.cu) instead of the tcgen05 tile /
+# resident kernels (a set, so that A/B runs can switch single levels).  Measured per block at batch
+# 256 on B200: C = 8 @256^2 292 vs 430 us, C = 16 @128^2 162 vs 199 us; C = 32 @64^2 126 us against
+# 89 us per block for the image-resident tcgen05 run, which therefore keeps that level.
+LOWC_MMA = {8, 16}
 # True: in "fp16" mode the NHWC tensors between tensor-core kernels are fp16 instead of fp32.  Built,
 # tested (tests/test_gpu_tc.py) and measured on B200 (round 2): halving the block-boundary bytes
 # changes the step time by < 1 % (4.56 vs 4.55 ms at batch 256 -- the tile kernels are latency /
@@ -370,6 +381,13 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
     tc = precision == "fp16" and pk.tc_ok(h, w)
     if tc and pk.chain_only:
         return run_blocks_nhwc([pk], x, "fp16")
+    if tc and pk.mode == L.MODE_SAME and c in LOWC_MMA and x.dtype == torch.float32 and \
+            lib.vqae_same_block_mma_supported(h, w, c):
+        if out is None:
+            out = torch.empty_like(x)
+        L.check(lib.vqae_same_block_mma_f16(_ptr(x), _ptr(out), _ptr(pk.mma_weights), pk.tc_scalars,
+                                            b, h, w, c, _stream(x.device)), "vqae_same_block_mma_f16")
+        return out
     if tc:
         if out is None:
             out = torch.empty(b, ho, wo, pk.c_out, dtype=x.dtype, device=x.device)
@@ -420,7 +438,8 @@ def _chain_runs(packed: Sequence[PackedFixup], h: int, w: int, batch: int = 1 <<
                 j += 1
             resident = TRUNK_RESIDENT and pk.has_resident and \
                 lib.vqae_trunk_resident_supported(batch, hh, ww, pk.c_in)
-            if (j - i >= 2 or pk.chain_only) and \
+            lowc = pk.c_in in LOWC_MMA and lib.vqae_same_block_mma_supported(hh, ww, pk.c_in)
+            if not lowc and (j - i >= 2 or pk.chain_only) and \
                     (resident or lib.vqae_same_chain_supported(batch, hh, ww, pk.c_in)):
                 runs.append((i, j))
             i = j

@@ -70,7 +70,7 @@ int vqae_pack_conv_weight_f32(const float* w_oihw, float* packed, int out_ch, in
  * split-bf16 operands of precision "bf16x3".  n_elems = vqae_pack_elems(kind, c_in, c_out, taps).
  * descs_device: the table in DEVICE memory; max_elems: the largest n_elems in it.             */
 enum { VQAE_PACK_F32_CONV = 0, VQAE_PACK_SAME_F16 = 1, VQAE_PACK_RESIDENT_F16 = 2,
-       VQAE_PACK_DOWN_F16 = 3, VQAE_PACK_LO = 0x100 };
+       VQAE_PACK_DOWN_F16 = 3, VQAE_PACK_SAME_MMA_F16 = 4, VQAE_PACK_LO = 0x100 };
 typedef struct vqae_pack_desc {
     int32_t kind, c_in, c_out, taps;
     float scale;
@@ -157,6 +157,16 @@ int vqae_pack_same_block_f16(const float* w1_oihw, const float* w2_oihw, const f
 int vqae_same_block_f16(const void* x, void* out, int io_dtype, const void* w_packed,
                         const float* scalars8_host, int64_t batch, int height, int width, int c,
                         void* stream);
+/* The same block at LOW channel counts (c in {8, 16, 32}: the full-resolution pyramid levels) on
+ * warp-level tensor-core MMAs with the three GEMMs chained through registers (csrc/mma_same.cu):
+ * for N = c <= 32 the activation arithmetic and the memory stream are the cost, not the GEMMs, and
+ * many independent warps beat one 512-pixel tile per CTA behind tensor-memory round trips.
+ * w_packed: 11 * c * c fp16 from vqae_pack_batched(VQAE_PACK_SAME_MMA_F16); scalars8_host as for
+ * vqae_same_block_f16; x, out: NHWC fp32, must not alias; height % 16 == 0, width % 32 == 0.   */
+int vqae_same_block_mma_supported(int height, int width, int c);
+int vqae_same_block_mma_f16(const float* x, float* out, const void* w_packed,
+                            const float* scalars8_host, int64_t batch, int height, int width, int c,
+                            void* stream);
 /* A run of n_blocks consecutive 'same' blocks of equal width in ONE persistent launch (the 50-block
  * trunks model.py:150-153,240-263 and the post layers of DownBlock/UpBlock): every (block, tile)
  * task is scheduled round-robin over the resident CTAs and ordered by per-(block, image) completion

@@ -319,8 +319,8 @@ def test_encoder_nd4_512_bf16_agreement_with_fp32():
 @pytest.mark.parametrize("mode,c,hw,batch", [("same", 8, 64, 3), ("same", 16, 32, 5), ("same", 32, 64, 2),
                                              ("same", 64, 32, 3), ("down", 8, 64, 2), ("down", 16, 32, 3),
                                              ("down", 32, 64, 2)])
-def test_fp16_stream_is_the_fp32_stream_rounded_once(mode, c, hw, batch):
-    """The tile kernels read / write fp32 or fp16 NHWC tensors; everything between load and store is
+def test_fp16_stream_is_the_fp32_stream_rounded_once(mode, c, hw, batch, monkeypatch):
+    """The tcgen05 tile kernels read / write fp32 or fp16 NHWC tensors; everything between load and store is
     the same arithmetic, so on an fp16-representable input the fp16-stream output is exactly the
     fp32-stream output rounded to fp16."""
     from vqae_b200.config import pre_activation_fixup
@@ -332,6 +332,7 @@ def test_fp16_stream_is_the_fp32_stream_rounded_once(mode, c, hw, batch):
     blk = PreActFixupResBlock(in_channels=c, out_channels=co, mode=mode, **conf).eval()
     blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=17, regime="perturbed", n_layers=12))
     pk = blk.to(DEV).packed()
+    monkeypatch.setattr(E, "LOWC_MMA", set())          # this test is about the tcgen05 tile kernels
     xh = torch.randn(batch, hw, hw, c, device=DEV).half()
     y32 = E.fixup_forward_nhwc(pk, xh.float(), precision="fp16")
     y16 = E.fixup_forward_nhwc(pk, xh, precision="fp16")
@@ -351,3 +352,67 @@ def test_stem_in_fp16_stream_output():
     assert torch.equal(E.stem_in(x, w, b, out_dtype=torch.float16), E.stem_in(x, w, b).half())
     xs = torch.randn(1, 3, 48, 48, device=DEV)                 # not tileable: stays fp32
     assert E.stem_in(xs, w, b, out_dtype=torch.float16).dtype == torch.float32
+
+
+@pytest.mark.parametrize("c,hw,batch", [(8, 256, 1), (8, 64, 5), (16, 128, 2), (16, 32, 9), (32, 64, 3),
+                                        (32, 32, 4), (16, 16 * 3, 2)])
+def test_low_channel_mma_same_block(c, hw, batch, monkeypatch):
+    """csrc/mma_same.cu ('same' blocks with C <= 32 on warp-level MMAs, GEMMs chained through
+    registers) against the fp32 exact path (1e-2 of the branch magnitude: the fp16-operand bar) and
+    against the tcgen05 tile kernel, which rounds the same operands to fp16 at the same places (the
+    two differ only by fp32 accumulation order: 1e-3 of the branch)."""
+    w = 32 if hw == 48 else hw
+    blocks = _same_blocks(c, 1, 123)
+    pk = E.pack_blocks(blocks)[0]
+    E.ensure_packed([pk], [True], [True])
+    x = torch.randn(batch, hw, w, c, generator=torch.Generator().manual_seed(c + hw)).to(DEV)
+    y32 = E.fixup_forward_nhwc(pk, x, precision="fp32")
+    monkeypatch.setattr(E, "LOWC_MMA", {8, 16, 32})
+    before = E.launch_count()
+    y_mma = E.fixup_forward_nhwc(pk, x, precision="fp16")
+    assert E.launch_count() - before == 1
+    monkeypatch.setattr(E, "LOWC_MMA", set())
+    y_tc = E.fixup_forward_nhwc(pk, x, precision="fp16")
+    torch.cuda.synchronize()
+    branch = float((y32 - x).abs().max())
+    assert float((y_mma - y32).abs().max()) / branch < 1e-2
+    assert float((y_mma - y_tc).abs().max()) / branch < 1e-3, float((y_mma - y_tc).abs().max()) / branch
+    monkeypatch.setattr(E, "LOWC_MMA", {8, 16, 32})
+    assert torch.equal(y_mma, E.fixup_forward_nhwc(pk, x, precision="fp16"))      # deterministic
+
+
+@pytest.mark.parametrize("c", [8, 16, 32])
+def test_low_channel_mma_wrap_and_taps_exact(c):
+    """Identity 1x1 weights and a single unit tap make the block a pure circular shift on fp16-exact
+    positive inputs: checks the halo wrap, the tap -> row-shift mapping and the fragment layouts of
+    mma_same.cu without any tolerance."""
+    blk = _same_blocks(c, 1, 91)[0]
+    with torch.no_grad():
+        for name in ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4"):
+            getattr(blk, name).zero_()
+        blk.scale.fill_(1.0)
+        eye = torch.eye(c, device=DEV)
+        blk.branch_conv1.weight.copy_(eye[:, :, None, None])
+        blk.branch_conv3.weight.copy_(eye[:, :, None, None])
+    for ky in range(3):
+        for kx in range(3):
+            with torch.no_grad():
+                blk.branch_conv2.weight.zero_()
+                blk.branch_conv2.weight[:, :, ky, kx] = eye
+            pk = E.pack_blocks([blk])[0]
+            x = torch.randint(1, 200, (2, 32, 64, c), device=DEV).float() / 8.0
+            out = E.fixup_forward_nhwc(pk, x, precision="fp16")
+            torch.cuda.synchronize()
+            ref = x + torch.roll(x, shifts=(-(ky - 1), -(kx - 1)), dims=(1, 2))
+            assert torch.equal(out, ref), (ky, kx, float((out - ref).abs().max()))
+    # a permutation in the 1x1 convs checks the channel order of the B fragments
+    perm = torch.randperm(c, generator=torch.Generator().manual_seed(c))
+    with torch.no_grad():
+        blk.branch_conv2.weight.zero_()
+        blk.branch_conv2.weight[:, :, 1, 1] = eye
+        blk.branch_conv1.weight.copy_(eye[perm][:, :, None, None])
+        blk.branch_conv3.weight.copy_((2 * eye)[:, :, None, None])
+    pk = E.pack_blocks([blk])[0]
+    x = torch.randint(1, 200, (1, 16, 32, c), device=DEV).float() / 8.0
+    out = E.fixup_forward_nhwc(pk, x, precision="fp16")
+    assert torch.equal(out, x + 2 * x[..., perm])
