@@ -90,6 +90,11 @@ bool same_block_mma_supported(int H, int W, int C);
 int same_block_mma(const float* x, float* out, const void* w_packed, const float* scalars8,
                    int64_t B, int H, int W, int C, int sm_count, cudaStream_t stream);
 
+// mma_down.cu ('down' blocks on warp-level MMAs, register-resident)
+bool down_block_mma_supported(int H, int W, int CI);
+int down_block_mma(const float* x, float* out, const void* w_packed, const float* scalars8,
+                   int64_t B, int H, int W, int CI, int sm_count, cudaStream_t stream);
+
 // tc_chain.cu (persistent multi-block 'same' chain)
 size_t same_chain_flag_bytes(int n_blocks, int64_t B);
 bool same_chain_supported(int64_t B, int H, int W, int C, int sm_count);

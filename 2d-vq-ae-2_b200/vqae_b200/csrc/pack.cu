@@ -91,6 +91,34 @@ __device__ void pack_element(const vqae_pack_desc& d, int i) {
         out[i] = to_bf16(v, lo);
         return;
     }
+    if (kind == VQAE_PACK_DOWN_MMA_F16) {
+        // dense [n][k] rows: W1 [CO][CI] | W2 x4 [CO][CO] | scale*W3 [CO][CO] | Ws x4 [CO][CI]
+        // (mma_down.cu).  Slot order as in SAME_MMA: input channels of W1 / Ws (c_in >= 16) and
+        // output channels of W3 / Ws are stored in fragment-slot order.
+        const int CI = d.c_in, CO = d.c_out;
+        auto perm = [](int s, int width) {
+            if (width < 16) return s;
+            const int r = s & 15;
+            return (s & ~15) + 4 * ((r & 7) >> 1) + 2 * (r >> 3) + (r & 1);
+        };
+        const int n1 = CO * CI, n2 = 4 * CO * CO, n3 = CO * CO;
+        int j = i;
+        float v;
+        if (j < n1) {
+            v = w1[(j / CI) * CI + perm(j % CI, CI)];
+        } else if ((j -= n1) < n2) {
+            const int tap = j / (CO * CO), r = j % (CO * CO);
+            v = w2[((size_t)(r / CO) * CO + r % CO) * 4 + tap];
+        } else if ((j -= n2) < n3) {
+            v = w3[perm(j / CO, CO) * CO + j % CO] * d.scale;
+        } else {
+            j -= n3;
+            const int tap = j / n1, r = j % n1;
+            v = ws[((size_t)perm(r / CI, CO) * CI + perm(r % CI, CI)) * 4 + tap];
+        }
+        out[i] = to_bf16(v, lo);
+        return;
+    }
     if (kind == VQAE_PACK_DOWN_F16) {
         const int CI = d.c_in, CIP = CI < 16 ? 16 : CI, CO = d.c_out;
         const int n1 = CO * CIP, no = CO * CO;
@@ -138,6 +166,9 @@ size_t pack_elems(int kind, int c_in, int c_out, int taps) {
             return 11 * cp * cp;
         }
         case VQAE_PACK_SAME_MMA_F16: return (size_t)11 * c_in * c_in;
+        case VQAE_PACK_DOWN_MMA_F16:
+            return (size_t)c_out * c_in + 4 * (size_t)c_out * c_out + (size_t)c_out * c_out +
+                   4 * (size_t)c_out * c_in;
         case VQAE_PACK_DOWN_F16: {
             const size_t cip = c_in < 16 ? 16 : c_in, co = c_out;
             return co * cip + 4 * co * co + co * co + 4 * co * cip;

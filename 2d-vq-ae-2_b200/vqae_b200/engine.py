@@ -253,6 +253,10 @@ class PackedFixup:
             self.tc_weights = torch.empty(n, dtype=torch.float16, device=self.device)
             out.append(self._desc(L.PACK_DOWN_F16, self.tc_weights, self.c_in, self.c_out, 4,
                                   self.src, sc["scale"]))
+            n = lib.vqae_pack_elems(L.PACK_DOWN_MMA_F16, self.c_in, self.c_out, 4)
+            self.mma_weights = torch.empty(n, dtype=torch.float16, device=self.device)
+            out.append(self._desc(L.PACK_DOWN_MMA_F16, self.mma_weights, self.c_in, self.c_out, 4,
+                                  self.src, sc["scale"]))
         return out
 
     def tc_ok(self, h: int, w: int) -> bool:
@@ -333,6 +337,8 @@ PRECISIONS = ("fp32", "fp16")
 # 256 on B200: C = 8 @256^2 292 vs 430 us, C = 16 @128^2 162 vs 199 us; C = 32 @64^2 126 us against
 # 89 us per block for the image-resident tcgen05 run, which therefore keeps that level.
 LOWC_MMA = {8, 16}
+# 'down' blocks with these input widths on warp-level MMAs (mma_down.cu) instead of tc_down.cu
+DOWN_MMA = {8, 16, 32}
 # True: in "fp16" mode the NHWC tensors between tensor-core kernels are fp16 instead of fp32.  Built,
 # tested (tests/test_gpu_tc.py) and measured on B200 (round 2): halving the block-boundary bytes
 # changes the step time by < 1 % (4.56 vs 4.55 ms at batch 256 -- the tile kernels are latency /
@@ -387,6 +393,13 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
             out = torch.empty_like(x)
         L.check(lib.vqae_same_block_mma_f16(_ptr(x), _ptr(out), _ptr(pk.mma_weights), pk.tc_scalars,
                                             b, h, w, c, _stream(x.device)), "vqae_same_block_mma_f16")
+        return out
+    if tc and pk.mode == L.MODE_DOWN and c in DOWN_MMA and x.dtype == torch.float32 and \
+            lib.vqae_down_block_mma_supported(h, w, c):
+        if out is None:
+            out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
+        L.check(lib.vqae_down_block_mma_f16(_ptr(x), _ptr(out), _ptr(pk.mma_weights), pk.tc_scalars,
+                                            b, h, w, c, _stream(x.device)), "vqae_down_block_mma_f16")
         return out
     if tc:
         if out is None:

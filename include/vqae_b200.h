@@ -70,7 +70,8 @@ int vqae_pack_conv_weight_f32(const float* w_oihw, float* packed, int out_ch, in
  * split-bf16 operands of precision "bf16x3".  n_elems = vqae_pack_elems(kind, c_in, c_out, taps).
  * descs_device: the table in DEVICE memory; max_elems: the largest n_elems in it.             */
 enum { VQAE_PACK_F32_CONV = 0, VQAE_PACK_SAME_F16 = 1, VQAE_PACK_RESIDENT_F16 = 2,
-       VQAE_PACK_DOWN_F16 = 3, VQAE_PACK_SAME_MMA_F16 = 4, VQAE_PACK_LO = 0x100 };
+       VQAE_PACK_DOWN_F16 = 3, VQAE_PACK_SAME_MMA_F16 = 4, VQAE_PACK_DOWN_MMA_F16 = 5,
+       VQAE_PACK_LO = 0x100 };
 typedef struct vqae_pack_desc {
     int32_t kind, c_in, c_out, taps;
     float scale;
@@ -167,6 +168,14 @@ int vqae_same_block_mma_supported(int height, int width, int c);
 int vqae_same_block_mma_f16(const float* x, float* out, const void* w_packed,
                             const float* scalars8_host, int64_t batch, int height, int width, int c,
                             void* stream);
+/* 'down' block (c_in in {8, 16, 32} -> 2 c_in) on warp-level MMAs, every intermediate in registers
+ * (csrc/mma_down.cu; a 2x2 stride-2 conv has no halo).  w_packed: vqae_pack_batched(
+ * VQAE_PACK_DOWN_MMA_F16); scalars8_host as for vqae_down_block_f16; x: NHWC fp32 [B,H,W,c_in],
+ * out: NHWC fp32 [B,H/2,W/2,2 c_in]; height % 2 == 0, width % 32 == 0.                        */
+int vqae_down_block_mma_supported(int height, int width, int c_in);
+int vqae_down_block_mma_f16(const float* x, float* out, const void* w_packed,
+                            const float* scalars8_host, int64_t batch, int height, int width,
+                            int c_in, void* stream);
 /* A run of n_blocks consecutive 'same' blocks of equal width in ONE persistent launch (the 50-block
  * trunks model.py:150-153,240-263 and the post layers of DownBlock/UpBlock): every (block, tile)
  * task is scheduled round-robin over the resident CTAs and ordered by per-(block, image) completion

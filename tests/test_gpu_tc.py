@@ -333,6 +333,7 @@ def test_fp16_stream_is_the_fp32_stream_rounded_once(mode, c, hw, batch, monkeyp
     blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=17, regime="perturbed", n_layers=12))
     pk = blk.to(DEV).packed()
     monkeypatch.setattr(E, "LOWC_MMA", set())          # this test is about the tcgen05 tile kernels
+    monkeypatch.setattr(E, "DOWN_MMA", set())
     xh = torch.randn(batch, hw, hw, c, device=DEV).half()
     y32 = E.fixup_forward_nhwc(pk, xh.float(), precision="fp16")
     y16 = E.fixup_forward_nhwc(pk, xh, precision="fp16")
@@ -416,3 +417,33 @@ def test_low_channel_mma_wrap_and_taps_exact(c):
     x = torch.randint(1, 200, (1, 16, 32, c), device=DEV).float() / 8.0
     out = E.fixup_forward_nhwc(pk, x, precision="fp16")
     assert torch.equal(out, x + 2 * x[..., perm])
+
+
+@pytest.mark.parametrize("c,hw,batch", [(8, 64, 3), (16, 32, 5), (32, 64, 2), (8, 256, 1)])
+def test_down_block_mma_vs_fp32_and_tcgen05(c, hw, batch, monkeypatch):
+    """csrc/mma_down.cu ('down' blocks on warp-level MMAs, every intermediate in registers) against
+    the fp32 exact path (fp16-operand bar: 1e-2 of the output range) and against the tcgen05 kernel
+    of tc_down.cu, which rounds the same operands at the same places (1e-3: accumulation order)."""
+    from vqae_b200.config import pre_activation_fixup
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blk = PreActFixupResBlock(in_channels=c, out_channels=2 * c, mode="down", **conf).eval()
+    blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=29, regime="perturbed", n_layers=12))
+    pk = blk.to(DEV).packed()
+    E.ensure_packed([pk], [True], [True])
+    x = torch.randn(batch, hw, hw, c, generator=torch.Generator().manual_seed(c)).to(DEV)
+    y32 = E.fixup_forward_nhwc(pk, x, precision="fp32")
+    monkeypatch.setattr(E, "DOWN_MMA", {8, 16, 32})
+    before = E.launch_count()
+    y_mma = E.fixup_forward_nhwc(pk, x, precision="fp16")
+    assert E.launch_count() - before == 1
+    monkeypatch.setattr(E, "DOWN_MMA", set())
+    y_tc = E.fixup_forward_nhwc(pk, x, precision="fp16")
+    torch.cuda.synchronize()
+    scale = float(y32.abs().max())
+    assert float((y_mma - y32).abs().max()) / scale < 1e-2
+    assert float((y_mma - y_tc).abs().max()) / scale < 1e-3
+    monkeypatch.setattr(E, "DOWN_MMA", {8, 16, 32})
+    assert torch.equal(y_mma, E.fixup_forward_nhwc(pk, x, precision="fp16"))
