@@ -48,7 +48,7 @@ class PackDesc(C.Structure):
 
 
 PACK_F32_CONV, PACK_SAME_F16, PACK_RESIDENT_F16, PACK_DOWN_F16, PACK_SAME_MMA_F16 = 0, 1, 2, 3, 4
-PACK_DOWN_MMA_F16 = 5
+PACK_DOWN_MMA_F16, PACK_UP_MMA_F16 = 5, 6
 PACK_LO = 0x100
 
 

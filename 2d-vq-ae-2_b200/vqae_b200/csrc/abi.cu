@@ -273,6 +273,23 @@ int vqae_down_block_mma_f16(const float* x, float* out, const void* w_packed,
                           (cudaStream_t)stream);
 }
 
+int vqae_up_block_mma_supported(int height, int width, int c_in) {
+    return up_block_mma_supported(height, width, c_in) ? 1 : 0;
+}
+
+size_t vqae_up_block_mma_scratch_bytes(int64_t batch, int height, int width, int c_in) {
+    return up_block_mma_scratch_bytes(batch, height, width, c_in);
+}
+
+int vqae_up_block_mma_f16(const float* x, float* out, const void* w_packed,
+                          const float* scalars8_host, void* scratch, size_t scratch_bytes,
+                          int64_t batch, int height, int width, int c_in, void* stream) {
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return up_block_mma(x, out, w_packed, scalars8_host, scratch, scratch_bytes, batch, height, width,
+                        c_in, sm_count, (cudaStream_t)stream);
+}
+
 size_t vqae_same_chain_flag_bytes(int n_blocks, int64_t batch) {
     return same_chain_flag_bytes(n_blocks, batch);
 }

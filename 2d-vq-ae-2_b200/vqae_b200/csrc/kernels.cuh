@@ -95,6 +95,13 @@ bool down_block_mma_supported(int H, int W, int CI);
 int down_block_mma(const float* x, float* out, const void* w_packed, const float* scalars8,
                    int64_t B, int H, int W, int CI, int sm_count, cudaStream_t stream);
 
+// mma_up.cu ('up' blocks on warp-level MMAs: low-resolution head + high-resolution tail)
+bool up_block_mma_supported(int H, int W, int CI);
+size_t up_block_mma_scratch_bytes(int64_t B, int H, int W, int CI);
+int up_block_mma(const float* x, float* out, const void* w_packed, const float* scalars8,
+                 void* scratch, size_t scratch_bytes, int64_t B, int H, int W, int CI, int sm_count,
+                 cudaStream_t stream);
+
 // tc_chain.cu (persistent multi-block 'same' chain)
 size_t same_chain_flag_bytes(int n_blocks, int64_t B);
 bool same_chain_supported(int64_t B, int H, int W, int C, int sm_count);

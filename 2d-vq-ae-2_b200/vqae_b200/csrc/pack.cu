@@ -119,6 +119,26 @@ __device__ void pack_element(const vqae_pack_desc& d, int i) {
         out[i] = to_bf16(v, lo);
         return;
     }
+    if (kind == VQAE_PACK_UP_MMA_F16) {
+        // dense [n][k] rows: W1 [CB][CI] | W2 [CB][CB] | Ws [CO][CI] | scale*W3 [CO][CB], CB = CI,
+        // CO = CI / 2 (mma_up.cu).  Slot order: k of W1 / Ws / W3 (their A fragments come from
+        // 128-bit channel groups), n of W2 / Ws / W3 (128-bit stores) where the width is >= 16.
+        const int CI = d.c_in, CB = d.c_in, CO = d.c_out;
+        auto perm = [](int s, int width) {
+            if (width < 16) return s;
+            const int r = s & 15;
+            return (s & ~15) + 4 * ((r & 7) >> 1) + 2 * (r >> 3) + (r & 1);
+        };
+        const int n1 = CB * CI, n2 = CB * CB, ns = CO * CI;
+        int j = i;
+        float v;
+        if (j < n1) v = w1[(j / CI) * CI + perm(j % CI, CI)];
+        else if ((j -= n1) < n2) v = w2[perm(j / CB, CB) * CB + j % CB];
+        else if ((j -= n2) < ns) v = ws[perm(j / CI, CO) * CI + perm(j % CI, CI)];
+        else { j -= ns; v = w3[perm(j / CB, CO) * CB + perm(j % CB, CB)] * d.scale; }
+        out[i] = to_bf16(v, lo);
+        return;
+    }
     if (kind == VQAE_PACK_DOWN_F16) {
         const int CI = d.c_in, CIP = CI < 16 ? 16 : CI, CO = d.c_out;
         const int n1 = CO * CIP, no = CO * CO;
@@ -166,6 +186,8 @@ size_t pack_elems(int kind, int c_in, int c_out, int taps) {
             return 11 * cp * cp;
         }
         case VQAE_PACK_SAME_MMA_F16: return (size_t)11 * c_in * c_in;
+        case VQAE_PACK_UP_MMA_F16:
+            return 2 * (size_t)c_in * c_in + 2 * (size_t)c_out * c_in;
         case VQAE_PACK_DOWN_MMA_F16:
             return (size_t)c_out * c_in + 4 * (size_t)c_out * c_out + (size_t)c_out * c_out +
                    4 * (size_t)c_out * c_in;

@@ -186,6 +186,13 @@ class PackedFixup:
             self.tc_kind = "same"
             self.tc_scalars = (C.c_float * 8)(*[float(sc[k]) for k in (
                 "bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "scale")])
+        elif self.mode == L.MODE_UP and self.c_in in (16, 32, 64) and \
+                self.c_branch == self.c_in and self.c_out * 2 == self.c_in:
+            self.tc_kind = "up"
+            self.tc_scalars = (C.c_float * 8)(*(
+                [float(sc[k]) for k in ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a",
+                                        "bias3b", "bias1c")]
+                + [float(sc["bias4"]) + float(sc["bias1d"])]))
         elif self.mode == L.MODE_DOWN and self.c_in in (8, 16, 32) and \
                 self.c_branch == 2 * self.c_in and self.c_out == 2 * self.c_in:
             self.tc_kind = "down"
@@ -248,6 +255,12 @@ class PackedFixup:
                 self.tc_weights_res = torch.empty(n, dtype=torch.float16, device=self.device)
                 out.append(self._desc(L.PACK_RESIDENT_F16, self.tc_weights_res, self.c_in,
                                       self.c_in, 9, self.src[:3], sc["scale"]))
+        elif self.tc_kind == "up":
+            n = lib.vqae_pack_elems(L.PACK_UP_MMA_F16, self.c_in, self.c_out, 1)
+            self.tc_weights = self.mma_weights = torch.empty(n, dtype=torch.float16,
+                                                             device=self.device)
+            out.append(self._desc(L.PACK_UP_MMA_F16, self.mma_weights, self.c_in, self.c_out, 1,
+                                  [self.src[0], self.src[1], self.src[2], self.src[3]], sc["scale"]))
         else:
             n = lib.vqae_pack_elems(L.PACK_DOWN_F16, self.c_in, self.c_out, 4)
             self.tc_weights = torch.empty(n, dtype=torch.float16, device=self.device)
@@ -262,6 +275,8 @@ class PackedFixup:
     def tc_ok(self, h: int, w: int) -> bool:
         """a tcgen05 kernel is built for this block at this size (16 x 32 pixel tiles; 8 x 32 for
         the C = 128 'same' blocks, which only exist in the persistent chain form)"""
+        if self.tc_kind == "up":
+            return h % 4 == 0 and w % 16 == 0
         if self.tc_kind is None or w % 32:
             return False
         return h % 8 == 0 if self.chain_only else h % 16 == 0
@@ -393,6 +408,15 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
             out = torch.empty_like(x)
         L.check(lib.vqae_same_block_mma_f16(_ptr(x), _ptr(out), _ptr(pk.mma_weights), pk.tc_scalars,
                                             b, h, w, c, _stream(x.device)), "vqae_same_block_mma_f16")
+        return out
+    if tc and pk.mode == L.MODE_UP:
+        x = _as_stream(x, False)
+        if out is None:
+            out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
+        ws = workspace(x.device, lib.vqae_up_block_mma_scratch_bytes(b, h, w, c))
+        L.check(lib.vqae_up_block_mma_f16(_ptr(x), _ptr(out), _ptr(pk.mma_weights), pk.tc_scalars,
+                                          _ptr(ws), ws.numel(), b, h, w, c, _stream(x.device)),
+                "vqae_up_block_mma_f16")
         return out
     if tc and pk.mode == L.MODE_DOWN and c in DOWN_MMA and x.dtype == torch.float32 and \
             lib.vqae_down_block_mma_supported(h, w, c):

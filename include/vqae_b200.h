@@ -71,7 +71,7 @@ int vqae_pack_conv_weight_f32(const float* w_oihw, float* packed, int out_ch, in
  * descs_device: the table in DEVICE memory; max_elems: the largest n_elems in it.             */
 enum { VQAE_PACK_F32_CONV = 0, VQAE_PACK_SAME_F16 = 1, VQAE_PACK_RESIDENT_F16 = 2,
        VQAE_PACK_DOWN_F16 = 3, VQAE_PACK_SAME_MMA_F16 = 4, VQAE_PACK_DOWN_MMA_F16 = 5,
-       VQAE_PACK_LO = 0x100 };
+       VQAE_PACK_UP_MMA_F16 = 6, VQAE_PACK_LO = 0x100 };
 typedef struct vqae_pack_desc {
     int32_t kind, c_in, c_out, taps;
     float scale;
@@ -176,6 +176,18 @@ int vqae_down_block_mma_supported(int height, int width, int c_in);
 int vqae_down_block_mma_f16(const float* x, float* out, const void* w_packed,
                             const float* scalars8_host, int64_t batch, int height, int width,
                             int c_in, void* stream);
+/* 'up' block (c_in in {16, 32, 64} -> c_in / 2, x2 bicubic; conv_block.py:196-216 with ResizeConv2D,
+ * conv.py:4-11) on warp-level MMAs in two kernels (csrc/mma_up.cu): the three 1x1 convs that
+ * commute with the upsample at LOW resolution (register-resident), then bicubic interpolation
+ * (index-clamped, separable) + branch_conv3 + skip sum at high resolution.  w_packed:
+ * vqae_pack_batched(VQAE_PACK_UP_MMA_F16, c_in, c_in / 2); scalars8_host = {bias1a, bias1b, bias2a,
+ * bias2b, bias3a, bias3b, bias1c, bias4 + bias1d}; x: NHWC fp32 [B,H,W,c_in], out: NHWC fp32
+ * [B,2H,2W,c_in/2]; height % 4 == 0, width % 16 == 0; scratch >= vqae_up_block_mma_scratch_bytes. */
+int vqae_up_block_mma_supported(int height, int width, int c_in);
+size_t vqae_up_block_mma_scratch_bytes(int64_t batch, int height, int width, int c_in);
+int vqae_up_block_mma_f16(const float* x, float* out, const void* w_packed,
+                          const float* scalars8_host, void* scratch, size_t scratch_bytes,
+                          int64_t batch, int height, int width, int c_in, void* stream);
 /* A run of n_blocks consecutive 'same' blocks of equal width in ONE persistent launch (the 50-block
  * trunks model.py:150-153,240-263 and the post layers of DownBlock/UpBlock): every (block, tile)
  * task is scheduled round-robin over the resident CTAs and ordered by per-(block, image) completion

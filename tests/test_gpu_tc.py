@@ -447,3 +447,63 @@ def test_down_block_mma_vs_fp32_and_tcgen05(c, hw, batch, monkeypatch):
     assert float((y_mma - y_tc).abs().max()) / scale < 1e-3
     monkeypatch.setattr(E, "DOWN_MMA", {8, 16, 32})
     assert torch.equal(y_mma, E.fixup_forward_nhwc(pk, x, precision="fp16"))
+
+
+def _up_block(c_in, seed):
+    from vqae_b200.config import pre_activation_fixup
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blk = PreActFixupResBlock(in_channels=c_in, out_channels=c_in // 2, mode="up", **conf).eval()
+    blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=seed, regime="perturbed", n_layers=12))
+    return blk.to(DEV)
+
+
+@pytest.mark.parametrize("c_in,h,w,batch", [(16, 128, 128, 1), (16, 16, 32, 3), (32, 64, 64, 2),
+                                            (32, 4, 16, 5), (64, 32, 32, 3), (64, 8, 48, 2)])
+def test_up_block_mma_vs_fp32_path(c_in, h, w, batch):
+    """csrc/mma_up.cu ('up' blocks on warp-level MMAs: low-resolution head, high-resolution tail with
+    the separable index-clamped bicubic) against the fp32 exact path, which is pinned to the
+    reference goldens (up16 / up64): fp16-operand bar 1e-2 of the output range, measured ~1e-3."""
+    blk = _up_block(c_in, 41)
+    pk = blk.packed()
+    E.ensure_packed([pk], [True], [True])
+    x = torch.randn(batch, h, w, c_in, generator=torch.Generator().manual_seed(h + w)).to(DEV)
+    y32 = E.fixup_forward_nhwc(pk, x, precision="fp32")
+    before = E.launch_count()
+    y16 = E.fixup_forward_nhwc(pk, x, precision="fp16")
+    torch.cuda.synchronize()
+    assert E.launch_count() - before == 2                        # head + tail
+    assert y16.shape == (batch, 2 * h, 2 * w, c_in // 2)
+    err = float((y16 - y32).abs().max()) / float(y32.abs().max())
+    assert err < 5e-3, err
+    assert torch.equal(y16, E.fixup_forward_nhwc(pk, x, precision="fp16"))
+
+
+@pytest.mark.parametrize("c_in", [16, 32, 64])
+def test_up_block_mma_bicubic_geometry(c_in):
+    """Identity 1x1 convs, zero biases, no skip and positive inputs reduce the block to
+    out = bicubic_x2(x)[..., :c_out]: every tap, both parities and the clamped borders of the tail's
+    separable interpolation against torch's upsample_bicubic2d (fp16 rounding of the operands only)."""
+    blk = _up_block(c_in, 43)
+    co = c_in // 2
+    with torch.no_grad():
+        for name in ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "bias1c", "bias1d"):
+            getattr(blk, name).zero_()
+        blk.scale.fill_(1.0)
+        eye = torch.eye(c_in, device=DEV)
+        blk.branch_conv1.weight.copy_(eye[:, :, None, None])
+        blk.branch_conv2.weight.copy_(eye[:, :, None, None])
+        blk.branch_conv3.weight.copy_(eye[:co][:, :, None, None])
+        blk.skip_conv.weight.zero_()
+    pk = E.pack_blocks([blk])[0]
+    # smooth positive field + offset: the interpolant stays positive, so every ELU is the identity
+    g = torch.Generator().manual_seed(c_in)
+    x = (torch.rand(2, 12, 48, c_in, generator=g) * 4.0 + 2.0).to(DEV)
+    out = E.fixup_forward_nhwc(pk, x, precision="fp16")
+    ref = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="bicubic",
+                                          align_corners=False).permute(0, 2, 3, 1)[..., :co]
+    torch.cuda.synchronize()
+    assert float(out.min()) > 0
+    assert float((out - ref).abs().max()) < 3e-3 * float(ref.abs().max())
