@@ -276,7 +276,7 @@ class PackedFixup:
         """a tcgen05 kernel is built for this block at this size (16 x 32 pixel tiles; 8 x 32 for
         the C = 128 'same' blocks, which only exist in the persistent chain form)"""
         if self.tc_kind == "up":
-            return h % 4 == 0 and w % 16 == 0
+            return bool(L.load().vqae_up_block_mma_supported(h, w, self.c_in))
         if self.tc_kind is None or w % 32:
             return False
         return h % 8 == 0 if self.chain_only else h % 16 == 0
