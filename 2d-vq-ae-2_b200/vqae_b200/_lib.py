@@ -44,7 +44,7 @@ class PackDesc(C.Structure):
     """struct vqae_pack_desc"""
     _fields_ = [("kind", C.c_int32), ("c_in", C.c_int32), ("c_out", C.c_int32), ("taps", C.c_int32),
                 ("scale", C.c_float), ("n_elems", C.c_int32), ("src", C.c_void_p * 4),
-                ("dst", C.c_void_p)]
+                ("dst", C.c_void_p), ("premul", C.c_float * 4)]
 
 
 PACK_F32_CONV, PACK_SAME_F16, PACK_RESIDENT_F16, PACK_DOWN_F16, PACK_SAME_MMA_F16 = 0, 1, 2, 3, 4
@@ -129,8 +129,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.vqae_abi_version() != 3:
-        raise RuntimeError(f"{path}: ABI version {lib.vqae_abi_version()} != 3")
+    if lib.vqae_abi_version() != 4:
+        raise RuntimeError(f"{path}: ABI version {lib.vqae_abi_version()} != 4")
     _lib = lib
     return lib
 

@@ -95,6 +95,16 @@ bool down_block_mma_supported(int H, int W, int CI);
 int down_block_mma(const float* x, float* out, const void* w_packed, const float* scalars8,
                    int64_t B, int H, int W, int CI, int sm_count, cudaStream_t stream);
 
+int down_block_split(const float* x, float* out, const void* w_hi, const void* w_lo,
+                     const float* scalars8, const float* premul3, int64_t B, int H, int W, int CI,
+                     int sm_count, cudaStream_t stream);
+
+// tc_split.cu (fp32-accurate 'same' block: split fp16 operands on tcgen05)
+bool same_block_split_supported(int H, int W, int C);
+int same_block_split(const float* x, float* out, const void* w_hi, const void* w_lo,
+                     const float* scalars8, const float* premul3, int64_t B, int H, int W, int C,
+                     int sm_count, cudaStream_t stream);
+
 // mma_up.cu ('up' blocks on warp-level MMAs: low-resolution head + high-resolution tail)
 bool up_block_mma_supported(int H, int W, int CI);
 size_t up_block_mma_scratch_bytes(int64_t B, int H, int W, int CI);

@@ -9,7 +9,10 @@
 //                 zero padded from c to max(c, 16) channels               (tc_kernels.cu, tc_chain.cu)
 //   RESIDENT_BF16 the same with branch_conv3 pre-multiplied by the Fixup scale      (tc_resident.cu)
 //   DOWN_BF16     [W1 | W2 x4 planes | scale*W3 | Ws x4 planes], C_in zero padded to >= 16 (tc_down.cu)
-// The *_LO variants hold bf16(w - bf16(w)): the low half of the split-bf16 ("bf16x3") operands.
+// kind | VQAE_PACK_LO holds f16(w - f16(w)): the low half of the split operands of the fp32-accurate
+// tensor-core mode (tc_split.cu, mma_down.cu SPLIT); there the matrices are first multiplied by the
+// powers of two vqae_pack_desc.premul[] (branch_conv1, 2, 3, skip; 0 = 1) so that the low halves stay
+// normal fp16 numbers.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -48,6 +51,8 @@ __device__ void pack_element(const vqae_pack_desc& d, int i) {
     const float* ws = reinterpret_cast<const float*>(d.src[3]);
     const int kind = d.kind & 0xff;
     const bool lo = (d.kind & VQAE_PACK_LO) != 0;
+    const float pm1 = d.premul[0] > 0.f ? d.premul[0] : 1.f, pm2 = d.premul[1] > 0.f ? d.premul[1] : 1.f;
+    const float pm3 = d.premul[2] > 0.f ? d.premul[2] : 1.f, pms = d.premul[3] > 0.f ? d.premul[3] : 1.f;
     if (kind == VQAE_PACK_F32_CONV) {
         // packed index i = (t * I + c) * O + o
         const int O = d.c_out, I = d.c_in, taps = d.taps;
@@ -64,9 +69,9 @@ __device__ void pack_element(const vqae_pack_desc& d, int i) {
         canon(i % per, CP, n, k);
         float v = 0.f;
         if (n < CR && k < CR) {
-            if (m == 0) v = w1[n * CR + k];
-            else if (m == 10) v = w3[n * CR + k] * (kind == VQAE_PACK_RESIDENT_F16 ? d.scale : 1.f);
-            else v = w2[((size_t)n * CR + k) * 9 + (m - 1)];
+            if (m == 0) v = w1[n * CR + k] * pm1;
+            else if (m == 10) v = w3[n * CR + k] * (kind == VQAE_PACK_RESIDENT_F16 ? d.scale : 1.f) * pm3;
+            else v = w2[((size_t)n * CR + k) * 9 + (m - 1)] * pm2;
         }
         out[i] = to_bf16(v, lo);
         return;
@@ -105,16 +110,16 @@ __device__ void pack_element(const vqae_pack_desc& d, int i) {
         int j = i;
         float v;
         if (j < n1) {
-            v = w1[(j / CI) * CI + perm(j % CI, CI)];
+            v = w1[(j / CI) * CI + perm(j % CI, CI)] * pm1;
         } else if ((j -= n1) < n2) {
             const int tap = j / (CO * CO), r = j % (CO * CO);
-            v = w2[((size_t)(r / CO) * CO + r % CO) * 4 + tap];
+            v = w2[((size_t)(r / CO) * CO + r % CO) * 4 + tap] * pm2;
         } else if ((j -= n2) < n3) {
-            v = w3[perm(j / CO, CO) * CO + j % CO] * d.scale;
+            v = w3[perm(j / CO, CO) * CO + j % CO] * d.scale * pm3;
         } else {
             j -= n3;
             const int tap = j / n1, r = j % n1;
-            v = ws[((size_t)perm(r / CI, CO) * CI + perm(r % CI, CI)) * 4 + tap];
+            v = ws[((size_t)perm(r / CI, CO) * CI + perm(r % CI, CI)) * 4 + tap] * pms;
         }
         out[i] = to_bf16(v, lo);
         return;

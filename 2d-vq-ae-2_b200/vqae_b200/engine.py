@@ -7,6 +7,7 @@ path: tensors that are not on a CUDA device raise.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -181,6 +182,10 @@ class PackedFixup:
         self.tc_weights = self.tc_weights_res = self.mma_weights = None
         self.tc_scalars = None
         self.tc_kind = None
+        # fp32-accurate tensor-core mode ("fp32tc"): split fp16 operand packs (hi, lo), the powers
+        # of two the matrices were multiplied by, and max|w| of the four convs they derive from
+        self.split_hi = self.split_lo = self.split_premul = None
+        self.wmax: Optional[List[float]] = None
         if self.mode == L.MODE_SAME and self.c_in in (8, 16, 32, 64, 128) and \
                 self.c_branch == self.c_in and self.c_out == self.c_in:
             self.tc_kind = "same"
@@ -272,6 +277,45 @@ class PackedFixup:
                                   self.src, sc["scale"]))
         return out
 
+    def split_ok(self, h: int, w: int) -> bool:
+        """a split-operand (fp32-accurate) tensor-core kernel is built for this block and size"""
+        lib = L.load()
+        if self.tc_kind == "same" and self.c_in in (8, 16, 32, 64):
+            return bool(lib.vqae_same_block_split_supported(h, w, self.c_in))
+        if self.tc_kind == "down":
+            return bool(lib.vqae_down_block_mma_supported(h, w, self.c_in))
+        return False
+
+    def descs_split(self) -> List["L.PackDesc"]:
+        if self.split_hi is not None or self.tc_kind not in ("same", "down"):
+            return []
+        assert self.wmax is not None, "ensure_wmax first"
+        lib = L.load()
+
+        def pm(m: float) -> float:
+            # power of two that moves max|w| into (2^13, 2^14]: every low half f16(w - f16(w)) of a
+            # weight within 2^-27 of the largest one is then a normal fp16 number
+            return 1.0 if not (m > 0.0 and math.isfinite(m)) else 2.0 ** (14 - math.ceil(math.log2(m)))
+        w1m, w2m, w3m, wsm = self.wmax
+        if self.tc_kind == "same":
+            kind, taps, srcs, scale = L.PACK_SAME_F16, 9, self.src[:3], 1.0
+            premul = [pm(w1m), pm(w2m), pm(w3m), 1.0]
+        else:
+            kind, taps, srcs, scale = L.PACK_DOWN_MMA_F16, 4, self.src, self.scalars["scale"]
+            p3 = pm(max(w3m * abs(scale), wsm))      # branch_conv3 and skip_conv share an accumulator
+            premul = [pm(w1m), pm(w2m), p3, p3]
+        n = lib.vqae_pack_elems(kind, self.c_in, self.c_out, taps)
+        self.split_hi = torch.empty(n, dtype=torch.float16, device=self.device)
+        self.split_lo = torch.empty(n, dtype=torch.float16, device=self.device)
+        self.split_premul = (C.c_float * 3)(*premul[:3])
+        out = []
+        for dst, flag in ((self.split_hi, 0), (self.split_lo, L.PACK_LO)):
+            d = self._desc(kind | flag, dst, self.c_in, self.c_out, taps, srcs, scale)
+            for i, v in enumerate(premul):
+                d.premul[i] = v
+            out.append(d)
+        return out
+
     def tc_ok(self, h: int, w: int) -> bool:
         """a tcgen05 kernel is built for this block at this size (16 x 32 pixel tiles; 8 x 32 for
         the C = 128 'same' blocks, which only exist in the persistent chain form)"""
@@ -313,14 +357,31 @@ def pack_blocks(blocks: Sequence) -> List[PackedFixup]:
     return [PackedFixup(b, host[i * n:(i + 1) * n]) for i, b in enumerate(blocks)]
 
 
-def ensure_packed(packed: Sequence[PackedFixup], f32: Sequence[bool], tc: Sequence[bool]) -> None:
+def ensure_wmax(packed: Sequence[PackedFixup]) -> None:
+    """max|w| of every conv of the blocks that do not have it yet, with ONE host copy."""
+    todo = [pk for pk in packed if pk.wmax is None]
+    if not todo:
+        return
+    zero = torch.zeros((), device=todo[0].device)
+    vals = torch.stack([t.abs().max() if t is not None else zero for pk in todo for t in pk.src])
+    host = vals.cpu().tolist()
+    for i, pk in enumerate(todo):
+        pk.wmax = host[4 * i:4 * i + 4]
+
+
+def ensure_packed(packed: Sequence[PackedFixup], f32: Sequence[bool], tc: Sequence[bool],
+                  split: Optional[Sequence[bool]] = None) -> None:
     """Pack whatever is still missing for the requested layouts -- one vqae_pack_batched launch."""
     descs, keep = [], []
-    for pk, want_f32, want_tc in zip(packed, f32, tc):
+    if split is not None and any(split):
+        ensure_wmax([pk for pk, want in zip(packed, split) if want and pk.split_hi is None])
+    for i, (pk, want_f32, want_tc) in enumerate(zip(packed, f32, tc)):
         if want_f32:
             descs += pk.descs_f32()
         if want_tc:
             descs += pk.descs_tc()
+        if split is not None and split[i]:
+            descs += pk.descs_split()
     if not descs:
         return
     dev = packed[0].device
@@ -333,20 +394,27 @@ def ensure_packed(packed: Sequence[PackedFixup], f32: Sequence[bool], tc: Sequen
 
 
 def _plan_layouts(packed: Sequence[PackedFixup], h: int, w: int, precision: str):
-    """(needs fp32 pack, needs tensor-core pack) per block for an input of h x w."""
-    f32, tc = [], []
+    """(needs fp32 pack, needs tensor-core pack, needs split-operand pack) per block for an input
+    of h x w."""
+    f32, tc, split = [], [], []
     for pk in packed:
-        use_tc = precision != "fp32" and pk.tc_ok(h, w)
+        use_tc = precision == "fp16" and pk.tc_ok(h, w)
+        use_split = precision == "fp32tc" and pk.split_ok(h, w)
         tc.append(use_tc)
-        f32.append(not use_tc)
+        split.append(use_split)
+        f32.append(not (use_tc or use_split))
         h, w = pk.out_hw(h, w)
-    return f32, tc
+    return f32, tc, split
 
 
 # ----------------------------------------------------------------------------------------------
 # single calls
 # ----------------------------------------------------------------------------------------------
-PRECISIONS = ("fp32", "fp16")
+# "fp32": CUDA-core exact path.  "fp16": tensor-core kernels with fp16 operands (what an active
+# torch.autocast('cuda') selects).  "fp32tc": tensor-core kernels with split fp16 operands
+# (hi + lo, three products each, exact activations) -- fp32-accurate, the reference's fp32 index
+# contract holds outside near-ties (csrc/tc_split.cu).
+PRECISIONS = ("fp32", "fp16", "fp32tc")
 # 'same' blocks of these widths run on warp-level MMAs (mma_same.cu) instead of the tcgen05 tile /
 # resident kernels (a set, so that A/B runs can switch single levels).  Measured per block at batch
 # 256 on B200: C = 8 @256^2 292 vs 430 us, C = 16 @128^2 162 vs 199 us; C = 32 @64^2 126 us against
@@ -400,6 +468,16 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
     ho, wo = pk.out_hw(h, w)
     ensure_packed([pk], *_plan_layouts([pk], h, w, precision))
     tc = precision == "fp16" and pk.tc_ok(h, w)
+    if precision == "fp32tc" and pk.split_ok(h, w):
+        x = _as_stream(x, False)
+        if out is None:
+            out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
+        fn, name = ((lib.vqae_down_block_split_f16, "vqae_down_block_split_f16")
+                    if pk.mode == L.MODE_DOWN
+                    else (lib.vqae_same_block_split_f16, "vqae_same_block_split_f16"))
+        L.check(fn(_ptr(x), _ptr(out), _ptr(pk.split_hi), _ptr(pk.split_lo), pk.tc_scalars,
+                   pk.split_premul, b, h, w, c, _stream(x.device)), name)
+        return out
     if tc and pk.chain_only:
         return run_blocks_nhwc([pk], x, "fp16")
     if tc and pk.mode == L.MODE_SAME and c in LOWC_MMA and x.dtype == torch.float32 and \

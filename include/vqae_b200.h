@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VQAE_ABI_VERSION 3
+#define VQAE_ABI_VERSION 4
 
 enum {
     VQAE_OK = 0,
@@ -66,8 +66,9 @@ int vqae_pack_conv_weight_f32(const float* w_oihw, float* packed, int out_ch, in
  * PreActFixupResBlock (SAME / RESIDENT: src = {branch_conv1, branch_conv2, branch_conv3};
  * DOWN: + skip_conv) and the destination; c_in / c_out are the block's channel counts (F32_CONV:
  * the conv's, with `taps` = kh*kw); `scale` is the Fixup scale folded into branch_conv3 by the
- * RESIDENT and DOWN layouts.  kind | VQAE_PACK_LO writes bf16(w - bf16(w)), the low half of the
- * split-bf16 operands of precision "bf16x3".  n_elems = vqae_pack_elems(kind, c_in, c_out, taps).
+ * RESIDENT and DOWN layouts.  kind | VQAE_PACK_LO writes f16(w - f16(w)), the low half of the
+ * split operands of precision "fp32tc" (vqae_same_block_split_f16, vqae_down_block_split_f16), where
+ * premul[] scales the matrices first.  n_elems = vqae_pack_elems(kind, c_in, c_out, taps).
  * descs_device: the table in DEVICE memory; max_elems: the largest n_elems in it.             */
 enum { VQAE_PACK_F32_CONV = 0, VQAE_PACK_SAME_F16 = 1, VQAE_PACK_RESIDENT_F16 = 2,
        VQAE_PACK_DOWN_F16 = 3, VQAE_PACK_SAME_MMA_F16 = 4, VQAE_PACK_DOWN_MMA_F16 = 5,
@@ -78,6 +79,8 @@ typedef struct vqae_pack_desc {
     int32_t n_elems;
     const void* src[4];
     void* dst;
+    float premul[4];   /* powers of two applied to branch_conv1, 2, 3, skip before rounding (0 = 1):
+                          the split-operand packs of the fp32-accurate tensor-core mode */
 } vqae_pack_desc;
 size_t vqae_pack_elems(int kind, int c_in, int c_out, int taps);
 int vqae_pack_batched(const vqae_pack_desc* descs_device, int n_descs, int max_elems, void* stream);
@@ -176,6 +179,24 @@ int vqae_down_block_mma_supported(int height, int width, int c_in);
 int vqae_down_block_mma_f16(const float* x, float* out, const void* w_packed,
                             const float* scalars8_host, int64_t batch, int height, int width,
                             int c_in, void* stream);
+/* fp32-ACCURATE tensor-core forms (precision "fp32tc"): every GEMM operand is a pair hi + lo of fp16
+ * numbers (22 significand bits), every product three tensor-core products hi.hi + lo.hi + hi.lo with
+ * fp32 accumulation, the activation is the fp32 path's expm1f -- the reference's fp32 index contract
+ * (vq.py:121-129) holds outside reported near-ties at tensor-core speed.
+ * 'same' block (csrc/tc_split.cu, tcgen05, 8 x 32 pixel tiles): c in {8, 16, 32, 64}, height % 8 == 0,
+ * width % 32 == 0.  w_hi / w_lo: vqae_pack_batched(VQAE_PACK_SAME_F16 [| VQAE_PACK_LO]) with
+ * premul = premul3_host (powers of two for branch_conv1, 2, 3: 2^(14 - ceil(log2 max|w|)) keeps every
+ * low half a normal fp16 number); scalars8_host as for vqae_same_block_f16.  fp32 NHWC in and out.
+ * 'down' block (csrc/mma_down.cu, SPLIT instantiation, register-resident): c_in in {8, 16, 32};
+ * w_hi / w_lo: VQAE_PACK_DOWN_MMA_F16 [| VQAE_PACK_LO] with premul = {p1, p2, p3, p3} (branch_conv3
+ * and skip_conv share an accumulator, hence a factor); scalars8_host as for vqae_down_block_f16. */
+int vqae_same_block_split_supported(int height, int width, int c);
+int vqae_same_block_split_f16(const float* x, float* out, const void* w_hi, const void* w_lo,
+                              const float* scalars8_host, const float* premul3_host, int64_t batch,
+                              int height, int width, int c, void* stream);
+int vqae_down_block_split_f16(const float* x, float* out, const void* w_hi, const void* w_lo,
+                              const float* scalars8_host, const float* premul3_host, int64_t batch,
+                              int height, int width, int c_in, void* stream);
 /* 'up' block (c_in in {16, 32, 64} -> c_in / 2, x2 bicubic; conv_block.py:196-216 with ResizeConv2D,
  * conv.py:4-11) on warp-level MMAs in two kernels (csrc/mma_up.cu): the three 1x1 convs that
  * commute with the upsample at LOW resolution (register-resident), then bicubic interpolation

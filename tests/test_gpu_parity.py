@@ -167,11 +167,15 @@ def test_resize_conv_vs_oracle():
     assert H.rel_err(conv(x).cpu(), ref) < 2e-5
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp32tc"])
 @pytest.mark.parametrize("tag", sorted(H.MODEL_CASES))
-def test_model_vs_reference_golden(tag):
+def test_model_vs_reference_golden(tag, precision):
+    """The parity-grade paths against the goldens of the unmodified reference: "fp32" (CUDA-core
+    kernels) and "fp32tc" (the same contract on the tensor cores: split fp16 operands, csrc/tc_split.cu
+    and the SPLIT form of csrc/mma_down.cu; blocks without a split kernel run the fp32 kernels)."""
     g = H.golden(tag)
     m, sd, x = H.model_and_state(tag)
-    m = vqae_b200.set_precision(m.to(DEV), "fp32")
+    m = vqae_b200.set_precision(m.to(DEV), precision)
     try:
         with torch.no_grad():
             (enc,), (idx,), (loss,) = m.encoder(x.to(DEV))
@@ -182,7 +186,7 @@ def test_model_vs_reference_golden(tag):
             enc_m = m.encoder
             stem_nhwc = E.stem_in(x.to(DEV), enc_m.in_stem.weight, enc_m.in_stem.bias)
             blocks = P.flat_blocks(enc_m.down_layers) + P.flat_blocks(enc_m.pre_enc_layers)
-            pre_vq = P.Plan().run(blocks, stem_nhwc, "fp32").permute(0, 3, 1, 2)
+            pre_vq = P.Plan().run(blocks, stem_nhwc, precision).permute(0, 3, 1, 2)
             stem = stem_nhwc.permute(0, 3, 1, 2)
         assert idx.dtype == torch.int64 and tuple(idx.shape) == g["idx"].shape
         assert loss.dim() == 0 and torch.equal(loss, loss2)

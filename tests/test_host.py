@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
     assert aid_declared == set(_lib_tc.AIDS_SIGNATURES) and not (aid_declared & declared)
     for name in sorted(aid_declared):
         assert hasattr(aids, name) and not hasattr(lib, name), name
-    assert lib.vqae_abi_version() == 3
+    assert lib.vqae_abi_version() == 4
     assert lib.vqae_error_string(3).decode().startswith("VQ dim != channel dim")
 
 
