@@ -295,6 +295,22 @@ int vqae_down_block_split_f16(const float* x, float* out, const void* w_hi, cons
                             c_in, sm_count, (cudaStream_t)stream);
 }
 
+int vqae_front_fused_supported(int height, int width) {
+    return front_fused_supported(height, width) ? 1 : 0;
+}
+
+int vqae_front_fused_f16(const void* x, int x_dtype, int x_layout, const float* stem_w,
+                         const float* stem_bias, const float* mean_host, const float* std_host,
+                         const void* same_w_packed, const float* same_scalars8_host,
+                         const void* down_w_packed, const float* down_scalars8_host, float* out,
+                         int64_t batch, int height, int width, void* stream) {
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return front_fused(x, x_dtype, x_layout, stem_w, stem_bias, mean_host, std_host, same_w_packed,
+                       same_scalars8_host, down_w_packed, down_scalars8_host, out, batch, height,
+                       width, sm_count, (cudaStream_t)stream);
+}
+
 int vqae_up_block_mma_supported(int height, int width, int c_in) {
     return up_block_mma_supported(height, width, c_in) ? 1 : 0;
 }

@@ -105,6 +105,13 @@ int same_block_split(const float* x, float* out, const void* w_hi, const void* w
                      const float* scalars8, const float* premul3, int64_t B, int H, int W, int C,
                      int sm_count, cudaStream_t stream);
 
+// mma_front.cu (in_stem + 'same' C = 8 + 'down' 8 -> 16 in one kernel)
+bool front_fused_supported(int H, int W);
+int front_fused(const void* x, int x_dtype, int x_layout, const float* stem_w, const float* stem_b,
+                const float* mean, const float* stdv, const void* same_w, const float* same_scalars8,
+                const void* down_w, const float* down_scalars8, float* out, int64_t B, int H, int W,
+                int sm_count, cudaStream_t stream);
+
 // mma_up.cu ('up' blocks on warp-level MMAs: low-resolution head + high-resolution tail)
 bool up_block_mma_supported(int H, int W, int CI);
 size_t up_block_mma_scratch_bytes(int64_t B, int H, int W, int CI);

@@ -18,7 +18,7 @@
 //
 // Structure = the tile kernel of tc_kernels.cu, simplified: tile 8 x 32 pixels + circular halo ring
 // (10 x 34 = 340 padded-linear pixels, 3 M-tiles), ONE operand region reused for A1 -> U -> V (two
-// planes: hi | lo), W1 / W3 resident, the W2 taps through a bulk-copy ring at C = 64.
+// planes: hi | lo), W1 / W3 resident, the W2 taps through a 3-slot bulk-copy ring at C = 64.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -34,7 +34,8 @@ constexpr int SP_MT = 3;                            // M-tiles of G1 / G2 (384 r
 constexpr int SP_MT3 = SP_TH * SP_TW / 128;         // M-tiles of G3 (interior, pixel-linear)
 constexpr int SP_RPIX = 455;                        // 35 + 3 * 128 + 35 = 454 pixels, odd pitch
 constexpr uint32_t SP_LBO = SP_RPIX * 16;
-constexpr int SP_RING = 4;
+constexpr int SP_RING = 3;                          // divides the 9 taps: a tap's slot is tap % 3, a
+                                                    // compile-time constant (descriptors stay uniform)
 
 template <int CP, int CR>
 struct SplitCfg {
@@ -282,9 +283,8 @@ same_block_split_kernel(SplitArgs a) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 uint64_t dW;
-                int slot = 0;
+                const int slot = tap % SP_RING;
                 if (Cfg::RING) {
-                    slot = taps_used % SP_RING;
                     mbar_wait(bar_full + 8 * slot, (taps_used / SP_RING) & 1);
                     tc_fence_after_sync();
                     dW = dW2 + (uint64_t)((slot * 2 * WMAT) >> 4);

@@ -650,6 +650,65 @@ def stem_in(x: Tensor, weight: Tensor, bias: Tensor, mean=None, std=None,
     return out
 
 
+# True: in "fp16" mode the encoder's in_stem + 'same' C = 8 + 'down' 8 -> 16 run as ONE kernel
+# (csrc/mma_front.cu) where the model starts that way.  Built, tested (tests/test_gpu_front.py) and
+# measured on B200 at batch 256 of 256^2 (round 2, profiles/run_front.py): DRAM traffic 261 MB
+# instead of 2.4 GB, but 869 us against 756 us for the three separate launches -- each phase of a
+# tile is a chain of dependent MMAs / MUFUs per warp with five CTA barriers per tile, and the kernel
+# is latency bound at 24 warps per SM (issue slots 60 % busy) -- so the separate launches stay the
+# default.
+FRONT_FUSED = False
+
+
+def encoder_front(x: Tensor, weight: Tensor, bias: Tensor, mean, std, packed: Sequence[PackedFixup],
+                  precision: str, half_stream: bool = False) -> Tuple[Tensor, int]:
+    """in_stem plus as many leading blocks of ``packed`` as one kernel covers: returns the NHWC
+    activation and the number of blocks consumed (0 = the stem alone, vqae_stem_in)."""
+    lib = L.load()
+    fuse = (FRONT_FUSED and precision == "fp16" and not half_stream and len(packed) >= 2
+            and weight.shape[0] == 8
+            and packed[0].tc_kind == "same" and packed[0].c_in == 8
+            and packed[1].tc_kind == "down" and packed[1].c_in == 8)
+    if fuse:
+        if x.dtype == torch.uint8:
+            hh, ww = x.shape[1], x.shape[2]
+        else:
+            hh, ww = x.shape[2], x.shape[3]
+        fuse = bool(lib.vqae_front_fused_supported(hh, ww))
+    if not fuse:
+        return stem_in(x, weight, bias, mean, std,
+                       torch.float16 if half_stream else torch.float32), 0
+    require_cuda(x, "encoder_front")
+    ensure_packed(packed[:2], [False, False], [True, True])
+    w = weight.detach().float().contiguous()
+    bi = bias.detach().float().contiguous()
+    if x.dtype == torch.uint8:
+        if x.dim() != 4 or x.shape[-1] != 3:
+            raise ValueError("uint8 input must be [B,H,W,3]")
+        x = x.contiguous()
+        b = x.shape[0]
+        dt, lay = L.DT_U8, L.LAYOUT_NHWC
+        mean_a, std_a = L.f3(mean or CAMELYON16_MEAN), L.f3(std or CAMELYON16_STD)
+    else:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected [B,3,H,W] input, got {tuple(x.shape)}")
+        b = x.shape[0]
+        if x.dtype != torch.float32:
+            x = x.float()
+        if is_channels_last(x):
+            lay = L.LAYOUT_NHWC
+        else:
+            x = x.contiguous()
+            lay = L.LAYOUT_NCHW
+        dt, mean_a, std_a = L.DT_F32, None, None
+    out = torch.empty(b, hh // 2, ww // 2, 16, dtype=torch.float32, device=x.device)
+    L.check(lib.vqae_front_fused_f16(_ptr(x), dt, lay, _ptr(w), _ptr(bi), mean_a, std_a,
+                                     _ptr(packed[0].mma_weights), packed[0].tc_scalars,
+                                     _ptr(packed[1].mma_weights), packed[1].tc_scalars, _ptr(out),
+                                     b, hh, ww, _stream(x.device)), "vqae_front_fused_f16")
+    return out, 2
+
+
 def stem_out(x_nhwc: Tensor, weight: Tensor, bias: Tensor, channels_last: bool) -> Tensor:
     """NHWC fp32 [B,H,W,8] -> [B,3,H,W] (contiguous NCHW, or channels_last strides)."""
     lib = L.load()

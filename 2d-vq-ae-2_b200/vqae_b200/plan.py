@@ -76,6 +76,14 @@ class Plan:
     def run(self, blocks: Sequence[nn.Module], h: Tensor, precision: str = "fp32") -> Tensor:
         return E.run_blocks_nhwc(self.get(blocks), h, precision, self.chains)
 
+    def run_from_input(self, stem, blocks: Sequence[nn.Module], x: Tensor, mean, std,
+                       precision: str, half_stream: bool) -> Tensor:
+        """in_stem + the chain; the stem and the leading blocks fuse into one launch where a kernel
+        is built for them (E.encoder_front)."""
+        packed = self.get(blocks)
+        h, used = E.encoder_front(x, stem.weight, stem.bias, mean, std, packed, precision, half_stream)
+        return E.run_blocks_nhwc(packed[used:], h, precision, self.chains)
+
 
 def _plan(module) -> Plan:
     st = state(module)
@@ -163,11 +171,12 @@ def encoder_encode(enc, x: Tensor, mean=None, std=None, want_quantized: bool = T
     precision = resolve_precision(enc)
     cl = x.dtype == torch.uint8 or E.is_channels_last(x)
     half = precision == "fp16" and E.STREAM_F16
-    h = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias, mean, std,
-                  torch.float16 if half else torch.float32)
-    # one plan over pyramid + trunk: the 'same' blocks that close the last DownBlock and the
-    # trunk are one run of equal-width blocks, i.e. ONE image-resident launch
-    h = _plan(enc).run(flat_blocks(enc.down_layers) + flat_blocks(enc.pre_enc_layers), h, precision)
+    # one plan over stem + pyramid + trunk: the 'same' blocks that close the last DownBlock and the
+    # trunk are one run of equal-width blocks, i.e. ONE image-resident launch; in_stem and the first
+    # two blocks are one launch in the reduced-precision mode
+    h = _plan(enc).run_from_input(enc.in_stem,
+                                  flat_blocks(enc.down_layers) + flat_blocks(enc.pre_enc_layers),
+                                  x, mean, std, precision, half)
     vq = enc.vq_layers[0]
     pq = packed_quantizer(vq)
     b, hh, ww, c = h.shape

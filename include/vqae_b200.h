@@ -179,6 +179,19 @@ int vqae_down_block_mma_supported(int height, int width, int c_in);
 int vqae_down_block_mma_f16(const float* x, float* out, const void* w_packed,
                             const float* scalars8_host, int64_t batch, int height, int width,
                             int c_in, void* stream);
+/* The encoder's FRONT END in one launch (csrc/mma_front.cu): in_stem (with the u8 normalisation of
+ * vqae_stem_in) + the C = 8 'same' block + the 'down' block 8 -> 16 of the first DownBlock
+ * (model.py:141,144-148,198-199) -- the input image is read once, the 16-channel half-resolution
+ * tensor written once, the two 8-channel full-resolution tensors in between never reach memory.
+ * Arithmetic of the "fp16" path: vqae_stem_in (fp32-accurate; split-operand tensor-core MMAs) ->
+ * vqae_same_block_mma_f16 -> vqae_down_block_mma_f16, same packed weights and host scalars as those
+ * calls.  x as for vqae_stem_in; out: NHWC fp32 [B,H/2,W/2,16]; height % 16 == 0, width % 32 == 0. */
+int vqae_front_fused_supported(int height, int width);
+int vqae_front_fused_f16(const void* x, int x_dtype, int x_layout, const float* stem_w_oihw,
+                         const float* stem_bias, const float* mean_host, const float* std_host,
+                         const void* same_w_packed, const float* same_scalars8_host,
+                         const void* down_w_packed, const float* down_scalars8_host, float* out,
+                         int64_t batch, int height, int width, void* stream);
 /* fp32-ACCURATE tensor-core forms (precision "fp32tc"): every GEMM operand is a pair hi + lo of fp16
  * numbers (22 significand bits), every product three tensor-core products hi.hi + lo.hi + hi.lo with
  * fp32 accumulation, the activation is the fp32 path's expm1f -- the reference's fp32 index contract

@@ -1,5 +1,5 @@
 """Launch one low-channel 'same' block (mma_same.cu or the tcgen05 tile kernel) at the bench shape.
-usage: python profiles/run_lowc.py C HW [mma|tc] [reps]"""
+usage: python profiles/run_lowc.py C HW [mma|tc|split] [reps]      (split = precision "fp32tc", tc_split.cu)"""
 import sys
 from pathlib import Path
 
@@ -24,15 +24,16 @@ blk = PreActFixupResBlock(in_channels=C, out_channels=C, mode="same", **conf).ev
 blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=3, regime="perturbed", n_layers=12))
 pk = blk.to(dev).packed()
 E.LOWC_MMA = {8, 16, 32} if kind == "mma" else set()
+prec = "fp32tc" if kind == "split" else "fp16"
 xs = [torch.randn(B, HW, HW, C, device=dev) for _ in range(2)]
 ys = [torch.empty_like(xs[0]) for _ in range(2)]
 for i in range(3):
-    E.fixup_forward_nhwc(pk, xs[i % 2], out=ys[i % 2], precision="fp16")
+    E.fixup_forward_nhwc(pk, xs[i % 2], out=ys[i % 2], precision=prec)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize()
 e0.record()
 for i in range(reps):
-    E.fixup_forward_nhwc(pk, xs[i % 2], out=ys[i % 2], precision="fp16")
+    E.fixup_forward_nhwc(pk, xs[i % 2], out=ys[i % 2], precision=prec)
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / reps * 1e3

@@ -26,6 +26,8 @@ for i in range(nblk):
     packs.append(pk)
 w_all = torch.cat(packs)
 scal = torch.tensor([[0.01, 0.02, -0.01, 0.03, 0.02, -0.02, 0.01, 0.2]] * nblk, dtype=torch.float32).to(dev)
+import types  # noqa: E402
+chain = types.SimpleNamespace(weights=w_all, scalars=scal, n=nblk)
 print("resident clusters per device:", lib.vqae_trunk_resident_max_clusters())
 xs = [torch.randn(B, H, W, C, device=dev) for _ in range(2)]
 y = torch.empty(B, H, W, C, device=dev)

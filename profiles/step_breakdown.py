@@ -41,16 +41,17 @@ def main():
                 e.record()
                 ev.append((label, e))
         mark("start")
-        h = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias)
-        mark("stem_in")
-        runs = dict(E._chain_runs(packed, h.shape[1], h.shape[2], h.shape[0])) if precision == "fp16" else {}
+        h, used = E.encoder_front(x, enc.in_stem.weight, enc.in_stem.bias, None, None, packed, precision)
+        mark("front: stem + same C8 + down C8->16" if used else "stem_in")
+        rest = packed[used:]
+        runs = dict(E._chain_runs(rest, h.shape[1], h.shape[2], h.shape[0])) if precision == "fp16" else {}
         i = 0
-        while i < len(packed):
-            pk = packed[i]
+        while i < len(rest):
+            pk = rest[i]
             hh = h.shape[1]
             if i in runs:
                 j = runs[i]
-                h = E.run_blocks_nhwc(packed[i:j], h, precision, chains)
+                h = E.run_blocks_nhwc(rest[i:j], h, precision, chains)
                 mark(f"chain {j - i}x same C{pk.c_in} @{hh}")
                 i = j
             else:
