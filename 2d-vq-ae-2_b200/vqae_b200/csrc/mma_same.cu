@@ -30,6 +30,8 @@
 // Two CTA barriers per tile, no tensor memory, no asynchronous-proxy fences.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "mma_common.cuh"
@@ -207,58 +209,84 @@ same_block_mma_kernel(MsArgs a) {
         }
         tc::mbar_wait(bar0 + 8 * buf, (Cfg::NXB == 2 ? (it >> 1) : it) & 1);     // x tile `buf` landed
 
+        // Both stages carry TWO M-tiles per warp step where the tile count allows: the per-M-tile work
+        // is a chain of dependent MMAs / MUFUs, so a second independent chain doubles what a warp
+        // keeps in flight, and in stage 2 the W2 fragments are read from shared memory once per pair.
         // ================= stage 1: U = f16(elu(W1 . f16(elu(x + b1a) + b1b) + b2a) + b2b) =============
-        for (int m = warp; m < Cfg::MT1; m += MS_WARPS) {
-            const int q0 = 16 * m + g, q1 = q0 + 8;       // rows g and g + 8 (slack rows are allocated)
-            uint32_t af[KS][4];
-            if constexpr (K8) {
-                const float2 v0 = *reinterpret_cast<const float2*>(xs + q0 * XP + 8 * t);
-                const float2 v1 = *reinterpret_cast<const float2*>(xs + q1 * XP + 8 * t);
-                af[0][0] = act1(v0.x, v0.y);
-                af[0][1] = act1(v1.x, v1.y);
-            } else {
-                // lane (g, t) takes channels 16s + 4t .. 4t + 3: fragment slots k' = 2t, 2t + 1, 2t + 8,
-                // 2t + 9 -- the k order of W1 is permuted to match at pack time (pack.cu)
+        auto stage1 = [&](auto np_c, int m0) {
+            constexpr int NP = decltype(np_c)::value;
+            uint32_t af[NP][KS][4];
 #pragma unroll
-                for (int s = 0; s < KS; ++s) {
-                    const int o0 = 16 * t + 64 * s;
-                    const int o1 = 16 * t + 64 * s;
-                    const float4 v0 = *reinterpret_cast<const float4*>(xs + q0 * XP + o0);
-                    const float4 v1 = *reinterpret_cast<const float4*>(xs + q1 * XP + o1);
-                    af[s][0] = act1(v0.x, v0.y);
-                    af[s][1] = act1(v1.x, v1.y);
-                    af[s][2] = act1(v0.z, v0.w);
-                    af[s][3] = act1(v1.z, v1.w);
+            for (int u = 0; u < NP; ++u) {
+                const int q0 = 16 * (m0 + u * MS_WARPS) + g, q1 = q0 + 8;   // rows g, g + 8 (slack rows allocated)
+                if constexpr (K8) {
+                    const float2 v0 = *reinterpret_cast<const float2*>(xs + q0 * XP + 8 * t);
+                    const float2 v1 = *reinterpret_cast<const float2*>(xs + q1 * XP + 8 * t);
+                    af[u][0][0] = act1(v0.x, v0.y);
+                    af[u][0][1] = act1(v1.x, v1.y);
+                } else {
+                    // lane (g, t) takes channels 16s + 4t .. 4t + 3: fragment slots k' = 2t, 2t + 1,
+                    // 2t + 8, 2t + 9 -- the k order of W1 is permuted to match at pack time (pack.cu)
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(xs + q0 * XP + 16 * t + 64 * s);
+                        const float4 v1 = *reinterpret_cast<const float4*>(xs + q1 * XP + 16 * t + 64 * s);
+                        af[u][s][0] = act1(v0.x, v0.y);
+                        af[u][s][1] = act1(v1.x, v1.y);
+                        af[u][s][2] = act1(v0.z, v0.w);
+                        af[u][s][3] = act1(v1.z, v1.w);
+                    }
                 }
             }
-            float d[NT][4];
+            float d[NP][NT][4];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f;
 #pragma unroll
-                for (int s = 0; s < KS; ++s) {
-                    if constexpr (K8) mma_1688(d[j], af[s][0], af[s][1], w1.b[j][s][0]);
-                    else mma_16816(d[j], af[s], w1.b[j][s][0], w1.b[j][s][1]);
+                for (int u = 0; u < NP; ++u) d[u][j][0] = d[u][j][1] = d[u][j][2] = d[u][j][3] = 0.f;
+#pragma unroll
+                for (int s = 0; s < KS; ++s)
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        if constexpr (K8) mma_1688(d[u][j], af[u][s][0], af[u][s][1], w1.b[j][s][0]);
+                        else mma_16816(d[u][j], af[u][s], w1.b[j][s][0], w1.b[j][s][1]);
+                    }
+            }
+#pragma unroll
+            for (int u = 0; u < NP; ++u) {
+                const int q0 = 16 * (m0 + u * MS_WARPS) + g, q1 = q0 + 8;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    *reinterpret_cast<uint32_t*>(smem + Cfg::OFF_U + q0 * UP + (8 * j + 2 * t) * 2) = act2(d[u][j][0], d[u][j][1]);
+                    *reinterpret_cast<uint32_t*>(smem + Cfg::OFF_U + q1 * UP + (8 * j + 2 * t) * 2) = act2(d[u][j][2], d[u][j][3]);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                *reinterpret_cast<uint32_t*>(smem + Cfg::OFF_U + q0 * UP + (8 * j + 2 * t) * 2) = act2(d[j][0], d[j][1]);
-                *reinterpret_cast<uint32_t*>(smem + Cfg::OFF_U + q1 * UP + (8 * j + 2 * t) * 2) = act2(d[j][2], d[j][3]);
-            }
+        };
+        for (int m = warp; m < Cfg::MT1; m += 2 * MS_WARPS) {
+            if (m + MS_WARPS < Cfg::MT1) stage1(std::integral_constant<int, 2>{}, m);
+            else stage1(std::integral_constant<int, 1>{}, m);
         }
         __syncthreads();
 
         // ================= stages 2 + 3 =================
-        for (int mt = warp; mt < Cfg::MT2; mt += MS_WARPS) {
-            const int r = mt >> 1, cb = (mt & 1) * 16;             // tile row, first column
-            const int qc = (r + 1) * MS_PW + cb + 1;                // padded-linear index of pixel 0
-            float d[NT][4];
-#pragma unroll
-            for (int j = 0; j < NT; ++j) d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f;
+        auto stage23 = [&](auto np_c, int mt0) {
+            constexpr int NP = decltype(np_c)::value;
+            int qc[NP], rr[NP], cbb[NP];
+            uint32_t lbase[NP];
             // ldmatrix row address of this lane: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
             const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
-            const uint32_t lbase = sU + (uint32_t)(qc + lrow) * UP + (K8 ? 0 : (lane >> 4) * 16);
+#pragma unroll
+            for (int u = 0; u < NP; ++u) {
+                const int mt = mt0 + u * MS_WARPS;
+                rr[u] = mt >> 1;                                   // tile row
+                cbb[u] = (mt & 1) * 16;                            // first column
+                qc[u] = (rr[u] + 1) * MS_PW + cbb[u] + 1;          // padded-linear index of pixel 0
+                lbase[u] = sU + (uint32_t)(qc[u] + lrow) * UP + (K8 ? 0 : (lane >> 4) * 16);
+            }
+            float d[NP][NT][4];
+#pragma unroll
+            for (int u = 0; u < NP; ++u)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) d[u][j][0] = d[u][j][1] = d[u][j][2] = d[u][j][3] = 0.f;
             // W2 fragments: matrices (n 0-7 | 8-15) x (k 0-7 | 8-15) of an n-tile pair
             const uint32_t wbase = sbase + Cfg::OFF_W + (uint32_t)((lane & 7) + (lane >> 4) * 8) * Cfg::WP +
                                    ((lane >> 3) & 1) * 16;
@@ -266,85 +294,103 @@ same_block_mma_kernel(MsArgs a) {
             for (int tap = 0; tap < 9; ++tap) {
                 const int shift = (tap / 3 - 1) * MS_PW + (tap % 3 - 1);
                 if constexpr (K8) {
-                    uint32_t a0, a1;
-                    ldmatrix_x2(a0, a1, lbase + shift * UP);
-                    mma_1688(d[0], a0, a1, w2r[tap].b[0][0][0]);
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        uint32_t a0, a1;
+                        ldmatrix_x2(a0, a1, lbase[u] + shift * UP);
+                        mma_1688(d[u][0], a0, a1, w2r[tap].b[0][0][0]);
+                    }
                 } else {
 #pragma unroll
                     for (int s = 0; s < KS; ++s) {
-                        uint32_t af[4];
-                        ldmatrix_x4(af, lbase + shift * UP + s * 32);
+                        uint32_t af[NP][4];
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) ldmatrix_x4(af[u], lbase[u] + shift * UP + s * 32);
 #pragma unroll
                         for (int p = 0; p < NT / 2; ++p) {
                             uint32_t bf[4];          // b(2p, s)[0], b(2p, s)[1], b(2p+1, s)[0], b(2p+1, s)[1]
                             ldmatrix_x4(bf, wbase + (uint32_t)(tap * C + 16 * p) * Cfg::WP + s * 32);
-                            mma_16816(d[2 * p], af, bf[0], bf[1]);
-                            mma_16816(d[2 * p + 1], af, bf[2], bf[3]);
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) {
+                                mma_16816(d[u][2 * p], af[u], bf[0], bf[1]);
+                                mma_16816(d[u][2 * p + 1], af[u], bf[2], bf[3]);
+                            }
                         }
                     }
                 }
             }
             // V = f16(elu(D2 + b3a) + b3b): accumulator fragments of n-tiles (2s, 2s + 1) are the A
             // fragment of k-step s
-            uint32_t vf[KS][4];
+            uint32_t vf[NP][KS][4];
 #pragma unroll
-            for (int s = 0; s < KS; ++s) {
-                if constexpr (K8) {
-                    vf[s][0] = act3(d[0][0], d[0][1]);
-                    vf[s][1] = act3(d[0][2], d[0][3]);
-                } else {
-                    vf[s][0] = act3(d[2 * s][0], d[2 * s][1]);
-                    vf[s][1] = act3(d[2 * s][2], d[2 * s][3]);
-                    vf[s][2] = act3(d[2 * s + 1][0], d[2 * s + 1][1]);
-                    vf[s][3] = act3(d[2 * s + 1][2], d[2 * s + 1][3]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f;
+            for (int u = 0; u < NP; ++u)
 #pragma unroll
                 for (int s = 0; s < KS; ++s) {
-                    if constexpr (K8) mma_1688(d[j], vf[s][0], vf[s][1], w3.b[j][s][0]);
-                    else mma_16816(d[j], vf[s], w3.b[j][s][0], w3.b[j][s][1]);
+                    if constexpr (K8) {
+                        vf[u][s][0] = act3(d[u][0][0], d[u][0][1]);
+                        vf[u][s][1] = act3(d[u][0][2], d[u][0][3]);
+                    } else {
+                        vf[u][s][0] = act3(d[u][2 * s][0], d[u][2 * s][1]);
+                        vf[u][s][1] = act3(d[u][2 * s][2], d[u][2 * s][3]);
+                        vf[u][s][2] = act3(d[u][2 * s + 1][0], d[u][2 * s + 1][1]);
+                        vf[u][s][3] = act3(d[u][2 * s + 1][2], d[u][2 * s + 1][3]);
+                    }
                 }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+#pragma unroll
+                for (int u = 0; u < NP; ++u) d[u][j][0] = d[u][j][1] = d[u][j][2] = d[u][j][3] = 0.f;
+#pragma unroll
+                for (int s = 0; s < KS; ++s)
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        if constexpr (K8) mma_1688(d[u][j], vf[u][s][0], vf[u][s][1], w3.b[j][s][0]);
+                        else mma_16816(d[u][j], vf[u][s], w3.b[j][s][0], w3.b[j][s][1]);
+                    }
             }
             // out = x + scale * D3 + b4: residual from the staged tile; C >= 16: the output-channel
             // order of W3 is permuted at pack time so that lane (g, t) owns channels 16p + 4t .. + 3
-            const int qa = qc + g, qb = qa + 8;
-            const size_t ooff0 = ((size_t)(r0 + r) * a.W + c0 + cb + g) * C + (K8 ? 2 : 4) * t;
-            const size_t ooff1 = ooff0 + (size_t)8 * C;
-            if constexpr (K8) {
-                const float2 x0 = *reinterpret_cast<const float2*>(xs + qa * XP + 8 * t);
-                const float2 x1 = *reinterpret_cast<const float2*>(xs + qb * XP + 8 * t);
-                float2 o0, o1;
-                o0.x = fmaf(d[0][0], a.scale, a.b4) + x0.x;
-                o0.y = fmaf(d[0][1], a.scale, a.b4) + x0.y;
-                o1.x = fmaf(d[0][2], a.scale, a.b4) + x1.x;
-                o1.y = fmaf(d[0][3], a.scale, a.b4) + x1.y;
-                *reinterpret_cast<float2*>(oimg + ooff0) = o0;
-                *reinterpret_cast<float2*>(oimg + ooff1) = o1;
-            } else {
 #pragma unroll
-                for (int p = 0; p < NT / 2; ++p) {
-                    const int oa = 16 * t + 64 * p;
-                    const int ob = 16 * t + 64 * p;
-                    const float4 x0 = *reinterpret_cast<const float4*>(xs + qa * XP + oa);
-                    const float4 x1 = *reinterpret_cast<const float4*>(xs + qb * XP + ob);
-                    const float (&e)[4] = d[2 * p], (&f)[4] = d[2 * p + 1];
-                    float4 o0, o1;
-                    o0.x = fmaf(e[0], a.scale, a.b4) + x0.x;
-                    o0.y = fmaf(e[1], a.scale, a.b4) + x0.y;
-                    o0.z = fmaf(f[0], a.scale, a.b4) + x0.z;
-                    o0.w = fmaf(f[1], a.scale, a.b4) + x0.w;
-                    o1.x = fmaf(e[2], a.scale, a.b4) + x1.x;
-                    o1.y = fmaf(e[3], a.scale, a.b4) + x1.y;
-                    o1.z = fmaf(f[2], a.scale, a.b4) + x1.z;
-                    o1.w = fmaf(f[3], a.scale, a.b4) + x1.w;
-                    *reinterpret_cast<float4*>(oimg + ooff0 + 16 * p) = o0;
-                    *reinterpret_cast<float4*>(oimg + ooff1 + 16 * p) = o1;
+            for (int u = 0; u < NP; ++u) {
+                const int qa = qc[u] + g, qb = qa + 8;
+                const size_t ooff0 = ((size_t)(r0 + rr[u]) * a.W + c0 + cbb[u] + g) * C + (K8 ? 2 : 4) * t;
+                const size_t ooff1 = ooff0 + (size_t)8 * C;
+                if constexpr (K8) {
+                    const float2 x0 = *reinterpret_cast<const float2*>(xs + qa * XP + 8 * t);
+                    const float2 x1 = *reinterpret_cast<const float2*>(xs + qb * XP + 8 * t);
+                    float2 o0, o1;
+                    o0.x = fmaf(d[u][0][0], a.scale, a.b4) + x0.x;
+                    o0.y = fmaf(d[u][0][1], a.scale, a.b4) + x0.y;
+                    o1.x = fmaf(d[u][0][2], a.scale, a.b4) + x1.x;
+                    o1.y = fmaf(d[u][0][3], a.scale, a.b4) + x1.y;
+                    *reinterpret_cast<float2*>(oimg + ooff0) = o0;
+                    *reinterpret_cast<float2*>(oimg + ooff1) = o1;
+                } else {
+#pragma unroll
+                    for (int p = 0; p < NT / 2; ++p) {
+                        const int oa = 16 * t + 64 * p;
+                        const float4 x0 = *reinterpret_cast<const float4*>(xs + qa * XP + oa);
+                        const float4 x1 = *reinterpret_cast<const float4*>(xs + qb * XP + oa);
+                        const float (&e)[4] = d[u][2 * p], (&f)[4] = d[u][2 * p + 1];
+                        float4 o0, o1;
+                        o0.x = fmaf(e[0], a.scale, a.b4) + x0.x;
+                        o0.y = fmaf(e[1], a.scale, a.b4) + x0.y;
+                        o0.z = fmaf(f[0], a.scale, a.b4) + x0.z;
+                        o0.w = fmaf(f[1], a.scale, a.b4) + x0.w;
+                        o1.x = fmaf(e[2], a.scale, a.b4) + x1.x;
+                        o1.y = fmaf(e[3], a.scale, a.b4) + x1.y;
+                        o1.z = fmaf(f[2], a.scale, a.b4) + x1.z;
+                        o1.w = fmaf(f[3], a.scale, a.b4) + x1.w;
+                        *reinterpret_cast<float4*>(oimg + ooff0 + 16 * p) = o0;
+                        *reinterpret_cast<float4*>(oimg + ooff1 + 16 * p) = o1;
+                    }
                 }
             }
-        }
+        };
+        constexpr int NP23 = (C <= 16) ? 2 : 1;          // C = 32: two chains do not fit the register budget
+        static_assert(Cfg::MT2 % (MS_WARPS * NP23) == 0, "M-tile pairs tile the stage");
+        for (int mt = warp; mt < Cfg::MT2; mt += NP23 * MS_WARPS)
+            stage23(std::integral_constant<int, NP23>{}, mt);
     }
 }
 
