@@ -295,6 +295,19 @@ int vqae_down_block_split_f16(const float* x, float* out, const void* w_hi, cons
                             c_in, sm_count, (cudaStream_t)stream);
 }
 
+int vqae_stem_out_mma_supported(int height, int width, int c_in) {
+    return stem_out_mma_supported(height, width, c_in) ? 1 : 0;
+}
+
+int vqae_stem_out_mma_f32(const float* x, const float* w_oihw, const float* bias, float* out,
+                          int out_layout, int64_t batch, int height, int width, int c_in,
+                          void* stream) {
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return stem_out_mma(x, w_oihw, bias, out, out_layout, batch, height, width, c_in, sm_count,
+                        (cudaStream_t)stream);
+}
+
 int vqae_front_fused_supported(int height, int width) {
     return front_fused_supported(height, width) ? 1 : 0;
 }

@@ -1,0 +1,198 @@
+// Decoder.out_stem (vq_ae/model.py:291: 3x3 conv, zero padding, bias, 8 -> 3) on warp-level tensor-core
+// MMAs, fp32-accurate: the nine taps are nine K = 8 GEMM steps over a staged tile whose pixels are 16-byte
+// rows of fp16 channels, so a tap is a row shift of the ldmatrix address (the scheme of stage 2 in
+// mma_same.cu); operands are split hi + lo (three MMAs per product, see tc_split.cu) because this is
+// the layer that produces the reconstruction.  The CUDA-core kernel it replaces (stems.cu) reads its
+// 3x3 x 8-channel window straight from global memory and runs at 98 % of the L1 data-pipe
+// (524 us at batch 256 of 256^2 against an HBM floor of 112 us); here every input pixel is read once.
+// Used by the "fp16" and "fp32tc" paths; "fp32" keeps the exact fp32 kernel.
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "mma_common.cuh"
+#include "tc_common.cuh"
+
+namespace vqae {
+namespace {
+
+using namespace mma;
+
+constexpr int SO_TH = 16, SO_TW = 32, SO_PW = SO_TW + 2;
+constexpr int SO_NPAD = (SO_TH + 2) * SO_PW;           // 612 pixels of tile + ring
+constexpr int SO_ROWS = SO_NPAD + 12;                  // + slack for the last ldmatrix rows
+constexpr int SO_MT = SO_TH * SO_TW / 16;              // 32 M-tiles
+constexpr int SO_THREADS = 256, SO_WARPS = 8;
+constexpr uint32_t SO_PLANE = SO_ROWS * 16;
+constexpr uint32_t SO_SMEM = 2 * SO_PLANE;
+
+struct StemOutArgs {
+    const float* x;          // NHWC fp32 [B,H,W,8]
+    const float* w;          // OIHW [3,8,3,3]
+    const float* bias;       // [3]
+    float* out;              // NCHW [B,3,H,W] or NHWC [B,H,W,3]
+    int n_tiles, H, W, tiles_x, tiles_per_img, nhwc_out;
+};
+
+__device__ __forceinline__ void so_split2(float f0, float f1, uint32_t& hi, uint32_t& lo) {
+    const __half2 hh = __floats2half2_rn(f0, f1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&hh);
+    lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+
+__global__ void __launch_bounds__(SO_THREADS, 3)
+stem_out_mma_kernel(StemOutArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = tc::smem_u32(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    // B fragments of the nine taps: B[k = channel][n = output], n < 3 real; hi / lo
+    uint32_t bh[9], bl[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        float w0 = 0.f, w1 = 0.f;
+        if (g < 3) {
+            w0 = __ldg(a.w + (g * 8 + 2 * t) * 9 + tap);
+            w1 = __ldg(a.w + (g * 8 + 2 * t + 1) * 9 + tap);
+        }
+        so_split2(w0, w1, bh[tap], bl[tap]);
+    }
+    const float bias0 = 2 * t < 3 ? __ldg(a.bias + 2 * t) : 0.f;
+    const float bias1 = 2 * t + 1 < 3 ? __ldg(a.bias + 2 * t + 1) : 0.f;
+    for (int i = tid; i < (int)(SO_SMEM / 16); i += SO_THREADS)
+        *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const size_t plane = (size_t)a.H * a.W;
+
+    // a thread stages the same (up to three) ring'd-tile pixels of every tile; the NEXT tile's pixels are
+    // loaded into registers before the current tile is computed, so their latency hides behind the MMAs
+    constexpr int PPT = (SO_NPAD + SO_THREADS - 1) / SO_THREADS;
+    float4 pv[PPT][2];
+    auto fetch = [&](int tile) {
+        const int img = tile / a.tiles_per_img;
+        const int trem = tile - img * a.tiles_per_img;
+        const int r0 = (trem / a.tiles_x) * SO_TH, c0 = (trem % a.tiles_x) * SO_TW;
+        const float* ximg = a.x + (size_t)img * plane * 8;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int q = tid + k * SO_THREADS;
+            const int lr = q / SO_PW, lc = q - lr * SO_PW;
+            const int y = r0 - 1 + lr, x = c0 - 1 + lc;
+            pv[k][0] = pv[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);           // zero padding
+            if (q < SO_NPAD && y >= 0 && y < a.H && x >= 0 && x < a.W) {
+                const float4* p = reinterpret_cast<const float4*>(ximg + ((size_t)y * a.W + x) * 8);
+                pv[k][0] = __ldg(p);
+                pv[k][1] = __ldg(p + 1);
+            }
+        }
+    };
+    if ((int)blockIdx.x < a.n_tiles) fetch(blockIdx.x);
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int img = tile / a.tiles_per_img;
+        const int trem = tile - img * a.tiles_per_img;
+        const int r0 = (trem / a.tiles_x) * SO_TH, c0 = (trem % a.tiles_x) * SO_TW;
+
+        // ---- stage tile + ring as fp16 hi / lo rows of 8 channels ----
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int q = tid + k * SO_THREADS;
+            if (q < SO_NPAD) {
+                uint4 hi, lo;
+                so_split2(pv[k][0].x, pv[k][0].y, hi.x, lo.x);
+                so_split2(pv[k][0].z, pv[k][0].w, hi.y, lo.y);
+                so_split2(pv[k][1].x, pv[k][1].y, hi.z, lo.z);
+                so_split2(pv[k][1].z, pv[k][1].w, hi.w, lo.w);
+                *reinterpret_cast<uint4*>(smem + q * 16) = hi;
+                *reinterpret_cast<uint4*>(smem + SO_PLANE + q * 16) = lo;
+            }
+        }
+        __syncthreads();
+        if (tile + (int)gridDim.x < a.n_tiles) fetch(tile + gridDim.x);
+
+        // ---- nine shifted K = 8 GEMM steps per M-tile (16 pixels of a row), two M-tiles per warp step
+        const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll 1
+        for (int mt0 = warp; mt0 < SO_MT; mt0 += 2 * SO_WARPS) {
+            float d[2][4];
+            uint32_t lbase[2];
+            int rr[2], cb[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int mt = mt0 + u * SO_WARPS;
+                rr[u] = mt >> 1;
+                cb[u] = (mt & 1) * 16;
+                lbase[u] = sbase + (uint32_t)((rr[u] + 1) * SO_PW + cb[u] + 1 + lrow) * 16;
+                d[u][0] = d[u][2] = bias0;
+                d[u][1] = d[u][3] = bias1;
+            }
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int shift = (tap / 3 - 1) * SO_PW + (tap % 3 - 1);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    uint32_t h0, h1, l0, l1;
+                    ldmatrix_x2(h0, h1, lbase[u] + shift * 16);
+                    ldmatrix_x2(l0, l1, lbase[u] + SO_PLANE + shift * 16);
+                    mma_1688(d[u], l0, l1, bh[tap]);
+                    mma_1688(d[u], h0, h1, bl[tap]);
+                    mma_1688(d[u], h0, h1, bh[tap]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int y = r0 + rr[u], x = c0 + cb[u] + g;
+                if (a.nhwc_out) {
+                    float* o = a.out + ((size_t)img * plane + (size_t)y * a.W + x) * 3;
+                    if (t == 0) {
+                        o[0] = d[u][0]; o[1] = d[u][1];
+                        o[24] = d[u][2]; o[25] = d[u][3];
+                    } else if (t == 1) {
+                        o[2] = d[u][0];
+                        o[26] = d[u][2];
+                    }
+                } else {
+                    float* o = a.out + (size_t)img * 3 * plane + (size_t)y * a.W + x;
+                    if (t == 0) {
+                        o[0] = d[u][0]; o[8] = d[u][2];
+                        o[plane] = d[u][1]; o[plane + 8] = d[u][3];
+                    } else if (t == 1) {
+                        o[2 * plane] = d[u][0]; o[2 * plane + 8] = d[u][2];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+bool stem_out_mma_supported(int H, int W, int c_in) {
+    return c_in == 8 && H >= SO_TH && W >= SO_TW && H % SO_TH == 0 && W % SO_TW == 0;
+}
+
+int stem_out_mma(const float* x, const float* w, const float* bias, float* out, int out_layout,
+                 int64_t B, int H, int W, int c_in, int sm_count, cudaStream_t stream) {
+    if (!x || !w || !bias || !out || B <= 0) return VQAE_ERR_BAD_ARG;
+    if (!stem_out_mma_supported(H, W, c_in)) return VQAE_ERR_UNSUPPORTED;
+    if (out_layout != VQAE_LAYOUT_NCHW && out_layout != VQAE_LAYOUT_NHWC) return VQAE_ERR_BAD_ARG;
+    StemOutArgs a;
+    a.x = x; a.w = w; a.bias = bias; a.out = out; a.H = H; a.W = W;
+    a.nhwc_out = out_layout == VQAE_LAYOUT_NHWC;
+    a.tiles_x = W / SO_TW; a.tiles_per_img = (H / SO_TH) * a.tiles_x;
+    const int64_t nt = B * a.tiles_per_img;
+    if (nt > 0x7fffffff) return VQAE_ERR_UNSUPPORTED;
+    a.n_tiles = (int)nt;
+    const int cap = sm_count * 3;
+    const int grid = a.n_tiles < cap ? a.n_tiles : cap;
+    stem_out_mma_kernel<<<grid, SO_THREADS, SO_SMEM, stream>>>(a);
+    return check_launch();
+}
+
+}  // namespace vqae

@@ -709,8 +709,11 @@ def encoder_front(x: Tensor, weight: Tensor, bias: Tensor, mean, std, packed: Se
     return out, 2
 
 
-def stem_out(x_nhwc: Tensor, weight: Tensor, bias: Tensor, channels_last: bool) -> Tensor:
-    """NHWC fp32 [B,H,W,8] -> [B,3,H,W] (contiguous NCHW, or channels_last strides)."""
+def stem_out(x_nhwc: Tensor, weight: Tensor, bias: Tensor, channels_last: bool,
+             precision: str = "fp32") -> Tensor:
+    """NHWC fp32 [B,H,W,8] -> [B,3,H,W] (contiguous NCHW, or channels_last strides).  "fp32": the
+    exact CUDA-core kernel; other precisions: split-operand tensor-core kernel (fp32-accurate,
+    csrc/mma_stem.cu) where it tiles the image."""
     lib = L.load()
     x_nhwc = _as_stream(x_nhwc, False)
     b, h, wd, c = x_nhwc.shape
@@ -722,8 +725,12 @@ def stem_out(x_nhwc: Tensor, weight: Tensor, bias: Tensor, channels_last: bool) 
     else:
         out = torch.empty(b, 3, h, wd, dtype=torch.float32, device=x_nhwc.device)
         lay = L.LAYOUT_NCHW
-    L.check(lib.vqae_stem_out_f32(_ptr(x_nhwc), _ptr(w), _ptr(bi), _ptr(out), lay, b, h, wd, c,
-                                  _stream(x_nhwc.device)), "vqae_stem_out_f32")
+    if precision != "fp32" and lib.vqae_stem_out_mma_supported(h, wd, c):
+        L.check(lib.vqae_stem_out_mma_f32(_ptr(x_nhwc), _ptr(w), _ptr(bi), _ptr(out), lay, b, h, wd, c,
+                                          _stream(x_nhwc.device)), "vqae_stem_out_mma_f32")
+    else:
+        L.check(lib.vqae_stem_out_f32(_ptr(x_nhwc), _ptr(w), _ptr(bi), _ptr(out), lay, b, h, wd, c,
+                                      _stream(x_nhwc.device)), "vqae_stem_out_f32")
     return out.permute(0, 3, 1, 2) if channels_last else out
 
 

@@ -210,7 +210,7 @@ def decoder_forward(dec, xs: Sequence[Tensor]) -> Tensor:
     precision = resolve_precision(dec)
     h, cl = E.to_nhwc(enc)
     h = _plan(dec).run(flat_blocks(dec.post_enc_layers) + flat_blocks(dec.up_layers), h, precision)
-    return E.stem_out(h, dec.out_stem.weight, dec.out_stem.bias, cl)
+    return E.stem_out(h, dec.out_stem.weight, dec.out_stem.bias, cl, precision)
 
 
 def block_forward(block, inp: Tensor) -> Tensor:

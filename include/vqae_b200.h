@@ -179,6 +179,13 @@ int vqae_down_block_mma_supported(int height, int width, int c_in);
 int vqae_down_block_mma_f16(const float* x, float* out, const void* w_packed,
                             const float* scalars8_host, int64_t batch, int height, int width,
                             int c_in, void* stream);
+/* out_stem on warp-level tensor-core MMAs with split fp16 operands (csrc/mma_stem.cu): fp32-accurate
+ * (not bit-identical to vqae_stem_out_f32), every input pixel read once; c_in == 8,
+ * height % 16 == 0, width % 32 == 0.  Same arguments as vqae_stem_out_f32.                     */
+int vqae_stem_out_mma_supported(int height, int width, int c_in);
+int vqae_stem_out_mma_f32(const float* x, const float* w_oihw, const float* bias, float* out,
+                          int out_layout, int64_t batch, int height, int width, int c_in,
+                          void* stream);
 /* The encoder's FRONT END in one launch (csrc/mma_front.cu): in_stem (with the u8 normalisation of
  * vqae_stem_in) + the C = 8 'same' block + the 'down' block 8 -> 16 of the first DownBlock
  * (model.py:141,144-148,198-199) -- the input image is read once, the 16-channel half-resolution

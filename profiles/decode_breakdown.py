@@ -53,7 +53,7 @@ def main():
                 h = E.fixup_forward_nhwc(pk, h, precision=precision)
                 mark(f"{names[pk.mode]} C{pk.c_in}->{pk.c_out} @{hh}")
                 i += 1
-        E.stem_out(h, dec.out_stem.weight, dec.out_stem.bias, False)
+        E.stem_out(h, dec.out_stem.weight, dec.out_stem.bias, False, precision)
         mark("stem_out")
         return ev
 

@@ -95,3 +95,26 @@ def test_front_fused_in_the_fp16_encoder():
         E.FRONT_FUSED = old
         vqae_b200.set_precision(m, None)
         m.cpu()
+
+
+@pytest.mark.parametrize("hw,batch,cl", [((256, 256), 2, False), ((16, 32), 3, False), ((48, 64), 2, True),
+                                         ((32, 32), 1, True)])
+def test_stem_out_mma_vs_exact_fp32_kernel(hw, batch, cl):
+    """csrc/mma_stem.cu (out_stem on split-operand MMAs, the decoder's last launch in the "fp16" and
+    "fp32tc" paths) against the exact fp32 kernel, which the model goldens pin to the reference:
+    fp32-accurate (1e-5 of the output range; zero padding at the image border included)."""
+    m, sd, _ = H.model_and_state("model_nd3_perturbed")
+    dec = m.to(DEV).decoder
+    try:
+        x = torch.randn(batch, hw[0], hw[1], 8, generator=torch.Generator().manual_seed(hw[0] + batch)).to(DEV)
+        ref = E.stem_out(x, dec.out_stem.weight, dec.out_stem.bias, cl, "fp32")
+        n0 = E.launch_count()
+        got = E.stem_out(x, dec.out_stem.weight, dec.out_stem.bias, cl, "fp16")
+        torch.cuda.synchronize()
+        assert E.launch_count() - n0 == 1
+        assert got.shape == ref.shape == (batch, 3, hw[0], hw[1])
+        assert E.is_channels_last(got) == cl or not cl
+        assert float((got - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+        assert torch.equal(got, E.stem_out(x, dec.out_stem.weight, dec.out_stem.bias, cl, "fp32tc"))
+    finally:
+        m.cpu()
