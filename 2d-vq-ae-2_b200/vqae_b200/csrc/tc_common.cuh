@@ -201,13 +201,31 @@ __device__ __forceinline__ float elu_fast(float x) {
     return x > 0.f ? x : e - 1.f;
 }
 
-// 8 fp32 -> 8 bf16 of  act(v + pre) + post  (the Fixup pre-activation, conv_block.py:199-208)
+// 8 fp32 -> 8 operand elements of  elu(v + pre) + post  (the Fixup pre-activation, conv_block.py:199-208)
+// with packed fp32x2 arithmetic: elu(v + pre) + post = (v > -pre) ? v + (pre + post)
+//                                                                  : exp2(v * log2e + pre * log2e) + (post - 1)
+// -- per pair FADD2, FFMA2, 2 x MUFU.EX2, FADD2, 2 x FSETP / FSEL, F2FP = 5 issue slots per element
+// against 9 for the element-wise form (the worker units of the resident kernel are issue bound:
+// DESIGN.md section 4.5).  Same formula as mma::ActC (mma_common.cuh).
+__device__ __forceinline__ uint32_t act_pair(float x0, float x1, float2 sum, float2 tl, float2 pm1,
+                                             float npre) {
+    const float2 x = make_float2(x0, x1);
+    const float2 lin = __fadd2_rn(x, sum);
+    const float2 tt = __ffma2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f), tl);
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(tt.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(tt.y));
+    const float2 ex = __fadd2_rn(e, pm1);
+    return pack_bf16(x0 > npre ? lin.x : ex.x, x1 > npre ? lin.y : ex.y);
+}
 __device__ __forceinline__ uint4 act_pack8(const float* v, float pre, float post) {
+    const float s = pre + post, t = pre * 1.4426950408889634f, m = post - 1.f, npre = -pre;
+    const float2 sum = make_float2(s, s), tl = make_float2(t, t), pm1 = make_float2(m, m);
     uint4 o;
-    o.x = pack_bf16(elu_fast(v[0] + pre) + post, elu_fast(v[1] + pre) + post);
-    o.y = pack_bf16(elu_fast(v[2] + pre) + post, elu_fast(v[3] + pre) + post);
-    o.z = pack_bf16(elu_fast(v[4] + pre) + post, elu_fast(v[5] + pre) + post);
-    o.w = pack_bf16(elu_fast(v[6] + pre) + post, elu_fast(v[7] + pre) + post);
+    o.x = act_pair(v[0], v[1], sum, tl, pm1, npre);
+    o.y = act_pair(v[2], v[3], sum, tl, pm1, npre);
+    o.z = act_pair(v[4], v[5], sum, tl, pm1, npre);
+    o.w = act_pair(v[6], v[7], sum, tl, pm1, npre);
     return o;
 }
 // 8 fp32 -> 8 bf16 of  v + add  (skip path: no activation, conv_block.py:211-213)
