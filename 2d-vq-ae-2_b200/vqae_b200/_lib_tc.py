@@ -17,6 +17,8 @@ SIGNATURES: dict = {
     "vqae_same_block_mma_f16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
     "vqae_down_block_mma_supported": (_i, [_i, _i, _i]),
     "vqae_down_block_mma_f16": (_i, [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp]),
+    "vqae_stem_in_mma_supported": (_i, [_i, _i, _i]),
+    "vqae_stem_in_mma_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _fp, _fp, _vp]),
     "vqae_stem_out_mma_supported": (_i, [_i, _i, _i]),
     "vqae_stem_out_mma_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "vqae_front_fused_supported": (_i, [_i, _i]),

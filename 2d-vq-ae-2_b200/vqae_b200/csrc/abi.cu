@@ -295,6 +295,19 @@ int vqae_down_block_split_f16(const float* x, float* out, const void* w_hi, cons
                             c_in, sm_count, (cudaStream_t)stream);
 }
 
+int vqae_stem_in_mma_supported(int height, int width, int c_out) {
+    return stem_in_mma_supported(height, width, c_out) ? 1 : 0;
+}
+
+int vqae_stem_in_mma_f32(const void* x, int x_dtype, int x_layout, const float* w_oihw,
+                         const float* bias, float* out, int64_t batch, int height, int width,
+                         int c_out, const float* mean_host, const float* std_host, void* stream) {
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return stem_in_mma(x, x_dtype, x_layout, w_oihw, bias, out, batch, height, width, c_out,
+                       mean_host, std_host, sm_count, (cudaStream_t)stream);
+}
+
 int vqae_stem_out_mma_supported(int height, int width, int c_in) {
     return stem_out_mma_supported(height, width, c_in) ? 1 : 0;
 }

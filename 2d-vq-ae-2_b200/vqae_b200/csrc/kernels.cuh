@@ -112,7 +112,11 @@ int front_fused(const void* x, int x_dtype, int x_layout, const float* stem_w, c
                 const void* down_w, const float* down_scalars8, float* out, int64_t B, int H, int W,
                 int sm_count, cudaStream_t stream);
 
-// mma_stem.cu (out_stem on split-operand MMAs)
+// mma_stem.cu (in_stem / out_stem on split-operand MMAs)
+bool stem_in_mma_supported(int H, int W, int c_out);
+int stem_in_mma(const void* x, int x_dtype, int x_layout, const float* w, const float* bias, float* out,
+                int64_t B, int H, int W, int c_out, const float* mean, const float* stdv, int sm_count,
+                cudaStream_t stream);
 bool stem_out_mma_supported(int H, int W, int c_in);
 int stem_out_mma(const float* x, const float* w, const float* bias, float* out, int out_layout,
                  int64_t B, int H, int W, int c_in, int sm_count, cudaStream_t stream);

@@ -615,7 +615,7 @@ def run_blocks_nhwc(packed: Sequence[PackedFixup], h: Tensor, precision: str = "
 
 
 def stem_in(x: Tensor, weight: Tensor, bias: Tensor, mean=None, std=None,
-            out_dtype: torch.dtype = torch.float32) -> Tensor:
+            out_dtype: torch.dtype = torch.float32, precision: str = "fp32") -> Tensor:
     """x: fp32 [B,3,H,W] (NCHW or channels_last strides) or u8 [B,H,W,3] -> NHWC [B,H,W,8], fp32 or
     (fp16 stream of the reduced-precision path; needs W % 128 == 0 and H % 8 == 0) fp16."""
     lib = L.load()
@@ -644,6 +644,13 @@ def stem_in(x: Tensor, weight: Tensor, bias: Tensor, mean=None, std=None,
     if out_dtype == torch.float16 and (wd % 128 or h % 8):
         out_dtype = torch.float32
     out = torch.empty(b, h, wd, w.shape[0], dtype=out_dtype, device=x.device)
+    if precision != "fp32" and out_dtype == torch.float32 and \
+            lib.vqae_stem_in_mma_supported(h, wd, w.shape[0]):
+        # fp32-accurate tensor-core form (csrc/mma_stem.cu); "fp32" keeps the exact CUDA-core kernel
+        L.check(lib.vqae_stem_in_mma_f32(_ptr(x), dt, lay, _ptr(w), _ptr(bi), _ptr(out), b, h, wd,
+                                         w.shape[0], mean_a, std_a, _stream(x.device)),
+                "vqae_stem_in_mma_f32")
+        return out
     L.check(lib.vqae_stem_in(_ptr(x), dt, lay, _ptr(w), _ptr(bi), _ptr(out), _TORCH_DT[out_dtype],
                              b, h, wd, w.shape[0], mean_a, std_a, _stream(x.device)),
             "vqae_stem_in")
@@ -677,7 +684,7 @@ def encoder_front(x: Tensor, weight: Tensor, bias: Tensor, mean, std, packed: Se
         fuse = bool(lib.vqae_front_fused_supported(hh, ww))
     if not fuse:
         return stem_in(x, weight, bias, mean, std,
-                       torch.float16 if half_stream else torch.float32), 0
+                       torch.float16 if half_stream else torch.float32, precision), 0
     require_cuda(x, "encoder_front")
     ensure_packed(packed[:2], [False, False], [True, True])
     w = weight.detach().float().contiguous()

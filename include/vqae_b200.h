@@ -179,6 +179,13 @@ int vqae_down_block_mma_supported(int height, int width, int c_in);
 int vqae_down_block_mma_f16(const float* x, float* out, const void* w_packed,
                             const float* scalars8_host, int64_t batch, int height, int width,
                             int c_in, void* stream);
+/* in_stem on warp-level tensor-core MMAs with split fp16 operands (csrc/mma_stem.cu): fp32-accurate
+ * (not bit-identical to vqae_stem_in_f32), nine MMAs per 16 pixels; c_out == 8, height % 16 == 0,
+ * width % 32 == 0.  Same arguments as vqae_stem_in_f32.                                        */
+int vqae_stem_in_mma_supported(int height, int width, int c_out);
+int vqae_stem_in_mma_f32(const void* x, int x_dtype, int x_layout, const float* w_oihw,
+                         const float* bias, float* out, int64_t batch, int height, int width,
+                         int c_out, const float* mean_host, const float* std_host, void* stream);
 /* out_stem on warp-level tensor-core MMAs with split fp16 operands (csrc/mma_stem.cu): fp32-accurate
  * (not bit-identical to vqae_stem_out_f32), every input pixel read once; c_in == 8,
  * height % 16 == 0, width % 32 == 0.  Same arguments as vqae_stem_out_f32.                     */

@@ -118,3 +118,31 @@ def test_stem_out_mma_vs_exact_fp32_kernel(hw, batch, cl):
         assert torch.equal(got, E.stem_out(x, dec.out_stem.weight, dec.out_stem.bias, cl, "fp32tc"))
     finally:
         m.cpu()
+
+
+@pytest.mark.parametrize("kind,hw,batch", [("u8", (256, 256), 2), ("u8", (16, 32), 3), ("nchw", (48, 64), 2),
+                                           ("channels_last", (32, 96), 1)])
+def test_stem_in_mma_vs_exact_fp32_kernel(kind, hw, batch):
+    """csrc/mma_stem.cu in_stem (nine split-operand MMAs per 16 pixels; the encoder's first launch in
+    the "fp16" and "fp32tc" paths) against the exact fp32 kernel, which the model goldens pin to the
+    reference (`in_stem_sub`): 1e-5 of the output range, zero padding at the border included."""
+    m, sd, _ = H.model_and_state("model_nd3_perturbed")
+    enc = m.to(DEV).encoder
+    try:
+        g = torch.Generator().manual_seed(hw[1] + batch)
+        if kind == "u8":
+            x = torch.randint(0, 256, (batch, hw[0], hw[1], 3), generator=g, dtype=torch.uint8).to(DEV)
+        else:
+            x = torch.randn(batch, 3, hw[0], hw[1], generator=g).to(DEV)
+            if kind == "channels_last":
+                x = x.contiguous(memory_format=torch.channels_last)
+        ref = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias)
+        n0 = E.launch_count()
+        got = E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias, precision="fp16")
+        torch.cuda.synchronize()
+        assert E.launch_count() - n0 == 1
+        assert got.shape == ref.shape == (batch, hw[0], hw[1], 8) and got.dtype == torch.float32
+        assert float((got - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+        assert not torch.equal(got, ref) or hw == (16, 32)       # it IS the other kernel
+    finally:
+        m.cpu()
