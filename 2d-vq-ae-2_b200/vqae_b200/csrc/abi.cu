@@ -409,6 +409,11 @@ int vqae_down_block_f16(const void* x, void* out, int io_dtype, const void* w_pa
                          void* stream) {
     int sm_count = 0;
     if (int rc = device_sm_count(&sm_count)) return rc;
+    if (c_in == 64) {                  // the wide block of the 512-model: streamed weights (tc_down128.cu)
+        if (io_dtype != VQAE_DT_F32) return VQAE_ERR_UNSUPPORTED;
+        return down128_tc(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(out), w_packed,
+                          scalars8_host, batch, height, width, c_in, sm_count, (cudaStream_t)stream);
+    }
     return down_block_tc(x, out, io_dtype, w_packed, scalars8_host, batch, height, width, c_in, sm_count,
                          (cudaStream_t)stream);
 }

@@ -112,6 +112,11 @@ int front_fused(const void* x, int x_dtype, int x_layout, const float* stem_w, c
                 const void* down_w, const float* down_scalars8, float* out, int64_t B, int H, int W,
                 int sm_count, cudaStream_t stream);
 
+// tc_down128.cu ('down' 64 -> 128 on tcgen05 with streamed weights)
+bool down128_tc_supported(int H, int W, int CI);
+int down128_tc(const float* x, float* out, const void* w_packed, const float* scalars8, int64_t B,
+               int H, int W, int CI, int sm_count, cudaStream_t stream);
+
 // mma_stem.cu (in_stem / out_stem on split-operand MMAs)
 bool stem_in_mma_supported(int H, int W, int c_out);
 int stem_in_mma(const void* x, int x_dtype, int x_layout, const float* w, const float* bias, float* out,

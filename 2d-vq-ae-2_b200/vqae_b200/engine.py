@@ -198,7 +198,7 @@ class PackedFixup:
                 [float(sc[k]) for k in ("bias1a", "bias1b", "bias2a", "bias2b", "bias3a",
                                         "bias3b", "bias1c")]
                 + [float(sc["bias4"]) + float(sc["bias1d"])]))
-        elif self.mode == L.MODE_DOWN and self.c_in in (8, 16, 32) and \
+        elif self.mode == L.MODE_DOWN and self.c_in in (8, 16, 32, 64) and \
                 self.c_branch == 2 * self.c_in and self.c_out == 2 * self.c_in:
             self.tc_kind = "down"
             self.tc_scalars = (C.c_float * 8)(*(
@@ -271,10 +271,11 @@ class PackedFixup:
             self.tc_weights = torch.empty(n, dtype=torch.float16, device=self.device)
             out.append(self._desc(L.PACK_DOWN_F16, self.tc_weights, self.c_in, self.c_out, 4,
                                   self.src, sc["scale"]))
-            n = lib.vqae_pack_elems(L.PACK_DOWN_MMA_F16, self.c_in, self.c_out, 4)
-            self.mma_weights = torch.empty(n, dtype=torch.float16, device=self.device)
-            out.append(self._desc(L.PACK_DOWN_MMA_F16, self.mma_weights, self.c_in, self.c_out, 4,
-                                  self.src, sc["scale"]))
+            if self.c_in in DOWN_MMA:
+                n = lib.vqae_pack_elems(L.PACK_DOWN_MMA_F16, self.c_in, self.c_out, 4)
+                self.mma_weights = torch.empty(n, dtype=torch.float16, device=self.device)
+                out.append(self._desc(L.PACK_DOWN_MMA_F16, self.mma_weights, self.c_in, self.c_out, 4,
+                                      self.src, sc["scale"]))
         return out
 
     def split_ok(self, h: int, w: int) -> bool:
@@ -282,7 +283,7 @@ class PackedFixup:
         lib = L.load()
         if self.tc_kind == "same" and self.c_in in (8, 16, 32, 64):
             return bool(lib.vqae_same_block_split_supported(h, w, self.c_in))
-        if self.tc_kind == "down":
+        if self.tc_kind == "down" and self.c_in in (8, 16, 32):
             return bool(lib.vqae_down_block_mma_supported(h, w, self.c_in))
         return False
 

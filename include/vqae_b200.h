@@ -276,9 +276,12 @@ int vqae_trunk_resident_f16(const void* x, void* out, int io_dtype, const void* 
                             const float* scalars_dev, int n_blocks, int64_t batch, int height,
                             int width, int c, void* stream);
 /* PreActFixupResBlock in mode 'down' (conv specs pre_activation_fixup.yaml:35-45): c_in ->
- * 2*c_in, stride 2, branch + skip fused in one tcgen05 kernel; c_in in {8, 16, 32},
- * height % 16 == 0, width % 32 == 0.  w_packed: vqae_down_block_pack_elems(c_in) bf16 from
- * vqae_pack_down_block_f16 (scale is folded into branch_conv3 there);
+ * 2*c_in, stride 2, branch + skip fused in one tcgen05 kernel; c_in in {8, 16, 32} (csrc/tc_down.cu:
+ * weights and all four parity planes resident in shared memory) and c_in == 64 (csrc/tc_down128.cu,
+ * the 64 -> 128 block of the 512-model: planes one at a time, the 288 KB of weights per tile streamed
+ * through a bulk-copy ring; fp32 I/O only); height % 16 == 0, width % 32 == 0.
+ * w_packed: vqae_down_block_pack_elems(c_in) fp16 from vqae_pack_down_block_f16 /
+ * vqae_pack_batched(VQAE_PACK_DOWN_F16) (scale is folded into branch_conv3 there);
  * scalars8_host = {bias1a, bias1b, bias2a, bias2b, bias3a, bias3b, bias1c, bias4 + bias1d}.
  * x: NHWC fp32 [B,H,W,c_in];  out: NHWC fp32 [B,H/2,W/2,2*c_in].                             */
 size_t vqae_down_block_pack_elems(int c_in);

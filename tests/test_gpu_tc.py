@@ -507,3 +507,31 @@ def test_up_block_mma_bicubic_geometry(c_in):
     torch.cuda.synchronize()
     assert float(out.min()) > 0
     assert float((out - ref).abs().max()) < 3e-3 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("h,w,batch", [(64, 64, 3), (16, 32, 5), (32, 96, 2)])
+def test_down_block_64_to_128_tcgen05_vs_fp32_path(h, w, batch):
+    """csrc/tc_down128.cu (the wide 'down' block of the 512-model: parity planes one at a time, weights
+    streamed through a bulk-copy ring) against the fp32 exact path, which is pinned to the reference
+    goldens; the block golden itself: test_block_at_tensor_core_sizes_vs_reference_golden[fp16-down64]."""
+    from vqae_b200.config import pre_activation_fixup
+    from vqae_b200.layers.conv_block import PreActFixupResBlock
+    conf = pre_activation_fixup(n_layers=12)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blk = PreActFixupResBlock(in_channels=64, out_channels=128, mode="down", **conf).eval()
+    blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=61, regime="perturbed", n_layers=12))
+    pk = blk.to(DEV).packed()
+    x = torch.randn(batch, h, w, 64, generator=torch.Generator().manual_seed(h + w)).to(DEV)
+    y32 = E.fixup_forward_nhwc(pk, x, precision="fp32")
+    y16 = E.fixup_forward_nhwc(pk, x, precision="fp16")              # packs
+    before = E.launch_count()
+    again = E.fixup_forward_nhwc(pk, x, precision="fp16")
+    torch.cuda.synchronize()
+    assert E.launch_count() - before == 1
+    assert y16.shape == (batch, h // 2, w // 2, 128)
+    err = float((y16 - y32).abs().max()) / float(y32.abs().max())
+    assert err < 5e-3, err
+    assert torch.equal(y16, again)
+    for _ in range(20):                                              # ring / barrier protocol: repeat
+        assert torch.equal(E.fixup_forward_nhwc(pk, x, precision="fp16"), y16)
