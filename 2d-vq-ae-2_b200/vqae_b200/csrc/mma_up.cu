@@ -387,7 +387,7 @@ int launch_up_tail(UtArgs a, int64_t B, int sm_count, cudaStream_t stream) {
 
 bool up_block_mma_supported(int H, int W, int CI) {
     // low-res extent H x W; the tail tiles the 2H x 2W output in 8 x 32 pixel tiles
-    return (CI == 16 || CI == 32 || CI == 64) && H >= 4 && W >= 16 && H % 4 == 0 && W % 16 == 0;
+    return (CI == 16 || CI == 32 || CI == 64 || CI == 128) && H >= 4 && W >= 16 && H % 4 == 0 && W % 16 == 0;
 }
 
 size_t up_block_mma_scratch_bytes(int64_t B, int H, int W, int CI) {
@@ -415,7 +415,8 @@ int up_block_mma(const float* x, float* out, const void* w_packed, const float* 
     switch (CI) {
         case 16: rc = launch_up_head<16>(h, sm_count, stream); break;
         case 32: rc = launch_up_head<32>(h, sm_count, stream); break;
-        default: rc = launch_up_head<64>(h, sm_count, stream); break;
+        case 64: rc = launch_up_head<64>(h, sm_count, stream); break;
+        default: rc = launch_up_head<128>(h, sm_count, stream); break;
     }
     if (rc) return rc;
     UtArgs u;
@@ -424,7 +425,8 @@ int up_block_mma(const float* x, float* out, const void* w_packed, const float* 
     switch (CI) {
         case 16: return launch_up_tail<16>(u, B, sm_count, stream);
         case 32: return launch_up_tail<32>(u, B, sm_count, stream);
-        default: return launch_up_tail<64>(u, B, sm_count, stream);
+        case 64: return launch_up_tail<64>(u, B, sm_count, stream);
+        default: return launch_up_tail<128>(u, B, sm_count, stream);
     }
 }
 

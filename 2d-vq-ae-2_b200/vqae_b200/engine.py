@@ -191,7 +191,7 @@ class PackedFixup:
             self.tc_kind = "same"
             self.tc_scalars = (C.c_float * 8)(*[float(sc[k]) for k in (
                 "bias1a", "bias1b", "bias2a", "bias2b", "bias3a", "bias3b", "bias4", "scale")])
-        elif self.mode == L.MODE_UP and self.c_in in (16, 32, 64) and \
+        elif self.mode == L.MODE_UP and self.c_in in (16, 32, 64, 128) and \
                 self.c_branch == self.c_in and self.c_out * 2 == self.c_in:
             self.tc_kind = "up"
             self.tc_scalars = (C.c_float * 8)(*(

@@ -224,7 +224,7 @@ int vqae_same_block_split_f16(const float* x, float* out, const void* w_hi, cons
 int vqae_down_block_split_f16(const float* x, float* out, const void* w_hi, const void* w_lo,
                               const float* scalars8_host, const float* premul3_host, int64_t batch,
                               int height, int width, int c_in, void* stream);
-/* 'up' block (c_in in {16, 32, 64} -> c_in / 2, x2 bicubic; conv_block.py:196-216 with ResizeConv2D,
+/* 'up' block (c_in in {16, 32, 64, 128} -> c_in / 2, x2 bicubic; conv_block.py:196-216 with ResizeConv2D,
  * conv.py:4-11) on warp-level MMAs in two kernels (csrc/mma_up.cu): the three 1x1 convs that
  * commute with the upsample at LOW resolution (register-resident), then bicubic interpolation
  * (index-clamped, separable) + branch_conv3 + skip sum at high resolution.  w_packed:

@@ -461,7 +461,8 @@ def _up_block(c_in, seed):
 
 
 @pytest.mark.parametrize("c_in,h,w,batch", [(16, 128, 128, 1), (16, 16, 32, 3), (32, 64, 64, 2),
-                                            (32, 4, 16, 5), (64, 32, 32, 3), (64, 8, 48, 2)])
+                                            (32, 4, 16, 5), (64, 32, 32, 3), (64, 8, 48, 2),
+                                            (128, 32, 32, 2), (128, 4, 16, 3)])
 def test_up_block_mma_vs_fp32_path(c_in, h, w, batch):
     """csrc/mma_up.cu ('up' blocks on warp-level MMAs: low-resolution head, high-resolution tail with
     the separable index-clamped bicubic) against the fp32 exact path, which is pinned to the
