@@ -77,8 +77,12 @@ __device__ __forceinline__ void split2(float f0, float f1, uint32_t& hi, uint32_
     lo = *reinterpret_cast<const uint32_t*>(&ll);
 }
 
+// resident CTAs per SM of the SPLIT form (twice the shared memory, ~1.5x the registers)
+template <int CI>
+constexpr int md_split_ctas() { return CI == 8 ? 2 : 1; }
+
 template <int CI, bool SPLIT>
-__global__ void __launch_bounds__(MD_THREADS, SPLIT ? 1 : MdCfg<CI>::MIN_CTAS)
+__global__ void __launch_bounds__(MD_THREADS, SPLIT ? md_split_ctas<CI>() : MdCfg<CI>::MIN_CTAS)
 down_block_mma_kernel(MdArgs a) {
     using Cfg = MdCfg<CI>;
     constexpr int CO = Cfg::CO, NT = Cfg::NT, KSI = Cfg::KSI, KSO = Cfg::KSO;
@@ -331,7 +335,7 @@ int launch_down_mma(MdArgs a, int64_t B, int sm_count, cudaStream_t stream) {
     a.fd_img = make_fastdiv(a.mt_per_img);
     a.fd_row = make_fastdiv(a.mt_per_row);
     const int64_t ctas_needed = (n + MD_WARPS - 1) / MD_WARPS;
-    const int cap = sm_count * (SPLIT ? 1 : Cfg::MIN_CTAS);
+    const int cap = sm_count * (SPLIT ? md_split_ctas<CI>() : Cfg::MIN_CTAS);
     const int grid = ctas_needed < cap ? (int)ctas_needed : cap;
     kern<<<grid, MD_THREADS, SMEM, stream>>>(a);
     return check_launch();
