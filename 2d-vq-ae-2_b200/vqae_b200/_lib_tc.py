@@ -23,6 +23,8 @@ SIGNATURES: dict = {
     "vqae_stem_out_mma_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "vqae_front_fused_supported": (_i, [_i, _i]),
     "vqae_front_fused_f16": (_i, [_vp, _i, _i, _vp, _vp, _fp, _fp, _vp, _fp, _vp, _fp, _vp, _i64, _i, _i, _vp]),
+    "vqae_same_block_mma_split_supported": (_i, [_i, _i, _i]),
+    "vqae_same_block_mma_split_f16": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _i64, _i, _i, _i, _vp]),
     "vqae_same_block_split_supported": (_i, [_i, _i, _i]),
     "vqae_same_block_split_f16": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _i64, _i, _i, _i, _vp]),
     "vqae_down_block_split_f16": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _i64, _i, _i, _i, _vp]),

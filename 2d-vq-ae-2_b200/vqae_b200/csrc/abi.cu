@@ -273,6 +273,19 @@ int vqae_down_block_mma_f16(const float* x, float* out, const void* w_packed,
                           (cudaStream_t)stream);
 }
 
+int vqae_same_block_mma_split_supported(int height, int width, int c) {
+    return same_block_mma_split_supported(height, width, c) ? 1 : 0;
+}
+
+int vqae_same_block_mma_split_f16(const float* x, float* out, const void* w_hi, const void* w_lo,
+                                  const float* scalars8_host, const float* premul3_host,
+                                  int64_t batch, int height, int width, int c, void* stream) {
+    int sm_count = 0;
+    if (int rc = device_sm_count(&sm_count)) return rc;
+    return same_block_mma_split(x, out, w_hi, w_lo, scalars8_host, premul3_host, batch, height, width,
+                                c, sm_count, (cudaStream_t)stream);
+}
+
 int vqae_same_block_split_supported(int height, int width, int c) {
     return same_block_split_supported(height, width, c) ? 1 : 0;
 }

@@ -33,6 +33,20 @@ inline int check_launch() {
 // nn.ELU(alpha=1) (conf/model/layers/activation/elu.yaml): x > 0 ? x : expm1(x)
 __device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : expm1f(x); }
 
+// ELU of the fp32-accurate tensor-core mode ("fp32tc"): expm1f costs ~25 instructions per element and the
+// split-operand kernels are bound by exactly that arithmetic.  For x <= 0:
+//   |x| < 1/4 : expm1(x) = x (1 + x/2 + x^2/6 + ... + x^6/5040)     truncation < 2e-9 |x|
+//   otherwise : exp2(x log2 e) - 1 with the SFU exponential          |error| < 2.5e-7 e^x  (<= 9e-7 relative)
+// i.e. fp32-grade (one to a few ulps of the value) at a third of the instructions; the model goldens hold
+// with the same bars as the exact path (tests/test_gpu_parity.py::test_model_vs_reference_golden[fp32tc-*]).
+__device__ __forceinline__ float elu1_tc(float x) {
+    const float p = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 5040.0f, 1.0f / 720.0f),
+                                                              1.0f / 120.0f), 1.0f / 24.0f), 1.0f / 6.0f), 0.5f), 1.0f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.0f ? x : (x > -0.25f ? p : e - 1.0f);
+}
+
 // the pre-activation in front of every branch conv of PreActFixupResBlock
 // (layers/conv_block.py:199-208):  conv(act(x + a) + b);  act optional (skip path has none)
 struct PreOp {

@@ -99,6 +99,12 @@ int down_block_split(const float* x, float* out, const void* w_hi, const void* w
                      const float* scalars8, const float* premul3, int64_t B, int H, int W, int CI,
                      int sm_count, cudaStream_t stream);
 
+// mma_same_split.cu (fp32-accurate 'same' block at C = 8, 16: split fp16 operands on warp-level MMAs)
+bool same_block_mma_split_supported(int H, int W, int C);
+int same_block_mma_split(const float* x, float* out, const void* w_hi, const void* w_lo,
+                         const float* scalars8, const float* premul3, int64_t B, int H, int W, int C,
+                         int sm_count, cudaStream_t stream);
+
 // tc_split.cu (fp32-accurate 'same' block: split fp16 operands on tcgen05)
 bool same_block_split_supported(int H, int W, int C);
 int same_block_split(const float* x, float* out, const void* w_hi, const void* w_lo,

@@ -16,7 +16,7 @@
 // SPLIT = true is the fp32-accurate form ("fp32tc" precision, see tc_split.cu): every operand is a
 // pair hi + lo of fp16 numbers, every product three MMAs (hi.hi + lo.hi + hi.lo), the weights are
 // pre-multiplied by powers of two at pack time (the accumulators by the inverse) and the activation
-// is the fp32 path's exact one.
+// is the fp32-grade elu1_tc (common.cuh).
 //
 // Weights sit in shared memory ([n][k] rows, padded pitch) and are read as B fragments with ldmatrix.
 // As in mma_same.cu the input-channel order of W1 / Ws and the output-channel order of W3 / Ws are
@@ -66,7 +66,7 @@ struct MdArgs {
 // exact pre-activation of the fp32 path on a scaled accumulator: elu(v * mul + pre) + post
 struct ActX {
     float pre, post, mul;
-    __device__ __forceinline__ float operator()(float v) const { return elu1(fmaf(v, mul, pre)) + post; }
+    __device__ __forceinline__ float operator()(float v) const { return elu1_tc(fmaf(v, mul, pre)) + post; }
 };
 // (f0, f1) -> fp16 pair of the high halves and fp16 pair of the remainders
 __device__ __forceinline__ void split2(float f0, float f1, uint32_t& hi, uint32_t& lo) {

@@ -90,9 +90,9 @@ __device__ void pack_element(const vqae_pack_desc& d, int i) {
             return (s & ~15) + 4 * ((r & 7) >> 1) + 2 * (r >> 3) + (r & 1);
         };
         float v;
-        if (m == 0) v = w1[n * Cc + perm(k)];
-        else if (m == 10) v = w3[perm(n) * Cc + k];
-        else v = w2[((size_t)n * Cc + k) * 9 + (m - 1)];
+        if (m == 0) v = w1[n * Cc + perm(k)] * pm1;
+        else if (m == 10) v = w3[perm(n) * Cc + k] * pm3;
+        else v = w2[((size_t)n * Cc + k) * 9 + (m - 1)] * pm2;
         out[i] = to_bf16(v, lo);
         return;
     }

@@ -11,8 +11,8 @@
 // (pack.cu, vqae_pack_desc.premul) -- their low halves stay normal numbers down to 2^-27 of the
 // largest weight -- and the accumulators are multiplied by the inverse, which is exact.  Activations
 // are O(1): their low halves are normal for |v| >= 2^-3 and carry an absolute error <= 2^-25 below.
-// The activation function is the fp32 path's own (expm1f), not the fast exponential of the
-// reduced-precision kernels.  Purpose: the reference's index contract (vq.py:121-129: the argmin
+// The activation is an fp32-grade ELU (elu1_tc, common.cuh: Taylor series near zero, SFU exponential
+// beyond), not the fast exponential of the reduced-precision kernels.  Purpose: the reference's index contract (vq.py:121-129: the argmin
 // of fp32 distances) holds on this path outside reported near-ties, at tensor-core speed
 // (tests/test_gpu_split.py pins it to the reference goldens).
 //
@@ -219,7 +219,7 @@ same_block_split_kernel(SplitArgs a) {
                     if (dst[u] >= 0) {
                         float f[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = elu1(vv[u][e] + a.b1a) + a.b1b;
+                        for (int e = 0; e < 8; ++e) f[e] = elu1_tc(vv[u][e] + a.b1a) + a.b1b;
                         uint4 hi, lo;
                         split8(f, hi, lo);
                         *reinterpret_cast<uint4*>(smem + Cfg::OFF_R + dst[u]) = hi;
@@ -256,7 +256,7 @@ same_block_split_kernel(SplitArgs a) {
                 for (int j = 0; j < UCH; ++j) {
                     float f[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = elu1(fmaf(v[8 * j + e], a.inv1, a.b2a)) + a.b2b;
+                    for (int e = 0; e < 8; ++e) f[e] = elu1_tc(fmaf(v[8 * j + e], a.inv1, a.b2a)) + a.b2b;
                     uint4 hi, lo;
                     split8(f, hi, lo);
                     const uint32_t off = Cfg::OFF_R + (kc0 + j) * SP_LBO + q * 16;
@@ -321,7 +321,7 @@ same_block_split_kernel(SplitArgs a) {
                     for (int j = 0; j < UCH; ++j) {
                         float f[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = elu1(fmaf(v[8 * j + e], a.inv2, a.b3a)) + a.b3b;
+                        for (int e = 0; e < 8; ++e) f[e] = elu1_tc(fmaf(v[8 * j + e], a.inv2, a.b3a)) + a.b3b;
                         uint4 hi, lo;
                         split8(f, hi, lo);
                         const uint32_t off = Cfg::OFF_R + (kc0 + j) * SP_LBO + p * 16;

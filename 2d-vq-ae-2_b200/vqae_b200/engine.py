@@ -185,6 +185,7 @@ class PackedFixup:
         # fp32-accurate tensor-core mode ("fp32tc"): split fp16 operand packs (hi, lo), the powers
         # of two the matrices were multiplied by, and max|w| of the four convs they derive from
         self.split_hi = self.split_lo = self.split_premul = None
+        self.split_mma_hi = self.split_mma_lo = None       # C = 8, 16 'same': warp-MMA layout
         self.wmax: Optional[List[float]] = None
         if self.mode == L.MODE_SAME and self.c_in in (8, 16, 32, 64, 128) and \
                 self.c_branch == self.c_in and self.c_out == self.c_in:
@@ -310,11 +311,18 @@ class PackedFixup:
         self.split_lo = torch.empty(n, dtype=torch.float16, device=self.device)
         self.split_premul = (C.c_float * 3)(*premul[:3])
         out = []
-        for dst, flag in ((self.split_hi, 0), (self.split_lo, L.PACK_LO)):
-            d = self._desc(kind | flag, dst, self.c_in, self.c_out, taps, srcs, scale)
-            for i, v in enumerate(premul):
-                d.premul[i] = v
-            out.append(d)
+        packs = [(kind, self.split_hi, self.split_lo)]
+        if self.tc_kind == "same" and self.c_in in SPLIT_MMA:
+            n2 = 11 * self.c_in * self.c_in
+            self.split_mma_hi = torch.empty(n2, dtype=torch.float16, device=self.device)
+            self.split_mma_lo = torch.empty(n2, dtype=torch.float16, device=self.device)
+            packs.append((L.PACK_SAME_MMA_F16, self.split_mma_hi, self.split_mma_lo))
+        for k, hi, lo in packs:
+            for dst, flag in ((hi, 0), (lo, L.PACK_LO)):
+                d = self._desc(k | flag, dst, self.c_in, self.c_out, taps, srcs, scale)
+                for i, v in enumerate(premul):
+                    d.premul[i] = v
+                out.append(d)
         return out
 
     def tc_ok(self, h: int, w: int) -> bool:
@@ -423,6 +431,9 @@ PRECISIONS = ("fp32", "fp16", "fp32tc")
 LOWC_MMA = {8, 16}
 # 'down' blocks with these input widths on warp-level MMAs (mma_down.cu) instead of tc_down.cu
 DOWN_MMA = {8, 16, 32}
+# "fp32tc": 'same' blocks of these widths on warp-level MMAs (mma_same_split.cu) instead of tc_split.cu
+# (B200, batch 256: C = 8 @256^2 and C = 16 @128^2 at 1.66 / 0.76 ms per block on the tcgen05 form)
+SPLIT_MMA = {8, 16}
 # True: in "fp16" mode the NHWC tensors between tensor-core kernels are fp16 instead of fp32.  Built,
 # tested (tests/test_gpu_tc.py) and measured on B200 (round 2): halving the block-boundary bytes
 # changes the step time by < 1 % (4.56 vs 4.55 ms at batch 256 -- the tile kernels are latency /
@@ -473,10 +484,16 @@ def fixup_forward_nhwc(pk: PackedFixup, x: Tensor, out: Optional[Tensor] = None,
         x = _as_stream(x, False)
         if out is None:
             out = torch.empty(b, ho, wo, pk.c_out, dtype=torch.float32, device=x.device)
-        fn, name = ((lib.vqae_down_block_split_f16, "vqae_down_block_split_f16")
-                    if pk.mode == L.MODE_DOWN
-                    else (lib.vqae_same_block_split_f16, "vqae_same_block_split_f16"))
-        L.check(fn(_ptr(x), _ptr(out), _ptr(pk.split_hi), _ptr(pk.split_lo), pk.tc_scalars,
+        hi, lo = pk.split_hi, pk.split_lo
+        if pk.mode == L.MODE_DOWN:
+            fn, name = lib.vqae_down_block_split_f16, "vqae_down_block_split_f16"
+        elif c in SPLIT_MMA and pk.split_mma_hi is not None and \
+                lib.vqae_same_block_mma_split_supported(h, w, c):
+            fn, name = lib.vqae_same_block_mma_split_f16, "vqae_same_block_mma_split_f16"
+            hi, lo = pk.split_mma_hi, pk.split_mma_lo
+        else:
+            fn, name = lib.vqae_same_block_split_f16, "vqae_same_block_split_f16"
+        L.check(fn(_ptr(x), _ptr(out), _ptr(hi), _ptr(lo), pk.tc_scalars,
                    pk.split_premul, b, h, w, c, _stream(x.device)), name)
         return out
     if tc and pk.chain_only:

@@ -217,6 +217,12 @@ int vqae_front_fused_f16(const void* x, int x_dtype, int x_layout, const float* 
  * 'down' block (csrc/mma_down.cu, SPLIT instantiation, register-resident): c_in in {8, 16, 32};
  * w_hi / w_lo: VQAE_PACK_DOWN_MMA_F16 [| VQAE_PACK_LO] with premul = {p1, p2, p3, p3} (branch_conv3
  * and skip_conv share an accumulator, hence a factor); scalars8_host as for vqae_down_block_f16. */
+ /* the same contract at c in {8, 16} on register-chained warp-level MMAs (csrc/mma_same_split.cu;
+ * w_hi / w_lo: VQAE_PACK_SAME_MMA_F16 [| VQAE_PACK_LO] with premul) */
+int vqae_same_block_mma_split_supported(int height, int width, int c);
+int vqae_same_block_mma_split_f16(const float* x, float* out, const void* w_hi, const void* w_lo,
+                                  const float* scalars8_host, const float* premul3_host,
+                                  int64_t batch, int height, int width, int c, void* stream);
 int vqae_same_block_split_supported(int height, int width, int c);
 int vqae_same_block_split_f16(const float* x, float* out, const void* w_hi, const void* w_lo,
                               const float* scalars8_host, const float* premul3_host, int64_t batch,
