@@ -94,6 +94,12 @@ SIGNATURES = {
     "vqae_embed_codes_f32": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i64, _i64, _vp]),
     "vqae_codemap_place_u8": (_i, [_vp, _i64, _i, _i, _i64, _i, _vp, _i64, _i64, _vp]),
     "vqae_codemap_place_i64": (_i, [_vp, _i64, _i, _i, _i64, _i, _vp, _i64, _i64, _vp]),
+    "vqae_ema_scratch_bytes": (_sz, [_i64, _i, _i]),
+    "vqae_ema_accumulate_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "vqae_ema_update_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp]),
+    "vqae_column_stats_f32": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
+    "vqae_ema_init_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "vqae_add_f32": (_i, [_vp, _vp, _vp, _i64, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

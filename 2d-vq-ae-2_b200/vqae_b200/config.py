@@ -144,3 +144,81 @@ def compose_vqae_conf(
         encoder_conf=encoder_conf,
         decoder_conf=decoder_conf,
     )
+
+
+def compose_multilevel_conf(
+    level_downs=(2, 1),
+    n_pre_enc_layers=(2, 3),
+    n_pre_layers: int = 1,
+    n_post_layers: int = 1,
+    stem_channels: int = 8,
+    in_channels: int = 3,
+    num_embeddings: int = 256,
+    projection_dim: int = 8,
+    fixup_n_layers: Optional[int] = 12,
+    shortcut_mode: str = "up",
+) -> Dict[str, Any]:
+    """A MULTI-LEVEL hierarchy in the reference's own configuration language (scope row f-4): one
+    DownBlock / VQ layer / pre-enc trunk per level and a Fixup shortcut block from each lower level to
+    the one above it (model.py:144-187, 203-215; conf/model/encoder/default.yaml:5 is where a shortcut
+    conf would be plugged in -- the shipped tree sets it to null).
+
+    ``level_downs[i]`` = n_down of level i's DownBlock, listed high-res first like ``vq_conf`` '0', '1', ...
+    The encoder is valid in the reference for any ``level_downs``.  The reference's Decoder hands every
+    shortcut block the channel count of the level it comes FROM (model.py:252-256 after the
+    prepended-None shift), so a decoder only exists where consecutive levels have equal widths, i.e.
+    ``level_downs[i > 0] == 0`` with ``shortcut_mode='same'`` -- ``decoder_conf`` is None otherwise."""
+    fixup = pre_activation_fixup(fixup_n_layers)
+    n_levels = len(level_downs)
+    widths, c = [], stem_channels
+    for nd in level_downs:
+        c *= 2 ** nd
+        widths.append(c)
+
+    def down(nd):
+        return dict(_target_="vq_ae.layers.conv_block.DownBlock", _recursive_=False, in_channels=None,
+                    n_down=nd, n_pre_layers=n_pre_layers, n_post_layers=n_post_layers,
+                    conv_conf=deepcopy(fixup))
+
+    def up(nu):
+        return dict(_target_="vq_ae.layers.conv_block.UpBlock", _recursive_=False, out_channels=None,
+                    n_up=nu, n_pre_layers=n_pre_layers, n_post_layers=n_post_layers,
+                    conv_conf=deepcopy(fixup))
+
+    # encoder shortcut i: from level i+1 (lower) to level i; instantiated with in_channels = widths[i+1]
+    enc_shortcuts = [{**deepcopy(fixup), "mode": shortcut_mode, "out_channels": widths[i]}
+                     for i in range(n_levels - 1)]
+    vq_conf: Dict[str, Any] = {"_target_": "utils.conf_helpers.instantiate_dictified_listconf",
+                               "_recursive_": False}
+    for i, w in enumerate(widths):
+        vq_conf[str(i)] = projected_ema_vq_2d(w, num_embeddings, projection_dim)
+    encoder_conf = dict(
+        _target_="vq_ae.model.Encoder", _recursive_=False,
+        stem_conf=same2d(in_channels=in_channels, out_channels=stem_channels),
+        down_block_conf=[down(nd) for nd in level_downs],
+        conv_block_conf=deepcopy(fixup),
+        shortcut_block_conf=enc_shortcuts,
+        vq_conf=vq_conf,
+        n_pre_enc_layers=list(n_pre_enc_layers),
+    )
+    decoder_conf = None
+    if all(nd == 0 for nd in level_downs[1:]) and shortcut_mode == "same":
+        # decoder shortcut i: instantiated with out_channels = widths[i+1] (== widths[i] here)
+        dec_shortcuts = [{**deepcopy(fixup), "mode": "same", "in_channels": widths[i + 1]}
+                         for i in range(n_levels - 1)]
+        decoder_conf = dict(
+            _target_="vq_ae.model.Decoder", _recursive_=False,
+            n_enc_layers=n_levels,
+            stem_conf=same2d(in_channels=stem_channels, out_channels=in_channels),
+            up_block_conf=[up(nd) for nd in level_downs],
+            conv_block_conf=deepcopy(fixup),
+            shortcut_block_conf=dec_shortcuts,
+            n_post_enc_layers=list(n_pre_enc_layers),
+        )
+    return dict(
+        _target_="vq_ae.model.VQAE", _recursive_=False,
+        optim_conf=dict(_target_="torch.optim.AdamW", lr=1e-4),
+        loss_f_conf=dict(_target_="torch.nn.modules.loss.HuberLoss", reduction="mean", delta=1.0),
+        encoder_conf=encoder_conf,
+        decoder_conf=decoder_conf,
+    )

@@ -921,5 +921,64 @@ def codemap_place_i64(tiles: Tensor, first_patch: int, grid_cols: int, code_map:
                                        _stream(tiles.device)), "vqae_codemap_place_i64")
 
 
+# ---- f-4: training-mode codebook maintenance, level sums -------------------------------------------
+def add_nhwc(a: Tensor, b: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """a + b for two contiguous fp32 tensors of one shape (the level sums of model.py:208, 283-288)."""
+    lib = L.load()
+    if a.shape != b.shape:
+        raise ValueError(f"level sum of tensors of different shapes: {tuple(a.shape)} + {tuple(b.shape)}")
+    a = a.float().contiguous()
+    b = b.float().contiguous()
+    if out is None:
+        out = torch.empty_like(a)
+    L.check(lib.vqae_add_f32(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream(a.device)), "vqae_add_f32")
+    return out
+
+
+def column_stats(z: Tensor) -> Tuple[Tensor, Tensor]:
+    """(mean, unbiased std) over the rows of z [N, D] fp32 (vq.py:77-78)."""
+    lib = L.load()
+    n, d = z.shape
+    mean = torch.empty(d, dtype=torch.float32, device=z.device)
+    std = torch.empty(d, dtype=torch.float32, device=z.device)
+    ws = workspace(z.device, lib.vqae_ema_scratch_bytes(n, 1, d))
+    L.check(lib.vqae_column_stats_f32(_ptr(z), n, d, _ptr(mean), _ptr(std), _ptr(ws), ws.numel(),
+                                      _stream(z.device)), "vqae_column_stats_f32")
+    return mean, std
+
+
+def ema_init(embed: Tensor, embed_avg: Tensor, cluster_size: Tensor, mean: Tensor, std: Tensor,
+             cluster_add: float) -> None:
+    """vq.py:90-94, in place on the three buffers."""
+    k, d = embed.shape
+    L.check(L.load().vqae_ema_init_f32(_ptr(embed), _ptr(embed_avg), _ptr(cluster_size), _ptr(mean),
+                                       _ptr(std), k, d, float(cluster_add), _stream(embed.device)),
+            "vqae_ema_init_f32")
+
+
+def ema_accumulate(z: Tensor, idx: Tensor, num_codes: int) -> Tensor:
+    """One buffer [K * (D + 1)]: dw [K, D] (sum of the z rows of each code) followed by counts [K]
+    (vq.py:49-54) -- one buffer so that a data-parallel job needs ONE all-reduce, not two."""
+    lib = L.load()
+    n, d = z.shape
+    buf = torch.empty(num_codes * (d + 1), dtype=torch.float32, device=z.device)
+    ws = workspace(z.device, lib.vqae_ema_scratch_bytes(n, num_codes, d))
+    dw, counts = buf[:num_codes * d], buf[num_codes * d:]
+    L.check(lib.vqae_ema_accumulate_f32(_ptr(z), _ptr(idx), n, num_codes, d, _ptr(counts), _ptr(dw),
+                                        _ptr(ws), ws.numel(), _stream(z.device)),
+            "vqae_ema_accumulate_f32")
+    return buf
+
+
+def ema_update(embed: Tensor, embed_avg: Tensor, cluster_size: Tensor, acc: Tensor, decay: float,
+               laplace_alpha: float) -> None:
+    """vq.py:60-74, in place; `acc` is the (all-reduced) buffer of ema_accumulate."""
+    k, d = embed.shape
+    dw, counts = acc[:k * d], acc[k * d:]
+    L.check(L.load().vqae_ema_update_f32(_ptr(embed), _ptr(embed_avg), _ptr(cluster_size), _ptr(counts),
+                                         _ptr(dw), k, d, float(decay), float(laplace_alpha),
+                                         _stream(embed.device)), "vqae_ema_update_f32")
+
+
 def launch_count() -> int:
     return int(L.load().vqae_launch_count())

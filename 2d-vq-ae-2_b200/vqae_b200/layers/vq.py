@@ -1,8 +1,9 @@
 """Counterpart of vq_ae/layers/vq.py: same classes, constructor signatures, buffers and return
 tuples; eval-mode ``forward`` runs the fused sm_100a quantiser kernel.
 
-Out of scope (training only): ``_update_ema`` / ``_init_ema`` (vq.py:47-94).  ``forward`` in
-training mode raises instead of silently running something else.
+Training mode (scope row f-4): ``forward`` runs ``_init_ema`` / ``_update_ema`` (vq.py:47-94) as
+CUDA kernels (csrc/ema.cu) around the same nearest-code search, with the reference's all-reduce of the
+batch statistics under ``torch.distributed``; no autograd graph is built.
 """
 from __future__ import annotations
 
@@ -49,9 +50,11 @@ class EMAVectorQuantizer(nn.Module):
 
     def forward(self, inputs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         if self.training:
-            raise RuntimeError(
-                "EMAVectorQuantizer: training-mode forward (EMA codebook update, vq.py:47-94) "
-                "is outside the B200 inference path; call .eval()")
+            # first-pass initialisation + nearest codes + EMA update of the buffers (vq.py:47-94,
+            # 118-133); tensors come back detached (no autograd graph is built)
+            quantized, idx, loss = P.quantizer_forward_training(self, inputs)
+            self.last_near_ties = P.state(self).last_near_ties
+            return quantized, idx, loss
         quantized, idx, loss, _ = P.quantizer_forward(self, inputs)
         self.last_near_ties = P.state(self).last_near_ties
         return quantized, idx, loss

@@ -2,10 +2,11 @@
 constructor signatures, attribute names, ``state_dict`` keys and return tuples.
 
 ``Encoder.forward`` / ``Decoder.forward`` in eval mode run a packed, NHWC, kernel-by-kernel
-plan over the C-ABI library instead of dispatching module by module.  The plan supports the
-shipped topology (one VQ level, no shortcut blocks: conf/model/vq_ae.yaml); the multi-level
-hierarchy of model.py:144-148,203-215 is row (f)-4 of the scope table and raises
-NotImplementedError.  Training (``shared_step``, SAM, logging) is out of scope.
+plan over the C-ABI library instead of dispatching module by module.  The shipped topology (one VQ
+level, no shortcut blocks: conf/model/vq_ae.yaml) runs one fused plan; the multi-level hierarchy of
+model.py:144-148,203-215 (row (f)-4 of the scope table) runs the same kernels level by level
+(plan.encoder_forward_levels / decoder_forward_levels).  Training (``shared_step``, SAM, logging) is
+out of scope.
 """
 from __future__ import annotations
 
@@ -81,6 +82,8 @@ class Encoder(nn.Module):
 
     def forward(self, x: Tensor) -> Tuple[Sequence[Tensor], Sequence[Tensor], Sequence[Tensor]]:
         """((enc,), (indices,), (loss,)) -- low-res to high-res order (model.py:189-217)."""
+        if len(self.vq_layers) > 1 or any(sc is not None for sc in self.shortcut_layers):
+            return P.encoder_forward_levels(self, x)          # multi-level hierarchy (scope row f-4)
         enc, idx, loss, _, _ = self.encode(x)
         return (enc,), (idx,), (loss,)
 
@@ -147,7 +150,11 @@ class VQAE(nn.Module):
 
     @torch.no_grad()
     def decode_codes(self, indices: Tensor, channels_last: bool = False) -> Tensor:
-        """Decompress stored code maps: embed_code -> proj_out -> Decoder (scope row f-2)."""
+        """Decompress stored code maps: embed_code -> proj_out -> Decoder (scope row f-2).  A sequence of
+        index maps (low-res first, like the encoder returns them) decodes a multi-level hierarchy."""
+        if isinstance(indices, (list, tuple)):
+            return self.decoder(tuple(P.decode_codes(vq, idx, channels_last)
+                                      for vq, idx in zip(self.encoder.vq_layers, indices)))
         enc = self.encoder.vq_layers[0].decode_codes(indices, channels_last)
         return self.decoder((enc,))
 

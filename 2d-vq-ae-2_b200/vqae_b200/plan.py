@@ -150,12 +150,150 @@ def decode_codes(vq, embed_idx: Tensor, channels_last: bool = False) -> Tensor:
     return out.view(b, pq.c, h, w)
 
 
+def _world() -> int:
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def quantizer_forward_training(vq, inputs: Tensor):
+    """EMAVectorQuantizer.forward in TRAINING mode (vq.py:96-154; scope row f-4): on the first pass the
+    codebook is re-centred on the batch statistics (``_init_ema``, vq.py:76-94), the nearest codes are
+    searched with the codebook as it stands, and the EMA buffers are updated from this batch
+    (``_update_ema``, vq.py:47-74) -- ``quantized`` and ``loss`` belong to the codebook BEFORE the update,
+    like the reference.  Under ``torch.distributed`` the batch statistics are all-reduced exactly where the
+    reference does it (vq.py:56-58, 81-88), as ONE collective per step instead of two.
+    The search and the update run under no_grad in the reference too (vq.py:106); what is NOT built is the
+    autograd graph of the straight-through estimator and of the loss: tensors come back detached."""
+    import torch.distributed as dist
+    check_quantizer_input(vq, inputs)
+    b, s = inputs.shape[0], prod(inputs.shape[2:])
+    cl = E.is_channels_last(inputs)
+    x = inputs.detach()
+    x = x if x.dtype == torch.float32 else x.float()
+    x = x.permute(0, 2, 3, 1).contiguous() if cl else x.contiguous()
+    k, d = vq.embed.shape
+    world = _world()
+    if bool(vq.first_pass):                                             # vq.py:118-119
+        _, _, _, _, z = E.quantize(packed_quantizer(vq), x, cl, cl, b, s, want_out=False, want_z=True)
+        mean, std = E.column_stats(z)
+        if world > 1:                                                   # vq.py:81-88
+            ms = torch.cat([mean, std])
+            dist.all_reduce(ms)
+            ms /= world
+            mean, std = ms[:d].contiguous(), ms[d:].contiguous()
+        E.ema_init(vq.embed, vq.embed_avg, vq.cluster_size, mean, std, (b * s * world) / k)
+        vq.first_pass.mul_(0)                                           # vq.py:94
+        state(vq).packed = None                                         # the codebook moved
+    pq = packed_quantizer(vq)
+    out, idx, loss, ties, z = E.quantize(pq, x, cl, cl, b, s, want_out=True, want_z=True)
+    acc = E.ema_accumulate(z, idx, k)                                   # vq.py:49-54
+    if world > 1:
+        dist.all_reduce(acc)                                            # vq.py:56-58
+    E.ema_update(vq.embed, vq.embed_avg, vq.cluster_size, acc, vq.decay, vq.laplace_alpha)
+    state(vq).packed = None
+    state(vq).last_near_ties = ties
+    sp = tuple(inputs.shape[2:])
+    quantized = out.view(b, *sp, pq.c).permute(0, 3, 1, 2) if cl else out.view(b, pq.c, *sp)
+    if inputs.dtype != torch.float32:
+        quantized = quantized.to(inputs.dtype)
+    return quantized, idx.view(b, *sp), loss
+
+
 # ---- encoder / decoder (model.py) --------------------------------------------------------------
+def _single_level(levels: int, shortcuts) -> bool:
+    return levels == 1 and all(sc is None for sc in shortcuts)
+
+
 def _check_single_level(levels: int, shortcuts, who: str) -> None:
-    if levels != 1 or any(s is not None for s in shortcuts):
+    if not _single_level(levels, shortcuts):
         raise NotImplementedError(
-            f"the B200 plan covers the shipped single-level {who} "
-            "(conf/model/vq_ae.yaml); multi-level / shortcut hierarchies are not built")
+            f"{who} is the single-level entry point (conf/model/vq_ae.yaml); multi-level hierarchies "
+            "go through forward() (plan.encoder_forward_levels / decoder_forward_levels)")
+
+
+def _run_module(module, h: Tensor, precision: str) -> Tensor:
+    """A shortcut / pyramid module on an NHWC tensor: every container the reference builds these from
+    (DownBlock, UpBlock, EnvelopBlock, nn.Sequential, a bare PreActFixupResBlock) is a chain of Fixup
+    blocks in ``modules()`` order."""
+    blocks = flat_blocks(module)
+    leaves = [m for m in module.modules() if not list(m.children())]
+    inside = {id(l) for blk in blocks for l in blk.modules()}
+    foreign = [type(l).__name__ for l in leaves if id(l) not in inside
+               and not (isinstance(l, (nn.Sequential, nn.ModuleList)) and len(l) == 0)]
+    if foreign:
+        raise NotImplementedError(
+            f"{type(module).__name__}: only chains of PreActFixupResBlocks have B200 kernels "
+            f"(found {sorted(set(foreign))})")
+    if not blocks:
+        return h                                        # n_down = 0 / n_up = 0: an empty Sequential
+    return _plan(module).run(blocks, h, precision)
+
+
+def _level_out(out: Tensor, b: int, hh: int, ww: int, c: int, cl: bool) -> Tensor:
+    return out.view(b, hh, ww, c).permute(0, 3, 1, 2) if cl else out.view(b, c, hh, ww)
+
+
+def encoder_forward_levels(enc, x: Tensor, mean=None, std=None):
+    """Encoder.forward for any number of VQ levels (model.py:189-217): the pyramid of DownBlocks, then
+    from the LOWEST resolution up: ``enc(pre_enc(down + shortcut(aux[0])))`` with ``aux`` the previous
+    (lower) level's quantiser output.  Returns ((enc..), (idx..), (loss..)), low-res first."""
+    if enc.training:
+        raise RuntimeError("Encoder: training-mode forward is outside the B200 inference "
+                           "path; call .eval()")
+    E.require_cuda(x, "Encoder.forward")
+    precision = resolve_precision(enc)
+    cl = x.dtype == torch.uint8 or E.is_channels_last(x)
+    downs: List[Tensor] = []
+    h = _plan(enc.down_layers[0]).run_from_input(enc.in_stem, flat_blocks(enc.down_layers[0]), x, mean,
+                                                 std, precision, False)
+    downs.append(h)
+    for down_layer in list(enc.down_layers)[1:]:
+        h = _run_module(down_layer, h, precision)
+        downs.append(h)
+    outs = []
+    aux: Optional[Tensor] = None                        # NHWC quantiser output of the previous level
+    for down, pre_enc, vq, shortcut in zip(reversed(downs), enc.pre_enc_layers, enc.vq_layers,
+                                           enc.shortcut_layers):
+        if shortcut is not None:
+            down = E.add_nhwc(down, _run_module(shortcut, aux, precision))      # model.py:208
+        h = _run_module(pre_enc, down, precision)
+        pq = packed_quantizer(vq)
+        b, hh, ww, c = h.shape
+        if c != pq.c:
+            raise NotImplementedError(
+                'VQ dim != channel dim not supported;'
+                f' found channel dim of {c}, expected {pq.c}')
+        out, idx, loss, ties, _ = E.quantize(pq, h.float(), True, True, b, hh * ww, want_out=True)
+        state(vq).last_near_ties = ties
+        aux = out.view(b, hh, ww, c)
+        q = aux.permute(0, 3, 1, 2)
+        outs.append((q if cl else q.contiguous(), idx.view(b, hh, ww), loss))
+    return tuple(zip(*outs))
+
+
+def decoder_forward_levels(dec, xs: Sequence[Tensor]) -> Tensor:
+    """Decoder.forward for any number of levels (model.py:274-291), x low-res first:
+    ``prev_up = up(prev_up + post_enc(shortcut(aux) + enc))`` with ``aux`` the previous level's ``enc``."""
+    if dec.training:
+        raise RuntimeError("Decoder: training-mode forward is outside the B200 inference "
+                           "path; call .eval()")
+    if len(xs) != len(dec.up_layers):
+        raise ValueError(f"Decoder: {len(xs)} encodings for {len(dec.up_layers)} levels")
+    precision = resolve_precision(dec)
+    prev_up: Optional[Tensor] = None
+    aux: Optional[Tensor] = None
+    cl = False
+    for enc_t, shortcut, post_enc, up in zip(xs, dec.shortcut_layers, dec.post_enc_layers,
+                                             dec.up_layers):
+        E.require_cuda(enc_t, "Decoder.forward")
+        e, cl = E.to_nhwc(enc_t)
+        h = e if shortcut is None else E.add_nhwc(_run_module(shortcut, aux, precision), e)
+        aux = e                                                          # model.py:286
+        h = _run_module(post_enc, h, precision)
+        if prev_up is not None:
+            h = E.add_nhwc(prev_up, h)                                   # model.py:283
+        prev_up = _run_module(up, h, precision)
+    return E.stem_out(prev_up, dec.out_stem.weight, dec.out_stem.bias, cl, precision)
 
 
 def encoder_encode(enc, x: Tensor, mean=None, std=None, want_quantized: bool = True,
@@ -163,7 +301,7 @@ def encoder_encode(enc, x: Tensor, mean=None, std=None, want_quantized: bool = T
     """Run the encoder plan.  x: float [B,3,H,W] (NCHW or channels_last) or uint8 [B,H,W,3]
     (normalised on the fly, a-N fused into the stem).  Returns
     (enc or None, indices int64 [B,h,w], loss 0-dim, near_ties 0-dim int32, z or None)."""
-    _check_single_level(len(enc.vq_layers), enc.shortcut_layers, "encoder")
+    _check_single_level(len(enc.vq_layers), enc.shortcut_layers, "Encoder.encode")
     if enc.training:
         raise RuntimeError("Encoder: training-mode forward is outside the B200 inference "
                            "path; call .eval()")
@@ -199,9 +337,10 @@ def encoder_encode(enc, x: Tensor, mean=None, std=None, want_quantized: bool = T
 
 
 def decoder_forward(dec, xs: Sequence[Tensor]) -> Tensor:
+    if not _single_level(len(dec.up_layers), dec.shortcut_layers):
+        return decoder_forward_levels(dec, xs)
     if len(xs) != 1:
-        raise NotImplementedError("the B200 plan covers the shipped single-level decoder")
-    _check_single_level(len(dec.up_layers), dec.shortcut_layers, "decoder")
+        raise ValueError(f"Decoder: {len(xs)} encodings for 1 level")
     if dec.training:
         raise RuntimeError("Decoder: training-mode forward is outside the B200 inference "
                            "path; call .eval()")
@@ -249,9 +388,15 @@ def _bind(module, fast):
     module.forward = types.MethodType(forward, module)
 
 
-def _enc_fast(enc, x):
+def encoder_forward(enc, x):
+    """Encoder.forward (model.py:189-217): the single-level fast plan, or the level loop."""
+    if not _single_level(len(enc.vq_layers), enc.shortcut_layers):
+        return encoder_forward_levels(enc, x)
     e, idx, loss, _, _ = encoder_encode(enc, x)
     return (e,), (idx,), (loss,)
+
+
+_enc_fast = encoder_forward
 
 
 def _vq_fast(vq, inputs):

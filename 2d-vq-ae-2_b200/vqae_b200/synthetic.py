@@ -42,7 +42,7 @@ def make_state_dict(template: Mapping[str, Tensor], seed: int = 0, regime: str =
     if n_layers is None:
         n_layers = sum(1 for k in template if k.endswith("branch_conv3.weight"))
     out: Dict[str, Tensor] = {}
-    embed_key = None
+    embed_keys = []
     for key, ref in template.items():
         g = _gen(key, seed)
         shape = tuple(ref.shape)
@@ -72,7 +72,7 @@ def make_state_dict(template: Mapping[str, Tensor], seed: int = 0, regime: str =
                 v = _uniform(shape, 1.0 / math.sqrt(wshape[1] * wshape[2] * wshape[3]), g)
         elif leaf == "embed":
             v = torch.randn(shape, generator=g)
-            embed_key = key
+            embed_keys.append(key)
         elif leaf == "embed_avg":
             v = None  # filled from embed below
         elif leaf == "cluster_size":
@@ -82,7 +82,7 @@ def make_state_dict(template: Mapping[str, Tensor], seed: int = 0, regime: str =
         else:
             raise KeyError(f"make_state_dict: no rule for {key} {shape}")
         out[key] = v if v is None else v.to(ref.dtype)
-    if embed_key is not None:
+    for embed_key in embed_keys:                      # one per VQ level
         out[embed_key[:-5] + "embed_avg"] = out[embed_key].clone()
     return out
 

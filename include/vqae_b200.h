@@ -378,6 +378,36 @@ int vqae_codemap_place_i64(const int64_t* tiles, int64_t n_tiles, int th, int tw
                            int64_t first_patch, int grid_cols, int64_t* map, int64_t map_rows,
                            int64_t map_cols, void* stream);
 
+/* ---- f-4  training-mode codebook maintenance (layers/vq.py:47-94) -----------------------------
+ * EMAVectorQuantizer._update_ema / _init_ema without the N x K one-hot matrix of the reference:
+ *   vqae_ema_accumulate_f32   counts[k] = #{n : idx[n] = k},  dw[k,:] = sum of z[n,:] over those n
+ *                             (vq.py:49-54: one_hot.sum(0), one_hot.T @ flat_input); deterministic
+ *                             (fixed summation order, no atomics).  The all-reduce of counts / dw
+ *                             across ranks (vq.py:56-58) is the caller's, between this and the update.
+ *   vqae_ema_update_f32       vq.py:60-74: EMA of cluster_size / embed_avg, Laplace smoothing,
+ *                             embed = embed_avg / smoothed cluster size; all three buffers in place.
+ *   vqae_column_stats_f32     mean and unbiased std of z over its rows (vq.py:77-78)
+ *   vqae_ema_init_f32         vq.py:90-94: embed = embed * std + mean, embed_avg = embed,
+ *                             cluster_size += cluster_add  (= N * world_size / K)
+ * z: [n, dim] fp32 row-major (the `z_out` of vqae_quantize), indices: int64 [n].                 */
+size_t vqae_ema_scratch_bytes(int64_t n, int num_codes, int dim);
+int vqae_ema_accumulate_f32(const float* z, const int64_t* indices, int64_t n, int num_codes, int dim,
+                            float* counts, float* dw, void* scratch, size_t scratch_bytes,
+                            void* stream);
+int vqae_ema_update_f32(float* embed, float* embed_avg, float* cluster_size, const float* counts,
+                        const float* dw, int num_codes, int dim, float decay, float laplace_alpha,
+                        void* stream);
+int vqae_column_stats_f32(const float* z, int64_t n, int dim, float* mean, float* std_unbiased,
+                          void* scratch, size_t scratch_bytes, void* stream);
+int vqae_ema_init_f32(float* embed, float* embed_avg, float* cluster_size, const float* mean,
+                      const float* std_unbiased, int num_codes, int dim, float cluster_add,
+                      void* stream);
+
+/* out = a + b over n fp32 elements (16-byte aligned pointers): the level sums of the multi-level
+ * hierarchy, `down + shortcut(aux)` (model.py:208) and `shortcut(aux) + enc`, `prev_up + ...`
+ * (model.py:283-288).  out may alias a or b.                                                     */
+int vqae_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

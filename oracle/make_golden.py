@@ -25,7 +25,8 @@ sys.path.insert(0, str(REPO / "2d-vq-ae-2_b200"))
 
 import ref_shim  # noqa: E402
 from vqae_b200 import synthetic as S  # noqa: E402
-from vqae_b200.config import compose_vqae_conf, pre_activation_fixup  # noqa: E402
+from vqae_b200.config import (compose_multilevel_conf, compose_vqae_conf,  # noqa: E402
+                              pre_activation_fixup)
 
 GOLDEN = REPO / "tests" / "golden"
 
@@ -193,12 +194,108 @@ def model_case(model_mod, n_down: int, regime: str, batch: int, size: int, seed:
     return out
 
 
+@torch.no_grad()
+def _settle_codebooks(enc, x, sd):
+    """Rescale every level's codebook to the statistics of ITS latents (what _init_ema would do on the
+    first training batch).  A level's latents depend on the codebooks below it, so levels settle one
+    forward at a time, lowest first; latents are read with forward hooks on the reference's proj_in."""
+    zs = {}
+    hooks = [vq.proj_in.register_forward_hook(
+        lambda _m, _i, o, i=i: zs.__setitem__(i, o.permute(0, 2, 3, 1).reshape(-1, o.shape[1]).clone()))
+        for i, vq in enumerate(enc.vq_layers)]
+    for i, vq in enumerate(enc.vq_layers):                  # low-res first = dependency order
+        enc(x)
+        vq.embed.copy_(S.rescale_codebook(sd[f"encoder.vq_layers.{i}.embed"], zs[i]))
+        vq.embed_avg.copy_(vq.embed)
+    out = enc(x)
+    for h in hooks:
+        h.remove()
+    return out, zs
+
+
+@torch.no_grad()
+def multilevel_cases(model_mod):
+    """Scope row f-4: the multi-level hierarchy of model.py:144-187, 203-215, 274-291 run by the reference's
+    own Encoder / Decoder classes on configurations written in its configuration language."""
+    out = {}
+    # (1) a real hierarchy: 32 ch @ 64x64 above 64 ch @ 32x32, 'up' shortcut block between them
+    conf = compose_multilevel_conf(level_downs=(2, 1), n_pre_enc_layers=(2, 3), shortcut_mode="up")
+    econf = dict(conf["encoder_conf"])
+    econf.pop("_target_"), econf.pop("_recursive_")
+    torch.manual_seed(42)
+    enc = model_mod.Encoder(**econf).eval()
+    sd = S.make_state_dict({"encoder." + k: v for k, v in enc.state_dict().items()}, seed=11,
+                           regime="perturbed")
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items()})
+    x = S.synthetic_patches(2, 256, 1011)
+    (encs, idxs, losses), zs = _settle_codebooks(enc, x, sd)
+    for i, (e, idx, loss) in enumerate(zip(encs, idxs, losses)):
+        vq = enc.vq_layers[i]
+        out.update({f"hier_embed{i}": _np(vq.embed), f"hier_idx{i}": _np(idx).astype(np.int16),
+                    f"hier_loss{i}": _np(loss), f"hier_enc_sub{i}": _np(e[:, ::8, ::4, ::4]),
+                    f"hier_enc_stats{i}": stats(e), f"hier_z{i}": _np(zs[i]),
+                    f"hier_gap{i}": _np(top2_gap(zs[i], vq.embed)),
+                    f"hier_codes_used{i}": np.array(idx.unique().numel())})
+    out["hier_n_state"] = np.array(len(sd))
+    # (2) a full VQAE with two levels of equal width (the only shape the reference's Decoder accepts)
+    conf = compose_multilevel_conf(level_downs=(3, 0), n_pre_enc_layers=(2, 2), shortcut_mode="same")
+    conf.pop("_target_"), conf.pop("_recursive_")
+    torch.manual_seed(42)
+    m = model_mod.VQAE(**conf).eval()
+    sd = S.make_state_dict(m.state_dict(), seed=12, regime="perturbed")
+    m.load_state_dict(sd)
+    x = S.synthetic_patches(2, 256, 1012)
+    (encs, idxs, losses), zs = _settle_codebooks(m.encoder, x, sd)
+    recon, losses2 = m(x)
+    assert all(torch.equal(a, b) for a, b in zip(losses, losses2))
+    for i, (e, idx, loss) in enumerate(zip(encs, idxs, losses)):
+        vq = m.encoder.vq_layers[i]
+        out.update({f"flat_embed{i}": _np(vq.embed), f"flat_idx{i}": _np(idx).astype(np.int16),
+                    f"flat_loss{i}": _np(loss), f"flat_enc_sub{i}": _np(e[:, ::8, ::4, ::4]),
+                    f"flat_z{i}": _np(zs[i]), f"flat_gap{i}": _np(top2_gap(zs[i], vq.embed))})
+    out.update(flat_recon_sub=_np(recon[:, :, ::8, ::8]), flat_recon_stats=stats(recon),
+               flat_n_state=np.array(len(sd)))
+    return out
+
+
+def ema_training_cases(vq_mod):
+    """Scope row f-4: TRAINING-mode forwards of the reference's quantisers (vq.py:47-94, 118-133): the
+    first pass initialises the codebook from the batch, every pass updates the EMA buffers."""
+    out = {}
+    for tag, c in (("bare", 8), ("proj", 64)):
+        torch.manual_seed(7)
+        q = (vq_mod.EMAVectorQuantizer(256, 8, 0.25, 0.99, 1e-5) if tag == "bare"
+             else vq_mod.ProjectedEMAVectorQuantizer2d(256, c, 0.25, 0.99, 1e-5, 8))
+        sd = S.make_state_dict(q.state_dict(), seed=21, regime="perturbed")
+        q.load_state_dict(sd)
+        q.train()
+        g = torch.Generator().manual_seed(300 + c)
+        out[f"{tag}_embed0"] = _np(q.embed)
+        for step in range(3):
+            hw = 32 if tag == "bare" else 16
+            # fp16-representable values, stored as fp16 (exact, half the fixture size)
+            x = (torch.randn(2, c, hw, hw, generator=g) * (1.0 + 0.5 * step) + 0.3 * step).half().float()
+            with torch.no_grad():
+                quant, idx, loss = q(x)
+            out.update({f"{tag}_x{step}": _np(x.half()), f"{tag}_idx{step}": _np(idx).astype(np.int16),
+                        f"{tag}_loss{step}": _np(loss), f"{tag}_quant_stats{step}": stats(quant),
+                        f"{tag}_embed_after{step}": _np(q.embed),
+                        f"{tag}_embed_avg_after{step}": _np(q.embed_avg),
+                        f"{tag}_cluster_size_after{step}": _np(q.cluster_size),
+                        f"{tag}_first_pass_after{step}": _np(q.first_pass)})
+    return out
+
+
 def main():
     if not ref_shim.reference_available():
         raise SystemExit("reference checkout not found; run this in the build container")
     model_mod, vq_mod, cb_mod, _ = ref_shim.load_reference()
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if "--only-f4" in sys.argv:                      # the round-2 additions only (scope row f-4)
+        np.savez_compressed(GOLDEN / "multilevel.npz", **multilevel_cases(model_mod))
+        np.savez_compressed(GOLDEN / "ema_training.npz", **ema_training_cases(vq_mod))
+        return
 
     np.savez_compressed(GOLDEN / "quantizer.npz", **quantizer_cases(vq_mod))
     np.savez_compressed(GOLDEN / "blocks.npz", **block_cases(cb_mod))
@@ -213,6 +310,8 @@ def main():
                             **model_case(model_mod, n_down, regime, batch, size, seed),
                             meta=np.array([n_down, batch, size, seed]))
         print("wrote", tag)
+    np.savez_compressed(GOLDEN / "multilevel.npz", **multilevel_cases(model_mod))
+    np.savez_compressed(GOLDEN / "ema_training.npz", **ema_training_cases(vq_mod))
     for f in sorted(GOLDEN.glob("*.npz")):
         print(f.name, f.stat().st_size // 1024, "KiB")
 

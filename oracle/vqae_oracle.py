@@ -277,6 +277,86 @@ def decode_from_codes(idx: Tensor, sd: StateDict) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------
+# f-4  multi-level hierarchy (model.py:144-148, 189-217, 274-291) and training-mode EMA update
+# ------------------------------------------------------------------------------------
+def module_chain(x: Tensor, sd: StateDict, prefix: str) -> Tensor:
+    """Whatever chain of PreActFixupResBlocks lives under ``prefix``: a bare block, an nn.Sequential of
+    blocks (``prefix{i}.``) or a DownBlock / UpBlock (``prefix`` + ``layers.{j}.layers.{i}.``)."""
+    if not any(k.startswith(prefix) for k in sd):
+        return x                                   # n_down = 0 / n_up = 0: an empty nn.Sequential
+    if prefix + "bias1a" in sd:
+        return fixup_block(x, _blk(sd, prefix))
+    if any(k.startswith(prefix + "layers.") for k in sd):
+        return envelop_pyramid(x, sd, prefix + "layers.")
+    return block_sequence(x, sd, prefix)
+
+
+def _quantizer_any(h: Tensor, sd: StateDict, prefix: str):
+    if prefix + "proj_in.weight" in sd:
+        enc, idx, loss, _gap, _z = projected_quantizer_forward(h, sd, prefix)
+        return enc, idx, loss
+    enc, idx, loss, _gap = ema_quantizer_forward(h, sd[prefix + "embed"])
+    return enc, idx, loss
+
+
+def encoder_forward_levels(x: Tensor, sd: StateDict, prefix: str = "encoder."):
+    """Encoder.forward (model.py:189-217) for any number of levels.  Module lists are stored low-res
+    first (model.py:182-187) except ``down_layers`` (execution order); ``shortcut_layers.{i}`` is absent
+    from the state_dict where the reference holds ``None``."""
+    h = F.conv2d(x, sd[prefix + "in_stem.weight"], sd[prefix + "in_stem.bias"], padding=1)
+    n = len(_indexed_children(sd, prefix + "vq_layers."))
+    downs = []
+    for i in range(n):
+        h = module_chain(h, sd, prefix + f"down_layers.{i}.")
+        downs.append(h)
+    outs, aux = [], None
+    for i, down in enumerate(reversed(downs)):                          # model.py:203-215
+        sc = prefix + f"shortcut_layers.{i}."
+        has_sc = any(k.startswith(sc) for k in sd)
+        h = down + (module_chain(aux, sd, sc) if has_sc else 0)
+        h = block_sequence(h, sd, prefix + f"pre_enc_layers.{i}.")
+        enc, idx, loss = _quantizer_any(h, sd, prefix + f"vq_layers.{i}.")
+        aux = enc
+        outs.append((enc, idx, loss))
+    return tuple(zip(*outs))
+
+
+def decoder_forward_levels(encs: Sequence[Tensor], sd: StateDict, prefix: str = "decoder.") -> Tensor:
+    """Decoder.forward (model.py:274-291) for any number of levels, encodings low-res first."""
+    prev_up, aux = 0, None
+    for i, enc in enumerate(encs):
+        sc = prefix + f"shortcut_layers.{i}."
+        has_sc = any(k.startswith(sc) for k in sd)
+        h = (module_chain(aux, sd, sc) if has_sc else 0) + enc          # model.py:285-286
+        aux = enc
+        h = block_sequence(h, sd, prefix + f"post_enc_layers.{i}.")
+        prev_up = module_chain(prev_up + h, sd, prefix + f"up_layers.{i}.")
+    return F.conv2d(prev_up, sd[prefix + "out_stem.weight"], sd[prefix + "out_stem.bias"], padding=1)
+
+
+def ema_init(flat: Tensor, embed: Tensor, cluster_size: Tensor, world: int = 1):
+    """EMAVectorQuantizer._init_ema (vq.py:76-94) on one rank's rows; returns the new
+    (embed, embed_avg, cluster_size)."""
+    mean, std = flat.mean(dim=0), flat.std(dim=0)                       # vq.py:77-78
+    e = embed * std + mean                                              # vq.py:90-91
+    return e, e.clone(), cluster_size + flat.shape[0] * world / embed.shape[0]
+
+
+def ema_update(flat: Tensor, idx: Tensor, embed_avg: Tensor, cluster_size: Tensor, decay: float,
+               laplace_alpha: float):
+    """EMAVectorQuantizer._update_ema (vq.py:47-74) without the one-hot matrix; returns the new
+    (embed, embed_avg, cluster_size)."""
+    k, d = embed_avg.shape
+    counts = torch.bincount(idx.reshape(-1), minlength=k).to(flat.dtype)            # one_hot.sum(0)
+    dw = torch.zeros(k, d, dtype=torch.float64).index_add_(0, idx.reshape(-1), flat.double())
+    cs = cluster_size * decay + counts * (1 - decay)                                # vq.py:60-62
+    avg = embed_avg * decay + dw.to(flat.dtype) * (1 - decay)                       # vq.py:64
+    n = cs.sum()
+    smoothed = n * ((cs + laplace_alpha) / (n + k * laplace_alpha))                 # vq.py:67-71
+    return avg / smoothed.unsqueeze(-1), avg, cs
+
+
+# ------------------------------------------------------------------------------------
 # a-X  slide tiling / code-map stitching (host-side geometry)
 # ------------------------------------------------------------------------------------
 def slide_grid(level_shape: Tuple[int, int], patch: int) -> Tuple[int, int]:

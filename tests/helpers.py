@@ -8,7 +8,7 @@ import torch
 
 import vqae_b200
 from vqae_b200 import synthetic as S
-from vqae_b200.config import compose_vqae_conf, pre_activation_fixup
+from vqae_b200.config import compose_multilevel_conf, compose_vqae_conf, pre_activation_fixup
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -113,3 +113,33 @@ def index_mismatches_outside_ties(idx, ref_idx, gap, thresh=NEAR_TIE_REL_GAP):
     idx, ref_idx, gap = (np.asarray(v).reshape(-1) for v in (idx, ref_idx, gap))
     bad = idx != ref_idx
     return int((bad & (gap >= thresh)).sum()), int(bad.sum()), int((gap < thresh).sum())
+
+
+# ---- scope row f-4: multi-level hierarchies (tests/golden/multilevel.npz, oracle/make_golden.py) ----
+MULTILEVEL_CASES = {
+    # tag -> (compose_multilevel_conf kwargs, seed, input seed, whole VQAE?)
+    "hier": (dict(level_downs=(2, 1), n_pre_enc_layers=(2, 3), shortcut_mode="up"), 11, 1011, False),
+    "flat": (dict(level_downs=(3, 0), n_pre_enc_layers=(2, 2), shortcut_mode="same"), 12, 1012, True),
+}
+
+
+def multilevel_model_and_state(tag: str):
+    """(package module on CPU in eval mode -- an Encoder for "hier", a VQAE for "flat" -- with the golden's
+    weights and codebooks, its state_dict in ``encoder.`` / ``decoder.`` naming, x)."""
+    kwargs, seed, xseed, whole = MULTILEVEL_CASES[tag]
+    conf = compose_multilevel_conf(**kwargs)
+    g = golden("multilevel")
+    if whole:
+        m = vqae_b200.instantiate(conf).eval()
+        sd = S.make_state_dict(m.state_dict(), seed=seed, regime="perturbed")
+    else:
+        m = vqae_b200.instantiate(conf["encoder_conf"]).eval()
+        sd = S.make_state_dict({"encoder." + k: v for k, v in m.state_dict().items()}, seed=seed,
+                               regime="perturbed")
+    n_levels = len(kwargs["level_downs"])
+    for i in range(n_levels):
+        e = torch.from_numpy(g[f"{tag}_embed{i}"])
+        sd[f"encoder.vq_layers.{i}.embed"] = e
+        sd[f"encoder.vq_layers.{i}.embed_avg"] = e.clone()
+    m.load_state_dict(sd if whole else {k[len("encoder."):]: v for k, v in sd.items()})
+    return m, sd, S.synthetic_patches(2, 256, xseed)

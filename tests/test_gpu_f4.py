@@ -1,0 +1,285 @@
+"""GPU: scope row f-4 -- multi-level hierarchies (model.py:144-187, 203-215, 274-291) and the training-mode
+codebook maintenance of the quantisers (vq.py:47-94) -- against the goldens of the unmodified reference
+(tests/golden/multilevel.npz, ema_training.npz; oracle/make_golden.py) and the CPU oracle."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import vqae_b200
+import vqae_oracle as O
+from vqae_b200 import engine as E
+from vqae_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+REPO = Path(__file__).resolve().parent.parent
+
+
+def _check_levels(g, tag, encs, idxs, losses, idx_bar_outside_ties, enc_tol, loss_tol):
+    """Per level: indices outside near-ties, quantised tensor where the code agrees, loss."""
+    all_same = True
+    for i, (e, idx, loss) in enumerate(zip(encs, idxs, losses)):
+        ref = g[f"{tag}_idx{i}"].astype(np.int64)
+        assert idx.dtype == torch.int64 and tuple(idx.shape) == ref.shape
+        same = idx.cpu().numpy() == ref
+        bad = (~same).reshape(-1) & (g[f"{tag}_gap{i}"] >= idx_bar_outside_ties)
+        assert int(bad.sum()) == 0, (i, int(bad.sum()), int((~same).sum()))
+        msk = torch.from_numpy(same)[:, ::4, ::4]
+        e_ref = torch.from_numpy(g[f"{tag}_enc_sub{i}"])
+        err = float(((e.cpu()[:, ::8, ::4, ::4] - e_ref).abs() * msk[:, None]).max() / e_ref.abs().max())
+        assert err < enc_tol, (i, err)
+        ref_loss = float(g[f"{tag}_loss{i}"])
+        assert abs(loss.item() - ref_loss) < loss_tol * ref_loss, (i, loss.item(), ref_loss)
+        all_same &= bool(same.all())
+        if not same.all():
+            break            # a flipped code below changes the inputs of every level above it
+    return all_same
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp32tc"])
+def test_hierarchy_encoder_vs_reference_golden(precision):
+    """Two VQ levels (64 ch @ 32x32 below 32 ch @ 64x64) joined by an 'up' shortcut block."""
+    g = H.golden("multilevel")
+    enc, _, x = H.multilevel_model_and_state("hier")
+    enc = vqae_b200.set_precision(enc.to(DEV), precision)
+    try:
+        with torch.no_grad():
+            encs, idxs, losses = enc(x.to(DEV))
+            encs_cl, idxs_cl, _ = enc(x.to(DEV).contiguous(memory_format=torch.channels_last))
+        assert len(encs) == len(idxs) == len(losses) == 2
+        assert tuple(encs[0].shape) == (2, 64, 32, 32) and tuple(encs[1].shape) == (2, 32, 64, 64)
+        # fp32-grade latents (|dz| of a few 1e-7): the un-rooted L4 sums move by ~1e-4 relative at most, as
+        # in test_model_vs_reference_golden, so codes may differ only below that gap
+        bar = 2e-4
+        _check_levels(g, "hier", encs, idxs, losses, bar, 1e-4, 1e-4)
+        for a, b in zip(idxs, idxs_cl):
+            assert torch.equal(a, b)
+        assert all(E.is_channels_last(e) for e in encs_cl) and all(e.is_contiguous() for e in encs)
+    finally:
+        enc.cpu()
+
+
+def test_hierarchy_encoder_fp16_agreement_with_reference_golden():
+    g = H.golden("multilevel")
+    enc, _, x = H.multilevel_model_and_state("hier")
+    enc = vqae_b200.set_precision(enc.to(DEV), "fp16")
+    try:
+        with torch.no_grad():
+            encs, idxs, losses = enc(x.to(DEV))
+        # level 0 (lowest) is a function of the input only: the single-level bars of
+        # tests/test_gpu_golden_reduced.py apply; level 1 also sees level 0's flipped codes
+        for i, bar in ((0, 0.99), (1, 0.98)):
+            ref = g[f"hier_idx{i}"].astype(np.int64)
+            agree = float((idxs[i].cpu().numpy() == ref).mean())
+            assert agree >= bar, (i, agree)
+            big_gap = g[f"hier_gap{i}"] >= (1e-2 if i == 0 else 5e-2)
+            flipped = (idxs[i].cpu().numpy() != ref).reshape(-1)
+            if i == 0:
+                assert int((flipped & big_gap).sum()) == 0
+            assert abs(losses[i].item() - float(g[f"hier_loss{i}"])) < 2e-2 * float(g[f"hier_loss{i}"])
+    finally:
+        enc.cpu()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp32tc"])
+def test_multilevel_vqae_vs_reference_golden(precision):
+    """Whole VQAE, two equal-width levels with 'same' shortcut blocks in encoder and decoder."""
+    g = H.golden("multilevel")
+    m, sd, x = H.multilevel_model_and_state("flat")
+    m = vqae_b200.set_precision(m.to(DEV), precision)
+    try:
+        with torch.no_grad():
+            encs, idxs, losses = m.encoder(x.to(DEV))
+            recon, losses2 = m(x.to(DEV))
+            ref_idx = [torch.from_numpy(g[f"flat_idx{i}"].astype(np.int64)).to(DEV) for i in range(2)]
+            dec_ref = m.decode_codes(ref_idx)
+        assert all(torch.equal(a, b) for a, b in zip(losses, losses2))
+        all_same = _check_levels(g, "flat", encs, idxs, losses, 2e-4, 1e-4, 1e-4)
+        # decoder on the REFERENCE's codes (well-posed whatever the encoder did)
+        assert H.rel_err(dec_ref.cpu()[:, :, ::8, ::8], torch.from_numpy(g["flat_recon_sub"])) < 1e-4
+        if all_same:
+            assert H.rel_err(recon.cpu()[:, :, ::8, ::8], torch.from_numpy(g["flat_recon_sub"])) < 1e-4
+    finally:
+        m.cpu()
+
+
+def test_multilevel_vqae_fp16_decoder_on_reference_codes():
+    g = H.golden("multilevel")
+    m, sd, x = H.multilevel_model_and_state("flat")
+    m = vqae_b200.set_precision(m.to(DEV), "fp16")
+    try:
+        with torch.no_grad():
+            ref_idx = [torch.from_numpy(g[f"flat_idx{i}"].astype(np.int64)).to(DEV) for i in range(2)]
+            dec_ref = m.decode_codes(ref_idx)
+        assert H.rel_err(dec_ref.cpu()[:, :, ::8, ::8], torch.from_numpy(g["flat_recon_sub"])) < 1e-2
+    finally:
+        m.cpu()
+
+
+def test_single_level_entry_points_reject_hierarchies():
+    enc, _, x = H.multilevel_model_and_state("hier")
+    enc = enc.to(DEV)
+    try:
+        with pytest.raises(NotImplementedError):
+            enc.encode(x.to(DEV))
+    finally:
+        enc.cpu()
+
+
+def test_level_sum_kernel():
+    for n in (1, 3, 4, 1023, 1 << 20, (1 << 20) + 5):
+        a, b = torch.randn(n, device=DEV), torch.randn(n, device=DEV)
+        assert torch.equal(E.add_nhwc(a, b), a + b)
+    with pytest.raises(ValueError):
+        E.add_nhwc(torch.zeros(4, device=DEV), torch.zeros(5, device=DEV))
+
+
+# ---- training-mode codebook maintenance -----------------------------------------------------------------
+def _make_quantizer(tag):
+    from vqae_b200.layers.vq import EMAVectorQuantizer, ProjectedEMAVectorQuantizer2d
+    q = (EMAVectorQuantizer(256, 8, 0.25, 0.99, 1e-5) if tag == "bare"
+         else ProjectedEMAVectorQuantizer2d(256, 64, 0.25, 0.99, 1e-5, 8))
+    q.load_state_dict(S.make_state_dict(q.state_dict(), seed=21, regime="perturbed"))
+    return q
+
+
+@pytest.mark.parametrize("tag", ["bare", "proj"])
+def test_training_forward_updates_codebook_like_the_reference(tag):
+    """Three training-mode forwards: first-pass initialisation, then EMA updates (vq.py:47-94, 118-133);
+    codes, loss and all four buffers after every step against the reference's."""
+    g = H.golden("ema_training")
+    q = _make_quantizer(tag).to(DEV).train()
+    assert int(q.first_pass) == 1
+    for step in range(3):
+        x = torch.from_numpy(g[f"{tag}_x{step}"]).float().to(DEV)
+        quant, idx, loss = q(x)
+        assert not quant.requires_grad and quant.shape == x.shape
+        ref = g[f"{tag}_idx{step}"].astype(np.int64)
+        flips = int((idx.cpu().numpy() != ref).sum())
+        assert flips <= 1, (step, flips)                 # a near-tie may flip; none observed
+        assert abs(loss.item() - float(g[f"{tag}_loss{step}"])) < 1e-5 * float(g[f"{tag}_loss{step}"])
+        assert int(q.first_pass) == int(g[f"{tag}_first_pass_after{step}"]) == 0
+        tol = dict(rtol=2e-5, atol=2e-6) if flips == 0 else dict(rtol=1e-2, atol=1e-2)
+        np.testing.assert_allclose(q.cluster_size.cpu().numpy(), g[f"{tag}_cluster_size_after{step}"], **tol)
+        np.testing.assert_allclose(q.embed_avg.cpu().numpy(), g[f"{tag}_embed_avg_after{step}"], **tol)
+        np.testing.assert_allclose(q.embed.cpu().numpy(), g[f"{tag}_embed_after{step}"], **tol)
+    # eval mode afterwards uses the updated codebook and leaves the buffers alone
+    q.eval()
+    before = q.embed.clone()
+    x = torch.from_numpy(g[f"{tag}_x2"]).float().to(DEV)
+    with torch.no_grad():
+        _, idx_eval, _ = q(x)
+        z = x if tag == "bare" else torch.nn.functional.conv2d(x, q.proj_in.weight, q.proj_in.bias)
+        _, idx_ref, _, gap = O.ema_quantizer_forward(z.cpu(), q.embed.cpu(), 0.25)
+    assert torch.equal(q.embed, before)
+    assert H.index_mismatches_outside_ties(idx_eval.cpu().numpy(), idx_ref.numpy(), gap.numpy())[0] == 0
+
+
+def test_ema_kernels_vs_oracle_full_size_and_deterministic():
+    """N = 262 144 rows (the encode step's quantiser call at batch 256): accumulate + update against the
+    oracle restatement, and bit-identical buffers from repeated launches (no atomics)."""
+    gen = torch.Generator().manual_seed(5)
+    n, k, d = 262144, 256, 8
+    z = torch.randn(n, d, generator=gen)
+    idx = torch.randint(0, k, (n,), generator=gen)
+    idx[idx == 17] = 3                                            # an unused code
+    embed_avg, cs = torch.randn(k, d, generator=gen), torch.rand(k, generator=gen) * 50
+    o_embed, o_avg, o_cs = O.ema_update(z, idx, embed_avg, cs, 0.99, 1e-5)
+    zd, idxd = z.to(DEV), idx.to(DEV)
+    results = []
+    for _ in range(3):
+        e, a, c = torch.zeros(k, d, device=DEV), embed_avg.to(DEV), cs.to(DEV)
+        acc = E.ema_accumulate(zd, idxd, k)
+        E.ema_update(e, a, c, acc, 0.99, 1e-5)
+        results.append((e.clone(), a.clone(), c.clone(), acc.clone()))
+    counts = results[0][3][k * d:].cpu()
+    assert torch.equal(counts, torch.bincount(idx, minlength=k).float()) and counts[17] == 0
+    np.testing.assert_allclose(results[0][2].cpu().numpy(), o_cs.numpy(), rtol=3e-6)
+    np.testing.assert_allclose(results[0][1].cpu().numpy(), o_avg.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(results[0][0].cpu().numpy(), o_embed.numpy(), rtol=1e-5, atol=1e-6)
+    for r in results[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(r, results[0]))
+
+
+@pytest.mark.parametrize("n,d", [(2, 8), (1000, 8), (50000, 24), (4097, 130)])
+def test_column_stats_and_init_vs_oracle(n, d):
+    gen = torch.Generator().manual_seed(n + d)
+    z = torch.randn(n, d, generator=gen) * 3 + 1.5
+    mean, std = E.column_stats(z.to(DEV))
+    np.testing.assert_allclose(mean.cpu().numpy(), z.mean(0).numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(std.cpu().numpy(), z.std(0).numpy(), rtol=1e-5, atol=1e-6)
+    k = 64
+    embed, cs = torch.randn(k, d, generator=gen), torch.zeros(k)
+    o_e, o_a, o_c = O.ema_init(z, embed, cs, world=2)
+    e, a, c = embed.to(DEV), torch.zeros(k, d, device=DEV), cs.to(DEV)
+    E.ema_init(e, a, c, mean, std, n * 2 / k)
+    np.testing.assert_allclose(e.cpu().numpy(), o_e.numpy(), rtol=1e-5, atol=1e-5)
+    assert torch.equal(e, a)
+    np.testing.assert_allclose(c.cpu().numpy(), o_c.numpy(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("k,d", [(512, 8), (100, 20)])
+def test_ema_accumulate_other_codebook_shapes(k, d):
+    gen = torch.Generator().manual_seed(k)
+    n = 5000
+    z, idx = torch.randn(n, d, generator=gen), torch.randint(0, k, (n,), generator=gen)
+    acc = E.ema_accumulate(z.to(DEV), idx.to(DEV), k).cpu()
+    dw = torch.zeros(k, d, dtype=torch.float64).index_add_(0, idx, z.double()).float()
+    np.testing.assert_allclose(acc[:k * d].view(k, d).numpy(), dw.numpy(), rtol=1e-5, atol=1e-5)
+    assert torch.equal(acc[k * d:], torch.bincount(idx, minlength=k).float())
+
+
+_DDP_SCRIPT = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path[:0] = [os.path.join(sys.argv[1], "2d-vq-ae-2_b200"), os.path.join(sys.argv[1], "oracle"),
+                os.path.join(sys.argv[1], "tests")]
+import helpers as H, vqae_oracle as O
+from vqae_b200 import synthetic as S
+from vqae_b200.layers.vq import EMAVectorQuantizer
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl")
+dev = torch.device("cuda", rank)
+q = EMAVectorQuantizer(256, 8, 0.25, 0.99, 1e-5)
+sd = S.make_state_dict(q.state_dict(), seed=21, regime="perturbed")
+q.load_state_dict(sd); q = q.to(dev).train()
+gen = torch.Generator().manual_seed(9)
+xs = [torch.randn(world, 2, 8, 32, 32, generator=gen) * (1 + s) for s in range(2)]
+for x in xs:
+    q(x[rank].to(dev))
+# the reference's arithmetic on ALL ranks' rows: mean / std are averaged over ranks (vq.py:81-88),
+# counts and sums are added (vq.py:56-58)
+embed, avg, cs = sd["embed"], sd["embed_avg"], sd["cluster_size"]
+for step, x in enumerate(xs):
+    flats = [x[r].permute(0, 2, 3, 1).reshape(-1, 8) for r in range(world)]
+    if step == 0:
+        mean = sum(f.mean(0) for f in flats) / world
+        std = sum(f.std(0) for f in flats) / world
+        embed = embed * std + mean; avg = embed.clone(); cs = cs + flats[0].shape[0] * world / 256
+    idx = torch.cat([O.quantize_flat(f, embed)[0] for f in flats])
+    embed, avg, cs = O.ema_update(torch.cat(flats), idx, avg, cs, 0.99, 1e-5)
+np.testing.assert_allclose(q.cluster_size.cpu().numpy(), cs.numpy(), rtol=2e-5, atol=2e-6)
+np.testing.assert_allclose(q.embed.cpu().numpy(), embed.numpy(), rtol=2e-5, atol=2e-6)
+mine = q.embed.clone(); ref = mine.clone(); dist.broadcast(ref, 0)
+assert torch.equal(mine, ref), "ranks diverged"
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL all-reduce of the statistics)")
+def test_training_forward_all_reduces_statistics_across_ranks(tmp_path):
+    script = tmp_path / "ddp_ema.py"
+    script.write_text(_DDP_SCRIPT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script), str(REPO)],
+                       capture_output=True, text=True, timeout=600,
+                       env={**os.environ, "OMP_NUM_THREADS": "4"})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

@@ -121,3 +121,62 @@ def test_slide_geometry_and_stitching():
     assert m.shape == (8, 12) and m.dtype == np.uint8
     assert np.array_equal(m[4:8, 8:12], tiles[5])
     assert O.cast_to_lowest_dtype(np.array([0, 1])).dtype == bool
+
+
+# ---- scope row f-4 ---------------------------------------------------------------------------------
+def test_multilevel_hierarchy_matches_reference_golden():
+    """Encoder with two VQ levels and an 'up' shortcut block (model.py:144-187, 203-215)."""
+    g = H.golden("multilevel")
+    _, sd, x = H.multilevel_model_and_state("hier")
+    assert int(g["hier_n_state"]) == len(sd)
+    with torch.no_grad():
+        encs, idxs, losses = O.encoder_forward_levels(x, sd)
+    assert len(encs) == 2
+    assert tuple(encs[0].shape) == (2, 64, 32, 32) and tuple(encs[1].shape) == (2, 32, 64, 64)
+    for i in range(2):
+        ref = g[f"hier_idx{i}"].astype(np.int64)
+        bad = (idxs[i].numpy() != ref).reshape(-1) & (g[f"hier_gap{i}"] >= H.NEAR_TIE_REL_GAP)
+        assert int(bad.sum()) == 0
+        assert H.rel_err(encs[i][:, ::8, ::4, ::4], torch.from_numpy(g[f"hier_enc_sub{i}"])) < 1e-5
+        assert abs(losses[i].item() - float(g[f"hier_loss{i}"])) < 1e-5 * float(g[f"hier_loss{i}"])
+
+
+def test_multilevel_vqae_matches_reference_golden():
+    """Whole VQAE with two equal-width levels (the shape the reference's Decoder accepts)."""
+    g = H.golden("multilevel")
+    _, sd, x = H.multilevel_model_and_state("flat")
+    assert int(g["flat_n_state"]) == len(sd)
+    with torch.no_grad():
+        encs, idxs, losses = O.encoder_forward_levels(x, sd)
+        recon = O.decoder_forward_levels(encs, sd)
+    for i in range(2):
+        assert np.array_equal(idxs[i].numpy(), g[f"flat_idx{i}"].astype(np.int64))
+        assert abs(losses[i].item() - float(g[f"flat_loss{i}"])) < 1e-5 * float(g[f"flat_loss{i}"])
+    assert H.rel_err(recon[:, :, ::8, ::8], torch.from_numpy(g["flat_recon_sub"])) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["bare", "proj"])
+def test_ema_training_updates_match_reference_golden(tag):
+    """_init_ema / _update_ema restated without the one-hot matrix (vq.py:47-94) against three
+    training-mode forwards of the reference's quantisers."""
+    g = H.golden("ema_training")
+    from vqae_b200.layers.vq import EMAVectorQuantizer, ProjectedEMAVectorQuantizer2d
+    c = 8 if tag == "bare" else 64
+    q = (EMAVectorQuantizer(256, 8, 0.25, 0.99, 1e-5) if tag == "bare"
+         else ProjectedEMAVectorQuantizer2d(256, c, 0.25, 0.99, 1e-5, 8))
+    sd = H.S.make_state_dict(q.state_dict(), seed=21, regime="perturbed")
+    embed, avg, cs = sd["embed"], sd["embed_avg"], sd["cluster_size"]
+    assert np.array_equal(embed.numpy(), g[f"{tag}_embed0"])
+    for step in range(3):
+        x = torch.from_numpy(g[f"{tag}_x{step}"]).float()
+        z = x if tag == "bare" else torch.nn.functional.conv2d(x, sd["proj_in.weight"], sd["proj_in.bias"])
+        flat = z.permute(0, 2, 3, 1).reshape(-1, 8)
+        if step == 0:
+            embed, avg, cs = O.ema_init(flat, embed, cs)
+        _, idx, loss, _ = O.ema_quantizer_forward(z, embed, 0.25)
+        assert np.array_equal(idx.numpy(), g[f"{tag}_idx{step}"].astype(np.int64))
+        assert abs(loss.item() - float(g[f"{tag}_loss{step}"])) < 1e-5 * float(g[f"{tag}_loss{step}"])
+        embed, avg, cs = O.ema_update(flat, idx, avg, cs, 0.99, 1e-5)
+        np.testing.assert_allclose(cs.numpy(), g[f"{tag}_cluster_size_after{step}"], rtol=1e-6)
+        np.testing.assert_allclose(avg.numpy(), g[f"{tag}_embed_avg_after{step}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(embed.numpy(), g[f"{tag}_embed_after{step}"], rtol=1e-5, atol=1e-6)
