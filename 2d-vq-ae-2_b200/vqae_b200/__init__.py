@@ -16,7 +16,7 @@ import types
 from . import _instantiate, config, engine  # noqa: F401
 from ._instantiate import instantiate
 from .config import compose_vqae_conf
-from .layers import conv, conv_block, vq  # noqa: F401
+from .layers import conv, conv_block, misc, vq  # noqa: F401
 from .model import VQAE, Decoder, Encoder  # noqa: F401
 from .plan import accelerate  # noqa: F401
 
@@ -62,5 +62,5 @@ def install_as_vq_ae() -> None:
     sys.modules.update({
         "vq_ae": root, "vq_ae.model": model, "vq_ae.layers": layers,
         "vq_ae.layers.vq": layers.vq, "vq_ae.layers.conv_block": layers.conv_block,
-        "vq_ae.layers.conv": layers.conv,
+        "vq_ae.layers.conv": layers.conv, "vq_ae.layers.misc": layers.misc,
     })

@@ -19,6 +19,7 @@ _ALIASES: Dict[str, str] = {
     "vq_ae.layers.vq": "vqae_b200.layers.vq",
     "vq_ae.layers.conv_block": "vqae_b200.layers.conv_block",
     "vq_ae.layers.conv": "vqae_b200.layers.conv",
+    "vq_ae.layers.misc": "vqae_b200.layers.misc",
     "utils.conf_helpers": "vqae_b200._instantiate",
 }
 

@@ -100,6 +100,9 @@ SIGNATURES = {
     "vqae_column_stats_f32": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
     "vqae_ema_init_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "vqae_add_f32": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "vqae_pointwise_conv_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "vqae_depthwise_conv_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "vqae_se_gate_f32": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

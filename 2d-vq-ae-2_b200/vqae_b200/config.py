@@ -222,3 +222,48 @@ def compose_multilevel_conf(
         encoder_conf=encoder_conf,
         decoder_conf=decoder_conf,
     )
+
+
+def up2d(**over) -> Dict[str, Any]:
+    """conv_layer/up2d.yaml over convtranspose2d.yaml: ConvTranspose2d kernel 2, stride 2."""
+    base = dict(_target_="torch.nn.ConvTranspose2d", in_channels=None, out_channels=None, kernel_size=2,
+                stride=2, padding=0, output_padding=0, groups=1, bias=True, dilation=1,
+                padding_mode="zeros")
+    base.update(over)
+    return base
+
+
+def mbconv(expand_ratio: float = 4, batchnorm: bool = True, se: bool = True) -> Dict[str, Any]:
+    """conf/model/layers/conv_block/mbconv.yaml:1-80 resolved (SiLU, BatchNorm2d, SELayer with bottleneck
+    divisor 4; depthwise branch_conv2 whose ``groups`` the block fills in)."""
+    nb = dict(bias=False)
+    circ = dict(bias=False, padding_mode="circular")
+    return dict(
+        _target_="vq_ae.layers.conv_block.MBConv", _recursive_=False,
+        in_channels=None, out_channels=None, mode=None, expand_ratio=expand_ratio,
+        activation_conf=dict(_target_="torch.nn.SiLU"),
+        batchnorm_conf=(dict(_target_="torch.nn.BatchNorm2d", num_features=None, eps=1e-05, momentum=0.1,
+                             affine=True, track_running_stats=True) if batchnorm else None),
+        se_conf=(dict(_target_="vq_ae.layers.misc.SELayer", in_channels=None, out_channels=None,
+                      bottleneck_divisor=4) if se else None),
+        conv_conf=dict(
+            down=dict(branch_conv1=proj2d(**nb), branch_conv2={**down2d(**circ), "groups": None},
+                      branch_conv3=proj2d(**nb), skip_conv=down2d(**circ)),
+            up=dict(branch_conv1=proj2d(**nb), branch_conv2={**up2d(**nb), "groups": None},
+                    branch_conv3=proj2d(**nb), skip_conv=up2d(**nb)),
+            same=dict(branch_conv1=proj2d(**nb), branch_conv2={**same2d(**circ), "groups": None},
+                      branch_conv3=proj2d(**nb), skip_conv=proj2d(**nb)),
+            out=dict(branch_conv1=proj2d(**nb), branch_conv2={**out2d(**circ), "groups": None},
+                     branch_conv3=proj2d(**nb), skip_conv=out2d(**nb)),
+        ),
+    )
+
+
+def compose_efficientnetv2_conf(n_down: int = 3, n_enc_layers_trunk: int = 3, **kwargs) -> Dict[str, Any]:
+    """conf/model/{encoder,decoder}/efficientnetv2.yaml: the shipped tree with every conv block swapped
+    for MBConv (pyramid blocks and trunks; stems and quantiser unchanged)."""
+    conf = compose_vqae_conf(n_down=n_down, n_enc_layers_trunk=n_enc_layers_trunk, **kwargs)
+    for part, pyramid in (("encoder_conf", "down_block_conf"), ("decoder_conf", "up_block_conf")):
+        conf[part][pyramid]["conv_conf"] = mbconv()
+        conf[part]["conv_block_conf"] = mbconv()
+    return conf

@@ -1,8 +1,8 @@
 """Counterpart of vq_ae/layers/conv_block.py: DownBlock, UpBlock, EnvelopBlock and
 PreActFixupResBlock with the reference's constructor signatures, parameter names and
-initialisation; eval-mode ``forward`` of the residual block runs the fused kernels.
-
-Out of scope: ``MBConv`` (alternative EfficientNetV2 block, not in the shipped config).
+initialisation; eval-mode ``forward`` of the residual block runs the fused kernels.  ``MBConv`` (the
+alternative EfficientNetV2 block of conf/model/encoder/efficientnetv2.yaml, scope row f-4) runs the fp32
+kernels of csrc/mbconv.cu.
 """
 from __future__ import annotations
 
@@ -16,6 +16,7 @@ import torch
 from torch import nn
 
 from .. import engine as E
+from .. import mbconv as M
 from .. import plan as P
 from .._instantiate import instantiate
 
@@ -166,3 +167,40 @@ class PreActFixupResBlock(nn.Module):
         nn.init.constant_(self.branch_conv3.weight, val=0)
         if self.skip_conv is not None:
             nn.init.xavier_normal_(self.skip_conv.weight)
+
+
+class MBConv(nn.Module):
+    """expand 1x1 -> depthwise -> squeeze-excite -> project 1x1, BatchNorm after every conv, plus a skip
+    path (conv_block.py:240-321).  ``branch`` holds the same modules at the same indices as the
+    reference's (absent BatchNorm / SELayer configs leave no gap), which is the ``state_dict`` contract."""
+
+    def __init__(self, in_channels: int, out_channels: int, mode: str, expand_ratio: float,
+                 activation_conf, conv_conf, batchnorm_conf, se_conf):
+        super().__init__()
+        assert mode in ("down", "same", "up", "out")
+        conv_conf = conv_conf[mode]
+        widest = max(in_channels, out_channels)
+        assert isclose(widest * expand_ratio % 1, 0), (
+            f"max_channels: {widest} x expand_ratio: {expand_ratio} % 1 !\u2248 0!")
+        mid = round(widest * expand_ratio)
+        stages = (
+            (conv_conf['branch_conv1'], dict(in_channels=in_channels, out_channels=mid)),
+            (batchnorm_conf, dict(num_features=mid)),
+            (activation_conf, {}),
+            (conv_conf['branch_conv2'], dict(in_channels=mid, out_channels=mid, groups=mid)),
+            (batchnorm_conf, dict(num_features=mid)),
+            (activation_conf, {}),
+            (se_conf, dict(in_channels=mid, out_channels=mid)),
+            (conv_conf['branch_conv3'], dict(in_channels=mid, out_channels=out_channels)),
+            (batchnorm_conf, dict(num_features=out_channels)),
+        )
+        built = (instantiate(conf, **kw) for conf, kw in stages)
+        self.branch = nn.Sequential(*(m for m in built if m is not None))
+        needs_skip_conv = not (mode in ("same", "out") and in_channels == out_channels)
+        self.skip_conv = (instantiate(conv_conf['skip_conv'], in_channels=in_channels,
+                                      out_channels=out_channels) if needs_skip_conv else None)
+        with torch.no_grad():
+            self.branch[-1].weight *= 0            # last BatchNorm's gamma starts at zero (:312-313)
+
+    def forward(self, x):
+        return M.block_forward(self, x)

@@ -82,10 +82,12 @@ class Encoder(nn.Module):
 
     def forward(self, x: Tensor) -> Tuple[Sequence[Tensor], Sequence[Tensor], Sequence[Tensor]]:
         """((enc,), (indices,), (loss,)) -- low-res to high-res order (model.py:189-217)."""
-        if len(self.vq_layers) > 1 or any(sc is not None for sc in self.shortcut_layers):
-            return P.encoder_forward_levels(self, x)          # multi-level hierarchy (scope row f-4)
-        enc, idx, loss, _, _ = self.encode(x)
-        return (enc,), (idx,), (loss,)
+        # one fused plan for the shipped topology; multi-level hierarchies and MBConv pyramids (scope row
+        # f-4) run level by level
+        out = P.encoder_forward(self, x)
+        for vq in self.vq_layers:
+            vq.last_near_ties = P.state(vq).last_near_ties
+        return out
 
 
 class Decoder(nn.Module):

@@ -21,6 +21,7 @@ import torch
 from torch import Tensor, nn
 
 from . import engine as E
+from . import mbconv as M
 
 REDUCED = "fp16"        # what an active torch.autocast('cuda') selects
 
@@ -204,6 +205,11 @@ def _single_level(levels: int, shortcuts) -> bool:
     return levels == 1 and all(sc is None for sc in shortcuts)
 
 
+def _fused_plan_applies(module, levels: int, shortcuts) -> bool:
+    """The one-plan fast path: one VQ level, no shortcut blocks, Fixup blocks only."""
+    return _single_level(levels, shortcuts) and not any(M.is_mbconv(m) for m in module.modules())
+
+
 def _check_single_level(levels: int, shortcuts, who: str) -> None:
     if not _single_level(levels, shortcuts):
         raise NotImplementedError(
@@ -211,22 +217,53 @@ def _check_single_level(levels: int, shortcuts, who: str) -> None:
             "go through forward() (plan.encoder_forward_levels / decoder_forward_levels)")
 
 
+def compute_blocks(module: nn.Module) -> List[nn.Module]:
+    """The residual blocks below ``module`` in execution order: PreActFixupResBlocks and MBConvs."""
+    out: List[nn.Module] = []
+
+    def walk(m):
+        if is_fixup_block(m) or M.is_mbconv(m):
+            out.append(m)
+            return
+        for child in m.children():
+            walk(child)
+
+    walk(module)
+    return out
+
+
 def _run_module(module, h: Tensor, precision: str) -> Tensor:
-    """A shortcut / pyramid module on an NHWC tensor: every container the reference builds these from
-    (DownBlock, UpBlock, EnvelopBlock, nn.Sequential, a bare PreActFixupResBlock) is a chain of Fixup
-    blocks in ``modules()`` order."""
-    blocks = flat_blocks(module)
+    """A shortcut / pyramid / trunk module on an NHWC tensor: every container the reference builds these
+    from (DownBlock, UpBlock, EnvelopBlock, nn.Sequential, a bare block) is a chain of residual blocks in
+    ``modules()`` order.  Runs of Fixup blocks execute as packed plans (fused / resident kernels where
+    they apply); MBConv blocks (fp32 kernels in every precision mode) one by one."""
+    blocks = compute_blocks(module)
     leaves = [m for m in module.modules() if not list(m.children())]
     inside = {id(l) for blk in blocks for l in blk.modules()}
     foreign = [type(l).__name__ for l in leaves if id(l) not in inside
                and not (isinstance(l, (nn.Sequential, nn.ModuleList)) and len(l) == 0)]
     if foreign:
         raise NotImplementedError(
-            f"{type(module).__name__}: only chains of PreActFixupResBlocks have B200 kernels "
+            f"{type(module).__name__}: only chains of PreActFixupResBlocks / MBConvs have B200 kernels "
             f"(found {sorted(set(foreign))})")
-    if not blocks:
-        return h                                        # n_down = 0 / n_up = 0: an empty Sequential
-    return _plan(module).run(blocks, h, precision)
+    st = state(module)
+    if not hasattr(st, "runs"):
+        st.runs = {}
+    i = 0
+    while i < len(blocks):
+        if M.is_mbconv(blocks[i]):
+            h = M.forward_nhwc(M.packed(blocks[i]), h)
+            i += 1
+            continue
+        j = i
+        while j < len(blocks) and is_fixup_block(blocks[j]):
+            j += 1
+        plan = st.runs.get(i)
+        if plan is None:
+            plan = st.runs[i] = Plan()
+        h = plan.run(blocks[i:j], h, precision)
+        i = j
+    return h
 
 
 def _level_out(out: Tensor, b: int, hh: int, ww: int, c: int, cl: bool) -> Tensor:
@@ -244,8 +281,13 @@ def encoder_forward_levels(enc, x: Tensor, mean=None, std=None):
     precision = resolve_precision(enc)
     cl = x.dtype == torch.uint8 or E.is_channels_last(x)
     downs: List[Tensor] = []
-    h = _plan(enc.down_layers[0]).run_from_input(enc.in_stem, flat_blocks(enc.down_layers[0]), x, mean,
-                                                 std, precision, False)
+    first = compute_blocks(enc.down_layers[0])
+    if first and all(is_fixup_block(b) for b in first):
+        h = _plan(enc.down_layers[0]).run_from_input(enc.in_stem, first, x, mean, std, precision, False)
+    else:
+        h = _run_module(enc.down_layers[0],
+                        E.stem_in(x, enc.in_stem.weight, enc.in_stem.bias, mean, std, precision=precision),
+                        precision)
     downs.append(h)
     for down_layer in list(enc.down_layers)[1:]:
         h = _run_module(down_layer, h, precision)
@@ -337,7 +379,7 @@ def encoder_encode(enc, x: Tensor, mean=None, std=None, want_quantized: bool = T
 
 
 def decoder_forward(dec, xs: Sequence[Tensor]) -> Tensor:
-    if not _single_level(len(dec.up_layers), dec.shortcut_layers):
+    if not _fused_plan_applies(dec, len(dec.up_layers), dec.shortcut_layers):
         return decoder_forward_levels(dec, xs)
     if len(xs) != 1:
         raise ValueError(f"Decoder: {len(xs)} encodings for 1 level")
@@ -390,7 +432,7 @@ def _bind(module, fast):
 
 def encoder_forward(enc, x):
     """Encoder.forward (model.py:189-217): the single-level fast plan, or the level loop."""
-    if not _single_level(len(enc.vq_layers), enc.shortcut_layers):
+    if not _fused_plan_applies(enc, len(enc.vq_layers), enc.shortcut_layers):
         return encoder_forward_levels(enc, x)
     e, idx, loss, _, _ = encoder_encode(enc, x)
     return (e,), (idx,), (loss,)
@@ -424,6 +466,8 @@ def accelerate(model: nn.Module, precision: Optional[str] = None) -> nn.Module:
             _bind(m, _vq_fast)
         elif is_fixup_block(m):
             _bind(m, block_forward)
+        elif M.is_mbconv(m):
+            _bind(m, M.block_forward)
         else:
             continue
         state(m).precision = precision

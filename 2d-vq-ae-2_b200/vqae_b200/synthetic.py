@@ -79,6 +79,33 @@ def make_state_dict(template: Mapping[str, Tensor], seed: int = 0, regime: str =
             v = torch.zeros(shape)
         elif leaf == "first_pass":
             v = torch.as_tensor(1)
+        elif ".branch." in key or key.startswith("branch."):
+            # MBConv / SELayer tensors (layers/conv_block.py:264-309, layers/misc.py:16-21): convs,
+            # BatchNorm2d affine + running statistics, the two Linear layers of the squeeze-excite
+            stem = key.rsplit(".", 1)[0]
+            if len(shape) == 4:
+                v = _normal(shape, math.sqrt(2.0 / (shape[1] * shape[2] * shape[3])), g)
+            elif len(shape) == 2:
+                v = _uniform(shape, 1.0 / math.sqrt(shape[1]), g)
+            elif leaf == "bias" and ".fc." in key:
+                v = _uniform(shape, 1.0 / math.sqrt(template[stem + ".weight"].shape[1]), g)
+            elif leaf == "weight":
+                # BatchNorm gamma; the block's LAST BatchNorm (the reference starts it at zero,
+                # conv_block.py:312-313) stays small so that deep stacks of blocks keep O(1) activations
+                head, _, idx = stem.rpartition(".")
+                last = not any(k.startswith(head + ".") and k[len(head) + 1:].split(".")[0].isdigit()
+                               and int(k[len(head) + 1:].split(".")[0]) > int(idx) for k in template)
+                v = _normal(shape, 0.05, g, mean=0.25) if last else _normal(shape, 0.1, g, mean=1.0)
+            elif leaf == "bias":
+                v = _normal(shape, 0.05, g)                       # BatchNorm beta
+            elif leaf == "running_mean":
+                v = _normal(shape, 0.1, g)
+            elif leaf == "running_var":
+                v = torch.rand(shape, generator=g) + 0.5
+            elif leaf == "num_batches_tracked":
+                v = torch.zeros(shape, dtype=torch.int64)
+            else:
+                raise KeyError(f"make_state_dict: no rule for {key} {shape}")
         else:
             raise KeyError(f"make_state_dict: no rule for {key} {shape}")
         out[key] = v if v is None else v.to(ref.dtype)

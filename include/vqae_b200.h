@@ -408,6 +408,32 @@ int vqae_ema_init_f32(float* embed, float* embed_avg, float* cluster_size, const
  * (model.py:283-288).  out may alias a or b.                                                     */
 int vqae_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 
+/* ---- f-4  MBConv (layers/conv_block.py:240-321) and SELayer (layers/misc.py:7-30), eval mode --------
+ * The block is  out = BN3(W3 . (t2 * gate)) + skip(x),  t2 = SiLU(BN2(depthwise(SiLU(BN1(W1 . x))))),
+ * gate = SELayer(t2); BatchNorm in eval mode arrives folded as per-channel (scale, shift).  NHWC fp32.
+ *
+ * vqae_pointwise_conv_f32: a full conv as a GEMM over pixels with a fused epilogue
+ *     out[p, n] = act(scale[n] * sum_k A[p, k] w[n, k] + shift[n]) + res[p, n]
+ *   mode 0: 1x1 conv, A = the input rows, K = c_in                         (nn.Conv2d k=1; proj2d.yaml)
+ *   mode 1: 2x2 stride-2 conv, A = space-to-depth rows, K = 4 c_in,        (down2d.yaml)
+ *           w[n][(dy*2+dx)*c_in + ci]
+ *   mode 2: 2x2 stride-2 transposed conv, w = [4][n_out][c_in], one matrix (up2d.yaml, ConvTranspose2d)
+ *           per output parity (dy, dx); out is [B, 2 hi, 2 wi, n_out]
+ *   scale / shift / gate ([B, c_in], mode 0 only: A[p, k] *= gate[image(p), k]) / res may be NULL.
+ * vqae_depthwise_conv_f32: one filter per channel, w_taps = [taps][c]; mode 0: 3x3 circular, 1: 2x2 stride 2,
+ *   2: 2x2 stride-2 transposed; then affine + SiLU; row_sums [B, rows_out, c] (or NULL) receives each
+ *   output row's channel sums for the squeeze of the SELayer (fixed summation order).
+ * vqae_se_gate_f32: gate[b, :] = sigmoid(w2 . SiLU(w1 . mean + b1) + b2), mean = sum of row_sums / pixels. */
+int vqae_pointwise_conv_f32(const float* a, const float* w, const float* scale, const float* shift,
+                            const float* gate, const float* res, float* out, int64_t batch, int hi, int wi,
+                            int c_in, int n_out, int mode, int act_silu, void* stream);
+int vqae_depthwise_conv_f32(const float* in, const float* w_taps, const float* scale, const float* shift,
+                            float* out, float* row_sums, int64_t batch, int hi, int wi, int c, int mode,
+                            void* stream);
+int vqae_se_gate_f32(const float* row_sums, int64_t batch, int rows, int pixels_per_image, int c,
+                     const float* w1, const float* b1, const float* w2, const float* b2, int c_hidden,
+                     float* gate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,8 +25,8 @@ sys.path.insert(0, str(REPO / "2d-vq-ae-2_b200"))
 
 import ref_shim  # noqa: E402
 from vqae_b200 import synthetic as S  # noqa: E402
-from vqae_b200.config import (compose_multilevel_conf, compose_vqae_conf,  # noqa: E402
-                              pre_activation_fixup)
+from vqae_b200.config import (compose_efficientnetv2_conf, compose_multilevel_conf,  # noqa: E402
+                              compose_vqae_conf, mbconv, pre_activation_fixup)
 
 GOLDEN = REPO / "tests" / "golden"
 
@@ -286,6 +286,47 @@ def ema_training_cases(vq_mod):
     return out
 
 
+MBCONV_BLOCK_CASES = {                   # name -> (c_in, c_out, mode, hw, batchnorm, se)
+    "same16": (16, 16, "same", 16, True, True), "same8to16": (8, 16, "same", 12, True, True),
+    "down16": (16, 32, "down", 16, True, True), "up32": (32, 16, "up", 8, True, True),
+    "same16_plain": (16, 16, "same", 8, False, False), "down8_nose": (8, 16, "down", 8, True, False),
+}
+
+
+@torch.no_grad()
+def mbconv_cases(model_mod, cb_mod):
+    """Scope row f-4: the reference's MBConv blocks (conv_block.py:240-321) one by one, and a whole VQAE
+    built from them (conf/model/{encoder,decoder}/efficientnetv2.yaml)."""
+    out = {}
+    for name, (cin, cout, mode, hw, use_bn, use_se) in MBCONV_BLOCK_CASES.items():
+        conf = mbconv(batchnorm=use_bn, se=use_se)
+        for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+            conf.pop(k)
+        torch.manual_seed(42)
+        blk = cb_mod.MBConv(in_channels=cin, out_channels=cout, mode=mode, **conf).eval()
+        blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=41, regime="perturbed"))
+        gen = torch.Generator().manual_seed(500 + cin + hw)
+        x = torch.randn(2, cin, hw, hw, generator=gen)
+        out[f"blk_{name}_x"] = _np(x)
+        out[f"blk_{name}_y"] = _np(blk(x))
+    conf = compose_efficientnetv2_conf(n_down=3, n_enc_layers_trunk=3)
+    conf.pop("_target_"), conf.pop("_recursive_")
+    torch.manual_seed(42)
+    m = model_mod.VQAE(**conf).eval()
+    sd = S.make_state_dict(m.state_dict(), seed=31, regime="perturbed")
+    m.load_state_dict(sd)
+    x = S.synthetic_patches(2, 256, 1031)
+    ((e,), (idx,), (loss,)), zs = _settle_codebooks(m.encoder, x, sd)
+    recon, _ = m(x)
+    vq = m.encoder.vq_layers[0]
+    out.update(model_embed=_np(vq.embed), model_idx=_np(idx).astype(np.int16), model_loss=_np(loss),
+               model_z=_np(zs[0]), model_gap=_np(top2_gap(zs[0], vq.embed)),
+               model_enc_sub=_np(e[:, ::8, ::4, ::4]), model_recon_sub=_np(recon[:, :, ::8, ::8]),
+               model_recon_stats=stats(recon), model_n_state=np.array(len(sd)),
+               model_codes_used=np.array(idx.unique().numel()))
+    return out
+
+
 def main():
     if not ref_shim.reference_available():
         raise SystemExit("reference checkout not found; run this in the build container")
@@ -295,6 +336,7 @@ def main():
     if "--only-f4" in sys.argv:                      # the round-2 additions only (scope row f-4)
         np.savez_compressed(GOLDEN / "multilevel.npz", **multilevel_cases(model_mod))
         np.savez_compressed(GOLDEN / "ema_training.npz", **ema_training_cases(vq_mod))
+        np.savez_compressed(GOLDEN / "mbconv.npz", **mbconv_cases(model_mod, cb_mod))
         return
 
     np.savez_compressed(GOLDEN / "quantizer.npz", **quantizer_cases(vq_mod))
@@ -312,6 +354,7 @@ def main():
         print("wrote", tag)
     np.savez_compressed(GOLDEN / "multilevel.npz", **multilevel_cases(model_mod))
     np.savez_compressed(GOLDEN / "ema_training.npz", **ema_training_cases(vq_mod))
+    np.savez_compressed(GOLDEN / "mbconv.npz", **mbconv_cases(model_mod, cb_mod))
     for f in sorted(GOLDEN.glob("*.npz")):
         print(f.name, f.stat().st_size // 1024, "KiB")
 

@@ -21,7 +21,7 @@ albumentations 1.1.0 ``Normalize`` (pdm.lock:35-36), restated from its published
 from __future__ import annotations
 
 import re
-from typing import Dict, List, Mapping, Sequence, Tuple
+from typing import Optional, Dict, List, Mapping, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -150,6 +150,76 @@ def fixup_block(x: Tensor, p: Mapping[str, Tensor]) -> Tensor:
     return out + x
 
 
+def mbconv_block(x: Tensor, p: Mapping[str, Tensor], mode: Optional[str] = None) -> Tensor:
+    """MBConv.forward in eval mode (layers/conv_block.py:240-321) with SELayer (layers/misc.py:7-30):
+    ``branch`` = conv1x1 [BN] SiLU depthwise [BN] SiLU [SE] conv1x1 [BN] at consecutive indices, absent
+    stages leaving no gap.  A state_dict cannot tell a depthwise 2x2 conv from a depthwise transposed 2x2
+    conv (same shapes), so the mode follows the channel change like the reference's pyramids do
+    (DownBlock doubles, UpBlock halves) unless given."""
+    stages = []
+    for i in range(9):                                                   # at most nine stages (:264-309)
+        if f"branch.{i}.running_mean" in p:
+            stages.append(("bn", i))
+        elif f"branch.{i}.fc.0.weight" in p:
+            stages.append(("se", i))
+        elif f"branch.{i}.weight" in p:
+            stages.append(("conv", i))                                   # activations hold no tensors
+    convs = [j for kind, j in stages if kind == "conv"]
+    assert len(convs) == 3
+    c_in, c_out = p[f"branch.{convs[0]}.weight"].shape[1], p[f"branch.{convs[2]}.weight"].shape[0]
+    k2 = p[f"branch.{convs[1]}.weight"].shape[-1]
+    if mode is None:
+        mode = "same" if k2 == 3 else ("down" if c_out > c_in else "up")
+        assert k2 == 3 or c_in != c_out, "2x2 depthwise with equal widths: pass mode="
+
+    def bn(h, j):
+        return F.batch_norm(h, p[f"branch.{j}.running_mean"], p[f"branch.{j}.running_var"],
+                            p.get(f"branch.{j}.weight"), p.get(f"branch.{j}.bias"), False, 0.0, 1e-5)
+
+    h, n_conv = x, 0
+    for pos, (kind, j) in enumerate(stages):
+        if kind == "conv":
+            w = p[f"branch.{j}.weight"]
+            b = p.get(f"branch.{j}.bias")
+            if n_conv == 1:                                              # depthwise stage
+                c = w.shape[0]
+                if mode == "same":
+                    h = F.conv2d(F.pad(h, (1, 1, 1, 1), mode="circular"), w, b, groups=c)
+                elif mode == "down":
+                    h = F.conv2d(h, w, b, stride=2, groups=c)
+                else:
+                    h = F.conv_transpose2d(h, w, b, stride=2, groups=c)
+            else:
+                h = F.conv2d(h, w, b)
+            n_conv += 1
+            nxt = stages[pos + 1][0] if pos + 1 < len(stages) else None
+            if nxt != "bn" and n_conv < 3:
+                h = F.silu(h)
+        elif kind == "bn":
+            h = bn(h, j)
+            if n_conv < 3:
+                h = F.silu(h)
+        else:                                                            # squeeze-excite
+            y = h.mean(dim=(2, 3))
+            y = F.silu(F.linear(y, p[f"branch.{j}.fc.0.weight"], p[f"branch.{j}.fc.0.bias"]))
+            y = torch.sigmoid(F.linear(y, p[f"branch.{j}.fc.2.weight"], p[f"branch.{j}.fc.2.bias"]))
+            h = h * y[:, :, None, None]
+    if "skip_conv.weight" in p:
+        ws, bs = p["skip_conv.weight"], p.get("skip_conv.bias")
+        if ws.shape[-1] == 1:
+            s = F.conv2d(x, ws, bs)
+        elif mode == "down":
+            s = F.conv2d(x, ws, bs, stride=2)
+        else:
+            s = F.conv_transpose2d(x, ws, bs, stride=2)
+        return h + s
+    return h + x
+
+
+def any_block(x: Tensor, p: Mapping[str, Tensor]) -> Tensor:
+    return mbconv_block(x, p) if "branch.0.weight" in p else fixup_block(x, p)
+
+
 def _indexed_children(sd: StateDict, prefix: str) -> List[str]:
     pat = re.compile(re.escape(prefix) + r"(\d+)\.")
     idx = sorted({int(m.group(1)) for k in sd for m in [pat.match(k)] if m})
@@ -159,7 +229,7 @@ def _indexed_children(sd: StateDict, prefix: str) -> List[str]:
 def block_sequence(x: Tensor, sd: StateDict, prefix: str) -> Tensor:
     """nn.Sequential of PreActFixupResBlocks stored under ``prefix{i}.``."""
     for child in _indexed_children(sd, prefix):
-        x = fixup_block(x, _blk(sd, child))
+        x = any_block(x, _blk(sd, child))
     return x
 
 
@@ -284,8 +354,8 @@ def module_chain(x: Tensor, sd: StateDict, prefix: str) -> Tensor:
     blocks (``prefix{i}.``) or a DownBlock / UpBlock (``prefix`` + ``layers.{j}.layers.{i}.``)."""
     if not any(k.startswith(prefix) for k in sd):
         return x                                   # n_down = 0 / n_up = 0: an empty nn.Sequential
-    if prefix + "bias1a" in sd:
-        return fixup_block(x, _blk(sd, prefix))
+    if prefix + "bias1a" in sd or prefix + "branch.0.weight" in sd:
+        return any_block(x, _blk(sd, prefix))
     if any(k.startswith(prefix + "layers.") for k in sd):
         return envelop_pyramid(x, sd, prefix + "layers.")
     return block_sequence(x, sd, prefix)

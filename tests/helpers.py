@@ -8,7 +8,8 @@ import torch
 
 import vqae_b200
 from vqae_b200 import synthetic as S
-from vqae_b200.config import compose_multilevel_conf, compose_vqae_conf, pre_activation_fixup
+from vqae_b200.config import (compose_efficientnetv2_conf, compose_multilevel_conf, compose_vqae_conf,
+                              mbconv, pre_activation_fixup)
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -143,3 +144,31 @@ def multilevel_model_and_state(tag: str):
         sd[f"encoder.vq_layers.{i}.embed_avg"] = e.clone()
     m.load_state_dict(sd if whole else {k[len("encoder."):]: v for k, v in sd.items()})
     return m, sd, S.synthetic_patches(2, 256, xseed)
+
+
+# ---- scope row f-4: MBConv blocks and the efficientnetv2 model (tests/golden/mbconv.npz) -------------
+MBCONV_BLOCK_CASES = {                   # name -> (c_in, c_out, mode, hw, batchnorm, se)
+    "same16": (16, 16, "same", 16, True, True), "same8to16": (8, 16, "same", 12, True, True),
+    "down16": (16, 32, "down", 16, True, True), "up32": (32, 16, "up", 8, True, True),
+    "same16_plain": (16, 16, "same", 8, False, False), "down8_nose": (8, 16, "down", 8, True, False),
+}
+
+
+def make_mbconv(name: str):
+    from vqae_b200.layers.conv_block import MBConv
+    cin, cout, mode, hw, use_bn, use_se = MBCONV_BLOCK_CASES[name]
+    conf = mbconv(batchnorm=use_bn, se=use_se)
+    for k in ("_target_", "_recursive_", "in_channels", "out_channels", "mode"):
+        conf.pop(k)
+    blk = MBConv(in_channels=cin, out_channels=cout, mode=mode, **conf).eval()
+    blk.load_state_dict(S.make_state_dict(blk.state_dict(), seed=41, regime="perturbed"))
+    return blk, mode
+
+
+def mbconv_model_and_state():
+    m = vqae_b200.instantiate(compose_efficientnetv2_conf(n_down=3, n_enc_layers_trunk=3)).eval()
+    sd = S.make_state_dict(m.state_dict(), seed=31, regime="perturbed")
+    e = torch.from_numpy(golden("mbconv")["model_embed"])
+    sd["encoder.vq_layers.0.embed"], sd["encoder.vq_layers.0.embed_avg"] = e, e.clone()
+    m.load_state_dict(sd)
+    return m, sd, S.synthetic_patches(2, 256, 1031)

@@ -283,3 +283,70 @@ def test_training_forward_all_reduces_statistics_across_ranks(tmp_path):
                        capture_output=True, text=True, timeout=600,
                        env={**os.environ, "OMP_NUM_THREADS": "4"})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ---- MBConv (layers/conv_block.py:240-321) ----------------------------------------------------------------
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("name", sorted(H.MBCONV_BLOCK_CASES))
+def test_mbconv_block_vs_reference_golden(name, channels_last):
+    g = H.golden("mbconv")
+    blk, _ = H.make_mbconv(name)
+    blk = blk.to(DEV)
+    x = torch.from_numpy(g[f"blk_{name}_x"]).to(DEV)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y = blk(x)
+    ref = torch.from_numpy(g[f"blk_{name}_y"])
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert E.is_channels_last(y) == channels_last
+    assert H.rel_err(y.cpu(), ref) < 2e-5
+    blk.train()
+    with pytest.raises(RuntimeError):
+        blk(x)
+
+
+def test_mbconv_model_vs_reference_golden():
+    """The efficientnetv2 variant end to end: stem, MBConv pyramids and trunks, quantiser, decoder."""
+    g = H.golden("mbconv")
+    m, sd, x = H.mbconv_model_and_state()
+    m = m.to(DEV)
+    try:
+        with torch.no_grad():
+            (enc,), (idx,), (loss,) = m.encoder(x.to(DEV))
+            recon, (loss2,) = m(x.to(DEV))
+            dec_ref = m.decode_codes(torch.from_numpy(g["model_idx"].astype(np.int64)).to(DEV))
+        assert torch.equal(loss, loss2)
+        ref = g["model_idx"].astype(np.int64)
+        same = idx.cpu().numpy() == ref
+        bad = (~same).reshape(-1) & (g["model_gap"] >= 2e-4)
+        assert int(bad.sum()) == 0, (int(bad.sum()), int((~same).sum()))
+        assert (~same).mean() < 2e-3
+        msk = torch.from_numpy(same)[:, ::4, ::4]
+        e_ref = torch.from_numpy(g["model_enc_sub"])
+        assert float(((enc.cpu()[:, ::8, ::4, ::4] - e_ref).abs() * msk[:, None]).max() / e_ref.abs().max()) < 1e-4
+        assert abs(loss.item() - float(g["model_loss"])) < 1e-4 * float(g["model_loss"])
+        assert H.rel_err(dec_ref.cpu()[:, :, ::8, ::8], torch.from_numpy(g["model_recon_sub"])) < 1e-4
+        if same.all():
+            assert H.rel_err(recon.cpu()[:, :, ::8, ::8], torch.from_numpy(g["model_recon_sub"])) < 1e-4
+    finally:
+        m.cpu()
+
+
+def test_pointwise_conv_kernel_shapes_vs_torch():
+    """The GEMM kernel at sizes off its 64 x 64 x 16 tile grid, every mode, against torch fp32 on the CPU."""
+    from vqae_b200 import mbconv as M
+    gen = torch.Generator().manual_seed(3)
+    for (b, h, w, cin, n) in [(1, 5, 7, 12, 20), (3, 8, 8, 36, 68), (2, 6, 10, 64, 128)]:
+        x = torch.randn(b, cin, h, w, generator=gen)
+        xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+        w1 = torch.randn(n, cin, 1, 1, generator=gen) * 0.2
+        y = M.pointwise_conv(xn, w1.reshape(n, cin).contiguous().to(DEV), n)
+        assert H.rel_err(y.cpu().permute(0, 3, 1, 2), torch.nn.functional.conv2d(x, w1)) < 1e-5
+        if h % 2 == 0 and w % 2 == 0:
+            w2 = torch.randn(n, cin, 2, 2, generator=gen) * 0.2
+            y = M.pointwise_conv(xn, w2.permute(0, 2, 3, 1).reshape(n, 4 * cin).contiguous().to(DEV), n, M.PW_S2D)
+            assert H.rel_err(y.cpu().permute(0, 3, 1, 2), torch.nn.functional.conv2d(x, w2, stride=2)) < 1e-5
+        wt = torch.randn(cin, n, 2, 2, generator=gen) * 0.2
+        y = M.pointwise_conv(xn, wt.permute(2, 3, 1, 0).reshape(4, n, cin).contiguous().to(DEV), n, M.PW_CONVT)
+        assert H.rel_err(y.cpu().permute(0, 3, 1, 2), torch.nn.functional.conv_transpose2d(x, wt, stride=2)) < 1e-5

@@ -180,3 +180,25 @@ def test_ema_training_updates_match_reference_golden(tag):
         np.testing.assert_allclose(cs.numpy(), g[f"{tag}_cluster_size_after{step}"], rtol=1e-6)
         np.testing.assert_allclose(avg.numpy(), g[f"{tag}_embed_avg_after{step}"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(embed.numpy(), g[f"{tag}_embed_after{step}"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", sorted(H.MBCONV_BLOCK_CASES))
+def test_mbconv_block_matches_reference_golden(name):
+    g = H.golden("mbconv")
+    blk, mode = H.make_mbconv(name)
+    with torch.no_grad():
+        y = O.mbconv_block(torch.from_numpy(g[f"blk_{name}_x"]), blk.state_dict(), mode)
+    assert H.rel_err(y, torch.from_numpy(g[f"blk_{name}_y"])) < 1e-6
+
+
+def test_mbconv_model_matches_reference_golden():
+    """conf/model/{encoder,decoder}/efficientnetv2.yaml: every conv block an MBConv."""
+    g = H.golden("mbconv")
+    _, sd, x = H.mbconv_model_and_state()
+    assert int(g["model_n_state"]) == len(sd)
+    with torch.no_grad():
+        (enc,), (idx,), (loss,) = O.encoder_forward_levels(x, sd)
+        recon = O.decoder_forward_levels((enc,), sd)
+    assert np.array_equal(idx.numpy(), g["model_idx"].astype(np.int64))
+    assert abs(loss.item() - float(g["model_loss"])) < 1e-5 * float(g["model_loss"])
+    assert H.rel_err(recon[:, :, ::8, ::8], torch.from_numpy(g["model_recon_sub"])) < 1e-5
