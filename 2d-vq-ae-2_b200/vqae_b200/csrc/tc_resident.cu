@@ -45,6 +45,9 @@ using namespace tc;
 constexpr int RS_TH = 8;
 constexpr int RS_NW = 16;                               // worker warps
 constexpr int RS_SCAL_BLOCKS = 128;                     // runs up to this length keep their scalars in shared memory
+constexpr int RS_NPUSH = 4;                             // halo pusher warps (a st.async holds its warp for
+                                                        // about one DSMEM round trip: one warp alone needed
+                                                        // ~1.7 k cycles for the 17 stores of a push)
 constexpr int RS_PR = RS_TH + 2;                        // rows per stored column (with halo rows)
 constexpr uint32_t RS_SBO = RS_PR * 16;                 // 8-row group stride = one column
 
@@ -76,8 +79,8 @@ struct RsCfg {
     static constexpr bool SHARED_W = C <= 64;
     static constexpr int RING = SHARED_W ? 11 : 4;
     static constexpr int NRING = SHARED_W ? 1 : NSLOT;  // rings (and producer warps) per CTA
-    // + one weight producer warp per ring + one halo pusher warp
-    static constexpr int THREADS = (RS_NW + ISSUERS + NRING + 1) * 32;
+    // + one weight producer warp per ring + the halo pusher warps
+    static constexpr int THREADS = (RS_NW + ISSUERS + NRING + RS_NPUSH) * 32;
     static constexpr int NPIX = (W + 2) * RS_PR;        // stored pixels per operand buffer
     static constexpr uint32_t LBO = NPIX * 16;          // k-chunk (8 channels) stride
     static constexpr uint32_t BUF = (C / 8) * LBO;      // operand buffer of one slot
@@ -287,8 +290,8 @@ trunk_resident_tc_kernel(ResidentArgs a) {
         }
         mbar_init(bar_u, 2 * RS_NW);
         mbar_init(bar_u + 8, 2 * RS_NW);
-        mbar_init(bar_pushed, 1);
-        mbar_init(bar_pushed + 8, 1);
+        mbar_init(bar_pushed, RS_NPUSH);
+        mbar_init(bar_pushed + 8, RS_NPUSH);
         for (int s = 0; s < NRING * RS_RING; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             // every issue warp that reads the entry: both of a slot, of all active slots if shared
@@ -309,14 +312,17 @@ trunk_resident_tc_kernel(ResidentArgs a) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint32_t idesc = make_idesc_bf16(128, C);
 
-    if (warp == RS_NW + RS_ISSUERS + NRING) {
-        // ---------------- halo pusher: one warp, off the workers' critical path --------------------
-        // After E1 of (slot b, step j1) it copies stored rows 1 and 8 of the slot's U buffer (all W + 2
+    if (warp >= RS_NW + RS_ISSUERS + NRING) {
+        // ---------------- halo pushers: RS_NPUSH warps, off the workers' critical path --------------
+        // After E1 of (slot b, step j1) they copy stored rows 1 and 8 of the slot's U buffer (all W + 2
         // stored columns, i.e. including the wrap-around duplicates E1 wrote) into stored row 9 of the
         // CTA above and stored row 0 of the CTA below with st.async: the data travel in the async proxy
         // the MMA reads operands with and complete bytes on the receiver's halo barrier (dir 0 = from
-        // above), so neither side needs a fence.  Distributed shared memory moves ~20 B/clk per SM:
-        // 8.7 KB per push is ~700 cycles, which used to stall the worker warps at every half-round.
+        // above), so neither side needs a fence.  A st.async keeps its warp busy for about a DSMEM round
+        // trip (~200 cycles), so the 2 x 272 16-byte pieces of a push are spread over several warps; the
+        // neighbours' "old rows consumed" barriers are waited for BEFORE U is complete (they have long
+        // fired by then, and a cluster-scope acquire wait costs 400-800 cycles).
+        const int pw = warp - (RS_NW + RS_ISSUERS + NRING);
         const uint32_t up_rank = (rank + RS_CL - 1) % RS_CL, dn_rank = (rank + 1) % RS_CL;
         const uint32_t up_base = mapa_u32(sbase, up_rank), dn_base = mapa_u32(sbase, dn_rank);
         const uint32_t up_bar = mapa_u32(bar_halo + 8, up_rank);     // its "from below" barrier
@@ -326,13 +332,18 @@ trunk_resident_tc_kernel(ResidentArgs a) {
             const HalfRound h = half_round(hr, T0, T1);
             if (!h.g1) continue;
             const int b = h.b, j1 = h.jprev + 1;
-            mbar_wait_wd(bar_u + 8 * b, j1 & 1);         // both halves of U written (E1)
+            const bool pf = a.prof && blockIdx.x == 0 && lane == 0 && pw == 0 && b == 0 &&
+                            j1 >= RS_PROF_HR0 / 2 && j1 < (RS_PROF_HR0 + RS_PROF_HR) / 2;
+            long long* pp = a.prof + (j1 - RS_PROF_HR0 / 2) * 64;
             if (j1 > 0) {                                // the neighbours' taps of the previous block
                 mbar_wait_cluster(bar_free + 16 * b, (j1 - 1) & 1);          // have read the old rows
                 mbar_wait_cluster(bar_free + 16 * b + 8, (j1 - 1) & 1);
             }
+            if (pf) pp[19] = clock64();
+            mbar_wait_wd(bar_u + 8 * b, j1 & 1);         // both halves of U written (E1)
+            if (pf) pp[18] = clock64();
             const uint32_t buf = (uint32_t)b * RS_BUF;
-            for (int p = lane; p < PIECES; p += 32) {
+            for (int p = pw * 32 + lane; p < PIECES; p += 32 * RS_NPUSH) {
                 const int kc = p / (RS_W + 2), cs = p - kc * (RS_W + 2);     // k-chunk, stored column
                 const uint32_t off = buf + kc * RS_LBO + (uint32_t)(cs * RS_PR) * 16;
                 const uint4 top = *reinterpret_cast<const uint4*>(smem + off + 1 * 16);       // my row 0
@@ -341,6 +352,7 @@ trunk_resident_tc_kernel(ResidentArgs a) {
                 st_async_v4(dn_base + off, bot, dn_bar + 16 * b);
             }
             __syncwarp();
+            if (pf) pp[21] = clock64();
             if (lane == 0) mbar_arrive(bar_pushed + 8 * b);
         }
     } else if (warp >= RS_NW + RS_ISSUERS) {

@@ -56,4 +56,7 @@ for r in range(8):
         print("step%2d issuer " % (r // 2), " ".join("%7d" % (int(v) - t0) for v in p[r, 0:7]),
               "| G2_complete %d, cumulative ring-wait cycles %d" % (int(p[r, 7]) - t0, int(p[r, 20])))
         print("        tap issue starts (after halo waits):", " ".join("%7d" % (int(v) - t0) for v in p[r, 23:32]))
+        print("        pusher (slot 0): U_seen  free_waits_done  pushes_issued:",
+              " ".join("%7d" % (int(v) - t0) for v in (p[r, 18], p[r, 19], p[r, 21])))
     print("   hr%2d workers" % r, " ".join("%7d" % (int(v) - t0) for v in p[r, 8:18]))
+
