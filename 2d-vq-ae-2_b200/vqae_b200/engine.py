@@ -980,5 +980,16 @@ def ema_update(embed: Tensor, embed_avg: Tensor, cluster_size: Tensor, acc: Tens
                                          _stream(embed.device)), "vqae_ema_update_f32")
 
 
-def launch_count() -> int:
+# launches executed through CUDA-graph replays minus launches merely recorded during a capture
+# (graphs.CapturedStep keeps it up to date)
+_graph_launch_adjust = 0
+
+
+def raw_launch_count() -> int:
+    """Calls of the library's launching entry points (executed or recorded into a graph)."""
     return int(L.load().vqae_launch_count())
+
+
+def launch_count() -> int:
+    """Kernels of libvqae_b200.so executed so far, graph replays included."""
+    return raw_launch_count() + _graph_launch_adjust

@@ -17,6 +17,8 @@ import numpy as np
 import torch
 
 from . import engine as E
+from .graphs import CapturedStep
+from .plan import resolve_precision
 from .sharding import gather_code_tiles, shard_range, slide_grid  # noqa: F401
 
 
@@ -142,18 +144,33 @@ class StreamingEncoder:
     By default every yielded tensor is an independent copy (safe to collect with ``list``).  With
     ``reuse_buffers=True`` the pinned staging buffers themselves are yielded (no host copy): there
     are ``N_OUT`` = 4 of them and results lag one batch behind submission, so a yielded tensor stays
-    valid only until the generator has been resumed ``N_OUT - 2`` = 2 more times."""
+    valid only until the generator has been resumed ``N_OUT - 2`` = 2 more times.
+
+    ``graphs=True`` (default): the encode of a full-size batch is captured into one CUDA graph per
+    staging buffer after its first eager run and replayed from then on (``graphs.CapturedStep``): no
+    per-launch host work, no idle gaps between the step's kernels.  The graphs read the packed weights
+    that existed at capture time: build the ``StreamingEncoder`` after loading the checkpoint, or call
+    ``reset_graphs()`` when the weights change."""
 
     N_OUT = 4
 
-    def __init__(self, encoder, device: torch.device, mean=None, std=None):
+    def __init__(self, encoder, device: torch.device, mean=None, std=None, graphs: bool = True):
         self.encoder, self.device, self.mean, self.std = encoder, device, mean, std
+        self._step = CapturedStep(lambda x: encode_patches(self.encoder, x, self.mean, self.std),
+                                  key_extra=lambda: resolve_precision(self.encoder)) if graphs else None
+        self._idx_read = [None, None]                   # last D2H event of each staging slot's codes
         self.copy_stream = torch.cuda.Stream(device)
+        self.out_stream = torch.cuda.Stream(device)     # D2H of the codes: off the compute stream, so
+        self._done = torch.cuda.Event()                 # the next batch's kernels start right away
         self._dev_in = [None, None]
         self._host_out = [None] * self.N_OUT
         self._h2d = [torch.cuda.Event() for _ in range(2)]
         self._free = [torch.cuda.Event() for _ in range(2)]     # device input buffer consumed
         self._d2h = [torch.cuda.Event() for _ in range(self.N_OUT)]
+
+    def reset_graphs(self) -> None:
+        if self._step is not None:
+            self._step.reset()
 
     def _stage(self, slot: int, host_batch: torch.Tensor, first_use: bool) -> None:
         if self._dev_in[slot] is None or self._dev_in[slot].shape != host_batch.shape \
@@ -191,16 +208,28 @@ class StreamingEncoder:
             if nxt is not None:
                 self._stage(slot ^ 1, nxt, i == 0)
             main.wait_event(self._h2d[slot])
-            idx = encode_patches(self.encoder, self._dev_in[slot], self.mean, self.std)
+            if self._step is not None:
+                # a replay overwrites the codes of the batch that used this slot two steps ago
+                if self._idx_read[slot] is not None:
+                    main.wait_event(self._idx_read[slot])
+                idx = self._step(self._dev_in[slot])
+            else:
+                idx = encode_patches(self.encoder, self._dev_in[slot], self.mean, self.std)
             self._free[slot].record(main)
             if not to_host:
-                yield idx
+                yield idx.clone() if self._step is not None else idx
                 i += 1
                 continue
             if self._host_out[oslot] is None or self._host_out[oslot].shape != idx.shape:
                 self._host_out[oslot] = torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
-            self._host_out[oslot].copy_(idx, non_blocking=True)
-            self._d2h[oslot].record(main)
+            self._done.record(main)
+            with torch.cuda.stream(self.out_stream):
+                self.out_stream.wait_event(self._done)
+                self._host_out[oslot].copy_(idx, non_blocking=True)
+                self._d2h[oslot].record(self.out_stream)
+            self._idx_read[slot] = self._d2h[oslot]
+            if self._step is None:
+                idx.record_stream(self.out_stream)
             pending.append(oslot)
             if len(pending) == 2:                  # results lag one batch behind the submission
                 yield result(pending.pop(0))

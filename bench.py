@@ -364,8 +364,11 @@ def run_gpu(args):
     from vqae_b200 import engine as E
     from vqae_b200 import synthetic as S
     from vqae_b200.extract import StreamingEncoder, encode_patches
-    from vqae_b200.sharding import gather_code_tiles, shard_range, slide_grid
+    from vqae_b200.graphs import CapturedStep
+    from vqae_b200.plan import resolve_precision
+    from vqae_b200.sharding import bind_host_to_gpu_numa_node, gather_code_tiles, shard_range, slide_grid
 
+    numa_node = bind_host_to_gpu_numa_node(local) if world > 1 else None   # before any pinned allocation
     w = WORKLOADS[args.workload]
     peaks, peaks_kind = load_peaks()
     model, sd = build_model_and_state(w["n_down"])
@@ -386,6 +389,14 @@ def run_gpu(args):
         return float(t.item())
 
     # ---- per-workload step functions --------------------------------------------------------
+    # every step is captured into a CUDA graph per input buffer after its first eager run and replayed
+    # from then on (vqae_b200.graphs.CapturedStep; --no-graphs: eager launches every step)
+    def captured(fn):
+        if args.no_graphs:
+            return fn
+        return CapturedStep(fn, key_extra=lambda: (resolve_precision(enc), resolve_precision(model.decoder)))
+
+    encode_step = captured(lambda x: encode_patches(enc, x))
     extra = {}
     if args.workload == "slide":
         rows, cols = slide_grid(SLIDE_LEVEL, PATCH)
@@ -397,7 +408,7 @@ def run_gpu(args):
         gather_ms = []
 
         def step_resident(i):
-            tiles = torch.cat([encode_patches(enc, p).to(torch.uint8) for _, p in batches])
+            tiles = torch.cat([encode_step(p).to(torch.uint8) for _, p in batches])
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
             full = gather_code_tiles(tiles, n_total)   # NCCL all-gather (N > 1)
@@ -410,7 +421,7 @@ def run_gpu(args):
         h2d = sum(int(p.numel()) for _, p in batches)
         d2h = int(code_map.numel()) if rank == 0 else 0
         host_map = torch.empty(code_map.shape, dtype=torch.uint8).pin_memory()
-        streamer = StreamingEncoder(enc, dev)
+        streamer = StreamingEncoder(enc, dev, graphs=not args.no_graphs)
 
         def run_e2e(n_steps):
             """Per slide: this rank's patch batches from pinned host memory (a pool of 4 distinct
@@ -436,8 +447,8 @@ def run_gpu(args):
         units_per_step = world * B
         if args.workload == "encode256":
             def step_resident(i):
-                return encode_patches(enc, resident[i % 2])
-            streamer = StreamingEncoder(enc, dev)
+                return encode_step(resident[i % 2])
+            streamer = StreamingEncoder(enc, dev, graphs=not args.no_graphs)
             h2d, d2h = int(B * PATCH * PATCH * 3), int(B * 32 * 32 * 8)
 
             def run_e2e(n_steps):
@@ -451,31 +462,53 @@ def run_gpu(args):
             api = ("vqae_b200.extract.StreamingEncoder(model.encoder).encode_stream(pinned uint8 "
                    "tiles): double-buffered H2D on a side stream, D2H of int64 codes")
         else:                                           # roundtrip512
+            def roundtrip(x):
+                _, idx, _, _, _ = enc.encode(x, want_quantized=True)
+                return idx, model.decode_codes(idx)
+            roundtrip_step = captured(roundtrip)
+
             def step_resident(i):
-                _, idx, _, _, _ = enc.encode(resident[i % 2], want_quantized=True)
-                return model.decode_codes(idx)
+                return roundtrip_step(resident[i % 2])[1]
             dev_in = [torch.empty_like(resident[0]) for _ in range(2)]
             host_idx = [torch.empty(B, 32, 32, dtype=torch.int64).pin_memory() for _ in range(2)]
             host_stat = torch.empty(2, dtype=torch.float32).pin_memory()
             h2d, d2h = int(B * PATCH * PATCH * 3), int(B * 32 * 32 * 8 + 8)
 
+            copy_stream = torch.cuda.Stream(dev)
+            ev_in = [torch.cuda.Event() for _ in range(2)]
+            ev_free = [torch.cuda.Event() for _ in range(2)]
+
             def run_e2e(n_steps):
-                """Pinned uint8 tiles -> H2D -> encode -> decode_codes -> D2H of the int64 codes (the
-                stored representation) and of two reconstruction statistics (mean, mean |.|); the
+                """Pinned uint8 tiles -> H2D (side stream: the copy of batch i + 1 runs under the compute of
+                batch i) -> encode -> decode_codes -> D2H of the int64 codes (the stored representation)
+                and of two reconstruction statistics (mean, mean |.|), read on the host every step; the
                 200 MB fp32 reconstruction itself stays on the device."""
                 acc = 0.0
+                cur = torch.cuda.current_stream(dev)
+
+                def prefetch(j):
+                    t = j & 1
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(ev_free[t])       # the compute that last read this buffer
+                        dev_in[t].copy_(host[t], non_blocking=True)
+                        ev_in[t].record(copy_stream)
+                for t in range(2):
+                    ev_free[t].record(cur)
+                prefetch(0)
                 for i in range(n_steps):
                     s = i & 1
-                    dev_in[s].copy_(host[s], non_blocking=True)
-                    _, idx, _, _, _ = enc.encode(dev_in[s], want_quantized=True)
-                    rec = model.decode_codes(idx)
+                    if i + 1 < n_steps:
+                        prefetch(i + 1)
+                    cur.wait_event(ev_in[s])
+                    idx, rec = roundtrip_step(dev_in[s])
+                    ev_free[s].record(cur)
                     host_idx[s].copy_(idx, non_blocking=True)
                     host_stat.copy_(torch.stack([rec.mean(), rec.abs().mean()]), non_blocking=True)
-                    torch.cuda.synchronize(dev)
+                    cur.synchronize()
                     acc += float(host_stat[1]) + int(host_idx[s][0, 0, 0])
                 return acc
-            api = ("Encoder.encode(uint8 tiles) + VQAE.decode_codes: H2D of pinned uint8 tiles, D2H of "
-                   "int64 codes + reconstruction statistics")
+            api = ("Encoder.encode(uint8 tiles) + VQAE.decode_codes: double-buffered H2D of pinned uint8 tiles "
+                   "on a side stream, D2H of int64 codes + reconstruction statistics every step")
 
     def timed(fn, steps, warmup):
         with torch.no_grad():
@@ -542,6 +575,8 @@ def run_gpu(args):
                        "parallelism": f"patch-sharded x{world}, no data-path collective"
                        + (" (one NCCL all-gather of u8 code tiles per slide)"
                           if args.workload == "slide" else ""),
+                       "host_numa_node_rank0": numa_node,
+                       "cuda_graphs": not args.no_graphs,
                        "l2": "two rotating resident batches; per-step activation traffic >> 126 MB L2",
                        "whole_step_tflops_per_gpu": value * w["flop_per_patch"] / 1e12 / world,
                        "whole_step_frac_of_sustained_bf16_peak":
@@ -603,6 +638,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="encode256", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp16")
+    ap.add_argument("--no-graphs", action="store_true",
+                    help="launch every kernel of every step from the host instead of replaying CUDA graphs")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the side measurements (other precisions, config 2, CPU baseline)")
     args = ap.parse_args()
