@@ -221,7 +221,14 @@ class StreamingEncoder:
                 i += 1
                 continue
             if self._host_out[oslot] is None or self._host_out[oslot].shape != idx.shape:
-                self._host_out[oslot] = torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
+                if self._host_out[oslot] is None:
+                    # all pinned result buffers at once: a cudaHostAlloc in the middle of the stream
+                    # (slot 3 is first used by the fourth batch) stalls the pipeline for milliseconds
+                    for o in range(self.N_OUT):
+                        if self._host_out[o] is None:
+                            self._host_out[o] = torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
+                else:                                  # a batch of another size (the short last one)
+                    self._host_out[oslot] = torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
             self._done.record(main)
             with torch.cuda.stream(self.out_stream):
                 self.out_stream.wait_event(self._done)
