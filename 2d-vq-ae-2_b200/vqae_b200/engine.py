@@ -42,7 +42,12 @@ _workspaces: Dict[Tuple[int, int], Tensor] = {}
 
 
 def workspace(device: torch.device, nbytes: int) -> Tensor:
-    """Grow-only scratch buffer per (device, stream)."""
+    """Grow-only scratch buffer per (device, stream).  While the current stream is being captured
+    into a CUDA graph the buffer comes from the graph's own memory pool instead (one allocation per
+    call, released to that pool after the call): a cached buffer that is replaced by a larger one in the
+    middle of a capture would be freed while earlier nodes of the graph still point into it."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)

@@ -65,3 +65,32 @@ def test_streaming_encoder_with_and_without_graphs_agree():
     finally:
         vqae_b200.set_precision(m, None)
         m.cpu()
+
+
+def test_graph_outlives_workspace_growth_of_later_captures():
+    """A captured encode must stay valid after another capture (here a decode, whose 'up' blocks need a
+    larger scratch buffer) has been taken, dropped, and the allocator's cache emptied: scratch buffers
+    used inside a capture belong to the graph's own pool (engine.workspace).  Regression: a buffer
+    cached across captures was freed while nodes of an earlier graph still pointed into it."""
+    m, _, _ = H.model_and_state("model_nd3_perturbed")
+    m = vqae_b200.set_precision(m.to(DEV), "fp16")
+    try:
+        x = S.synthetic_patches_u8(4, 256, 90).to(DEV)
+        with torch.no_grad():
+            enc_step = CapturedStep(lambda t: X.encode_patches(m.encoder, t))
+            ref = X.encode_patches(m.encoder, x).clone()
+            for _ in range(3):
+                assert torch.equal(enc_step(x), ref)
+            dec_step = CapturedStep(lambda i: m.decode_codes(i))
+            rec_ref = m.decode_codes(ref).clone()
+            for _ in range(3):
+                assert torch.equal(dec_step(ref), rec_ref)
+            del dec_step
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            for _ in range(3):
+                assert torch.equal(enc_step(x), ref)
+            torch.cuda.synchronize()
+    finally:
+        vqae_b200.set_precision(m, None)
+        m.cpu()
