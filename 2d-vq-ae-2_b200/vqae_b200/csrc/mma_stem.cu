@@ -295,6 +295,157 @@ stem_in_mma_kernel(StemInArgs a) {
     }
 }
 
+// ---- in_stem on uint8 tiles ------------------------------------------------------------------------
+// A uint8 pixel value is EXACT in fp16, so the activation side needs no hi / lo split: the
+// normalisation (u8 - 255 mean_c) / (255 std_c) is folded into the weights,
+//     sum_c,tap W (u8 - sub_c) mul_c  =  sum W' u8  +  sum Wm inside,      W' = W mul_c,  Wm = -sum_c W mul_c sub_c,
+// with `inside` (1 inside the image, 0 in the zero padding, which pads the NORMALISED tensor) as a fourth
+// input channel in the slot the fp32 form pads with zero.  Only the weights are split (hi + lo, scaled by
+// the power of two that moves the largest of them into (2^13, 2^14]): two MMAs per kernel row instead
+// of three, 8-byte pixel records, and the window is staged from aligned 32-bit loads issued one tile
+// ahead (the fp32 form spends a third of its time waiting for three byte loads per pixel).
+constexpr int SU_RAW_W = 26;                                  // raw words per staged row: bytes -4 .. 99 of the row
+constexpr uint32_t SU_REC = SI_SROWS * SI_SPW * 8;            // fp16 records (R, G | B, inside), 8 B each
+constexpr int SU_NRAW = SI_SROWS * SU_RAW_W;
+constexpr uint32_t SU_SMEM = SU_REC + SU_NRAW * 4;
+
+__global__ void __launch_bounds__(SO_THREADS, 4)
+stem_in_u8_mma_kernel(StemInArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ float wq[8 * 3 * 3 * 4];                       // [g][ky][kx][c]: W' (c < 3), Wm (c = 3)
+    __shared__ int wmax_bits;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    if (tid == 0) wmax_bits = 0;
+    for (int i = tid; i < (int)(SU_REC / 16); i += SO_THREADS)
+        *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = tid; i < 8 * 36; i += SO_THREADS) {
+        const int gg = i / 36, r = i - gg * 36, ky = r / 12, kx = (r - ky * 12) >> 2, c = r & 3;
+        float v;
+        if (c < 3) {
+            v = __fmul_rn(__ldg(a.w + gg * 27 + c * 9 + ky * 3 + kx), a.n.mul[c]);
+        } else {
+            v = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+                v = fmaf(-__fmul_rn(__ldg(a.w + gg * 27 + cc * 9 + ky * 3 + kx), a.n.mul[cc]), a.n.sub[cc], v);
+        }
+        wq[i] = v;
+        atomicMax(&wmax_bits, __float_as_int(fabsf(v)));      // non-negative floats order like their bits
+    }
+    __syncthreads();
+    // scale = 2^(14 - e) with max|w| = m 2^e, m in [0.5, 1): the largest scaled weight lies in [2^13, 2^14)
+    const float wmax = __int_as_float(wmax_bits);
+    int e = 0;
+    if (wmax > 0.f && wmax < INFINITY) (void)frexpf(wmax, &e);
+    const float scale = wmax > 0.f ? ldexpf(1.f, 14 - e) : 1.f, inv = wmax > 0.f ? ldexpf(1.f, e - 14) : 1.f;
+    uint32_t bh[3][2], bl[3][2];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float w[2];
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2)
+                w[e2] = t < 3 ? wq[((g * 3 + ky) * 3 + t) * 4 + 2 * h + e2] * scale : 0.f;
+            so_split2(w[0], w[1], bh[ky][h], bl[ky][h]);
+        }
+    const float bias0 = __ldg(a.bias + 2 * t), bias1 = __ldg(a.bias + 2 * t + 1);
+    uint32_t* raw = reinterpret_cast<uint32_t*>(smem + SU_REC);
+    const uint8_t* rawb = smem + SU_REC;
+    const int64_t hw = (int64_t)a.H * a.W;
+
+    // the raw words of a tile's window: word wi of staged row si covers bytes 4 wi - 4 .. 4 wi - 1 counted from
+    // the first byte of pixel (r0 - 1 + si, c0); pixel (., c0 - 1 + sj) sits at raw bytes 1 + 3 sj .. 3 + 3 sj
+    constexpr int PPT = (SU_NRAW + SO_THREADS - 1) / SO_THREADS;
+    uint32_t rv[PPT];
+    auto fetch = [&](int tile) {
+        const int img = tile / a.tiles_per_img;
+        const int trem = tile - img * a.tiles_per_img;
+        const int r0 = (trem / a.tiles_x) * SI_TH, c0 = (trem % a.tiles_x) * SI_TW;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int q = tid + k * SO_THREADS;
+            rv[k] = 0u;
+            if (q < SU_NRAW) {
+                const int si = q / SU_RAW_W, wi = q - si * SU_RAW_W;
+                const int iy = r0 - 1 + si;
+                // the first / last word reach into the neighbouring row at the image's left / right edge
+                const bool ok = iy >= 0 && iy < a.H && !(wi == 0 && c0 == 0) &&
+                                !(wi == SU_RAW_W - 1 && c0 + SI_TW == a.W);
+                if (ok)
+                    rv[k] = __ldg(reinterpret_cast<const uint32_t*>(
+                        reinterpret_cast<const uint8_t*>(a.x) + ((int64_t)img * hw + (int64_t)iy * a.W + c0) * 3 - 4) + wi);
+            }
+        }
+    };
+    if ((int)blockIdx.x < a.n_tiles) fetch(blockIdx.x);
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int img = tile / a.tiles_per_img;
+        const int trem = tile - img * a.tiles_per_img;
+        const int r0 = (trem / a.tiles_x) * SI_TH, c0 = (trem % a.tiles_x) * SI_TW;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int q = tid + k * SO_THREADS;
+            if (q < SU_NRAW) raw[q] = rv[k];
+        }
+        __syncthreads();
+        if (tile + (int)gridDim.x < a.n_tiles) fetch(tile + gridDim.x);      // in flight during this tile
+        // ---- records: (R, G | B, inside) as fp16, zero outside the image (= the conv's padding) ----
+        for (int i = tid; i < SI_SROWS * SI_SREAL_C; i += SO_THREADS) {
+            const int si = i / SI_SREAL_C, sj = i - si * SI_SREAL_C;
+            const int iy = r0 - 1 + si, ix = c0 - 1 + sj;
+            uint2 rec = make_uint2(0u, 0u);
+            if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+                const uint8_t* b = rawb + si * (SU_RAW_W * 4) + 1 + 3 * sj;
+                // 0x6400 | n is the fp16 number 1024 + n (n < 1024): subtracting 1024 leaves n exactly
+                const uint32_t p01 = 0x64006400u | (uint32_t)b[0] | ((uint32_t)b[1] << 16);
+                const uint32_t p2m = 0x3C006400u | (uint32_t)b[2];                 // high half: 1.0 = inside
+                const __half2 h01 = __hsub2(*reinterpret_cast<const __half2*>(&p01), __floats2half2_rn(1024.f, 1024.f));
+                const __half2 h2m = __hsub2(*reinterpret_cast<const __half2*>(&p2m), __floats2half2_rn(1024.f, 0.f));
+                rec.x = *reinterpret_cast<const uint32_t*>(&h01);
+                rec.y = *reinterpret_cast<const uint32_t*>(&h2m);
+            }
+            *reinterpret_cast<uint2*>(smem + (uint32_t)(si * SI_SPW + sj) * 8) = rec;
+        }
+        __syncthreads();
+        // ---- 32 M-tiles of 16 pixels of a row, two per warp step ----
+        float* oimg = a.out + (size_t)img * hw * 8;
+#pragma unroll 1
+        for (int mt0 = warp; mt0 < SI_MT; mt0 += 2 * SO_WARPS) {
+            float d[2][4];
+            const uint8_t* p0[2];
+            int rr[2], cb[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int mt = mt0 + u * SO_WARPS;
+                rr[u] = mt >> 1;
+                cb[u] = (mt & 1) * 16;
+                p0[u] = smem + (uint32_t)(rr[u] * SI_SPW + cb[u] + g + t) * 8;
+                d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
+            }
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint2 u0 = *reinterpret_cast<const uint2*>(p0[u] + ky * SI_SPW * 8);
+                    const uint2 u1 = *reinterpret_cast<const uint2*>(p0[u] + ky * SI_SPW * 8 + 8 * 8);
+                    const uint32_t av[4] = {u0.x, u1.x, u0.y, u1.y};
+                    mma_16816(d[u], av, bl[ky][0], bl[ky][1]);
+                    mma_16816(d[u], av, bh[ky][0], bh[ky][1]);
+                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float* o = oimg + ((size_t)(r0 + rr[u]) * a.W + c0 + cb[u] + g) * 8 + 2 * t;
+                *reinterpret_cast<float2*>(o) = make_float2(fmaf(d[u][0], inv, bias0), fmaf(d[u][1], inv, bias1));
+                *reinterpret_cast<float2*>(o + 64) = make_float2(fmaf(d[u][2], inv, bias0), fmaf(d[u][3], inv, bias1));
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <int XKIND>
 int launch_stem_in_mma(const StemInArgs& a, int sm_count, cudaStream_t stream) {
     const int cap = sm_count * 4;
@@ -326,6 +477,12 @@ int stem_in_mma(const void* x, int x_dtype, int x_layout, const float* w, const 
         for (int c = 0; c < 3; ++c) {
             a.n.sub[c] = mean[c] * 255.0f;
             a.n.mul[c] = 1.0f / (stdv[c] * 255.0f);
+        }
+        if ((reinterpret_cast<uintptr_t>(x) & 3u) == 0) {            // 32-bit window loads
+            const int cap = sm_count * 4;
+            const int grid = a.n_tiles < cap ? a.n_tiles : cap;
+            stem_in_u8_mma_kernel<<<grid, SO_THREADS, SU_SMEM, stream>>>(a);
+            return check_launch();
         }
         return launch_stem_in_mma<2>(a, sm_count, stream);
     }

@@ -53,28 +53,66 @@ def gather_code_tiles(tiles: torch.Tensor, n_total: int, group: Optional[dist.Pr
     return out[:n_total]
 
 
-def bind_host_to_gpu_numa_node(device_index: int) -> Optional[int]:
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _gpu_local_cpus(device_index: int):
+    """(cpus, where) of the NUMA node the GPU hangs off: sysfs first, `nvidia-smi topo -m`'s CPU-affinity
+    column second (containers often hide the sysfs node); (None, None) when neither says."""
+    import re
+    import subprocess
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node >= 0:
+            return _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()), f"node{node}"
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    try:
+        # CUDA_VISIBLE_DEVICES may renumber: match the row by PCI bus id through nvidia-smi's own query
+        q = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"],
+                           capture_output=True, text=True, timeout=20).stdout
+        pr = torch.cuda.get_device_properties(device_index)
+        want = f"{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".lower()
+        smi_index = None
+        for line in q.splitlines():
+            idx, _, bus = line.partition(",")
+            if bus.strip().lower().endswith(want):
+                smi_index = int(idx)
+        if smi_index is None:
+            return None, None
+        topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in topo.splitlines():
+            cols = line.split()
+            if cols and cols[0] == f"GPU{smi_index}":
+                for tok in cols[1:]:
+                    if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", tok) and ("-" in tok or "," in tok):
+                        return _parse_cpulist(tok), "nvidia-smi topo"
+    except (OSError, ValueError, subprocess.SubprocessError):
+        pass
+    return None, None
+
+
+def bind_host_to_gpu_numa_node(device_index: int) -> Optional[str]:
     """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that pinned host
     buffers allocated afterwards (first touch) and the staging thread are node-local.  With one rank
     per GPU all ranks otherwise stage their uint8 batches through whichever node the scheduler put
-    them on: at 8 ranks x 50 MB per 4 ms step the cross-socket hops cost ~3 % of the end-to-end rate.
-    Best effort: returns the node, or None (and changes nothing) when sysfs does not say."""
+    them on: at 8 ranks x 50 MB per 4 ms step the cross-socket hops cost several % of the end-to-end
+    rate.  Best effort: returns where the CPU list came from, or None (and changes nothing)."""
     try:
-        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
-        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
-        dev = torch.cuda.get_device_properties(device_index).pci_device_id
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
-        node = int(open(path).read().strip())
-        if node < 0:
+        cpus, where = _gpu_local_cpus(device_index)
+        if not cpus:
             return None
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
         cpus &= os.sched_getaffinity(0)
         if not cpus:
             return None
         os.sched_setaffinity(0, cpus)
-        return node
+        return f"{where}: {len(cpus)} cpus"
     except (OSError, ValueError, AttributeError, RuntimeError):
         return None

@@ -146,3 +146,31 @@ def test_stem_in_mma_vs_exact_fp32_kernel(kind, hw, batch):
         assert not torch.equal(got, ref) or hw == (16, 32)       # it IS the other kernel
     finally:
         m.cpu()
+
+
+@pytest.mark.parametrize("hw,batch,wscale", [((48, 96), 3, 1.0), ((16, 64), 5, 1.0), ((32, 32), 2, 300.0),
+                                             ((64, 128), 2, 1e-4)])
+def test_stem_in_u8_folded_normalisation_kernel(hw, batch, wscale):
+    """The uint8 form of the in_stem MMA kernel (pixels exact in fp16, normalisation folded into split
+    weights that are scaled by a power of two, `inside` as a fourth input channel) against the exact fp32
+    kernel: interior and border tiles, batch slices (the window is read with aligned 32-bit loads),
+    saturated pixels, and weights far from O(1)."""
+    m, sd, _ = H.model_and_state("model_nd3_perturbed")
+    enc = m.to(DEV).encoder
+    try:
+        g = torch.Generator().manual_seed(hw[0] + 3 * hw[1] + batch)
+        big = torch.randint(0, 256, (batch + 1, hw[0], hw[1], 3), generator=g, dtype=torch.uint8)
+        big[0, :, : hw[1] // 2] = 255                      # saturated and black regions
+        big[-1, hw[0] // 2:] = 0
+        big = big.to(DEV)
+        w = (enc.in_stem.weight.detach() * wscale).contiguous()
+        b = enc.in_stem.bias.detach()
+        for x in (big, big[1:], big[:1]):
+            ref = E.stem_in(x, w, b)
+            got = E.stem_in(x, w, b, precision="fp16")
+            torch.cuda.synchronize()
+            assert got.shape == ref.shape
+            assert float((got - ref).abs().max()) < 4e-6 * float(ref.abs().max())
+        assert torch.equal(E.stem_in(big, w, b, precision="fp16"), E.stem_in(big, w, b, precision="fp16"))
+    finally:
+        m.cpu()
