@@ -7,10 +7,7 @@ python bench.py --workload slide > gpurun_out/r2f_bench_slide.json 2> gpurun_out
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2f_bench_reference.json 2> gpurun_out/r2f_bench_reference.err
 python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/r2f_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/r2f_ncu_launches.log 2>&1
-python profiles/run_resident.py 54 3 > gpurun_out/r2f_res_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:trunk_resident -s 1 -c 1 -o gpurun_out/r2f_trunk_resident python profiles/run_resident.py 54 3 > gpurun_out/r2f_res_ncu.log 2>&1
+python profiles/run_stem.py > gpurun_out/r2f_stem_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:stem_in -s 2 -c 1 -o gpurun_out/r2f_stem_in_u8 python profiles/run_stem.py > gpurun_out/r2f_stem_ncu.log 2>&1
 python profiles/step_breakdown.py fp16 256 3 > gpurun_out/r2f_breakdown.txt 2>&1
-python profiles/step_breakdown.py fp16 64 4 > gpurun_out/r2f_breakdown512.txt 2>&1
-python profiles/decode_breakdown.py > gpurun_out/r2f_decode.txt 2>&1
-python profiles/host_overhead.py encode256 > gpurun_out/r2f_host_overhead.txt 2>&1; python profiles/host_overhead.py roundtrip512 >> gpurun_out/r2f_host_overhead.txt 2>&1
 cut -c1-300 gpurun_out/r2f_bench_encode256.json
