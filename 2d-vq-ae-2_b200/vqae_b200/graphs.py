@@ -35,6 +35,7 @@ class CapturedStep:
         self.fn, self.warmup, self.key_extra = fn, warmup, key_extra
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, object, int]] = {}
         self._seen: Dict[Tuple, int] = {}
+        self._eager_only = set()
         self._pool = None
 
     def _key(self, tensors) -> Tuple:
@@ -46,6 +47,7 @@ class CapturedStep:
         packed weight buffers that existed when it was captured)."""
         self._graphs.clear()
         self._seen.clear()
+        self._eager_only.clear()
 
     @torch.no_grad()
     def __call__(self, *tensors: torch.Tensor):
@@ -61,12 +63,24 @@ class CapturedStep:
         if seen < self.warmup:
             self._seen[shape_key] = seen + 1
             return self.fn(*tensors)
+        if key in self._eager_only:
+            return self.fn(*tensors)
         graph = torch.cuda.CUDAGraph()
         if self._pool is None:
             self._pool = torch.cuda.graph_pool_handle()
         l0 = E.raw_launch_count()
-        with torch.cuda.graph(graph, pool=self._pool, capture_error_mode="thread_local"):
-            out = self.fn(*tensors)
+        try:
+            with torch.cuda.graph(graph, pool=self._pool, capture_error_mode="thread_local"):
+                out = self.fn(*tensors)
+        except RuntimeError as exc:
+            # a step that cannot be captured (it allocates or synchronises outside torch's allocator)
+            # keeps running as plain launches of the same kernels; say so once
+            E._graph_launch_adjust -= E.raw_launch_count() - l0
+            self._eager_only.add(key)
+            import warnings
+            warnings.warn(f"vqae_b200.graphs: capture failed, this step runs eagerly ({exc})")
+            torch.cuda.synchronize()
+            return self.fn(*tensors)
         n_launch = E.raw_launch_count() - l0    # recorded during the capture, not executed
         self._graphs[key] = (graph, out, n_launch)
         graph.replay()                          # adjust: - n_launch (recorded) + n_launch (this replay)
