@@ -324,7 +324,8 @@ stem_in_u8_mma_kernel(StemInArgs a) {
         const int gg = i / 36, r = i - gg * 36, ky = r / 12, kx = (r - ky * 12) >> 2, c = r & 3;
         float v;
         if (c < 3) {
-            v = __fmul_rn(__ldg(a.w + gg * 27 + c * 9 + ky * 3 + kx), a.n.mul[c]);
+            const float mul = c == 0 ? a.n.mul[0] : (c == 1 ? a.n.mul[1] : a.n.mul[2]);   // no dynamic
+            v = __fmul_rn(__ldg(a.w + gg * 27 + c * 9 + ky * 3 + kx), mul);               // parameter index
         } else {
             v = 0.f;
 #pragma unroll
@@ -359,85 +360,112 @@ stem_in_u8_mma_kernel(StemInArgs a) {
     // the raw words of a tile's window: word wi of staged row si covers bytes 4 wi - 4 .. 4 wi - 1 counted from
     // the first byte of pixel (r0 - 1 + si, c0); pixel (., c0 - 1 + sj) sits at raw bytes 1 + 3 sj .. 3 + 3 sj
     constexpr int PPT = (SU_NRAW + SO_THREADS - 1) / SO_THREADS;
+    // Tile coordinates advance incrementally (a tile is only 512 pixels: two run-time divisions per
+    // tile and thread were a quarter of all instructions): tile = (img, ty, tx), step = gridDim.x tiles.
+    const int tiles_y = a.tiles_per_img / a.tiles_x;
+    const int st_img = (int)gridDim.x / a.tiles_per_img, st_rem = (int)gridDim.x - st_img * a.tiles_per_img;
+    const int st_ty = st_rem / a.tiles_x, st_tx = st_rem - st_ty * a.tiles_x;
+    int n_img, n_ty, n_tx;                                     // the tile whose window is being fetched
+    // the (up to PPT) raw words and (up to 3) records a thread handles sit at the same window positions in
+    // every tile
+    int raw_si[PPT], raw_wi[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int q = tid + k * SO_THREADS;
+        raw_si[k] = q / SU_RAW_W;
+        raw_wi[k] = q - raw_si[k] * SU_RAW_W;
+    }
+    constexpr int RROWS = SO_THREADS / SI_SPW;                // record rows per pass (7 of 18)
+    const int rec_si = tid / SI_SPW, rec_sj = tid - rec_si * SI_SPW;
+    const bool rec_on = rec_si < RROWS && rec_sj < SI_SREAL_C;
     uint32_t rv[PPT];
-    auto fetch = [&](int tile) {
-        const int img = tile / a.tiles_per_img;
-        const int trem = tile - img * a.tiles_per_img;
-        const int r0 = (trem / a.tiles_x) * SI_TH, c0 = (trem % a.tiles_x) * SI_TW;
+    auto fetch = [&]() {
+        const int r0 = n_ty * SI_TH, c0 = n_tx * SI_TW;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(a.x) + ((int64_t)n_img * hw + c0) * 3 - 4;
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
-            const int q = tid + k * SO_THREADS;
             rv[k] = 0u;
-            if (q < SU_NRAW) {
-                const int si = q / SU_RAW_W, wi = q - si * SU_RAW_W;
-                const int iy = r0 - 1 + si;
+            if (tid + k * SO_THREADS < SU_NRAW) {
+                const int iy = r0 - 1 + raw_si[k];
                 // the first / last word reach into the neighbouring row at the image's left / right edge
-                const bool ok = iy >= 0 && iy < a.H && !(wi == 0 && c0 == 0) &&
-                                !(wi == SU_RAW_W - 1 && c0 + SI_TW == a.W);
+                const bool ok = iy >= 0 && iy < a.H && !(raw_wi[k] == 0 && c0 == 0) &&
+                                !(raw_wi[k] == SU_RAW_W - 1 && c0 + SI_TW == a.W);
                 if (ok)
-                    rv[k] = __ldg(reinterpret_cast<const uint32_t*>(
-                        reinterpret_cast<const uint8_t*>(a.x) + ((int64_t)img * hw + (int64_t)iy * a.W + c0) * 3 - 4) + wi);
+                    rv[k] = __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)iy * a.W * 3) + raw_wi[k]);
             }
         }
     };
-    if ((int)blockIdx.x < a.n_tiles) fetch(blockIdx.x);
+    n_img = (int)blockIdx.x / a.tiles_per_img;
+    {
+        const int trem = (int)blockIdx.x - n_img * a.tiles_per_img;
+        n_ty = trem / a.tiles_x;
+        n_tx = trem - n_ty * a.tiles_x;
+    }
+    if ((int)blockIdx.x < a.n_tiles) fetch();
+    // per-warp constants of the MMA phase: M-tile mt = warp + 8 j (j = 0 .. 3) is pixels cb .. cb + 15 of
+    // tile row (warp >> 1) + 4 j, cb = 16 (warp & 1)
+    const int cb = (warp & 1) * 16, rr0 = warp >> 1;
+    const uint8_t* pw = smem + (uint32_t)(rr0 * SI_SPW + cb + g + t) * 8;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int img = tile / a.tiles_per_img;
-        const int trem = tile - img * a.tiles_per_img;
-        const int r0 = (trem / a.tiles_x) * SI_TH, c0 = (trem % a.tiles_x) * SI_TW;
+        const int r0 = n_ty * SI_TH, c0 = n_tx * SI_TW;
+        const int img = n_img;
 #pragma unroll
-        for (int k = 0; k < PPT; ++k) {
-            const int q = tid + k * SO_THREADS;
-            if (q < SU_NRAW) raw[q] = rv[k];
-        }
+        for (int k = 0; k < PPT; ++k)
+            if (tid + k * SO_THREADS < SU_NRAW) raw[tid + k * SO_THREADS] = rv[k];
         __syncthreads();
-        if (tile + (int)gridDim.x < a.n_tiles) fetch(tile + gridDim.x);      // in flight during this tile
+        n_img += st_img; n_ty += st_ty; n_tx += st_tx;                       // the next tile of this CTA
+        if (n_tx >= a.tiles_x) { n_tx -= a.tiles_x; ++n_ty; }
+        if (n_ty >= tiles_y) { n_ty -= tiles_y; ++n_img; }
+        if (tile + (int)gridDim.x < a.n_tiles) fetch();                      // in flight during this tile
         // ---- records: (R, G | B, inside) as fp16, zero outside the image (= the conv's padding) ----
-        for (int i = tid; i < SI_SROWS * SI_SREAL_C; i += SO_THREADS) {
-            const int si = i / SI_SREAL_C, sj = i - si * SI_SREAL_C;
-            const int iy = r0 - 1 + si, ix = c0 - 1 + sj;
-            uint2 rec = make_uint2(0u, 0u);
-            if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
-                const uint8_t* b = rawb + si * (SU_RAW_W * 4) + 1 + 3 * sj;
-                // 0x6400 | n is the fp16 number 1024 + n (n < 1024): subtracting 1024 leaves n exactly
-                const uint32_t p01 = 0x64006400u | (uint32_t)b[0] | ((uint32_t)b[1] << 16);
-                const uint32_t p2m = 0x3C006400u | (uint32_t)b[2];                 // high half: 1.0 = inside
-                const __half2 h01 = __hsub2(*reinterpret_cast<const __half2*>(&p01), __floats2half2_rn(1024.f, 1024.f));
-                const __half2 h2m = __hsub2(*reinterpret_cast<const __half2*>(&p2m), __floats2half2_rn(1024.f, 0.f));
-                rec.x = *reinterpret_cast<const uint32_t*>(&h01);
-                rec.y = *reinterpret_cast<const uint32_t*>(&h2m);
+        if (rec_on) {
+            const int ix = c0 - 1 + rec_sj;
+            const bool col_in = ix >= 0 && ix < a.W;
+#pragma unroll
+            for (int pass = 0; pass < (SI_SROWS + RROWS - 1) / RROWS; ++pass) {
+                const int si = pass * RROWS + rec_si;
+                if (si < SI_SROWS) {
+                    const int iy = r0 - 1 + si;
+                    uint2 rec = make_uint2(0u, 0u);
+                    if (col_in && iy >= 0 && iy < a.H) {
+                        const uint8_t* b = rawb + si * (SU_RAW_W * 4) + 1 + 3 * rec_sj;
+                        // 0x6400 | n is the fp16 number 1024 + n (n < 1024): subtracting 1024 leaves n exactly
+                        const uint32_t p01 = 0x64006400u | (uint32_t)b[0] | ((uint32_t)b[1] << 16);
+                        const uint32_t p2m = 0x3C006400u | (uint32_t)b[2];             // high half: 1.0 = inside
+                        const __half2 h01 = __hsub2(*reinterpret_cast<const __half2*>(&p01),
+                                                    __floats2half2_rn(1024.f, 1024.f));
+                        const __half2 h2m = __hsub2(*reinterpret_cast<const __half2*>(&p2m),
+                                                    __floats2half2_rn(1024.f, 0.f));
+                        rec.x = *reinterpret_cast<const uint32_t*>(&h01);
+                        rec.y = *reinterpret_cast<const uint32_t*>(&h2m);
+                    }
+                    *reinterpret_cast<uint2*>(smem + (uint32_t)(si * SI_SPW + rec_sj) * 8) = rec;
+                }
             }
-            *reinterpret_cast<uint2*>(smem + (uint32_t)(si * SI_SPW + sj) * 8) = rec;
         }
         __syncthreads();
-        // ---- 32 M-tiles of 16 pixels of a row, two per warp step ----
-        float* oimg = a.out + (size_t)img * hw * 8;
-#pragma unroll 1
-        for (int mt0 = warp; mt0 < SI_MT; mt0 += 2 * SO_WARPS) {
-            float d[2][4];
-            const uint8_t* p0[2];
-            int rr[2], cb[2];
+        // ---- 32 M-tiles of 16 pixels of a row: four per warp, two at a time ----
+        float* ow = a.out + (((size_t)img * a.H + r0 + rr0) * a.W + c0 + cb + g) * 8 + 2 * t;
+        const size_t orow4 = (size_t)4 * a.W * 8;                 // four tile rows further
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int mt = mt0 + u * SO_WARPS;
-                rr[u] = mt >> 1;
-                cb[u] = (mt & 1) * 16;
-                p0[u] = smem + (uint32_t)(rr[u] * SI_SPW + cb[u] + g + t) * 8;
-                d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
-            }
+        for (int jj = 0; jj < 2; ++jj) {
+            float d[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const uint2 u0 = *reinterpret_cast<const uint2*>(p0[u] + ky * SI_SPW * 8);
-                    const uint2 u1 = *reinterpret_cast<const uint2*>(p0[u] + ky * SI_SPW * 8 + 8 * 8);
+                    const uint8_t* p = pw + ((2 * jj + u) * 4 + ky) * SI_SPW * 8;
+                    const uint2 u0 = *reinterpret_cast<const uint2*>(p);
+                    const uint2 u1 = *reinterpret_cast<const uint2*>(p + 8 * 8);
                     const uint32_t av[4] = {u0.x, u1.x, u0.y, u1.y};
                     mma_16816(d[u], av, bl[ky][0], bl[ky][1]);
                     mma_16816(d[u], av, bh[ky][0], bh[ky][1]);
                 }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                float* o = oimg + ((size_t)(r0 + rr[u]) * a.W + c0 + cb[u] + g) * 8 + 2 * t;
+                float* o = ow + (2 * jj + u) * orow4;
                 *reinterpret_cast<float2*>(o) = make_float2(fmaf(d[u][0], inv, bias0), fmaf(d[u][1], inv, bias1));
                 *reinterpret_cast<float2*>(o + 64) = make_float2(fmaf(d[u][2], inv, bias0), fmaf(d[u][3], inv, bias1));
             }
