@@ -78,7 +78,8 @@ class CapturedStep:
             E._graph_launch_adjust -= E.raw_launch_count() - l0
             self._eager_only.add(key)
             import warnings
-            warnings.warn(f"vqae_b200.graphs: capture failed, this step runs eagerly ({exc})")
+            warnings.warn(f"vqae_b200.graphs: capture failed, this step runs eagerly ({exc}); note that "
+                          "torch leaves its CUDA random generator in capture mode after a failed capture")
             torch.cuda.synchronize()
             return self.fn(*tensors)
         n_launch = E.raw_launch_count() - l0    # recorded during the capture, not executed
