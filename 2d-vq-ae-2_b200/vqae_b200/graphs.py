@@ -29,10 +29,12 @@ class CapturedStep:
     the same buffers.  All graphs of one ``CapturedStep`` share one memory pool, so they must not
     run concurrently (they never do on one stream)."""
 
-    def __init__(self, fn: Callable, warmup: int = 1, key_extra: Callable = None):
+    def __init__(self, fn: Callable, warmup: int = 1, key_extra: Callable = None, max_graphs: int = 512):
         """``key_extra()``: extra hashable state a captured graph depends on (e.g. the precision the
-        step would pick); a change selects / captures another graph."""
-        self.fn, self.warmup, self.key_extra = fn, warmup, key_extra
+        step would pick); a change selects / captures another graph.  ``max_graphs``: graphs are keyed on
+        the input BUFFERS, so a caller that passes freshly allocated tensors every time would capture
+        without end -- beyond this many the oldest graph is dropped (use persistent staging buffers)."""
+        self.fn, self.warmup, self.key_extra, self.max_graphs = fn, warmup, key_extra, max_graphs
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, object, int]] = {}
         self._seen: Dict[Tuple, int] = {}
         self._eager_only = set()
@@ -83,6 +85,8 @@ class CapturedStep:
             torch.cuda.synchronize()
             return self.fn(*tensors)
         n_launch = E.raw_launch_count() - l0    # recorded during the capture, not executed
+        if len(self._graphs) >= self.max_graphs:
+            self._graphs.pop(next(iter(self._graphs)))
         self._graphs[key] = (graph, out, n_launch)
         graph.replay()                          # adjust: - n_launch (recorded) + n_launch (this replay)
         return out
