@@ -202,3 +202,9 @@ def test_hdf5_layout_matches_the_reference_converter(tmp_path):
     assert np.array_equal(masks[1], maps["masks/tumor_002_mask"])
     only_tumor, _ = F.read_code_maps(out, pattern="tumor", h5=_FakeH5)
     assert len(only_tumor) == 1 and np.array_equal(only_tumor[0], maps["images/tumor_002"])
+
+
+def test_cpulist_parsing_for_numa_binding():
+    from vqae_b200.sharding import _parse_cpulist
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("5") == {5}
