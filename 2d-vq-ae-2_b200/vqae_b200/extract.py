@@ -235,8 +235,9 @@ class StreamingEncoder:
                 self._host_out[oslot].copy_(idx, non_blocking=True)
                 self._d2h[oslot].record(self.out_stream)
             self._idx_read[slot] = self._d2h[oslot]
-            if self._step is None:
-                idx.record_stream(self.out_stream)
+            # eager results (no graphs, the first batch, a short last batch) are ordinary allocations: the
+            # allocator must not hand their memory out again before the copy stream has read it
+            idx.record_stream(self.out_stream)
             pending.append(oslot)
             if len(pending) == 2:                  # results lag one batch behind the submission
                 yield result(pending.pop(0))
